@@ -1,0 +1,406 @@
+#!/usr/bin/env python3
+"""bench.py -- the `haphic cluster` hot path on B200: Hi-C pairs/sec through the link-matrix build
+and MCL iterations/sec, on the synthetic 50k-contig / 200M-pair workload (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the CPU port of the reference path
+
+One "step" = one pass of the hot path over the whole synthetic input:
+    link counting (200M records) -> first-seen index -> symmetric CSC -> column normalise ->
+    pre-expansion M0.M0 -> Markov-cluster sweep over `--inflations`.
+`value` = pairs/s through the matrix build with the records already resident in HBM (CUDA events on
+the library's stream); `mcl.value` = MCL iterations/s over the sweep (normalise + pre-expansion +
+all iterations, the reference's own definition, HapHiC_cluster.py:2951-2953); `e2e` = the same
+quantities through the public host API with HOST (pinned) buffers, H2D and D2H inside the timed
+region.  Rank 0 prints ONE JSON line.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=2)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    p.add_argument("--contigs", type=int, default=50000)
+    p.add_argument("--pairs", type=int, default=200_000_000)
+    p.add_argument("--nchr", type=int, default=24)
+    p.add_argument("--mean-len", type=int, default=20000)
+    p.add_argument("--inflations", default="1.5,2.0,3.0")
+    p.add_argument("--max-iter", type=int, default=200)
+    p.add_argument("--pruning", type=float, default=1e-4)
+    p.add_argument("--seed", type=int, default=12345)
+    p.add_argument("--e2e-steps", type=int, default=1)
+    p.add_argument("--cpu-sample-pairs", type=int, default=400_000)
+    p.add_argument("--cpu-sample-cols", type=int, default=24)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--verbose", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(a):
+    return "{}k contigs / {}M pairs synthetic (nchr={}, mean_len={}, Nx=100, bin_size=0)".format(
+        a.contigs // 1000, a.pairs // 1_000_000, a.nchr, a.mean_len)
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            cols = [c.strip() for c in line.split(",")]
+            if len(cols) < 6:
+                continue
+            try:
+                sm.append(float(cols[0]))
+                mx = float(cols[1])
+            except ValueError:
+                continue
+            for nm, c in zip(names, cols[2:6]):
+                if c.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU port of the reference path (oracle) -- the `--impl reference` arm and the cpu_baseline leg
+# --------------------------------------------------------------------------------------------------
+
+def cpu_pairs_per_sec(asm, rank, in_nx, sample):
+    """The reference's per-read-pair Python loop (HapHiC_cluster.py:1622-1653) restated in
+    oracle/haphic_oracle.py, single thread by construction, on a bounded sample of the stream."""
+    from oracle import haphic_oracle as orc
+    t0 = time.perf_counter()
+    orc.count_links_loop(sample, asm.lengths, rank, in_nx, 500000)
+    dt = time.perf_counter() - t0
+    return len(sample) / dt, dt
+
+
+def cpu_mcl_iter_per_sec(m_csc, n_cols, inflation, pruning, seed=0):
+    """One MCL iteration (expand -> inflate -> normalise -> prune, HapHiC_cluster.py:2029-2042) of the CPU
+    port (scipy SpGEMM standing in for MKL) on a random sample of columns of the given iterate;
+    the full-iteration time is the sample time scaled by n / n_cols (every step is column-local)."""
+    from oracle import haphic_oracle as orc
+    n = m_csc.shape[0]
+    rng = np.random.default_rng(seed)
+    cols = np.sort(rng.choice(n, size=min(n_cols, n), replace=False))
+    sub = m_csc[:, cols]
+    t0 = time.perf_counter()
+    prod = (m_csc @ sub).tocsc()
+    prod = orc.inflate(prod, inflation)
+    orc.prune(prod, pruning)
+    dt = time.perf_counter() - t0
+    full = dt * n / len(cols)
+    return 1.0 / full, dt, len(cols)
+
+
+def make_inputs(a, device, rank_id=0, world=1):
+    """Synthetic assembly (host) and this rank's shard of the pair stream (on `device`)."""
+    import torch
+    from haphic_b200 import synth
+    from haphic_b200.links import name_rank
+    asm = synth.make_assembly(a.nchr, a.contigs, a.mean_len, seed=a.seed)
+    rank = name_rank(asm.names)
+    in_nx = np.ones(asm.n, np.uint8)                     # --Nx 100
+    per = a.pairs // world
+    lo = rank_id * per
+    hi = a.pairs if rank_id == world - 1 else lo + per
+    rec = synth.make_pairs(asm, hi - lo, seed=a.seed + 1 + rank_id, device=device)
+    return asm, rank, in_nx, rec, lo
+
+
+def run_reference(a):
+    """`--impl reference`: the CPU port of the reference path on the host cores, bounded samples."""
+    import torch
+    rank_id = int(os.environ.get("RANK", "0"))
+    if rank_id != 0:
+        return
+    from haphic_b200 import synth
+    from haphic_b200.links import name_rank
+    from oracle import haphic_oracle as orc
+    asm = synth.make_assembly(a.nchr, a.contigs, a.mean_len, seed=a.seed)
+    rank = name_rank(asm.names)
+    in_nx = np.ones(asm.n, np.uint8)
+    sample = synth.make_pairs(asm, a.cpu_sample_pairs, seed=a.seed + 1, device="cpu").numpy()
+    times = []
+    for s in range(a.warmup + a.steps):
+        v, dt = cpu_pairs_per_sec(asm, rank, in_nx, sample)
+        if s >= a.warmup:
+            times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    value = len(sample) / (ms / 1000.0)
+    # MCL on a reduced instance of the same generator (the port cannot hold the 50k-contig dense
+    # pre-expansion): 2,000 contigs, same pairs-per-contig ratio
+    small = synth.make_assembly(max(2, a.nchr // 8), 2000, a.mean_len, seed=a.seed)
+    sp_pairs = synth.make_pairs(small, min(a.pairs // max(1, a.contigs // 2000), 2_000_000), seed=a.seed + 1).numpy()
+    r = orc.count_links_numpy(sp_pairs, small.lengths, name_rank(small.names), np.ones(small.n, np.uint8), 500000)
+    m, _ = orc.dict_to_matrix(r["flank_keys"], r["flank_vals"], np.ones(small.n, np.uint8))
+    t0 = time.perf_counter()
+    sweep = orc.run_mcl_sweep(m, 2, [float(x) for x in a.inflations.split(",")], a.max_iter, a.pruning)
+    t_mcl = time.perf_counter() - t0
+    iters = sum(s[2] for s in sweep)
+    line = {
+        "impl": "reference", "metric": "hic_pairs_per_sec_matrix_build", "value": value, "unit": "pairs/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int32 counts / fp32 matrix", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": "first {} records of the stream per step".format(len(sample))},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": 1, "kind": "port",
+                         "sample": "{} records through oracle.count_links_loop (single-threaded like the reference's loop)"
+                         .format(len(sample))},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mcl": {"metric": "mcl_iterations_per_sec", "value": iters / t_mcl, "unit": "iter/s", "iterations": iters,
+                "sample": "full sweep on a 2,000-contig instance of the same generator (scipy SpGEMM standing in for MKL); "
+                          "the 50k-contig pre-expansion (10 GB dense) does not fit the port's budget",
+                "host_cores": os.cpu_count()},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank_id = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from haphic_b200 import dist as hdist
+        return hdist.bench_multi(a, world, rank_id, local)
+
+    from haphic_b200._lib import Context
+    from haphic_b200.links import LinkTable
+    from haphic_b200.mcl import Mcl, interpret_result
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    inflations = [float(x) for x in a.inflations.split(",")]
+    asm, rank, in_nx, rec, _ = make_inputs(a, dev)
+    n = asm.n
+    P = int(rec.shape[0])
+    keep = np.ones(n, np.uint8)
+    ctx = Context(0)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    hint = int(min(P, n * (n - 1) // 2) * (0.45 if P > 4_000_000 else 1.0))
+    torch.cuda.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def one_step(timed):
+        """Resident-input pass.  Returns per-stage device times (ms) and statistics."""
+        e = [ev() for _ in range(4)]
+        e[0].record(stream)
+        tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
+        tab.add(rec, asynchronous=True)
+        info = tab.finish()
+        e[1].record(stream)
+        index, n_linked = tab.linked_index(keep)
+        tail = np.nonzero(index < 0)[0].astype(np.int32)
+        mat = tab.to_matrix(keep, tail)
+        e[2].record(stream)
+        mc = Mcl(mat)
+        iters, kernel_ms, alg_bytes, products = 0, mc.normalize_ms + mc.preexp_ms, 0, mc.preexp_products
+        per_infl = []
+        for r in inflations:
+            st = mc.run(r, a.max_iter, a.pruning)
+            iters += st["rounds"]
+            kernel_ms += float(st["iter_ms"].sum())
+            alg_bytes += st["bytes"]
+            products += st["products"]
+            per_infl.append({"inflation": r, "rounds": st["rounds"], "converged": st["converged"],
+                             "ms": float(st["iter_ms"].sum()), "nnz_iter": st["iter_nnz"][:6].tolist(),
+                             "ms_iter": [round(float(x), 3) for x in st["iter_ms"][:6]]})
+        e[3].record(stream)
+        e[3].synchronize()
+        out = {
+            "build_ms": e[0].elapsed_time(e[1]), "matrix_ms": e[1].elapsed_time(e[2]), "mcl_ms": e[2].elapsed_time(e[3]),
+            "iters": iters, "kernel_ms": kernel_ms, "alg_bytes": alg_bytes, "products": products,
+            "nnz_full": int(info.nnz_full), "nnz_flank": int(info.nnz_flank), "n_used": int(info.n_used),
+            "nnz_m0": mc.nnz_m0, "preexp_ms": mc.preexp_ms, "preexp_products": mc.preexp_products,
+            "normalize_ms": mc.normalize_ms, "per_inflation": per_infl, "n_matrix": mat.n,
+        }
+        mc.close()
+        mat.close()
+        tab.close()
+        return out
+
+    for _ in range(a.warmup):
+        one_step(False)
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ctx.launches
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    steps = [one_step(True) for _ in range(a.steps)]
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+
+    build_ms = sum(s["build_ms"] for s in steps) / len(steps)
+    matrix_ms = sum(s["matrix_ms"] for s in steps) / len(steps)
+    mcl_ms = sum(s["mcl_ms"] for s in steps) / len(steps)
+    s0 = steps[-1]
+    pairs_per_s = P / ((build_ms + matrix_ms) / 1000.0)
+    iters_per_s = s0["iters"] / (mcl_ms / 1000.0)
+    peak, peak_src = measured_peaks()
+    # dominant kernel: the per-column MCL kernel (hh_k_col); algorithmic bytes per SURVEY.md 8(d)
+    mcl_bytes = s0["alg_bytes"] + 8 * s0["nnz_m0"] + 4 * s0["n_matrix"] ** 2
+    mcl_achieved = mcl_bytes / (s0["kernel_ms"] / 1000.0) / 1e9
+    build_bytes = 16 * P + 12 * s0["nnz_full"] + 12 * s0["nnz_flank"] + 4 * n
+    build_achieved = build_bytes / (build_ms / 1000.0) / 1e9
+
+    # ---- end to end through the host API: pinned host records in, host results out ------------------
+    rec_host = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
+    rec_host.copy_(rec)
+    torch.cuda.synchronize()
+    e2e_build, e2e_mcl, d2h = [], [], 0
+    for s in range(1 + a.e2e_steps):
+        t0 = time.perf_counter()
+        tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
+        tab.add(rec_host)                                   # H2D inside, double-buffered
+        info = tab.finish()
+        table = tab.fetch()                                 # D2H: the link dicts' arrays
+        tot = tab.fetch_ctg()
+        index, n_linked = tab.linked_index(keep)
+        tail = np.nonzero(index < 0)[0].astype(np.int32)
+        mat = tab.to_matrix(keep, tail)
+        ctx.sync()
+        t1 = time.perf_counter()
+        mc = Mcl(mat)
+        n_it = 0
+        d2h_mcl = 0
+        for r in inflations:
+            st = mc.run(r, a.max_iter, a.pruning)
+            n_it += st["rounds"]
+            fin = mc.result()                               # D2H: final matrix of this inflation
+            interpret_result(fin)
+            d2h_mcl += fin.nnz * 8 + (n + 1) * 8
+        t2 = time.perf_counter()
+        if s >= 1:
+            e2e_build.append(t1 - t0)
+            e2e_mcl.append((t2 - t1, n_it))
+            d2h = sum(v.nbytes for v in table.values()) + tot.nbytes + index.nbytes + d2h_mcl
+        mc.close()
+        mat.close()
+        tab.close()
+    e2e_pairs = P / (sum(e2e_build) / len(e2e_build))
+    e2e_iters = sum(x[1] for x in e2e_mcl) / sum(x[0] for x in e2e_mcl)
+
+    # ---- CPU baseline on this box's host cores (bounded samples) ------------------------------------
+    cpu = None
+    mcl_cpu = None
+    if not a.no_cpu_baseline:
+        sample = rec[: a.cpu_sample_pairs].cpu().numpy()
+        v, dt = cpu_pairs_per_sec(asm, rank, in_nx, sample)
+        cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
+               "sample": "first {} records through oracle.count_links_loop ({:.1f} s; the reference's loop is "
+                         "single-threaded Python)".format(len(sample), dt)}
+        # MCL: iterate M_1 (after iteration 0) of the last inflation, a sample of columns
+        tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
+        tab.add(rec, asynchronous=True)
+        tab.finish()
+        index, _ = tab.linked_index(keep)
+        mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))
+        mc = Mcl(mat)
+        mc.run(inflations[len(inflations) // 2], 1, a.pruning)
+        m_iter1 = mc.result()
+        ips, dt, ncols = cpu_mcl_iter_per_sec(m_iter1, a.cpu_sample_cols, inflations[len(inflations) // 2], a.pruning)
+        mcl_cpu = {"value": ips, "unit": "iter/s", "cores": 1, "kind": "port",
+                   "sample": "iteration 1 (expand+inflate+prune) of inflation {} on {} of {} columns, {:.1f} s, scaled by n/cols; "
+                             "scipy SpGEMM stands in for MKL".format(inflations[len(inflations) // 2], ncols, n, dt)}
+        mc.close()
+        mat.close()
+        tab.close()
+
+    line = {
+        "metric": "hic_pairs_per_sec_matrix_build", "value": pairs_per_s, "unit": "pairs/s", "n_gpus": 1,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * t_wall / a.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int32 counts / fp32 matrix", "data": "synthetic",
+        "config": {"workload": workload_name(a), "inflations": inflations, "max_iter": a.max_iter, "pruning": a.pruning,
+                   "cache": "inputs (16 B x pairs = {:.1f} GB) and the dense pre-expanded matrix exceed the 126 MB L2".format(
+                       16 * P / 1e9),
+                   "step": "link build + index + CSC + normalise + pre-expansion + MCL sweep"},
+        "stage_ms": {"link_build": build_ms, "matrix": matrix_ms, "mcl_sweep": mcl_ms},
+        "mcl": {"metric": "mcl_iterations_per_sec", "value": iters_per_s, "unit": "iter/s", "iterations": s0["iters"],
+                "products": s0["products"], "preexp_ms": s0["preexp_ms"], "normalize_ms": s0["normalize_ms"],
+                "per_inflation": s0["per_inflation"], "e2e": {"value": e2e_iters, "unit": "iter/s"},
+                "cpu_baseline": mcl_cpu},
+        "links": {"pairs": P, "used": s0["n_used"], "nnz_full": s0["nnz_full"], "nnz_flank": s0["nnz_flank"],
+                  "n_matrix": s0["n_matrix"], "nnz_m0": s0["nnz_m0"]},
+        "e2e": {"value": e2e_pairs, "unit": "pairs/s", "h2d_bytes_per_step": 16 * P + 13 * n, "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "hh_k_col (MCL column kernel: expansion + inflate/normalise/prune)", "bound": "hbm",
+                     "achieved": mcl_achieved, "peak": peak, "unit": "GB/s", "frac": mcl_achieved / peak, "traffic": None,
+                     "peak_source": peak_src},
+        "roofline_build": {"kernel": "hh_k_links_insert + finish", "bound": "hbm", "achieved": build_achieved, "peak": peak,
+                           "unit": "GB/s", "frac": build_achieved / peak, "traffic": None},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    ctx.close()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

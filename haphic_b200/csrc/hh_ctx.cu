@@ -1,0 +1,120 @@
+// Context, error string, small utilities of libhaphic_b200.
+#include "hh_common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void hh_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int hh_version(void) { return HH_VERSION; }
+extern "C" const char* hh_last_error(void) { return g_err; }
+
+extern "C" int hh_ctx_create(int device, hh_ctx** out) {
+    HH_REQUIRE(out != nullptr, HH_ERR_ARG, "hh_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        hh_set_error("hh_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return HH_ERR_CUDA;
+    }
+    HH_REQUIRE(device >= 0 && device < count, HH_ERR_ARG, "hh_ctx_create: device %d out of range [0,%d)", device, count);
+    HH_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HH_CUDA(cudaGetDeviceProperties(&prop, device));
+    HH_REQUIRE(prop.major >= 10, HH_ERR_UNSUPPORTED,
+               "hh_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+               prop.major, prop.minor);
+    hh_ctx* c = new (std::nothrow) hh_ctx();
+    HH_REQUIRE(c != nullptr, HH_ERR_NOMEM, "hh_ctx_create: out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    c->launches = 0;
+    c->stream = nullptr;
+    c->h_scratch = nullptr;
+    c->d_scratch = nullptr;
+    HH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    HH_CUDA(cudaMallocHost((void**)&c->h_scratch, 64 * sizeof(uint64_t)));
+    HH_CUDA(cudaMalloc((void**)&c->d_scratch, 64 * sizeof(uint64_t)));
+    *out = c;
+    return HH_OK;
+}
+
+extern "C" int hh_ctx_destroy(hh_ctx* c) {
+    if (!c) return HH_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    delete c;
+    return HH_OK;
+}
+
+extern "C" int hh_ctx_sync(hh_ctx* c) {
+    HH_REQUIRE(c != nullptr, HH_ERR_ARG, "hh_ctx_sync: ctx is NULL");
+    HH_CUDA(cudaSetDevice(c->device));
+    HH_CUDA(cudaStreamSynchronize(c->stream));
+    return HH_OK;
+}
+
+extern "C" void* hh_ctx_stream(hh_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int hh_ctx_device(hh_ctx* c) { return c ? c->device : -1; }
+extern "C" int hh_ctx_sm_count(hh_ctx* c) { return c ? c->sm_count : 0; }
+extern "C" int64_t hh_ctx_launches(hh_ctx* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// single-CTA exclusive scan (1024 threads, tiles of 1024 with a running carry)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) hh_k_scan_small(const int* __restrict__ in, int64_t* __restrict__ out, int n) {
+    __shared__ int64_t warp_tot[32];
+    __shared__ int64_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        int64_t v = (i < n) ? (int64_t)in[i] : 0;
+        int64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(HH_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = warp_tot[lane];
+            int64_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t t = __shfl_up_sync(HH_FULL_MASK, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_tot[lane] = wi - w;   // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        int64_t carry = carry_s;
+        int64_t excl = carry + warp_tot[warp] + incl - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+int hh_exclusive_scan_i32(hh_ctx* ctx, const int* d_in, int64_t* d_out, int n) {
+    HH_LAUNCH(ctx, hh_k_scan_small, 1, 1024, 0, d_in, d_out, n);
+    return HH_OK;
+}

@@ -1,0 +1,743 @@
+// Link counting on the GPU: the per-read-pair loop of parse_alignments_for_ctgs
+// (scripts/HapHiC_cluster.py:1596-1655) as a warp-aggregated atomic histogram over an
+// open-addressing hash table keyed by the (name-ordered) contig pair.
+//
+// Per record (16 B, one 128-bit streaming load) the kernel
+//   * drops ctg_a == ctg_b (generator filter, 1582 / 2862) and ids outside the FASTA (1625),
+//   * orders the two ends by contig NAME rank (1629),
+//   * evaluates is_flank on both 1-based coordinates and the Nx membership (1636, 299-307),
+//   * evaluates the head/tail halves `coord*2 > len` (404-416),
+//   * groups equal keys inside the warp with match.any so one lane issues the atomics for the
+//     whole group (coordinate- or name-sorted inputs collapse 32 records into one update),
+//   * updates {full, flank, HT, TH, TT} counters and the first-seen stream indices (dict
+//     insertion order of full_link_dict / flank_link_dict) of the key's slot, and the two
+//     per-fragment totals (ctg_link_dict, 1638-1639).
+// hh_links_finish orders the distinct keys by first appearance with a scatter + stream
+// compaction (no sort): order[first_full] = slot, then compact.
+#include "hh_common.cuh"
+
+#define HH_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define HH_NONE32 0xFFFFFFFFu
+
+struct __align__(32) hh_slot {
+    uint32_t first_full, first_flank, full, flank, ht, th, tt, pad;
+};
+
+struct hh_links {
+    hh_ctx* ctx;
+    int32_t n_ctg;
+    int64_t flank_bp;
+    int32_t* d_len;
+    int32_t* d_rank;
+    uint8_t* d_nx;
+    unsigned long long* d_ctg;       // [n_ctg] per-fragment flank-link totals
+    uint64_t* d_keys;                // [cap]
+    hh_slot* d_vals;                 // [cap]
+    uint64_t cap;                    // power of two
+    unsigned long long* d_counters;  // [0] distinct keys  [1] records used  [2] overflow flag  [3] nnz_flank
+                                     // [4] largest first-seen index merged from a peer
+    int64_t n_records, stream_end;
+    int64_t known_unique, since_known;   // growth bookkeeping (see ensure_capacity)
+    bool finished;
+    int64_t nnz, nnz_flank, n_used;
+    uint32_t* d_compact;             // [nnz][9]  {i, j, full, flank, first_full, first_flank, HT, TH, TT}
+    // host staging (double-buffered H2D)
+    int4* d_stage[2];
+    cudaEvent_t ev_copied[2], ev_consumed[2];
+    cudaStream_t copy_stream;
+    int64_t stage_records;
+    // dict_to_matrix support
+    int32_t* d_index;                // [n_ctg] matrix index of linked fragments (hh_links_linked_index)
+    int32_t n_linked;
+    uint8_t* d_keep;
+};
+
+__device__ __forceinline__ uint64_t hh_mix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+
+// find-or-insert; returns slot index, sets *inserted.  Returns cap (invalid) if the table is full.
+__device__ __forceinline__ uint64_t hh_probe_insert(uint64_t* __restrict__ keys, uint64_t cap, uint64_t key, bool* inserted) {
+    const uint64_t mask = cap - 1;
+    uint64_t slot = hh_mix64(key) & mask;
+    *inserted = false;
+    for (uint64_t probes = 0; probes < cap; ++probes) {
+        uint64_t k = *((volatile uint64_t*)(keys + slot));
+        if (k == key) return slot;
+        if (k == HH_EMPTY_KEY) {
+            unsigned long long prev = atomicCAS((unsigned long long*)(keys + slot), (unsigned long long)HH_EMPTY_KEY,
+                                                (unsigned long long)key);
+            if (prev == HH_EMPTY_KEY) {
+                *inserted = true;
+                return slot;
+            }
+            if (prev == key) return slot;
+        }
+        slot = (slot + 1) & mask;
+    }
+    return cap;
+}
+
+__global__ void hh_k_links_init(uint64_t* __restrict__ keys, hh_slot* __restrict__ vals, uint64_t cap) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride) {
+        keys[s] = HH_EMPTY_KEY;
+        uint4* v = reinterpret_cast<uint4*>(vals + s);
+        v[0] = make_uint4(HH_NONE32, HH_NONE32, 0u, 0u);
+        v[1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hh_k_links_insert(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_off, int32_t n_ctg,
+                  const int32_t* __restrict__ ctg_len, const int32_t* __restrict__ name_rank,
+                  const uint8_t* __restrict__ in_nx, int64_t flank_bp, uint64_t* __restrict__ keys,
+                  hh_slot* __restrict__ vals, uint64_t cap, unsigned long long* __restrict__ ctg_links,
+                  unsigned long long* __restrict__ counters) {
+    __shared__ unsigned int s_new, s_used, s_over;
+    if (threadIdx.x == 0) {
+        s_new = 0;
+        s_used = 0;
+        s_over = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int my_new = 0, my_used = 0;
+    // warp-uniform loop bounds: every lane of a warp runs the same number of trips
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n_rec; i0 += stride) {
+        const int64_t i = i0 + lane;
+        bool ok = i < n_rec;
+        int4 r = make_int4(-1, 0, -1, 0);
+        if (ok) r = hh_ld_stream(rec + i);
+        ok = ok && (r.x != r.z) && ((unsigned)r.x < (unsigned)n_ctg) && ((unsigned)r.z < (unsigned)n_ctg);
+        uint64_t key = HH_EMPTY_KEY - 1 - (uint64_t)lane;   // unique per lane: never groups, never a real key
+        int ci = 0, cj = 0;
+        bool fl = false, ti = false, tj = false;
+        if (ok) {
+            int a = r.x, b = r.z, pa = r.y, pb = r.w;
+            if (name_rank[a] > name_rank[b]) {            // sorted(((ref,pos+1),(mref,mpos+1))), 1629
+                int t = a; a = b; b = t;
+                t = pa; pa = pb; pb = t;
+            }
+            ci = a;
+            cj = b;
+            const int64_t coord_i = (int64_t)pa + 1, coord_j = (int64_t)pb + 1;   // 1-based
+            const int64_t li = ctg_len[a], lj = ctg_len[b];
+            const bool fi = (flank_bp == 0) || (coord_i <= flank_bp) || (coord_i > li - flank_bp);   // is_flank, 299-307
+            const bool fj = (flank_bp == 0) || (coord_j <= flank_bp) || (coord_j > lj - flank_bp);
+            fl = fi && fj && in_nx[a] && in_nx[b];                                                  // 1636
+            ti = coord_i * 2 > li;                                                                   // 404-416
+            tj = coord_j * 2 > lj;
+            key = ((uint64_t)(uint32_t)a << 32) | (uint64_t)(uint32_t)b;
+            my_used++;
+        }
+        const unsigned peers = __match_any_sync(HH_FULL_MASK, key);
+        const unsigned b_fl = __ballot_sync(HH_FULL_MASK, ok && fl);
+        const unsigned b_ht = __ballot_sync(HH_FULL_MASK, ok && !ti && tj);
+        const unsigned b_th = __ballot_sync(HH_FULL_MASK, ok && ti && !tj);
+        const unsigned b_tt = __ballot_sync(HH_FULL_MASK, ok && ti && tj);
+        if (ok && lane == (__ffs(peers) - 1)) {
+            bool inserted;
+            const uint64_t slot = hh_probe_insert(keys, cap, key, &inserted);
+            if (slot >= cap) {
+                s_over = 1;
+            } else {
+                if (inserted) my_new++;
+                hh_slot* v = vals + slot;
+                const unsigned c_full = __popc(peers);
+                const unsigned m_fl = peers & b_fl;
+                const unsigned c_fl = __popc(m_fl);
+                atomicAdd(&v->full, c_full);
+                atomicMin(&v->first_full, stream_off + (uint32_t)i);      // leader = lowest lane = earliest record
+                if (c_fl) {
+                    atomicAdd(&v->flank, c_fl);
+                    atomicMin(&v->first_flank, stream_off + (uint32_t)(i0 + (__ffs(m_fl) - 1)));
+                    atomicAdd(ctg_links + ci, (unsigned long long)c_fl);
+                    atomicAdd(ctg_links + cj, (unsigned long long)c_fl);
+                }
+                const unsigned c_ht = __popc(peers & b_ht), c_th = __popc(peers & b_th), c_tt = __popc(peers & b_tt);
+                if (c_ht) atomicAdd(&v->ht, c_ht);
+                if (c_th) atomicAdd(&v->th, c_th);
+                if (c_tt) atomicAdd(&v->tt, c_tt);
+            }
+        }
+    }
+    if (my_new) atomicAdd(&s_new, my_new);
+    if (my_used) atomicAdd(&s_used, my_used);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_new) atomicAdd(counters + 0, (unsigned long long)s_new);
+        if (s_used) atomicAdd(counters + 1, (unsigned long long)s_used);
+        if (s_over) atomicExch(counters + 2, 1ull);
+    }
+}
+
+// re-insert every live slot of the old table into a (larger) new one
+__global__ void hh_k_links_rehash(const uint64_t* __restrict__ okeys, const hh_slot* __restrict__ ovals, uint64_t ocap,
+                                  uint64_t* __restrict__ keys, hh_slot* __restrict__ vals, uint64_t cap,
+                                  unsigned long long* __restrict__ counters) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < ocap; s += stride) {
+        const uint64_t k = okeys[s];
+        if (k == HH_EMPTY_KEY) continue;
+        bool inserted;
+        const uint64_t slot = hh_probe_insert(keys, cap, k, &inserted);
+        if (slot >= cap) {
+            atomicExch(counters + 2, 1ull);
+            continue;
+        }
+        const uint4* src = reinterpret_cast<const uint4*>(ovals + s);
+        uint4* dst = reinterpret_cast<uint4*>(vals + slot);
+        dst[0] = src[0];
+        dst[1] = src[1];
+    }
+}
+
+// merge a peer's export (9 x u32 per entry) into this table
+__global__ void hh_k_links_merge(const uint32_t* __restrict__ ent, int64_t n_ent, uint64_t* __restrict__ keys,
+                                 hh_slot* __restrict__ vals, uint64_t cap, unsigned long long* __restrict__ counters) {
+    __shared__ unsigned int s_new;
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int my_new = 0, my_last = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_ent; e += stride) {
+        const uint32_t* p = ent + e * 9;
+        const uint64_t key = ((uint64_t)p[0] << 32) | (uint64_t)p[1];
+        bool inserted;
+        const uint64_t slot = hh_probe_insert(keys, cap, key, &inserted);
+        if (slot >= cap) {
+            atomicExch(counters + 2, 1ull);
+            continue;
+        }
+        if (inserted) my_new++;
+        hh_slot* v = vals + slot;
+        atomicAdd(&v->full, p[2]);
+        if (p[3]) atomicAdd(&v->flank, p[3]);
+        atomicMin(&v->first_full, p[4]);
+        atomicMin(&v->first_flank, p[5]);
+        my_last = max(my_last, p[4]);
+        if (p[6]) atomicAdd(&v->ht, p[6]);
+        if (p[7]) atomicAdd(&v->th, p[7]);
+        if (p[8]) atomicAdd(&v->tt, p[8]);
+    }
+    if (my_new) atomicAdd(&s_new, my_new);
+    my_last = __reduce_max_sync(HH_FULL_MASK, my_last);
+    if ((threadIdx.x & 31) == 0 && my_last) atomicMax(counters + 4, (unsigned long long)my_last);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_new) atomicAdd(counters + 0, (unsigned long long)s_new);
+}
+
+__global__ void hh_k_add_u64(unsigned long long* __restrict__ dst, const int64_t* __restrict__ src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += (unsigned long long)src[i];
+}
+
+// order[first_full] = slot
+__global__ void hh_k_links_scatter_order(const uint64_t* __restrict__ keys, const hh_slot* __restrict__ vals, uint64_t cap,
+                                         uint32_t* __restrict__ order, int64_t stream_end,
+                                         unsigned long long* __restrict__ counters) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride) {
+        if (keys[s] == HH_EMPTY_KEY) continue;
+        const uint32_t f = vals[s].first_full;
+        if ((int64_t)f < stream_end) order[f] = (uint32_t)s;
+        else atomicExch(counters + 2, 2ull);
+    }
+}
+
+#define HH_CMP_TILE 2048   // elements per block in the compaction kernels (256 threads x 8)
+
+__global__ void __launch_bounds__(256)
+hh_k_compact_count(const uint32_t* __restrict__ order, int64_t n, int* __restrict__ block_cnt) {
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * HH_CMP_TILE + (int64_t)threadIdx.x * 8;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t e = base + k;
+        if (e < n && order[e] != HH_NONE32) c++;
+    }
+    c = hh_warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(256)
+hh_k_compact_gather(const uint32_t* __restrict__ order, int64_t n, const int64_t* __restrict__ block_off,
+                    const uint64_t* __restrict__ keys, const hh_slot* __restrict__ vals,
+                    uint32_t* __restrict__ compact, unsigned long long* __restrict__ counters) {
+    __shared__ int s_warp[8];
+    __shared__ unsigned int s_flank;
+    if (threadIdx.x == 0) s_flank = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * HH_CMP_TILE + (int64_t)threadIdx.x * 8;
+    uint32_t slot[8];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t e = base + k;
+        slot[k] = (e < n) ? order[e] : HH_NONE32;
+        if (slot[k] != HH_NONE32) c++;
+    }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(HH_FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_warp[w];
+    int64_t q = block_off[blockIdx.x] + woff + incl - c;
+    unsigned int nfl = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (slot[k] == HH_NONE32) continue;
+        const uint64_t key = keys[slot[k]];
+        const uint4* v = reinterpret_cast<const uint4*>(vals + slot[k]);
+        const uint4 v0 = v[0], v1 = v[1];   // {first_full, first_flank, full, flank} {ht, th, tt, pad}
+        uint32_t* o = compact + q * 9;
+        o[0] = (uint32_t)(key >> 32);
+        o[1] = (uint32_t)key;
+        o[2] = v0.z;
+        o[3] = v0.w;
+        o[4] = v0.x;
+        o[5] = v0.y;
+        o[6] = v1.x;
+        o[7] = v1.y;
+        o[8] = v1.z;
+        if (v0.w) nfl++;
+        q++;
+    }
+    if (nfl) atomicAdd(&s_flank, nfl);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_flank) atomicAdd(counters + 3, (unsigned long long)s_flank);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dict_to_matrix index assignment (327-349): first touch of each fragment in flank-dict order
+// ---------------------------------------------------------------------------------------------
+__global__ void hh_k_touch(const uint32_t* __restrict__ compact, int64_t nnz, const uint8_t* __restrict__ keep,
+                           unsigned long long* __restrict__ touch) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        const uint32_t* p = compact + e * 9;
+        if (p[3] == 0) continue;                       // not in flank_link_dict
+        const uint32_t i = p[0], j = p[1];
+        if (!keep[i] || !keep[j]) continue;            // 329-330
+        const unsigned long long t = (unsigned long long)p[5] * 2ull;
+        atomicMin(touch + i, t);
+        atomicMin(touch + j, t + 1ull);
+    }
+}
+
+// index[c] = number of touched fragments touched earlier than c (touch values are unique)
+__global__ void __launch_bounds__(256)
+hh_k_rank_touch(const unsigned long long* __restrict__ touch, int n, int32_t* __restrict__ index, int* __restrict__ n_linked) {
+    __shared__ unsigned long long tile[1024];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long mine = (c < n) ? touch[c] : ~0ull;
+    int rank = 0;
+    for (int base = 0; base < n; base += 1024) {
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) tile[k] = (base + k < n) ? touch[base + k] : ~0ull;
+        __syncthreads();
+        if (mine != ~0ull) {
+#pragma unroll 8
+            for (int k = 0; k < 1024; ++k) rank += (tile[k] < mine) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+    if (c < n) {
+        index[c] = (mine != ~0ull) ? rank : -1;
+        if (mine != ~0ull) atomicAdd(n_linked, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline int hh_grid(hh_ctx* ctx, int per_sm) { return ctx->sm_count * per_sm; }
+
+static int links_alloc_table(hh_links* lk, uint64_t cap, uint64_t** keys, hh_slot** vals) {
+    HH_CHECK(hh_dmalloc(keys, cap));
+    int rc = hh_dmalloc(vals, cap);
+    if (rc != HH_OK) {
+        hh_dfree(*keys);
+        return rc;
+    }
+    HH_LAUNCH(lk->ctx, hh_k_links_init, hh_grid(lk->ctx, 8), 256, 0, *keys, *vals, cap);
+    return HH_OK;
+}
+
+static int links_read_counters(hh_links* lk, unsigned long long out[8]) {
+    hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaMemcpyAsync(ctx->h_scratch, lk->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 8; ++k) out[k] = ctx->h_scratch[k];
+    return HH_OK;
+}
+
+// make sure `incoming` more distinct keys fit under a 0.7 load factor
+static int links_ensure_capacity(hh_links* lk, int64_t incoming) {
+    const double max_load = 0.7;
+    if ((double)(lk->known_unique + lk->since_known + incoming) <= max_load * (double)lk->cap) return HH_OK;
+    unsigned long long c[8];
+    HH_CHECK(links_read_counters(lk, c));
+    HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY, "hh_links: hash table overflow (capacity %llu slots)", (unsigned long long)lk->cap);
+    lk->known_unique = (int64_t)c[0];
+    lk->since_known = 0;
+    if ((double)(lk->known_unique + incoming) <= max_load * (double)lk->cap) return HH_OK;
+    uint64_t ncap = lk->cap;
+    while ((double)(lk->known_unique + incoming) > max_load * (double)ncap) ncap <<= 1;
+    uint64_t* nkeys;
+    hh_slot* nvals;
+    HH_CHECK(links_alloc_table(lk, ncap, &nkeys, &nvals));
+    HH_LAUNCH(lk->ctx, hh_k_links_rehash, hh_grid(lk->ctx, 8), 256, 0, lk->d_keys, lk->d_vals, lk->cap, nkeys, nvals, ncap,
+              lk->d_counters);
+    HH_CUDA(cudaStreamSynchronize(lk->ctx->stream));
+    hh_dfree(lk->d_keys);
+    hh_dfree(lk->d_vals);
+    lk->d_keys = nkeys;
+    lk->d_vals = nvals;
+    lk->cap = ncap;
+    return HH_OK;
+}
+
+extern "C" int hh_links_create(hh_ctx* ctx, int32_t n_ctg, const int64_t* ctg_len, const int32_t* name_rank,
+                               const uint8_t* in_nx, int64_t flank_bp, int64_t capacity_hint, hh_links** out) {
+    HH_REQUIRE(ctx && out && ctg_len && name_rank && in_nx, HH_ERR_ARG, "hh_links_create: NULL argument");
+    HH_REQUIRE(n_ctg > 0, HH_ERR_ARG, "hh_links_create: n_ctg must be positive");
+    HH_REQUIRE(flank_bp >= 0, HH_ERR_ARG, "hh_links_create: flank_bp must be >= 0");
+    *out = nullptr;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int32_t> len32(n_ctg);
+    for (int32_t c = 0; c < n_ctg; ++c) {
+        HH_REQUIRE(ctg_len[c] > 0 && ctg_len[c] <= 0x7fffffffLL, HH_ERR_UNSUPPORTED,
+                   "hh_links_create: contig %d has length %lld; records carry int32 positions (pos_int_type int32, "
+                   "HapHiC_cluster.py:116-147)", c, (long long)ctg_len[c]);
+        HH_REQUIRE(name_rank[c] >= 0 && name_rank[c] < n_ctg, HH_ERR_ARG, "hh_links_create: name_rank[%d] out of range", c);
+        len32[c] = (int32_t)ctg_len[c];
+    }
+    hh_links* lk = new (std::nothrow) hh_links();
+    HH_REQUIRE(lk != nullptr, HH_ERR_NOMEM, "hh_links_create: out of host memory");
+    memset(lk, 0, sizeof(*lk));
+    lk->ctx = ctx;
+    lk->n_ctg = n_ctg;
+    lk->flank_bp = flank_bp;
+    int rc = HH_OK;
+    do {
+        if ((rc = hh_dmalloc(&lk->d_len, n_ctg)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_rank, n_ctg)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_nx, n_ctg)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_ctg, n_ctg)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_counters, 8)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_index, n_ctg)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_keep, n_ctg)) != HH_OK) break;
+    } while (0);
+    if (rc != HH_OK) {
+        hh_links_destroy(lk);
+        return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    HH_CUDA(cudaMemcpyAsync(lk->d_len, len32.data(), n_ctg * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    HH_CUDA(cudaMemcpyAsync(lk->d_rank, name_rank, n_ctg * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    HH_CUDA(cudaMemcpyAsync(lk->d_nx, in_nx, n_ctg * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
+    HH_CUDA(cudaMemsetAsync(lk->d_ctg, 0, n_ctg * sizeof(unsigned long long), st));
+    HH_CUDA(cudaMemsetAsync(lk->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    HH_CUDA(cudaStreamSynchronize(st));   // len32 goes out of scope
+    uint64_t cap = 1ull << 16;
+    const double want = capacity_hint > 0 ? (double)capacity_hint / 0.5 : 0.0;
+    while ((double)cap < want) cap <<= 1;
+    rc = links_alloc_table(lk, cap, &lk->d_keys, &lk->d_vals);
+    if (rc != HH_OK) {
+        hh_links_destroy(lk);
+        return rc;
+    }
+    lk->cap = cap;
+    HH_CUDA(cudaStreamCreateWithFlags(&lk->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        HH_CUDA(cudaEventCreateWithFlags(&lk->ev_copied[k], cudaEventDisableTiming));
+        HH_CUDA(cudaEventCreateWithFlags(&lk->ev_consumed[k], cudaEventDisableTiming));
+    }
+    *out = lk;
+    return HH_OK;
+}
+
+static int links_launch_insert(hh_links* lk, const int4* d_rec, int64_t n_rec, int64_t stream_offset) {
+    hh_ctx* ctx = lk->ctx;
+    int64_t blocks = (n_rec + 255) / 256;
+    int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
+    if (grid < 1) grid = 1;
+    HH_LAUNCH(ctx, hh_k_links_insert, grid, 256, 0, d_rec, n_rec, (uint32_t)stream_offset, lk->n_ctg, lk->d_len, lk->d_rank,
+              lk->d_nx, lk->flank_bp, lk->d_keys, lk->d_vals, lk->cap, lk->d_ctg, lk->d_counters);
+    return HH_OK;
+}
+
+extern "C" int hh_links_add_async(hh_links* lk, const int32_t* rec_dev, int64_t n_rec, int64_t stream_offset) {
+    HH_REQUIRE(lk && (rec_dev || n_rec == 0), HH_ERR_ARG, "hh_links_add_async: NULL argument");
+    HH_REQUIRE(!lk->finished, HH_ERR_STATE, "hh_links_add_async: stream already finished");
+    HH_REQUIRE(n_rec >= 0 && stream_offset >= 0 && stream_offset + n_rec <= 0xFFFFFFFELL, HH_ERR_UNSUPPORTED,
+               "hh_links_add: stream indices must fit 32 bits (offset %lld + %lld records)", (long long)stream_offset,
+               (long long)n_rec);
+    HH_REQUIRE(((uintptr_t)rec_dev & 15) == 0, HH_ERR_ARG, "hh_links_add: records must be 16-byte aligned");
+    if (n_rec == 0) return HH_OK;
+    HH_CUDA(cudaSetDevice(lk->ctx->device));
+    HH_CHECK(links_launch_insert(lk, reinterpret_cast<const int4*>(rec_dev), n_rec, stream_offset));
+    lk->n_records += n_rec;
+    lk->since_known += n_rec;
+    if (stream_offset + n_rec > lk->stream_end) lk->stream_end = stream_offset + n_rec;
+    return HH_OK;
+}
+
+extern "C" int hh_links_add(hh_links* lk, const int32_t* rec, int64_t n_rec, int64_t stream_offset, int mem) {
+    HH_REQUIRE(lk && (rec || n_rec == 0), HH_ERR_ARG, "hh_links_add: NULL argument");
+    HH_REQUIRE(!lk->finished, HH_ERR_STATE, "hh_links_add: stream already finished");
+    HH_REQUIRE(mem == HH_MEM_HOST || mem == HH_MEM_DEVICE, HH_ERR_ARG, "hh_links_add: bad mem flag %d", mem);
+    HH_REQUIRE(n_rec >= 0 && stream_offset >= 0 && stream_offset + n_rec <= 0xFFFFFFFELL, HH_ERR_UNSUPPORTED,
+               "hh_links_add: stream indices must fit 32 bits (offset %lld + %lld records)", (long long)stream_offset,
+               (long long)n_rec);
+    if (n_rec == 0) return HH_OK;
+    hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    const int64_t CH = 1ll << 23;   // 8 Mi records = 128 MiB per chunk
+    if (mem == HH_MEM_DEVICE) {
+        HH_REQUIRE(((uintptr_t)rec & 15) == 0, HH_ERR_ARG, "hh_links_add: records must be 16-byte aligned");
+        for (int64_t off = 0; off < n_rec; off += CH) {
+            const int64_t m = (n_rec - off < CH) ? (n_rec - off) : CH;
+            HH_CHECK(links_ensure_capacity(lk, m));
+            HH_CHECK(links_launch_insert(lk, reinterpret_cast<const int4*>(rec) + off, m, stream_offset + off));
+            lk->since_known += m;
+        }
+    } else {
+        if (!lk->d_stage[0]) {
+            lk->stage_records = CH;
+            HH_CHECK(hh_dmalloc(&lk->d_stage[0], (size_t)CH));
+            HH_CHECK(hh_dmalloc(&lk->d_stage[1], (size_t)CH));
+        }
+        int buf = 0;
+        for (int64_t off = 0; off < n_rec; off += CH, buf ^= 1) {
+            const int64_t m = (n_rec - off < CH) ? (n_rec - off) : CH;
+            // the copy engine may not overwrite a staging buffer the insert kernel still reads
+            HH_CUDA(cudaStreamWaitEvent(lk->copy_stream, lk->ev_consumed[buf], 0));
+            HH_CUDA(cudaMemcpyAsync(lk->d_stage[buf], rec + off * 4, (size_t)m * 16, cudaMemcpyHostToDevice, lk->copy_stream));
+            HH_CUDA(cudaEventRecord(lk->ev_copied[buf], lk->copy_stream));
+            HH_CHECK(links_ensure_capacity(lk, m));
+            HH_CUDA(cudaStreamWaitEvent(ctx->stream, lk->ev_copied[buf], 0));
+            HH_CHECK(links_launch_insert(lk, lk->d_stage[buf], m, stream_offset + off));
+            HH_CUDA(cudaEventRecord(lk->ev_consumed[buf], ctx->stream));
+            lk->since_known += m;
+        }
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may reuse `rec` on return
+    }
+    lk->n_records += n_rec;
+    if (stream_offset + n_rec > lk->stream_end) lk->stream_end = stream_offset + n_rec;
+    return HH_OK;
+}
+
+extern "C" int hh_links_finish(hh_links* lk, hh_links_info* info) {
+    HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_finish: NULL handle");
+    hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    if (!lk->finished) {
+        unsigned long long c[8];
+        HH_CHECK(links_read_counters(lk, c));
+        HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY,
+                   "hh_links_finish: hash table overflow (capacity %llu slots): pass a larger capacity_hint or use hh_links_add",
+                   (unsigned long long)lk->cap);
+        lk->nnz = (int64_t)c[0];
+        lk->n_used += (int64_t)c[1];
+        if (lk->nnz > 0 && (int64_t)c[4] + 1 > lk->stream_end) lk->stream_end = (int64_t)c[4] + 1;   // merged peers
+        const int64_t S = lk->stream_end;
+        hh_dfree(lk->d_compact);
+        HH_CHECK(hh_dmalloc(&lk->d_compact, (size_t)(lk->nnz > 0 ? lk->nnz : 1) * 9));
+        if (lk->nnz > 0) {
+            uint32_t* d_order = nullptr;
+            int* d_bcnt = nullptr;
+            int64_t* d_boff = nullptr;
+            const int64_t nb = (S + HH_CMP_TILE - 1) / HH_CMP_TILE;
+            int rc = HH_OK;
+            do {
+                if ((rc = hh_dmalloc(&d_order, (size_t)S)) != HH_OK) break;
+                if ((rc = hh_dmalloc(&d_bcnt, (size_t)nb)) != HH_OK) break;
+                if ((rc = hh_dmalloc(&d_boff, (size_t)nb + 1)) != HH_OK) break;
+            } while (0);
+            if (rc == HH_OK) {
+                rc = [&]() -> int {
+                    HH_CUDA(cudaMemsetAsync(d_order, 0xFF, (size_t)S * sizeof(uint32_t), ctx->stream));
+                    HH_LAUNCH(ctx, hh_k_links_scatter_order, hh_grid(ctx, 8), 256, 0, lk->d_keys, lk->d_vals, lk->cap, d_order, S,
+                              lk->d_counters);
+                    HH_LAUNCH(ctx, hh_k_compact_count, (unsigned)nb, 256, 0, d_order, S, d_bcnt);
+                    HH_CHECK(hh_exclusive_scan_i32(ctx, d_bcnt, d_boff, (int)nb));
+                    HH_LAUNCH(ctx, hh_k_compact_gather, (unsigned)nb, 256, 0, d_order, S, d_boff, lk->d_keys, lk->d_vals,
+                              lk->d_compact, lk->d_counters);
+                    HH_CHECK(links_read_counters(lk, c));
+                    return HH_OK;
+                }();
+            }
+            hh_dfree(d_order);
+            hh_dfree(d_bcnt);
+            hh_dfree(d_boff);
+            HH_CHECK(rc);
+            HH_REQUIRE(c[2] == 0, HH_ERR_STATE, "hh_links_finish: first-seen index beyond the stream end (stream_offset misuse)");
+            lk->nnz_flank = (int64_t)c[3];
+        }
+        lk->finished = true;
+    }
+    if (info) {
+        info->n_records = lk->n_records;
+        info->n_used = lk->n_used;
+        info->nnz_full = lk->nnz;
+        info->nnz_flank = lk->nnz_flank;
+        info->table_slots = (int64_t)lk->cap;
+    }
+    return HH_OK;
+}
+
+extern "C" int hh_links_fetch(hh_links* lk, int32_t* key_i, int32_t* key_j, uint32_t* full, uint32_t* flank,
+                              uint32_t* first_full, uint32_t* first_flank, uint32_t* ht) {
+    HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_fetch: NULL handle");
+    HH_REQUIRE(lk->finished, HH_ERR_STATE, "hh_links_fetch: call hh_links_finish first");
+    if (lk->nnz == 0) return HH_OK;
+    HH_CUDA(cudaSetDevice(lk->ctx->device));
+    std::vector<uint32_t> h((size_t)lk->nnz * 9);
+    HH_CUDA(cudaMemcpyAsync(h.data(), lk->d_compact, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, lk->ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(lk->ctx->stream));
+    for (int64_t e = 0; e < lk->nnz; ++e) {
+        const uint32_t* p = h.data() + e * 9;
+        if (key_i) key_i[e] = (int32_t)p[0];
+        if (key_j) key_j[e] = (int32_t)p[1];
+        if (full) full[e] = p[2];
+        if (flank) flank[e] = p[3];
+        if (first_full) first_full[e] = p[4];
+        if (first_flank) first_flank[e] = p[5];
+        if (ht) {
+            ht[4 * e + 1] = p[6];
+            ht[4 * e + 2] = p[7];
+            ht[4 * e + 3] = p[8];
+            ht[4 * e + 0] = p[2] - p[6] - p[7] - p[8];
+        }
+    }
+    return HH_OK;
+}
+
+extern "C" int hh_links_fetch_ctg(hh_links* lk, int64_t* ctg_links) {
+    HH_REQUIRE(lk && ctg_links, HH_ERR_ARG, "hh_links_fetch_ctg: NULL argument");
+    HH_CUDA(cudaSetDevice(lk->ctx->device));
+    HH_CUDA(cudaMemcpyAsync(ctg_links, lk->d_ctg, (size_t)lk->n_ctg * sizeof(int64_t), cudaMemcpyDeviceToHost, lk->ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(lk->ctx->stream));
+    return HH_OK;
+}
+
+extern "C" int hh_links_export(hh_links* lk, uint32_t* entries_dev, int64_t* ctg_links_dev) {
+    HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_export: NULL handle");
+    HH_REQUIRE(lk->finished, HH_ERR_STATE, "hh_links_export: call hh_links_finish first");
+    HH_CUDA(cudaSetDevice(lk->ctx->device));
+    if (entries_dev && lk->nnz)
+        HH_CUDA(cudaMemcpyAsync(entries_dev, lk->d_compact, (size_t)lk->nnz * 9 * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                lk->ctx->stream));
+    if (ctg_links_dev)
+        HH_CUDA(cudaMemcpyAsync(ctg_links_dev, lk->d_ctg, (size_t)lk->n_ctg * sizeof(int64_t), cudaMemcpyDeviceToDevice,
+                                lk->ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(lk->ctx->stream));
+    return HH_OK;
+}
+
+extern "C" int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t n_entries, const int64_t* ctg_links_dev,
+                              int64_t n_records, int64_t n_used) {
+    HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_merge: NULL handle");
+    HH_REQUIRE(!lk->finished, HH_ERR_STATE, "hh_links_merge: table already finished");
+    HH_REQUIRE(n_entries >= 0 && (entries_dev || n_entries == 0), HH_ERR_ARG, "hh_links_merge: bad entries");
+    hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    if (n_entries) {
+        HH_CHECK(links_ensure_capacity(lk, n_entries));
+        int64_t blocks = (n_entries + 255) / 256;
+        int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
+        HH_LAUNCH(ctx, hh_k_links_merge, grid, 256, 0, entries_dev, n_entries, lk->d_keys, lk->d_vals, lk->cap, lk->d_counters);
+        lk->since_known += n_entries;
+    }
+    if (ctg_links_dev)
+        HH_LAUNCH(ctx, hh_k_add_u64, (lk->n_ctg + 255) / 256, 256, 0, lk->d_ctg, ctg_links_dev, lk->n_ctg);
+    HH_CUDA(cudaStreamSynchronize(ctx->stream));
+    lk->n_records += n_records;
+    lk->n_used += n_used;
+    return HH_OK;
+}
+
+extern "C" int hh_links_linked_index(hh_links* lk, const uint8_t* keep, int32_t* index, int32_t* n_linked) {
+    HH_REQUIRE(lk && keep, HH_ERR_ARG, "hh_links_linked_index: NULL argument");
+    HH_REQUIRE(lk->finished, HH_ERR_STATE, "hh_links_linked_index: call hh_links_finish first");
+    hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long* d_touch = nullptr;
+    HH_CHECK(hh_dmalloc(&d_touch, (size_t)lk->n_ctg));
+    int rc = [&]() -> int {
+        HH_CUDA(cudaMemcpyAsync(lk->d_keep, keep, (size_t)lk->n_ctg, cudaMemcpyHostToDevice, ctx->stream));
+        HH_CUDA(cudaMemsetAsync(d_touch, 0xFF, (size_t)lk->n_ctg * sizeof(unsigned long long), ctx->stream));
+        int* d_nl = reinterpret_cast<int*>(ctx->d_scratch + 8);
+        HH_CUDA(cudaMemsetAsync(d_nl, 0, sizeof(int), ctx->stream));
+        if (lk->nnz) {
+            int64_t blocks = (lk->nnz + 255) / 256;
+            int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
+            HH_LAUNCH(ctx, hh_k_touch, grid, 256, 0, lk->d_compact, lk->nnz, lk->d_keep, d_touch);
+        }
+        HH_LAUNCH(ctx, hh_k_rank_touch, (lk->n_ctg + 255) / 256, 256, 0, d_touch, lk->n_ctg, lk->d_index, d_nl);
+        HH_CUDA(cudaMemcpyAsync(ctx->h_scratch + 8, d_nl, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (index)
+            HH_CUDA(cudaMemcpyAsync(index, lk->d_index, (size_t)lk->n_ctg * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        lk->n_linked = *reinterpret_cast<int*>(ctx->h_scratch + 8);
+        return HH_OK;
+    }();
+    hh_dfree(d_touch);
+    HH_CHECK(rc);
+    if (n_linked) *n_linked = lk->n_linked;
+    return HH_OK;
+}
+
+extern "C" int hh_links_destroy(hh_links* lk) {
+    if (!lk) return HH_OK;
+    cudaSetDevice(lk->ctx->device);
+    cudaStreamSynchronize(lk->ctx->stream);
+    if (lk->copy_stream) {
+        cudaStreamSynchronize(lk->copy_stream);
+        cudaStreamDestroy(lk->copy_stream);
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (lk->ev_copied[k]) cudaEventDestroy(lk->ev_copied[k]);
+        if (lk->ev_consumed[k]) cudaEventDestroy(lk->ev_consumed[k]);
+        hh_dfree(lk->d_stage[k]);
+    }
+    hh_dfree(lk->d_len);
+    hh_dfree(lk->d_rank);
+    hh_dfree(lk->d_nx);
+    hh_dfree(lk->d_ctg);
+    hh_dfree(lk->d_keys);
+    hh_dfree(lk->d_vals);
+    hh_dfree(lk->d_counters);
+    hh_dfree(lk->d_compact);
+    hh_dfree(lk->d_index);
+    hh_dfree(lk->d_keep);
+    delete lk;
+    return HH_OK;
+}
+
+// accessors used by hh_matrix.cu
+int32_t hh_links_n_ctg(hh_links* lk) { return lk->n_ctg; }
+hh_ctx* hh_links_ctx(hh_links* lk) { return lk->ctx; }
+const uint32_t* hh_links_compact(hh_links* lk, int64_t* nnz) { *nnz = lk->nnz; return lk->d_compact; }
+const unsigned long long* hh_links_ctg_totals(hh_links* lk) { return lk->d_ctg; }
+int32_t* hh_links_index_dev(hh_links* lk, int32_t* n_linked) { *n_linked = lk->n_linked; return lk->d_index; }
+uint8_t* hh_links_keep_dev(hh_links* lk) { return lk->d_keep; }
+bool hh_links_finished(hh_links* lk) { return lk->finished; }

@@ -1,0 +1,1022 @@
+// Markov clustering on the GPU (scripts/HapHiC_cluster.py:1987-2062, 2132-2162).
+//
+// Storage: "row-blocked slotted CSC".  Column j owns a fixed slot of `cap` entries
+// (idx/val at j*cap), rows ascending; blk[j*(W+1) + w] is the offset of the first entry whose
+// row lies in row block w (rows [w*T, (w+1)*T)), blk[..W] == len[j].  W is the number of warps
+// of the column kernel, so warp w finds "its" part of any column with two loads.
+//
+// One kernel template does every per-column job.  A CTA takes columns from a dynamic queue and
+// keeps a dense fp32 accumulator of the whole column in shared memory (n <= 57,600; a
+// global-memory accumulator otherwise).  Warp w owns accumulator rows [w*T, (w+1)*T): during
+// the Gustavson expansion  C[:,j] = sum_i B[i,j] * A[:,i]  it walks the B entries in order and adds
+// only the row-block-w segment of A[:,i], so every accumulator cell is updated by one warp, in
+// ascending i -- no atomics, and the fp32 sums are bit-reproducible for any grid size or GPU count.
+// The epilogue (inflate -> column L1 -> prune/keep-max -> column L1 -> convergence) runs on
+// the accumulator in place and writes the pruned column straight into its slot: the unpruned
+// product never reaches HBM.
+//
+//   SRC_CSC     scatter an unsorted CSC column            (dict_to_matrix output, 366-368)
+//   SRC_PRODUCT expansion, A.B column product             (mkl_matrix_power, 2017-2023)
+//   SRC_DENSE   stream a column of the dense pre-expanded M1 (iteration 0 skips expansion, 2030)
+//   EPI_NORM    column L1 normalise (sklearn normalize, 2144) or raw copy (canonical CSC)
+//   EPI_DUMP    write the accumulator as a dense column    (pre-expansion result, 2146-2149)
+//   EPI_PRUNE   inflate + normalise (2038), prune + keep first max + normalise (1987-2014),
+//               optional convergence term max(|M-L| - 1e-5|L|) (2045)
+#include "hh_common.cuh"
+#include "hh_internal.cuh"
+#include <math.h>
+
+struct hh_slotmat {
+    int n;       // rows == columns
+    int cap;     // entries per column slot
+    int W;       // row blocks per column
+    int* len;    // [n]
+    int* blk;    // [n * (W+1)]
+    int* idx;    // [n * cap]
+    float* val;  // [n * cap]
+};
+
+enum { SRC_CSC = 0, SRC_PRODUCT = 1, SRC_DENSE = 2 };
+enum { EPI_NORM = 0, EPI_DUMP = 1, EPI_PRUNE = 2 };
+
+struct hh_colargs {
+    int n, T, ch_shift, n_pad;
+    int col_lo, ncols;
+    int* counter;
+    hh_slotmat A, B, out;
+    const int64_t* csc_ptr;
+    const int32_t* csc_row;
+    const float* csc_val;
+    const float* dense_in;
+    float* dense_out;
+    int64_t ld;
+    int raw;
+    int inflate_square;
+    float inflation, prune;
+    int do_conv;
+    float* scratch;
+    unsigned long long* stats;   // [0] nnz written  [1] products
+    int* delta_bits;
+    int* err;
+};
+
+__device__ __forceinline__ uint64_t hh_warp_or64(uint64_t v) {
+    unsigned lo = __reduce_or_sync(HH_FULL_MASK, (unsigned)v);
+    unsigned hi = __reduce_or_sync(HH_FULL_MASK, (unsigned)(v >> 32));
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <int W, int SRC, int EPI, bool SMEM>
+__global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
+    extern __shared__ __align__(16) float hh_dyn_smem[];
+    __shared__ double s_d[32];
+    __shared__ float s_f[32];
+    __shared__ int s_k[32];
+    __shared__ int s_c[32];
+    __shared__ int s_col;
+
+    float* __restrict__ acc = SMEM ? hh_dyn_smem : (a.scratch + (size_t)blockIdx.x * a.n_pad);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int T = a.T;
+    const int tile0 = w * T;
+    const int ch_shift = a.ch_shift;
+    const int nch = (T + (1 << ch_shift) - 1) >> ch_shift;
+    const uint64_t ALL = (nch >= 64) ? ~0ull : ((1ull << nch) - 1ull);
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    if (SMEM) {
+        for (int k = threadIdx.x; k < a.n_pad; k += W * 32) acc[k] = 0.f;
+    }
+    __syncthreads();
+
+    float dmax = 0.f;
+    unsigned long long prod_acc = 0ull, nnz_acc = 0ull;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_col = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int jj = s_col;
+        if (jj >= a.ncols) break;
+        const int j = a.col_lo + jj;
+        uint64_t dirty = 0ull;
+
+        // ------------------------------------------------------------------ source
+        if (SRC == SRC_CSC) {
+            const int64_t p0 = a.csc_ptr[j], p1 = a.csc_ptr[j + 1];
+            for (int64_t p = p0 + threadIdx.x; p < p1; p += W * 32) atomicAdd(&acc[a.csc_row[p]], a.csc_val[p]);
+            __syncthreads();
+            dirty = ALL;
+        } else if (SRC == SRC_DENSE) {
+            const float* __restrict__ col = a.dense_in + (size_t)jj * (size_t)a.ld;
+            for (int r = tile0 + lane; r < tile0 + T; r += 32)
+                if (r < a.n) acc[r] = col[r];
+            __syncwarp();
+            dirty = ALL;
+        } else {
+            const int lenB = a.B.len[j];
+            const int* __restrict__ Bidx = a.B.idx + (size_t)j * (size_t)a.B.cap;
+            const float* __restrict__ Bval = a.B.val + (size_t)j * (size_t)a.B.cap;
+            const int* __restrict__ Aidx = a.A.idx;
+            const float* __restrict__ Aval = a.A.val;
+            const size_t capA = (size_t)a.A.cap;
+            unsigned long long warp_prod = 0ull;
+            for (int t0 = 0; t0 < lenB; t0 += 32) {
+                const int t = t0 + lane;
+                int il = 0, sl = 0, el = 0;
+                float vl = 0.f;
+                if (t < lenB) {
+                    il = Bidx[t];
+                    vl = Bval[t];
+                    const int* bp = a.A.blk + (size_t)il * (W + 1) + w;
+                    sl = bp[0];
+                    el = bp[1];
+                }
+                const int cnt = min(32, lenB - t0);
+                // two segments in flight: the loads of segment u+1 are issued before segment u is consumed
+                int s_c2 = __shfl_sync(HH_FULL_MASK, sl, 0), e_c2 = __shfl_sync(HH_FULL_MASK, el, 0);
+                float v_c = __shfl_sync(HH_FULL_MASK, vl, 0);
+                size_t base_c = (size_t)__shfl_sync(HH_FULL_MASK, il, 0) * capA;
+                int k_c = 0;
+                float a_c = 0.f;
+                if (s_c2 + lane < e_c2) {
+                    k_c = Aidx[base_c + s_c2 + lane];
+                    a_c = Aval[base_c + s_c2 + lane];
+                }
+                for (int u = 0; u < cnt; ++u) {
+                    int s_n = 0, e_n = 0, k_n = 0;
+                    float v_n = 0.f, a_n = 0.f;
+                    size_t base_n = 0;
+                    if (u + 1 < cnt) {
+                        s_n = __shfl_sync(HH_FULL_MASK, sl, u + 1);
+                        e_n = __shfl_sync(HH_FULL_MASK, el, u + 1);
+                        v_n = __shfl_sync(HH_FULL_MASK, vl, u + 1);
+                        base_n = (size_t)__shfl_sync(HH_FULL_MASK, il, u + 1) * capA;
+                        if (s_n + lane < e_n) {
+                            k_n = Aidx[base_n + s_n + lane];
+                            a_n = Aval[base_n + s_n + lane];
+                        }
+                    }
+                    if (s_c2 + lane < e_c2) {
+                        acc[k_c] = fmaf(v_c, a_c, acc[k_c]);
+                        dirty |= 1ull << ((k_c - tile0) >> ch_shift);
+                    }
+                    for (int p = s_c2 + lane + 32; p < e_c2; p += 32) {
+                        const int k = Aidx[base_c + p];
+                        const float av = Aval[base_c + p];
+                        acc[k] = fmaf(v_c, av, acc[k]);
+                        dirty |= 1ull << ((k - tile0) >> ch_shift);
+                    }
+                    warp_prod += (unsigned long long)(e_c2 - s_c2);
+                    __syncwarp();   // the next segment may hit the same rows from other lanes
+                    s_c2 = s_n;
+                    e_c2 = e_n;
+                    v_c = v_n;
+                    base_c = base_n;
+                    k_c = k_n;
+                    a_c = a_n;
+                }
+            }
+            if (lane == 0) prod_acc += warp_prod;
+            dirty = hh_warp_or64(dirty);
+        }
+
+        // ------------------------------------------------------------------ epilogue
+#define HH_FOR_DIRTY_ROWS(...)                                                    \
+    for (uint64_t _m = dirty; _m; _m &= _m - 1ull) {                              \
+        const int _c = __ffsll((long long)_m) - 1;                                \
+        const int _r0 = tile0 + (_c << ch_shift);                                 \
+        const int _r1 = min(_r0 + (1 << ch_shift), tile0 + T);                    \
+        for (int _r = _r0; _r < _r1; _r += 32) {                                  \
+            const int k = _r + lane;                                              \
+            __VA_ARGS__                                                           \
+        }                                                                         \
+    }
+
+        if (EPI == EPI_DUMP) {
+            float* __restrict__ col = a.dense_out + (size_t)jj * (size_t)a.ld;
+            for (int r = tile0 + lane; r < tile0 + T; r += 32) {
+                if (r < a.n) {
+                    col[r] = acc[r];
+                    acc[r] = 0.f;
+                }
+            }
+        } else if (EPI == EPI_NORM) {
+            double s = 0.0;
+            int cnt = 0;
+            HH_FOR_DIRTY_ROWS({
+                const float x = acc[k];
+                if (x != 0.f) {
+                    s += fabs((double)x);
+                    cnt++;
+                }
+            })
+            s = hh_warp_sum(s);
+            cnt = hh_warp_sum(cnt);
+            if (lane == 0) {
+                s_d[w] = s;
+                s_c[w] = cnt;
+            }
+            __syncthreads();
+            const double sv = (lane < W) ? s_d[lane] : 0.0;
+            const int cv = (lane < W) ? s_c[lane] : 0;
+            const double S = hh_warp_sum(sv);
+            int incl = cv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tt = __shfl_up_sync(HH_FULL_MASK, incl, o);
+                if (lane >= o) incl += tt;
+            }
+            const int base = __shfl_sync(HH_FULL_MASK, incl - cv, w);
+            const int total = __shfl_sync(HH_FULL_MASK, incl, 31);
+            int off = base;
+            int* __restrict__ oidx = a.out.idx + (size_t)j * (size_t)a.out.cap;
+            float* __restrict__ oval = a.out.val + (size_t)j * (size_t)a.out.cap;
+            HH_FOR_DIRTY_ROWS({
+                const float x = acc[k];
+                const bool f = (x != 0.f);
+                const unsigned bal = __ballot_sync(HH_FULL_MASK, f);
+                if (f) {
+                    const int pos = off + __popc(bal & lt_mask);
+                    if (pos < a.out.cap) {
+                        oidx[pos] = k;
+                        oval[pos] = (a.raw || S == 0.0) ? x : (float)((double)x / S);
+                    }
+                    acc[k] = 0.f;
+                }
+                off += __popc(bal);
+            })
+            if (lane == 0) a.out.blk[(size_t)j * (W + 1) + w] = base;
+            if (threadIdx.x == 0) {
+                a.out.blk[(size_t)j * (W + 1) + W] = min(total, a.out.cap);
+                a.out.len[j] = min(total, a.out.cap);
+                if (total > a.out.cap) atomicExch(a.err, 1);
+                nnz_acc += (unsigned long long)total;
+            }
+        } else {
+            // E1: inflate (matrix.power(r), fp32) and first column sum (fp64)
+            const float rf = a.inflation;
+            const bool sq = a.inflate_square != 0;
+            double s1 = 0.0;
+            HH_FOR_DIRTY_ROWS({
+                const float x = acc[k];
+                if (x != 0.f) {
+                    const float y = sq ? (x * x) : powf(x, rf);
+                    acc[k] = y;
+                    s1 += (double)y;
+                }
+            })
+            s1 = hh_warp_sum(s1);
+            if (lane == 0) s_d[w] = s1;
+            __syncthreads();
+            const double S1 = hh_warp_sum((lane < W) ? s_d[lane] : 0.0);
+            __syncthreads();   // s_d is reused below
+            // E2: normalise, threshold statistics, first maximum
+            const float p32 = a.prune;
+            double s2 = 0.0;
+            int cnt = 0;
+            float vbest = 0.f;
+            int kbest = 0x7fffffff;
+            HH_FOR_DIRTY_ROWS({
+                const float y = acc[k];
+                if (y != 0.f) {
+                    const float x1 = (S1 != 0.0) ? (float)((double)y / S1) : y;
+                    acc[k] = x1;
+                    if (x1 >= p32 && x1 > 0.f) {
+                        cnt++;
+                        s2 += (double)x1;
+                    }
+                    if (x1 > vbest) {   // rows ascend inside a lane: strict > keeps the first maximum
+                        vbest = x1;
+                        kbest = k;
+                    }
+                }
+            })
+            s2 = hh_warp_sum(s2);
+            cnt = hh_warp_sum(cnt);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(HH_FULL_MASK, vbest, o);
+                const int ok = __shfl_xor_sync(HH_FULL_MASK, kbest, o);
+                if (ov > vbest || (ov == vbest && ok < kbest)) {
+                    vbest = ov;
+                    kbest = ok;
+                }
+            }
+            if (lane == 0) {
+                s_d[w] = s2;
+                s_c[w] = cnt;
+                s_f[w] = vbest;
+                s_k[w] = kbest;
+            }
+            __syncthreads();
+            const double sv = (lane < W) ? s_d[lane] : 0.0;
+            const int cv = (lane < W) ? s_c[lane] : 0;
+            float vmax = (lane < W) ? s_f[lane] : 0.f;
+            int kmax = (lane < W) ? s_k[lane] : 0x7fffffff;
+            double S2 = hh_warp_sum(sv);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(HH_FULL_MASK, vmax, o);
+                const int ok = __shfl_xor_sync(HH_FULL_MASK, kmax, o);
+                if (ov > vmax || (ov == vmax && ok < kmax)) {
+                    vmax = ov;
+                    kmax = ok;
+                }
+            }
+            int incl = cv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tt = __shfl_up_sync(HH_FULL_MASK, incl, o);
+                if (lane >= o) incl += tt;
+            }
+            int base = __shfl_sync(HH_FULL_MASK, incl - cv, w);
+            int total = __shfl_sync(HH_FULL_MASK, incl, 31);
+            // keep the column maximum when nothing reaches the threshold (2009-2013)
+            const bool need_max = (total == 0) && (vmax > 0.f);
+            if (need_max) {
+                const int wk = kmax / T;
+                base = (w > wk) ? 1 : 0;
+                total = 1;
+                S2 = (double)vmax;
+            }
+            // E3: compact the survivors in row order, second normalisation (2014)
+            int off = base;
+            int* __restrict__ oidx = a.out.idx + (size_t)j * (size_t)a.out.cap;
+            float* __restrict__ oval = a.out.val + (size_t)j * (size_t)a.out.cap;
+            const bool conv = a.do_conv != 0;
+            HH_FOR_DIRTY_ROWS({
+                const float x1 = acc[k];
+                const bool f = need_max ? (k == kmax) : (x1 >= p32 && x1 > 0.f);
+                const unsigned bal = __ballot_sync(HH_FULL_MASK, f);
+                float keepv = 0.f;
+                if (f) {
+                    const int pos = off + __popc(bal & lt_mask);
+                    const float x2 = (float)((double)x1 / S2);
+                    if (pos < a.out.cap) {
+                        oidx[pos] = k;
+                        oval[pos] = x2;
+                    }
+                    keepv = x2;
+                }
+                if (x1 != 0.f) acc[k] = conv ? keepv : 0.f;
+                off += __popc(bal);
+            })
+            if (lane == 0) a.out.blk[(size_t)j * (W + 1) + w] = base;
+            if (threadIdx.x == 0) {
+                a.out.blk[(size_t)j * (W + 1) + W] = min(total, a.out.cap);
+                a.out.len[j] = min(total, a.out.cap);
+                if (total > a.out.cap) atomicExch(a.err, 1);
+                nnz_acc += (unsigned long long)total;
+            }
+            if (SRC == SRC_PRODUCT && conv) {
+                // E4: entries of the previous iterate L = B[:, j]  ->  |M - L| - 1e-5|L|  (fp32, 2045)
+                __syncwarp();
+                const int* bp = a.B.blk + (size_t)j * (W + 1) + w;
+                const int ps = bp[0], pe = bp[1];
+                const int* __restrict__ Lidx = a.B.idx + (size_t)j * (size_t)a.B.cap;
+                const float* __restrict__ Lval = a.B.val + (size_t)j * (size_t)a.B.cap;
+                for (int p = ps + lane; p < pe; p += 32) {
+                    const int k = Lidx[p];
+                    const float l = Lval[p];
+                    const float m = acc[k];
+                    const float d = __fsub_rn(fabsf(__fsub_rn(m, l)), __fmul_rn(1e-5f, fabsf(l)));
+                    dmax = fmaxf(dmax, d);
+                    acc[k] = 0.f;
+                }
+                __syncwarp();
+                // E5: entries only in M (L is an implicit zero there) and accumulator reset
+                HH_FOR_DIRTY_ROWS({
+                    const float m = acc[k];
+                    if (m != 0.f) {
+                        dmax = fmaxf(dmax, m);
+                        acc[k] = 0.f;
+                    }
+                })
+            }
+        }
+#undef HH_FOR_DIRTY_ROWS
+        __syncthreads();
+    }
+
+    // flush per-CTA statistics
+    dmax = hh_warp_max(dmax);
+    if (lane == 0) {
+        if (dmax > 0.f) atomicMax(a.delta_bits, __float_as_int(dmax));
+        if (prod_acc) atomicAdd(a.stats + 1, prod_acc);
+    }
+    if (threadIdx.x == 0 && nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack / unpack of column blocks (canonical CSC export, multi-GPU exchange)
+// ---------------------------------------------------------------------------------------------
+__global__ void hh_k_pack(const hh_slotmat m, int col_lo, int ncols, const int64_t* __restrict__ off, int* __restrict__ len_out,
+                          int* __restrict__ idx_out, float* __restrict__ val_out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int jj = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jj < ncols; jj += warps) {
+        const int c = col_lo + jj;
+        const int L = m.len[c];
+        if (lane == 0 && len_out) len_out[jj] = L;
+        const int* si = m.idx + (size_t)c * (size_t)m.cap;
+        const float* sv = m.val + (size_t)c * (size_t)m.cap;
+        const int64_t o = off[jj];
+        for (int p = lane; p < L; p += 32) {
+            idx_out[o + p] = si[p];
+            val_out[o + p] = sv[p];
+        }
+    }
+}
+
+__global__ void hh_k_unpack(const hh_slotmat m, int T, int col_lo, int ncols, const int* __restrict__ len_in,
+                            const int64_t* __restrict__ off, const int* __restrict__ idx_in, const float* __restrict__ val_in,
+                            int* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int W = m.W;
+    for (int jj = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jj < ncols; jj += warps) {
+        const int c = col_lo + jj;
+        int L = len_in[jj];
+        if (L > m.cap || L < 0) {
+            if (lane == 0) atomicExch(err, 1);
+            L = 0;
+        }
+        const int64_t o = off[jj];
+        int* di = m.idx + (size_t)c * (size_t)m.cap;
+        float* dv = m.val + (size_t)c * (size_t)m.cap;
+        for (int p = lane; p < L; p += 32) {
+            di[p] = idx_in[o + p];
+            dv[p] = val_in[o + p];
+        }
+        if (lane < W) {   // first entry with row >= lane*T
+            const int target = lane * T;
+            int lo = 0, hi = L;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (idx_in[o + mid] < target) lo = mid + 1;
+                else hi = mid;
+            }
+            m.blk[(size_t)c * (W + 1) + lane] = lo;
+        }
+        if (lane == 0) {
+            m.blk[(size_t)c * (W + 1) + W] = L;
+            m.len[c] = L;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct hh_mcl {
+    hh_ctx* ctx;
+    int n, W, T, ch_shift, n_pad;
+    int64_t ld;
+    int col_lo, col_hi;
+    int expansion;
+    bool smem_acc;
+    size_t smem_bytes;
+    int grid_cap;           // resident CTAs of the column kernel
+    float* d_scratch;       // global accumulators (large n only)
+    hh_slotmat m0;
+    float* d_m1;            // dense [ld x (col_hi-col_lo)]
+    hh_slotmat it[2];
+    int it_cap;
+    int cur;                // index of the current iterate in it[]; -1 before iteration 0
+    int pending;            // buffer hh_mcl_step wrote (to be committed)
+    bool have_pending;
+    float inflation, prune;
+    int inflate_square;
+    bool begun;
+    int* d_counter;
+    unsigned long long* d_stats;   // [0] nnz [1] products [2] delta bits [3] err
+    int64_t nnz_m0, preexp_products;
+    cudaEvent_t ev0, ev1;
+    float create_ms[2];            // device time of the normalisation / pre-expansion kernels
+};
+
+static void slot_free(hh_slotmat& s) {
+    hh_dfree(s.len);
+    hh_dfree(s.blk);
+    hh_dfree(s.idx);
+    hh_dfree(s.val);
+    s.cap = 0;
+}
+
+static int slot_alloc(hh_slotmat& s, int n, int cap, int W) {
+    memset(&s, 0, sizeof(s));
+    s.n = n;
+    s.cap = cap;
+    s.W = W;
+    int rc;
+    if ((rc = hh_dmalloc(&s.len, (size_t)n)) != HH_OK || (rc = hh_dmalloc(&s.blk, (size_t)n * (W + 1))) != HH_OK ||
+        (rc = hh_dmalloc(&s.idx, (size_t)n * (size_t)cap)) != HH_OK || (rc = hh_dmalloc(&s.val, (size_t)n * (size_t)cap)) != HH_OK) {
+        slot_free(s);
+        return rc;
+    }
+    return HH_OK;
+}
+
+struct hh_geom {
+    int W, T, ch_shift, n_pad;
+    bool smem_acc;
+    size_t smem_bytes;
+};
+
+static hh_geom geom_for(hh_ctx* ctx, int n) {
+    hh_geom g;
+    g.W = (n <= 12288) ? 8 : (n <= 28672 ? 16 : 32);
+    int T = (n + g.W - 1) / g.W;
+    T = (T + 31) & ~31;
+    g.T = T;
+    g.n_pad = T * g.W;
+    int s = 5;
+    while (((T + (1 << s) - 1) >> s) > 64) s++;
+    g.ch_shift = s;
+    const size_t need = (size_t)g.n_pad * sizeof(float);
+    const size_t static_smem = 1024;   // s_d/s_f/s_k/s_c/s_col, rounded up
+    g.smem_acc = need + static_smem <= ctx->smem_optin;
+    g.smem_bytes = g.smem_acc ? need : 0;
+    if (!g.smem_acc) {
+        g.W = 32;
+        T = (n + 31) / 32;
+        T = (T + 31) & ~31;
+        g.T = T;
+        g.n_pad = T * 32;
+        s = 5;
+        while (((T + (1 << s) - 1) >> s) > 64) s++;
+        g.ch_shift = s;
+    }
+    return g;
+}
+
+template <int W, int SRC, int EPI>
+static int launch_col_w(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
+    a.scratch = d_scratch;
+    int grid = a.ncols < grid_cap ? a.ncols : grid_cap;
+    if (grid < 1) return HH_OK;
+    HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
+    if (g.smem_acc) {
+        auto kern = hh_k_col<W, SRC, EPI, true>;
+        HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+        HH_LAUNCH(ctx, kern, grid, W * 32, g.smem_bytes, a);
+    } else {
+        auto kern = hh_k_col<W, SRC, EPI, false>;
+        HH_CUDA(cudaMemsetAsync(d_scratch, 0, (size_t)grid_cap * (size_t)g.n_pad * sizeof(float), ctx->stream));
+        HH_LAUNCH(ctx, kern, grid, W * 32, 0, a);
+    }
+    return HH_OK;
+}
+
+template <int SRC, int EPI>
+static int launch_col(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
+    a.n_pad = g.n_pad;
+    a.T = g.T;
+    a.ch_shift = g.ch_shift;
+    switch (g.W) {
+        case 8: return launch_col_w<8, SRC, EPI>(ctx, g, d_scratch, grid_cap, a);
+        case 16: return launch_col_w<16, SRC, EPI>(ctx, g, d_scratch, grid_cap, a);
+        default: return launch_col_w<32, SRC, EPI>(ctx, g, d_scratch, grid_cap, a);
+    }
+}
+
+static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
+    int per_sm = 0;
+    if (g.smem_acc) {
+        // every instantiation has the same footprint; query the heaviest (product + prune)
+        switch (g.W) {
+            case 8:
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)g.smem_bytes));
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true>, 256,
+                                                                     g.smem_bytes));
+                break;
+            case 16:
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)g.smem_bytes));
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true>, 512,
+                                                                     g.smem_bytes));
+                break;
+            default:
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)g.smem_bytes));
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true>, 1024,
+                                                                     g.smem_bytes));
+                break;
+        }
+    } else {
+        per_sm = 2;
+    }
+    HH_REQUIRE(per_sm >= 1, HH_ERR_UNSUPPORTED, "hh_mcl: the column kernel does not fit on an SM (W=%d, smem=%zu)", g.W, g.smem_bytes);
+    *out = per_sm * ctx->sm_count;
+    return HH_OK;
+}
+
+// unsorted CSC -> slotted (raw or column-normalised); cap must be >= the longest column
+static int slot_from_csc(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, int* d_counter, unsigned long long* d_stats,
+                         const hh_matrix* m, int raw, hh_slotmat& out) {
+    hh_colargs a;
+    memset(&a, 0, sizeof(a));
+    a.n = m->n;
+    a.col_lo = 0;
+    a.ncols = m->n;
+    a.counter = d_counter;
+    a.csc_ptr = m->d_colptr;
+    a.csc_row = m->d_row;
+    a.csc_val = m->d_val;
+    a.out = out;
+    a.raw = raw;
+    a.stats = d_stats;
+    a.delta_bits = reinterpret_cast<int*>(d_stats + 2);
+    a.err = reinterpret_cast<int*>(d_stats + 3);
+    return launch_col<SRC_CSC, EPI_NORM>(ctx, g, d_scratch, grid_cap, a);
+}
+
+static int max_col_len(hh_ctx* ctx, const hh_matrix* m, int* out) {
+    std::vector<int64_t> ptr((size_t)m->n + 1);
+    HH_CUDA(cudaMemcpyAsync(ptr.data(), m->d_colptr, ptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(ctx->stream));
+    int64_t mx = 1;
+    for (int c = 0; c < m->n; ++c) {
+        const int64_t l = ptr[c + 1] - ptr[c];
+        if (l > mx) mx = l;
+    }
+    *out = (int)(mx < m->n ? mx : m->n);
+    return HH_OK;
+}
+
+// slotted -> canonical CSC on the host
+static int slot_fetch_csc(hh_ctx* ctx, const hh_slotmat& s, int col_lo, int ncols, int64_t* indptr, int32_t* indices, float* data) {
+    int64_t* d_off = nullptr;
+    int* d_idx = nullptr;
+    float* d_val = nullptr;
+    HH_CHECK(hh_dmalloc(&d_off, (size_t)ncols + 1));
+    int rc = [&]() -> int {
+        HH_CHECK(hh_exclusive_scan_i32(ctx, s.len + col_lo, d_off, ncols));
+        if (indptr) HH_CUDA(cudaMemcpyAsync(indptr, d_off, ((size_t)ncols + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaMemcpyAsync(ctx->h_scratch, d_off + ncols, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int64_t nnz = (int64_t)ctx->h_scratch[0];
+        if (nnz == 0 || (!indices && !data)) return HH_OK;
+        HH_CHECK(hh_dmalloc(&d_idx, (size_t)nnz));
+        HH_CHECK(hh_dmalloc(&d_val, (size_t)nnz));
+        int grid = (ncols + 7) / 8;
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        HH_LAUNCH(ctx, hh_k_pack, grid, 256, 0, s, col_lo, ncols, d_off, (int*)nullptr, d_idx, d_val);
+        if (indices) HH_CUDA(cudaMemcpyAsync(indices, d_idx, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (data) HH_CUDA(cudaMemcpyAsync(data, d_val, (size_t)nnz * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        return HH_OK;
+    }();
+    hh_dfree(d_off);
+    hh_dfree(d_idx);
+    hh_dfree(d_val);
+    return rc;
+}
+
+static int read_stats(hh_ctx* ctx, unsigned long long* d_stats, unsigned long long out[4]) {
+    HH_CUDA(cudaMemcpyAsync(ctx->h_scratch + 16, d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 4; ++k) out[k] = ctx->h_scratch[16 + k];
+    return HH_OK;
+}
+
+extern "C" int hh_matrix_fetch_csc(hh_matrix* m, int64_t* indptr, int32_t* indices, float* data) {
+    HH_REQUIRE(m != nullptr, HH_ERR_ARG, "hh_matrix_fetch_csc: NULL handle");
+    hh_ctx* ctx = m->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    const hh_geom g = geom_for(ctx, m->n);
+    int grid_cap = 0;
+    HH_CHECK(grid_cap_for(ctx, g, &grid_cap));
+    int cap = 0;
+    HH_CHECK(max_col_len(ctx, m, &cap));
+    hh_slotmat s;
+    HH_CHECK(slot_alloc(s, m->n, cap, g.W));
+    float* d_scratch = nullptr;
+    int* d_counter = nullptr;
+    unsigned long long* d_stats = nullptr;
+    int rc = [&]() -> int {
+        if (!g.smem_acc) HH_CHECK(hh_dmalloc(&d_scratch, (size_t)grid_cap * (size_t)g.n_pad));
+        HH_CHECK(hh_dmalloc(&d_counter, 1));
+        HH_CHECK(hh_dmalloc(&d_stats, 4));
+        HH_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        HH_CHECK(slot_from_csc(ctx, g, d_scratch, grid_cap, d_counter, d_stats, m, 1, s));
+        unsigned long long st[4];
+        HH_CHECK(read_stats(ctx, d_stats, st));
+        HH_REQUIRE((int)st[3] == 0, HH_ERR_CAPACITY, "hh_matrix_fetch_csc: column slot overflow");
+        return slot_fetch_csc(ctx, s, 0, m->n, indptr, indices, data);
+    }();
+    hh_dfree(d_scratch);
+    hh_dfree(d_counter);
+    hh_dfree(d_stats);
+    slot_free(s);
+    return rc;
+}
+
+extern "C" int hh_mcl_destroy(hh_mcl* mc) {
+    if (!mc) return HH_OK;
+    cudaSetDevice(mc->ctx->device);
+    cudaStreamSynchronize(mc->ctx->stream);
+    slot_free(mc->m0);
+    slot_free(mc->it[0]);
+    slot_free(mc->it[1]);
+    hh_dfree(mc->d_m1);
+    hh_dfree(mc->d_scratch);
+    hh_dfree(mc->d_counter);
+    hh_dfree(mc->d_stats);
+    if (mc->ev0) cudaEventDestroy(mc->ev0);
+    if (mc->ev1) cudaEventDestroy(mc->ev1);
+    delete mc;
+    return HH_OK;
+}
+
+static hh_geom mcl_geom(const hh_mcl* mc) {
+    hh_geom g;
+    g.W = mc->W;
+    g.T = mc->T;
+    g.ch_shift = mc->ch_shift;
+    g.n_pad = mc->n_pad;
+    g.smem_acc = mc->smem_acc;
+    g.smem_bytes = mc->smem_bytes;
+    return g;
+}
+
+static void mcl_base_args(hh_mcl* mc, hh_colargs& a) {
+    memset(&a, 0, sizeof(a));
+    a.n = mc->n;
+    a.col_lo = mc->col_lo;
+    a.ncols = mc->col_hi - mc->col_lo;
+    a.counter = mc->d_counter;
+    a.ld = mc->ld;
+    a.stats = mc->d_stats;
+    a.delta_bits = reinterpret_cast<int*>(mc->d_stats + 2);
+    a.err = reinterpret_cast<int*>(mc->d_stats + 3);
+}
+
+extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, hh_mcl** out) {
+    HH_REQUIRE(m && out, HH_ERR_ARG, "hh_mcl_create: NULL argument");
+    *out = nullptr;
+    HH_REQUIRE(expansion == 2, HH_ERR_UNSUPPORTED,
+               "hh_mcl_create: expansion %d is not supported yet (only the default --expansion 2)", expansion);
+    HH_REQUIRE(0 <= col_lo && col_lo < col_hi && col_hi <= m->n, HH_ERR_ARG, "hh_mcl_create: bad column block [%d, %d) for n = %d",
+               col_lo, col_hi, m->n);
+    hh_ctx* ctx = m->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    hh_mcl* mc = new (std::nothrow) hh_mcl();
+    HH_REQUIRE(mc != nullptr, HH_ERR_NOMEM, "hh_mcl_create: out of host memory");
+    memset(mc, 0, sizeof(*mc));
+    mc->ctx = ctx;
+    mc->n = m->n;
+    mc->col_lo = col_lo;
+    mc->col_hi = col_hi;
+    mc->expansion = expansion;
+    mc->cur = -1;
+    const hh_geom g = geom_for(ctx, m->n);
+    mc->W = g.W;
+    mc->T = g.T;
+    mc->ch_shift = g.ch_shift;
+    mc->n_pad = g.n_pad;
+    mc->smem_acc = g.smem_acc;
+    mc->smem_bytes = g.smem_bytes;
+    mc->ld = ((int64_t)m->n + 31) & ~31ll;
+    int rc = [&]() -> int {
+        HH_CHECK(grid_cap_for(ctx, g, &mc->grid_cap));
+        HH_CUDA(cudaEventCreate(&mc->ev0));
+        HH_CUDA(cudaEventCreate(&mc->ev1));
+        if (!g.smem_acc) HH_CHECK(hh_dmalloc(&mc->d_scratch, (size_t)mc->grid_cap * (size_t)g.n_pad));
+        HH_CHECK(hh_dmalloc(&mc->d_counter, 1));
+        HH_CHECK(hh_dmalloc(&mc->d_stats, 4));
+        HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        // 1) M0 = normalize(link_matrix, 'l1', axis=0)   (2144)
+        int cap0 = 0;
+        HH_CHECK(max_col_len(ctx, m, &cap0));
+        HH_CHECK(slot_alloc(mc->m0, m->n, cap0, g.W));
+        HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
+        HH_CHECK(slot_from_csc(ctx, g, mc->d_scratch, mc->grid_cap, mc->d_counter, mc->d_stats, m, 0, mc->m0));
+        HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
+        unsigned long long st[4];
+        HH_CHECK(read_stats(ctx, mc->d_stats, st));
+        HH_CUDA(cudaEventElapsedTime(&mc->create_ms[0], mc->ev0, mc->ev1));
+        HH_REQUIRE((int)st[3] == 0, HH_ERR_CAPACITY, "hh_mcl_create: column slot overflow while normalising");
+        mc->nnz_m0 = (int64_t)st[0];
+        // 2) M1 = M0 . M0 for the owned columns, kept dense and resident   (2146-2149)
+        const int ncols = col_hi - col_lo;
+        HH_CHECK(hh_dmalloc(&mc->d_m1, (size_t)mc->ld * (size_t)ncols));
+        HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        hh_colargs a;
+        mcl_base_args(mc, a);
+        a.A = mc->m0;
+        a.B = mc->m0;
+        a.dense_out = mc->d_m1;
+        HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
+        HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+        HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
+        HH_CHECK(read_stats(ctx, mc->d_stats, st));
+        HH_CUDA(cudaEventElapsedTime(&mc->create_ms[1], mc->ev0, mc->ev1));
+        mc->preexp_products = (int64_t)st[1];
+        return HH_OK;
+    }();
+    if (rc != HH_OK) {
+        hh_mcl_destroy(mc);
+        return rc;
+    }
+    *out = mc;
+    return HH_OK;
+}
+
+extern "C" int hh_mcl_info(hh_mcl* mc, int32_t* n, int64_t* nnz_m0, int64_t* preexp_products, float* normalize_ms,
+                           float* preexp_ms) {
+    HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_info: NULL handle");
+    if (n) *n = mc->n;
+    if (nnz_m0) *nnz_m0 = mc->nnz_m0;
+    if (preexp_products) *preexp_products = mc->preexp_products;
+    if (normalize_ms) *normalize_ms = mc->create_ms[0];
+    if (preexp_ms) *preexp_ms = mc->create_ms[1];
+    return HH_OK;
+}
+
+extern "C" int hh_mcl_fetch_m0(hh_mcl* mc, int64_t* indptr, int32_t* indices, float* data) {
+    HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_fetch_m0: NULL handle");
+    HH_CUDA(cudaSetDevice(mc->ctx->device));
+    return slot_fetch_csc(mc->ctx, mc->m0, 0, mc->n, indptr, indices, data);
+}
+
+extern "C" int hh_mcl_fetch_m1(hh_mcl* mc, float* dense) {
+    HH_REQUIRE(mc && dense, HH_ERR_ARG, "hh_mcl_fetch_m1: NULL argument");
+    HH_CUDA(cudaSetDevice(mc->ctx->device));
+    const int ncols = mc->col_hi - mc->col_lo;
+    HH_CUDA(cudaMemcpy2DAsync(dense, (size_t)mc->n * sizeof(float), mc->d_m1, (size_t)mc->ld * sizeof(float),
+                              (size_t)mc->n * sizeof(float), (size_t)ncols, cudaMemcpyDeviceToHost, mc->ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(mc->ctx->stream));
+    return HH_OK;
+}
+
+extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
+    HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_begin: NULL handle");
+    HH_REQUIRE(inflation > 0.0, HH_ERR_ARG, "hh_mcl_begin: inflation must be positive");
+    HH_CUDA(cudaSetDevice(mc->ctx->device));
+    // a column that sums to 1 holds at most 1/pruning entries >= pruning (+ slack for fp32 rounding)
+    int cap = mc->n;
+    if (pruning > 0.0 && 1.0 / pruning + 16.0 < (double)mc->n) cap = (int)(1.0 / pruning) + 16;
+    if (cap != mc->it_cap) {
+        slot_free(mc->it[0]);
+        slot_free(mc->it[1]);
+        mc->it_cap = 0;
+        HH_CHECK(slot_alloc(mc->it[0], mc->n, cap, mc->W));
+        HH_CHECK(slot_alloc(mc->it[1], mc->n, cap, mc->W));
+        mc->it_cap = cap;
+    }
+    // matrix.power(inflation): fp32 array ** Python float = fp32 pow with the exponent cast to fp32
+    mc->inflation = (float)inflation;
+    mc->inflate_square = (mc->inflation == 2.0f) ? 1 : 0;
+    mc->prune = (float)pruning;   // `matrix >= pruning` compares in fp32
+    mc->cur = -1;
+    mc->have_pending = false;
+    mc->begun = true;
+    return HH_OK;
+}
+
+extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* products, float* delta, float* kernel_ms) {
+    HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_step: NULL handle");
+    HH_REQUIRE(mc->begun, HH_ERR_STATE, "hh_mcl_step: call hh_mcl_begin first");
+    HH_REQUIRE(!mc->have_pending, HH_ERR_STATE, "hh_mcl_step: previous step not committed");
+    HH_REQUIRE((it == 0) == (mc->cur < 0), HH_ERR_STATE, "hh_mcl_step: iteration %d out of sequence", it);
+    hh_ctx* ctx = mc->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    const hh_geom g = mcl_geom(mc);
+    HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    hh_colargs a;
+    mcl_base_args(mc, a);
+    a.inflation = mc->inflation;
+    a.inflate_square = mc->inflate_square;
+    a.prune = mc->prune;
+    const int dst = (mc->cur < 0) ? 0 : (mc->cur ^ 1);
+    a.out = mc->it[dst];
+    HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
+    if (it == 0) {
+        a.dense_in = mc->d_m1;
+        a.do_conv = 0;
+        HH_CHECK((launch_col<SRC_DENSE, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+    } else {
+        a.A = mc->it[mc->cur];
+        a.B = mc->it[mc->cur];
+        a.do_conv = 1;
+        HH_CHECK((launch_col<SRC_PRODUCT, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+    }
+    HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
+    unsigned long long st[4];
+    HH_CHECK(read_stats(ctx, mc->d_stats, st));
+    if (kernel_ms) HH_CUDA(cudaEventElapsedTime(kernel_ms, mc->ev0, mc->ev1));
+    HH_REQUIRE((int)(st[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY,
+               "hh_mcl_step: a pruned column exceeded its slot (%d entries); pruning threshold too small for this layout", mc->it_cap);
+    if (nnz_owned) *nnz_owned = (int64_t)st[0];
+    if (products) *products = (int64_t)st[1];
+    if (delta) {
+        const int bits = (int)(st[2] & 0xffffffffull);
+        float d;
+        memcpy(&d, &bits, sizeof(float));
+        *delta = d;
+    }
+    mc->pending = dst;
+    mc->have_pending = true;
+    return HH_OK;
+}
+
+extern "C" int hh_mcl_pack(hh_mcl* mc, int32_t* len_dev, int32_t* idx_dev, float* val_dev) {
+    HH_REQUIRE(mc && len_dev, HH_ERR_ARG, "hh_mcl_pack: NULL argument");
+    HH_REQUIRE(mc->have_pending, HH_ERR_STATE, "hh_mcl_pack: nothing to pack (call hh_mcl_step first)");
+    hh_ctx* ctx = mc->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    const int ncols = mc->col_hi - mc->col_lo;
+    int64_t* d_off = nullptr;
+    HH_CHECK(hh_dmalloc(&d_off, (size_t)ncols + 1));
+    int rc = [&]() -> int {
+        const hh_slotmat& s = mc->it[mc->pending];
+        HH_CHECK(hh_exclusive_scan_i32(ctx, s.len + mc->col_lo, d_off, ncols));
+        int grid = (ncols + 7) / 8;
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        HH_LAUNCH(ctx, hh_k_pack, grid, 256, 0, s, mc->col_lo, ncols, d_off, len_dev, idx_dev, val_dev);
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        return HH_OK;
+    }();
+    hh_dfree(d_off);
+    return rc;
+}
+
+extern "C" int hh_mcl_unpack(hh_mcl* mc, int32_t col_lo, int32_t col_hi, const int32_t* len_dev, const int32_t* idx_dev,
+                             const float* val_dev, int64_t nnz_block) {
+    HH_REQUIRE(mc && len_dev, HH_ERR_ARG, "hh_mcl_unpack: NULL argument");
+    HH_REQUIRE(mc->have_pending, HH_ERR_STATE, "hh_mcl_unpack: no pending iterate (call hh_mcl_step first)");
+    HH_REQUIRE(0 <= col_lo && col_lo < col_hi && col_hi <= mc->n, HH_ERR_ARG, "hh_mcl_unpack: bad column block");
+    HH_REQUIRE(col_hi <= mc->col_lo || col_lo >= mc->col_hi, HH_ERR_ARG, "hh_mcl_unpack: block overlaps the owned columns");
+    (void)nnz_block;
+    hh_ctx* ctx = mc->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    const int ncols = col_hi - col_lo;
+    int64_t* d_off = nullptr;
+    HH_CHECK(hh_dmalloc(&d_off, (size_t)ncols + 1));
+    int rc = [&]() -> int {
+        HH_CUDA(cudaMemsetAsync(mc->d_stats + 3, 0, sizeof(unsigned long long), ctx->stream));
+        HH_CHECK(hh_exclusive_scan_i32(ctx, len_dev, d_off, ncols));
+        int grid = (ncols + 7) / 8;
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        HH_LAUNCH(ctx, hh_k_unpack, grid, 256, 0, mc->it[mc->pending], mc->T, col_lo, ncols, len_dev, d_off, idx_dev, val_dev,
+                  reinterpret_cast<int*>(mc->d_stats + 3));
+        unsigned long long st[4];
+        HH_CHECK(read_stats(ctx, mc->d_stats, st));
+        HH_REQUIRE((int)(st[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY, "hh_mcl_unpack: a peer column exceeds the slot capacity");
+        return HH_OK;
+    }();
+    hh_dfree(d_off);
+    return rc;
+}
+
+extern "C" int hh_mcl_commit(hh_mcl* mc) {
+    HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_commit: NULL handle");
+    HH_REQUIRE(mc->have_pending, HH_ERR_STATE, "hh_mcl_commit: nothing to commit");
+    mc->cur = mc->pending;
+    mc->have_pending = false;
+    return HH_OK;
+}
+
+extern "C" int hh_mcl_run(hh_mcl* mc, double inflation, int max_iter, double pruning, hh_mcl_result* res, int64_t* iter_nnz,
+                          int64_t* iter_products, float* iter_delta, float* iter_ms) {
+    HH_REQUIRE(mc && res, HH_ERR_ARG, "hh_mcl_run: NULL argument");
+    HH_REQUIRE(mc->col_lo == 0 && mc->col_hi == mc->n, HH_ERR_STATE,
+               "hh_mcl_run needs a context that owns every column; use the step interface for column shards");
+    HH_REQUIRE(max_iter >= 1, HH_ERR_ARG, "hh_mcl_run: max_iter must be >= 1");
+    HH_CHECK(hh_mcl_begin(mc, inflation, pruning));
+    memset(res, 0, sizeof(*res));
+    int64_t nnz_prev = 0;
+    for (int it = 0; it < max_iter; ++it) {
+        int64_t nnz = 0, prod = 0;
+        float delta = 0.f, ms = 0.f;
+        HH_CHECK(hh_mcl_step(mc, it, &nnz, &prod, &delta, &ms));
+        HH_CHECK(hh_mcl_commit(mc));
+        if (iter_ms) iter_ms[it] = ms;
+        if (iter_nnz) iter_nnz[it] = nnz;
+        if (iter_products) iter_products[it] = prod;
+        if (iter_delta) iter_delta[it] = delta;
+        res->rounds = it + 1;
+        res->nnz = nnz;
+        res->products += prod;
+        // algorithmic bytes: it == 0 streams the dense M1 and writes the pruned result;
+        // it >= 1 reads the operand, writes the result, re-reads the operand for the convergence test
+        if (it == 0) res->bytes += 4ll * mc->n * (int64_t)mc->n + 8ll * nnz;
+        else res->bytes += 16ll * nnz_prev + 8ll * nnz + 12ll * ((int64_t)mc->n + 1);
+        nnz_prev = nnz;
+        // n > 1 and max(|M-L| - 1e-5|L|) <= 1e-8   (2044-2046)
+        if (it > 1 && (double)delta <= 1e-8) {
+            res->converged = 1;
+            break;
+        }
+    }
+    return HH_OK;
+}
+
+extern "C" int hh_mcl_fetch_result(hh_mcl* mc, int64_t* indptr, int32_t* indices, float* data) {
+    HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_fetch_result: NULL handle");
+    HH_REQUIRE(mc->cur >= 0 && !mc->have_pending, HH_ERR_STATE, "hh_mcl_fetch_result: no committed iterate");
+    HH_CUDA(cudaSetDevice(mc->ctx->device));
+    return slot_fetch_csc(mc->ctx, mc->it[mc->cur], 0, mc->n, indptr, indices, data);
+}

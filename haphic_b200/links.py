@@ -1,0 +1,238 @@
+"""Host side of the link-counting path (hh_links / hh_matrix handles).
+
+Mirrors the data the reference's ``parse_alignments_for_ctgs``
+(scripts/HapHiC_cluster.py:1596-1655) and ``dict_to_matrix`` (310-373) produce, with the
+per-read-pair loop running on the GPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from collections import defaultdict
+
+import numpy as np
+
+from . import _lib
+from ._lib import Context, HHError, LinksInfo, check, load, ptr
+
+NONE32 = 0xFFFFFFFF
+
+
+def name_rank(names) -> np.ndarray:
+    """Rank of every contig under Python ``str`` ordering of the names (the order
+    ``sorted(((ref, pos+1), (mref, mpos+1)))`` uses, HapHiC_cluster.py:1629)."""
+    order = sorted(range(len(names)), key=names.__getitem__)
+    rank = np.empty(len(names), dtype=np.int32)
+    rank[order] = np.arange(len(names), dtype=np.int32)
+    return rank
+
+
+class LinkTable:
+    """Device-resident link counters of one run (full / flank / HT / per-fragment totals)."""
+
+    def __init__(self, ctx: Context, ctg_len, rank, in_nx, flank_bp: int, capacity_hint: int = 0):
+        self.ctx = ctx
+        self.n_ctg = len(ctg_len)
+        self._len = np.ascontiguousarray(ctg_len, dtype=np.int64)
+        self._rank = np.ascontiguousarray(rank, dtype=np.int32)
+        self._nx = np.ascontiguousarray(in_nx, dtype=np.uint8)
+        if not (len(self._rank) == self.n_ctg == len(self._nx)):
+            raise ValueError("ctg_len, rank and in_nx must have one entry per contig")
+        self._h = C.c_void_p()
+        check(load().hh_links_create(ctx.handle, self.n_ctg, ptr(self._len), ptr(self._rank), ptr(self._nx),
+                                     int(flank_bp), int(capacity_hint), C.byref(self._h)))
+        self._stream_pos = 0
+        self.info = None
+
+    # -- streaming -------------------------------------------------------------------------
+    def add(self, rec, stream_offset: int | None = None, asynchronous: bool = False):
+        """Stream records: int32 [P, 4] (ctg_a, pos_a, ctg_b, pos_b); numpy array, pinned/pageable
+        torch CPU tensor or torch CUDA tensor."""
+        n_rec = int(rec.shape[0])
+        if n_rec == 0:
+            return
+        off = self._stream_pos if stream_offset is None else int(stream_offset)
+        if isinstance(rec, np.ndarray):
+            if rec.dtype != np.int32 or rec.ndim != 2 or rec.shape[1] != 4 or not rec.flags.c_contiguous:
+                rec = np.ascontiguousarray(rec, dtype=np.int32).reshape(-1, 4)
+            mem = _lib.HH_MEM_HOST
+        else:
+            import torch
+            if rec.dtype != torch.int32 or rec.dim() != 2 or rec.shape[1] != 4 or not rec.is_contiguous():
+                raise ValueError("records must be a contiguous int32 [P, 4] tensor")
+            mem = _lib.HH_MEM_DEVICE if rec.is_cuda else _lib.HH_MEM_HOST
+        if asynchronous:
+            if mem != _lib.HH_MEM_DEVICE:
+                raise ValueError("asynchronous add needs device-resident records")
+            check(load().hh_links_add_async(self._h, ptr(rec), n_rec, off))
+        else:
+            check(load().hh_links_add(self._h, ptr(rec), n_rec, off, mem))
+        self._stream_pos = max(self._stream_pos, off + n_rec)
+
+    def finish(self) -> LinksInfo:
+        info = LinksInfo()
+        check(load().hh_links_finish(self._h, C.byref(info)))
+        self.info = info
+        return info
+
+    # -- results ---------------------------------------------------------------------------
+    def fetch(self) -> dict:
+        """Arrays of nnz_full entries in full_link_dict insertion order."""
+        if self.info is None:
+            self.finish()
+        nnz = int(self.info.nnz_full)
+        out = {
+            "key_i": np.empty(nnz, np.int32), "key_j": np.empty(nnz, np.int32),
+            "full": np.empty(nnz, np.uint32), "flank": np.empty(nnz, np.uint32),
+            "first_full": np.empty(nnz, np.uint32), "first_flank": np.empty(nnz, np.uint32),
+            "ht": np.empty((nnz, 4), np.uint32),
+        }
+        check(load().hh_links_fetch(self._h, ptr(out["key_i"]), ptr(out["key_j"]), ptr(out["full"]), ptr(out["flank"]),
+                                    ptr(out["first_full"]), ptr(out["first_flank"]), ptr(out["ht"])))
+        return out
+
+    def fetch_ctg(self) -> np.ndarray:
+        tot = np.empty(self.n_ctg, np.int64)
+        check(load().hh_links_fetch_ctg(self._h, ptr(tot)))
+        return tot
+
+    def linked_index(self, keep):
+        """(index, n_linked): first-seen matrix index of every fragment present in
+        flank_link_dict restricted to ``keep`` (HapHiC_cluster.py:327-349); -1 elsewhere."""
+        if self.info is None:
+            self.finish()
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        index = np.empty(self.n_ctg, np.int32)
+        n_linked = C.c_int32()
+        check(load().hh_links_linked_index(self._h, ptr(keep), ptr(index), C.byref(n_linked)))
+        return index, int(n_linked.value)
+
+    def to_matrix(self, keep, tail=None, normalize_by_nlinks: bool = False) -> "LinkMatrix":
+        if self.info is None:
+            self.finish()
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        tail = np.ascontiguousarray(tail if tail is not None else [], dtype=np.int32)
+        h = C.c_void_p()
+        check(load().hh_matrix_from_links(self._h, ptr(keep), ptr(tail) if len(tail) else None, len(tail),
+                                          int(bool(normalize_by_nlinks)), C.byref(h)))
+        return LinkMatrix(self.ctx, h)
+
+    # -- multi-GPU -------------------------------------------------------------------------
+    def export(self):
+        """(entries [nnz, 9] uint32 CUDA tensor, ctg totals [n_ctg] int64 CUDA tensor, n_records, n_used)."""
+        import torch
+        if self.info is None:
+            self.finish()
+        dev = torch.device("cuda", self.ctx.device)
+        ent = torch.empty((int(self.info.nnz_full), 9), dtype=torch.int32, device=dev)
+        tot = torch.empty(self.n_ctg, dtype=torch.int64, device=dev)
+        check(load().hh_links_export(self._h, ptr(ent), ptr(tot)))
+        return ent, tot, int(self.info.n_records), int(self.info.n_used)
+
+    def merge(self, entries, ctg_totals, n_records: int, n_used: int):
+        n = int(entries.shape[0])
+        check(load().hh_links_merge(self._h, ptr(entries) if n else None, n, ptr(ctg_totals), int(n_records), int(n_used)))
+
+    def close(self):
+        if self._h:
+            load().hh_links_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LinkMatrix:
+    """The contig x contig link matrix on the device (hh_matrix): symmetric fp32, self loops = 1."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle
+        n = C.c_int32()
+        nnz = C.c_int64()
+        check(load().hh_matrix_info(self._h, C.byref(n), C.byref(nnz)))
+        self.n, self.nnz = int(n.value), int(nnz.value)
+
+    @classmethod
+    def from_csc(cls, ctx: Context, matrix) -> "LinkMatrix":
+        """From a scipy CSC / anything ``scipy.sparse.csc_matrix`` accepts (host)."""
+        import scipy.sparse as sp
+        m = sp.csc_matrix(matrix, dtype=np.float32)
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("link matrix must be square")
+        indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        data = np.ascontiguousarray(m.data, dtype=np.float32)
+        h = C.c_void_p()
+        check(load().hh_matrix_from_csc(ctx.handle, m.shape[0], ptr(indptr), ptr(indices), ptr(data), C.byref(h)))
+        return cls(ctx, h)
+
+    def to_scipy(self):
+        """Canonical (row-sorted, duplicates summed) CSC on the host."""
+        import scipy.sparse as sp
+        indptr = np.empty(self.n + 1, np.int64)
+        check(load().hh_matrix_fetch_csc(self._h, ptr(indptr), None, None))
+        nnz = int(indptr[-1])
+        indices = np.empty(nnz, np.int32)
+        data = np.empty(nnz, np.float32)
+        check(load().hh_matrix_fetch_csc(self._h, ptr(indptr), ptr(indices), ptr(data)))
+        return sp.csc_matrix((data, indices, indptr), shape=(self.n, self.n))
+
+    def close(self):
+        if self._h:
+            load().hh_matrix_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------
+# reference-shaped view of a finished LinkTable
+# ------------------------------------------------------------------------------------------
+
+def link_dicts(table: LinkTable, names):
+    """(full_link_dict, flank_link_dict, HT_link_dict, ctg_link_dict) as the reference builds them
+    (HapHiC_cluster.py:1605-1649): ``defaultdict(int)`` keyed by name tuples, in insertion order."""
+    f = table.fetch()
+    ki, kj = f["key_i"].tolist(), f["key_j"].tolist()
+    full_link_dict = defaultdict(int)
+    for a, b, v in zip(ki, kj, f["full"].tolist()):
+        full_link_dict[(names[a], names[b])] = v
+    # flank_link_dict is ordered by the first flank-qualifying record of each pair
+    sel = np.nonzero(f["flank"] > 0)[0]
+    sel = sel[np.argsort(f["first_flank"][sel], kind="stable")]
+    flank_link_dict = defaultdict(int)
+    for e in sel.tolist():
+        flank_link_dict[(names[ki[e]], names[kj[e]])] = int(f["flank"][e])
+    # HT_link_dict keys appear when their first record does; within the 4-way split of one pair the
+    # order is not recoverable from counters alone, so entries are grouped by pair (consumers look
+    # keys up, HapHiC_sort.py:126-131, and never iterate in order)
+    HT_link_dict = defaultdict(int)
+    suffix = ("_H", "_T")
+    ht = f["ht"]
+    for e, (a, b) in enumerate(zip(ki, kj)):
+        for c in range(4):
+            v = int(ht[e, c])
+            if v:
+                HT_link_dict[(names[a] + suffix[c >> 1], names[b] + suffix[c & 1])] = v
+    tot = table.fetch_ctg()
+    ctg_link_dict = defaultdict(int)
+    # insertion order = first touch (i before j) over flank-qualifying records
+    touch = {}
+    for e in sel.tolist():
+        t = int(f["first_flank"][e]) * 2
+        a, b = ki[e], kj[e]
+        if t < touch.get(a, 1 << 62):
+            touch[a] = t
+        if t + 1 < touch.get(b, 1 << 62):
+            touch[b] = t + 1
+    for c in sorted(touch, key=touch.__getitem__):
+        ctg_link_dict[names[c]] = int(tot[c])
+    return full_link_dict, flank_link_dict, HT_link_dict, ctg_link_dict

@@ -1,0 +1,191 @@
+"""GPU parity: Markov clustering (hh_matrix_* / hh_mcl_*) against the golden fixtures of the
+reference and against the CPU oracle, through the C ABI.
+
+Tolerances: the first normalisation M0 is bit-exact for integer link counts; every later float is
+compared at 1e-6 relative where the sparsity patterns agree (the reference's own SpGEMM, Intel MKL,
+has an unspecified accumulation order, so bit-equality of products is not defined); iteration
+counts, convergence flags and final cluster assignments must be identical."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests.util import canon, csc_from, load_golden, planted_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from haphic_b200._lib import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def labels(clusters, n):
+    lab = np.full(n, -1, np.int64)
+    for c in clusters:
+        lab[list(c)] = min(c)
+    return lab
+
+
+def compare_sparse(got, ref, rtol, what, max_pattern_diff=0, floor=0.0):
+    """Same pattern (up to `max_pattern_diff` borderline entries below `floor`) and close values."""
+    got, ref = canon(got), canon(ref)
+    if (got.nnz == ref.nnz and np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)):
+        assert np.allclose(got.data, ref.data, rtol=rtol, atol=0), what
+        return
+    d = abs(got - ref)
+    only = (got != 0).astype(np.int8) - (ref != 0).astype(np.int8)
+    only.eliminate_zeros()
+    assert only.nnz <= max_pattern_diff, "{}: {} pattern differences".format(what, only.nnz)
+    assert d.max() <= floor, "{}: max abs difference {}".format(what, d.max())
+
+
+@pytest.mark.parametrize("tag", ["links_a", "block200", "block600"])
+def test_mcl_matches_reference_golden(ctx, tag):
+    from haphic_b200.links import LinkMatrix
+    from haphic_b200.mcl import Mcl, interpret_result
+    g = load_golden("mcl_{}.npz".format(tag))
+    n = len(g["link_indptr"]) - 1
+    link = csc_from(g, "link", n)
+    mat = LinkMatrix.from_csc(ctx, link)
+    back = mat.to_scipy()
+    assert np.array_equal(back.indptr, link.indptr) and np.array_equal(back.indices, link.indices)
+    assert np.array_equal(back.data, link.data)
+    mc = Mcl(mat, expansion=int(g["expansion"]))
+    m0 = mc.m0()
+    ref0 = csc_from(g, "m0", n)
+    assert np.array_equal(m0.indptr, ref0.indptr) and np.array_equal(m0.indices, ref0.indices)
+    assert np.array_equal(m0.data, ref0.data), "first column normalisation must be bit-exact on integer counts"
+    m1 = mc.m1()
+    assert m1.shape == (n, n)
+    assert np.allclose(m1, g["m1_dense"], rtol=2e-6, atol=1e-12)
+    assert np.array_equal(m1 != 0, g["m1_dense"] != 0)
+    pruning = float(g["pruning"])
+    for r in g["inflations"].tolist():
+        key = "r{}".format(str(r).replace(".", "p"))
+        k = 1
+        while key + "_iter{}_indptr".format(k) in g.files:
+            st = mc.run(r, max_iter=k, pruning=pruning)
+            assert st["rounds"] == k
+            compare_sparse(mc.result(), csc_from(g, key + "_iter{}".format(k), n), 5e-6, (tag, key, k),
+                           max_pattern_diff=2, floor=2 * pruning)
+            k += 1
+        st = mc.run(r, max_iter=200, pruning=pruning)
+        assert st["rounds"] == int(g[key + "_niter"]), (key, st["rounds"], int(g[key + "_niter"]))
+        assert st["converged"] == bool(g[key + "_converged"])
+        fin = mc.result()
+        clusters = interpret_result(fin)
+        assert (clusters is not None) == bool(g[key + "_clusters_valid"])
+        if clusters is not None:
+            assert np.array_equal(labels(clusters, n), g[key + "_labels"])
+        compare_sparse(fin, csc_from(g, key + "_final", n), 1e-5, (tag, key, "final"))
+        # column-stochastic result
+        sums = np.asarray(fin.sum(axis=0)).ravel()
+        assert np.allclose(sums[sums != 0], 1.0, atol=1e-5)
+    mc.close()
+    mat.close()
+
+
+@pytest.mark.parametrize("n_blocks,block,noise", [(150, 100, 0.5), (310, 100, 0.3)])
+def test_mcl_matches_oracle_larger_geometry(ctx, n_blocks, block, noise):
+    """n = 15,000 (16 row blocks per column) and n = 31,000 (32 row blocks): same iteration count,
+    same clusters as the CPU oracle."""
+    from haphic_b200.links import LinkMatrix
+    from haphic_b200.mcl import Mcl, interpret_result
+    from oracle import haphic_oracle as orc
+    link, truth = planted_blocks(n_blocks, block, seed=n_blocks, noise=noise)
+    n = link.shape[0]
+    mat = LinkMatrix.from_csc(ctx, link)
+    mc = Mcl(mat)
+    m0 = orc.col_normalize_l1(link)
+    got0 = mc.m0()
+    assert np.array_equal(got0.indices, m0.indices) and np.array_equal(got0.data, m0.data)
+    m1 = orc.expand(m0, 2)
+    for r in (1.6, 2.0):
+        ofin, rounds, conv = orc.mcl(m1, 2, r, 200, 1e-4)
+        st = mc.run(r, 200, 1e-4)
+        assert (st["rounds"], st["converged"]) == (rounds, conv)
+        a = interpret_result(mc.result())
+        b = orc.interpret_result(ofin)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(labels(a, n), labels(b, n))
+    mc.close()
+    mat.close()
+
+
+def test_mcl_global_accumulator_path(ctx):
+    """n > 57,600 does not fit the shared-memory accumulator: the global-memory variant must give
+    the same clusters (planted, recoverable) and a column-stochastic result."""
+    from haphic_b200.links import LinkMatrix
+    from haphic_b200.mcl import Mcl, interpret_result
+    link, truth = planted_blocks(1200, 50, seed=5, noise=0.0)
+    n = link.shape[0]
+    assert n == 60000
+    mat = LinkMatrix.from_csc(ctx, link)
+    mc = Mcl(mat)
+    st = mc.run(2.0, 200, 1e-4)
+    fin = mc.result()
+    clusters = interpret_result(fin)
+    assert clusters is not None and st["converged"]
+    lab = labels(clusters, n)
+    # every cluster lies inside one planted block
+    for c in clusters:
+        assert len(set(truth[list(c)].tolist())) == 1
+    sums = np.asarray(fin.sum(axis=0)).ravel()
+    assert np.allclose(sums, 1.0, atol=1e-5)
+    mc.close()
+    mat.close()
+
+
+def test_mcl_step_interface_two_column_shards_equal_single(ctx):
+    """Two column shards stepped side by side and exchanged through pack/unpack (what two ranks do
+    with an all-gather) produce bit-identical iterates to the single-shard run."""
+    from haphic_b200.links import LinkMatrix
+    from haphic_b200.mcl import Mcl
+    link, _ = planted_blocks(40, 60, seed=2, noise=0.4)
+    n = link.shape[0]
+    mat = LinkMatrix.from_csc(ctx, link)
+    whole = Mcl(mat)
+    st = whole.run(1.8, 200, 1e-4)
+    want = canon(whole.result())
+    cut = n // 3
+    s0, s1 = Mcl(mat, col_lo=0, col_hi=cut), Mcl(mat, col_lo=cut, col_hi=n)
+    m1 = np.concatenate([s0.m1(), s1.m1()], axis=1)
+    assert np.array_equal(m1, whole.m1())
+    s0.begin(1.8, 1e-4)
+    s1.begin(1.8, 1e-4)
+    rounds = 0
+    for it in range(200):
+        n0, p0, d0 = s0.step(it)
+        n1, p1, d1 = s1.step(it)
+        b0, b1 = s0.pack(n0), s1.pack(n1)
+        s0.unpack(cut, n, *b1)
+        s1.unpack(0, cut, *b0)
+        s0.commit()
+        s1.commit()
+        rounds = it + 1
+        if it > 1 and max(d0, d1) <= 1e-8:
+            break
+    assert rounds == st["rounds"]
+    for s in (s0, s1):
+        got = canon(s.result())
+        assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+        assert np.array_equal(got.data, want.data)
+    for o in (whole, s0, s1):
+        o.close()
+    mat.close()
+
+
+def test_mcl_rejects_unsupported(ctx):
+    from haphic_b200._lib import HHError
+    from haphic_b200.links import LinkMatrix
+    from haphic_b200.mcl import Mcl
+    link, _ = planted_blocks(3, 10, seed=1)
+    mat = LinkMatrix.from_csc(ctx, link)
+    with pytest.raises(HHError):
+        Mcl(mat, expansion=3)
+    mat.close()
