@@ -135,6 +135,9 @@ def cpu_mcl_iter_per_sec(m_csc, n_cols, inflation, pruning, seed=0):
     from oracle import haphic_oracle as orc
     n = m_csc.shape[0]
     rng = np.random.default_rng(seed)
+    # size the sample for ~2e8 Gustavson products (a few seconds of scipy SpGEMM)
+    per_col = max(1.0, (m_csc.nnz / n) ** 2)
+    n_cols = int(min(n, max(n_cols, 2e8 / per_col)))
     cols = np.sort(rng.choice(n, size=min(n_cols, n), replace=False))
     sub = m_csc[:, cols]
     t0 = time.perf_counter()
