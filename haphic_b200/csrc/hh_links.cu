@@ -40,6 +40,7 @@ struct hh_links {
     int64_t known_unique, since_known;   // growth bookkeeping (see ensure_capacity)
     bool finished;
     int64_t nnz, nnz_flank, n_used;
+    int64_t peer_used;               // records counted by merged peers
     uint32_t* d_compact;             // [nnz][9]  {i, j, full, flank, first_full, first_flank, HT, TH, TT}
     // host staging (double-buffered H2D)
     int4* d_stage[2];
@@ -556,7 +557,8 @@ extern "C" int hh_links_finish(hh_links* lk, hh_links_info* info) {
                    "hh_links_finish: hash table overflow (capacity %llu slots): pass a larger capacity_hint or use hh_links_add",
                    (unsigned long long)lk->cap);
         lk->nnz = (int64_t)c[0];
-        lk->n_used += (int64_t)c[1];
+        lk->n_used = lk->peer_used + (int64_t)c[1];
+        HH_CUDA(cudaMemsetAsync(lk->d_counters + 3, 0, sizeof(unsigned long long), ctx->stream));
         if (lk->nnz > 0 && (int64_t)c[4] + 1 > lk->stream_end) lk->stream_end = (int64_t)c[4] + 1;   // merged peers
         const int64_t S = lk->stream_end;
         hh_dfree(lk->d_compact);
@@ -656,7 +658,7 @@ extern "C" int hh_links_export(hh_links* lk, uint32_t* entries_dev, int64_t* ctg
 extern "C" int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t n_entries, const int64_t* ctg_links_dev,
                               int64_t n_records, int64_t n_used) {
     HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_merge: NULL handle");
-    HH_REQUIRE(!lk->finished, HH_ERR_STATE, "hh_links_merge: table already finished");
+    lk->finished = false;   // a finished table is re-opened: the next hh_links_finish rebuilds the ordered view
     HH_REQUIRE(n_entries >= 0 && (entries_dev || n_entries == 0), HH_ERR_ARG, "hh_links_merge: bad entries");
     hh_ctx* ctx = lk->ctx;
     HH_CUDA(cudaSetDevice(ctx->device));
@@ -671,7 +673,7 @@ extern "C" int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t
         HH_LAUNCH(ctx, hh_k_add_u64, (lk->n_ctg + 255) / 256, 256, 0, lk->d_ctg, ctg_links_dev, lk->n_ctg);
     HH_CUDA(cudaStreamSynchronize(ctx->stream));
     lk->n_records += n_records;
-    lk->n_used += n_used;
+    lk->peer_used += n_used;
     return HH_OK;
 }
 

@@ -1,0 +1,228 @@
+"""Multi-GPU orchestration (one process per GPU, torch.distributed over NCCL/NVLink).
+
+The path shards in two places:
+
+* link counting -- the read-pair stream is cut into contiguous shards, one per rank; every rank
+  counts its shard into its own table, the finished tables are all-gathered once and merged, so each
+  rank ends with the whole table (integer adds and mins: bit-identical for any world size);
+* Markov clustering -- every step of an iteration is column-local, so each rank owns a contiguous
+  block of columns; per iteration there is ONE exchange, an all-gather of the pruned column blocks
+  (lengths, then packed row indices and values), plus a scalar max for the convergence test.
+  The dense pre-expanded matrix is never exchanged: each rank computes its own column block of it.
+
+The exchange code is device-agnostic (it moves whatever torch tensors the engine hands it), which is
+how the world_size-2 gloo tests exercise it on CPU.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def column_blocks(n: int, world: int):
+    """Contiguous, near-equal column blocks [(lo, hi)] * world."""
+    cuts = [(n * r) // world for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def balanced_column_blocks(cost, world: int):
+    """Contiguous blocks with near-equal total `cost` (e.g. per-column product estimates)."""
+    c = np.asarray(cost, dtype=np.float64)
+    n = len(c)
+    if n == 0 or c.sum() <= 0:
+        return column_blocks(n, world)
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(cum, cum[-1] * r / world))
+        cuts.append(min(max(k, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def allgather_varlen(t: torch.Tensor, group=None):
+    """All-gather 1-D (or [m, k]) tensors whose leading size differs per rank.
+    Returns the list of every rank's tensor (this rank's own included)."""
+    world = dist.get_world_size(group)
+    m = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(m) for _ in range(world)]
+    dist.all_gather(sizes, m, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(max(sizes), 1)
+    pad_shape = (mx,) + tuple(t.shape[1:])
+    padded = torch.zeros(pad_shape, dtype=t.dtype, device=t.device)
+    padded[: t.shape[0]] = t
+    outs = [torch.empty(pad_shape, dtype=t.dtype, device=t.device) for _ in range(world)]
+    dist.all_gather(outs, padded, group=group)
+    return [o[:s] for o, s in zip(outs, sizes)]
+
+
+def _wait_collectives(t: torch.Tensor):
+    """The library works on its own CUDA stream: make sure the collectives torch enqueued on its
+    current stream have landed before a library kernel reads their output."""
+    if t.is_cuda:
+        torch.cuda.current_stream(t.device).synchronize()
+
+
+def merge_link_tables(table, group=None):
+    """Every rank holds a table with its own shard counted.  Afterwards every rank's table holds
+    the whole stream (call table.finish() next).  One all-gather of the exported entries."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    table.finish()
+    ent, tot, n_rec, n_used = table.export()
+    ents = allgather_varlen(ent, group)
+    tots = [torch.empty_like(tot) for _ in range(world)]
+    dist.all_gather(tots, tot, group=group)
+    meta = torch.tensor([n_rec, n_used], dtype=torch.int64, device=ent.device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    _wait_collectives(ent)
+    for r in range(world):
+        if r == rank:
+            continue
+        table.merge(ents[r], tots[r], int(metas[r][0].item()), int(metas[r][1].item()))
+
+
+def sharded_mcl_run(engine, inflation: float, max_iter: int, pruning: float, blocks, group=None):
+    """One mcl() call (HapHiC_cluster.py:2026-2062) over column shards.
+
+    `engine` owns the block blocks[rank] and offers begin / step / pack / unpack / commit
+    (haphic_b200.mcl.Mcl, or a CPU stand-in in the gloo tests).  Returns
+    {"rounds", "converged", "iter_nnz", "iter_products"} identical on every rank."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    engine.begin(inflation, pruning)
+    rounds, converged = 0, False
+    it_nnz, it_prod, it_ms = [], [], []
+    for it in range(max_iter):
+        nnz, prod, delta = engine.step(it)
+        ln, idx, val = engine.pack(nnz)
+        lens = [torch.empty(blocks[r][1] - blocks[r][0], dtype=ln.dtype, device=ln.device) for r in range(world)]
+        dist.all_gather(lens, ln, group=group) if _equal_blocks(blocks) else _gather_lens(lens, ln, blocks, group)
+        idxs = allgather_varlen(idx, group)
+        vals = allgather_varlen(val, group)
+        _wait_collectives(ln)
+        for r in range(world):
+            if r != rank:
+                engine.unpack(blocks[r][0], blocks[r][1], lens[r], idxs[r], vals[r])
+        engine.commit()
+        stat = torch.tensor([float(delta), float(nnz), float(prod)], dtype=torch.float64, device=ln.device)
+        mx = stat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        sm = stat.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)
+        it_nnz.append(int(sm[1].item()))
+        it_prod.append(int(sm[2].item()))
+        it_ms.append(getattr(engine, "last_step_ms", 0.0))
+        rounds = it + 1
+        if it > 1 and float(mx[0].item()) <= 1e-8:
+            converged = True
+            break
+    return {"rounds": rounds, "converged": converged, "iter_nnz": it_nnz, "iter_products": it_prod, "iter_ms": it_ms}
+
+
+def _equal_blocks(blocks):
+    return len({hi - lo for lo, hi in blocks}) == 1
+
+
+def _gather_lens(lens, ln, blocks, group):
+    got = allgather_varlen(ln, group)
+    for r in range(len(blocks)):
+        lens[r] = got[r]
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py --gpus N (launched by torch.distributed.run, one rank per GPU)
+# ------------------------------------------------------------------------------------------------
+
+def bench_multi(a, world: int, rank_id: int, local: int):
+    import json
+    import time
+
+    import bench as B
+    from ._lib import Context
+    from .links import LinkTable
+    from .mcl import Mcl
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    inflations = [float(x) for x in a.inflations.split(",")]
+    asm, rank, in_nx, rec, stream_lo = B.make_inputs(a, dev, rank_id, world)
+    n = asm.n
+    P_local = int(rec.shape[0])
+    keep = np.ones(n, np.uint8)
+    ctx = Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    hint = int(min(a.pairs, n * (n - 1) // 2) * (0.45 if a.pairs > 4_000_000 else 1.0))
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        barrier()
+        ev[0].record(stream)
+        tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
+        tab.add(rec, stream_offset=stream_lo, asynchronous=True)
+        merge_link_tables(tab)
+        info = tab.finish()
+        index, n_linked = tab.linked_index(keep)
+        mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))
+        ev[1].record(stream)
+        blocks = column_blocks(mat.n, world)
+        mc = Mcl(mat, col_lo=blocks[rank_id][0], col_hi=blocks[rank_id][1])
+        iters = 0
+        for r in inflations:
+            st = sharded_mcl_run(mc, r, a.max_iter, a.pruning, blocks)
+            iters += st["rounds"]
+        ev[2].record(stream)
+        ev[2].synchronize()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks
+        out = {"build_ms": float(t[0].item()), "mcl_ms": float(t[1].item()), "iters": iters,
+               "nnz_full": int(info.nnz_full), "n_matrix": mat.n}
+        mc.close()
+        mat.close()
+        tab.close()
+        return out
+
+    for _ in range(a.warmup):
+        one_step()
+    sampler = B.ClockSampler(local)
+    if rank_id == 0:
+        sampler.start()
+    l0 = ctx.launches
+    barrier()
+    t0 = time.perf_counter()
+    steps = [one_step() for _ in range(a.steps)]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launches - l0
+    clocks = sampler.stop() if rank_id == 0 else None
+    if rank_id == 0:
+        build_ms = sum(s["build_ms"] for s in steps) / len(steps)
+        mcl_ms = sum(s["mcl_ms"] for s in steps) / len(steps)
+        line = {
+            "metric": "hic_pairs_per_sec_matrix_build", "value": a.pairs / (build_ms / 1000.0), "unit": "pairs/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * wall / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32 counts / fp32 matrix",
+            "data": "synthetic",
+            "config": {"workload": B.workload_name(a), "inflations": inflations, "max_iter": a.max_iter,
+                       "pruning": a.pruning, "parallelism": "pair stream sharded x{0}; MCL column blocks x{0}, one "
+                       "all-gather of pruned columns per iteration".format(world),
+                       "cache": "inputs and the dense pre-expanded matrix exceed the 126 MB L2"},
+            "stage_ms": {"link_build_and_matrix": build_ms, "mcl_sweep": mcl_ms},
+            "mcl": {"metric": "mcl_iterations_per_sec", "value": steps[-1]["iters"] / (mcl_ms / 1000.0), "unit": "iter/s",
+                    "iterations": steps[-1]["iters"]},
+            "links": {"pairs": a.pairs, "nnz_full": steps[-1]["nnz_full"], "n_matrix": steps[-1]["n_matrix"]},
+            "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    dist.destroy_process_group()

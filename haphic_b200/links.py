@@ -132,6 +132,7 @@ class LinkTable:
     def merge(self, entries, ctg_totals, n_records: int, n_used: int):
         n = int(entries.shape[0])
         check(load().hh_links_merge(self._h, ptr(entries) if n else None, n, ptr(ctg_totals), int(n_records), int(n_used)))
+        self.info = None        # re-opened: finish() again
 
     def close(self):
         if self._h:

@@ -106,7 +106,7 @@ int hh_links_fetch(hh_links* lk, int32_t* key_i, int32_t* key_j, uint32_t* full,
 /* ctg_link_dict (1638-1639): per-contig flank-link totals, [n_ctg] */
 int hh_links_fetch_ctg(hh_links* lk, int64_t* ctg_links);
 /* multi-GPU: export the finished table as device arrays / merge a peer's export into this
- * (unfinished) table.  An export is 9 uint32 per entry: {i, j, full, flank, first_full,
+ * table (a finished table is re-opened; call hh_links_finish again afterwards).  An export is 9 uint32 per entry: {i, j, full, flank, first_full,
  * first_flank, HT, TH, TT}.  ctg totals travel separately (int64 [n_ctg]). */
 int hh_links_export(hh_links* lk, uint32_t* entries_dev, int64_t* ctg_links_dev);
 int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t n_entries, const int64_t* ctg_links_dev,

@@ -9,8 +9,8 @@ echo "== launch list"
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py $ARGS > gpurun_out/launches_bench.log 2>&1
 tail -3 gpurun_out/launches_bench.log
-echo "== full capture: MCL column kernel (product+prune), 2 launches"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:hh_k_col -s 3 -c 2 -o gpurun_out/prof_col \
+echo "== full capture: MCL column kernel: pre-expansion, dense iteration 0, first sparse expansion"
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:hh_k_col -s 1 -c 3 -o gpurun_out/prof_col \
     python bench.py $ARGS > gpurun_out/prof_col.log 2>&1
 tail -2 gpurun_out/prof_col.log
 echo "== full capture: link insert kernel, 1 launch"
