@@ -1,0 +1,922 @@
+#!/usr/bin/env python3
+"""`haphic cluster` on the B200 -- a drop-in for scripts/HapHiC_cluster.py of zengxiaofei/HapHiC.
+
+Same command line, same ``parse_arguments() / run(args, log_file) / main()`` entry points, same
+files written into the working directory (HT_links.pkl, paired_links.clm, full_links.pkl,
+inflation_*/mcl_inflation_*.clusters.txt, inflation_*/group*.txt, inflation_*/*_statistics.txt,
+alignments.bed, HapHiC_cluster.log) and the same log messages (`haphic pipeline` greps the log for
+"You could try inflation from ...", HapHiC_pipeline.py:385), so reassign / sort / build run
+unchanged.  The per-read-pair link counting, dict_to_matrix and the Markov-cluster loop run in
+libhaphic_b200.so on the GPU; file parsing, fragment statistics, filters on per-fragment scalars,
+result interpretation and the writers are host Python, as in the reference.
+
+Not supported yet (raise, never silently degrade): contigs split into bins (``--bin_size`` other
+than 0 when a contig is longer than the bin size), ``--correct_nrounds``, ``--ul``, ``--gfa``,
+``--remove_allelic_links``, ``--remove_concentrated_links``.
+
+Reference line numbers below refer to scripts/HapHiC_cluster.py (v1.0.7).
+"""
+
+from __future__ import annotations
+
+import argparse
+import logging
+import os
+import pickle
+import random
+import sys
+import time
+from collections import OrderedDict, defaultdict
+from decimal import Decimal
+from itertools import combinations
+from math import ceil, inf
+
+import numpy as np
+
+__version__ = "1.0.7-b200.1"
+__update_time__ = "2026.09.24"
+
+logging.basicConfig(format="%(asctime)s <%(filename)s> [%(funcName)s] %(message)s", datefmt="%Y-%m-%d %H:%M:%S")
+logger = logging.getLogger(__name__)
+logger.setLevel(logging.INFO)
+
+
+# ------------------------------------------------------------------------------------------------
+# FASTA / fragment statistics (host; lines 56-147, 188-296)
+# ------------------------------------------------------------------------------------------------
+
+def parse_RE_sites(sites):
+    """Expand every 'N' of the recognition sites into A/T/C/G (56-72)."""
+    todo, done = list(sites), []
+    while todo:
+        s = todo.pop(0)
+        if "N" in s:
+            todo[0:0] = [s.replace("N", b, 1) for b in "ATCG"]
+        else:
+            done.append(s)
+    return done
+
+
+def count_RE_sites(seq, RE):
+    sites = [s.strip().upper() for s in RE.split(",") if s.strip()]
+    return sum(seq.count(s) for s in parse_RE_sites(sites))
+
+
+def parse_fasta(fasta, RE="GATC", keep_letter_case=False, logger=logger):
+    """{ctg: [seq, length, RE sites + 1]} in file order (87-113)."""
+    logger.info("Parsing input FASTA file...")
+    chunks = OrderedDict()
+    with open(fasta) as f:
+        cur = None
+        for line in f:
+            s = line.strip()
+            if not s:
+                continue
+            if line.startswith(">"):
+                cur = line.split()[0][1:]
+                chunks[cur] = []
+            else:
+                chunks[cur].append(s if keep_letter_case else s.upper())
+    fa_dict = dict()
+    for ctg, parts in chunks.items():
+        seq = "".join(parts)
+        fa_dict[ctg] = [seq, len(seq), count_RE_sites(seq, RE) + 1]     # pseudo-count as ALLHiC does
+    return fa_dict
+
+
+def determine_int_type(fa_dict, logger=logger):
+    """int32 / int64 for positions and CLM distances (116-147)."""
+    lens = sorted(info[1] for info in fa_dict.values())
+    longest = lens[-1]
+    second = lens[-2] if len(lens) > 1 else 0
+    limit = 2 ** 31 - 1
+    pos_t = "int64" if longest > limit else "int32"
+    dist_t = "int64" if longest + second > limit else "int32"
+    logger.info("The longest and second longest contigs are {} bp and {} bp, respectively. The data types for "
+                "contig positions and CLM distances are calculated to be {} and {}, respectively.".format(
+                    longest, second, pos_t, dist_t))
+    if pos_t == "int64":
+        logger.warning("Found at least one contig longer than {} bp in the input assembly. There could be a problem "
+                       "when visualizing it in Juicebox".format(limit))
+    return pos_t, dist_t
+
+
+def parse_gfa(gfa_list, fa_dict, logger=logger):
+    raise NotImplementedError("haphic_b200: --gfa (hifiasm read depth / phasing, HapHiC_cluster.py:150-185) is not supported")
+
+
+def remove_allelic_HiC_links(*_a, **_k):
+    raise NotImplementedError("haphic_b200: --remove_allelic_links (HapHiC_cluster.py:474-692) is not supported yet")
+
+
+def stat_fragments(fa_dict, RE, read_depth_dict, whitelist, nchrs=0, flank=0, Nx=100, bin_size=0, logger=logger):
+    """Fragment lengths, flank RE counts, bins and the Nx set (188-296).  Returns the reference's
+    7-tuple (sorted_frag_list, bin_set, bin_size, frag_len_dict, Nx_frag_set, RE_site_dict, split_ctg_set)."""
+    logger.info("Making some statistics of fragments (contigs / bins)")
+    flank_bp = flank * 1000
+
+    def flank_RE(seq, length):
+        if not flank_bp or length <= 2 * flank_bp:
+            return count_RE_sites(seq, RE) + 1
+        return count_RE_sites(seq[:flank_bp], RE) + count_RE_sites(seq[length - flank_bp:], RE) + 1
+
+    total_len = sum(info[1] for info in fa_dict.values())
+    if not bin_size:
+        logger.info("bin_size is set to {}, no fragments will be split".format(bin_size))
+        bin_size = inf
+    elif bin_size < 0:
+        bin_size = max(min(int(total_len / nchrs / 30), 2000000), 100000)
+        logger.info("bin_size is calculated to be {} bp".format(bin_size))
+    else:
+        bin_size *= 1000
+        logger.info("bin_size is manually designated to {} bp".format(bin_size))
+
+    frags, bin_set, split_ctg_set = [], set(), set()
+    RE_site_dict, frag_len_dict = dict(), dict()
+    for ctg, (seq, ctg_len, RE_sites) in fa_dict.items():
+        if ctg_len > bin_size:
+            split_ctg_set.add(ctg)
+            nbins = ceil(ctg_len / bin_size)
+            for m in range(nbins):
+                name = "{}_bin{}".format(ctg, m + 1)
+                assert name not in fa_dict
+                frags.append(name)
+                bin_set.add(name)
+                last = m + 1 == nbins
+                blen = ctg_len - m * bin_size if last else bin_size
+                bseq = seq[m * bin_size:] if last else seq[m * bin_size:(m + 1) * bin_size]
+                RE_site_dict[name] = flank_RE(bseq, blen)
+                frag_len_dict[name] = blen
+                if read_depth_dict:
+                    read_depth_dict[name] = read_depth_dict[ctg]
+            if read_depth_dict:
+                del read_depth_dict[ctg]
+        else:
+            frags.append(ctg)
+            frag_len_dict[ctg] = ctg_len
+            RE_site_dict[ctg] = RE_sites if (not flank_bp or ctg_len <= 2 * flank_bp) else flank_RE(seq, ctg_len)
+        fa_dict[ctg][0] = None          # sequences are not needed any more
+
+    # seeded shuffle before the stable sort so equal-length fragments are not biased (273-275)
+    random.seed(12345)
+    random.shuffle(frags)
+    sorted_frag_list = sorted(((f, frag_len_dict[f]) for f in frags), key=lambda x: x[1], reverse=True)
+    len_sum = 0
+    Nx_frag_set = set()
+    for frag, flen in sorted_frag_list:
+        len_sum += flen
+        if len_sum / total_len * 100 < Nx or Nx == 100:
+            Nx_frag_set.add(frag)
+    if Nx != 100:
+        Nx_frag_set.add(sorted_frag_list[len(Nx_frag_set)][0])
+    if whitelist:
+        for frag, _ in sorted_frag_list:
+            if frag.rsplit("_bin", 1)[0] in whitelist:
+                Nx_frag_set.add(frag)
+    return sorted_frag_list, bin_set, bin_size, frag_len_dict, Nx_frag_set, RE_site_dict, split_ctg_set
+
+
+def is_flank(coord, length, flank):
+    """1-based ``coord`` inside the flanking regions (299-307)."""
+    return (not flank) or coord <= flank or coord > length - flank
+
+
+# ------------------------------------------------------------------------------------------------
+# link counting on the GPU (1596-1655)
+# ------------------------------------------------------------------------------------------------
+
+_CTX = None
+
+
+def _context():
+    global _CTX
+    if _CTX is None:
+        from ._lib import Context
+        _CTX = Context(int(os.environ.get("HAPHIC_DEVICE", "0")))
+    return _CTX
+
+
+def count_links(batches, names, ctg_len, Nx_ctg_set, flank_kb, want_clm=True):
+    """Stream record batches through the GPU link table.  Returns (table, clm_records) where
+    clm_records is the concatenation of the usable records (for the CLM writer) or None."""
+    from .links import LinkTable, name_rank
+    ctx = _context()
+    in_nx = np.fromiter((n in Nx_ctg_set for n in names), dtype=np.uint8, count=len(names))
+    table = LinkTable(ctx, ctg_len, name_rank(names), in_nx, flank_kb * 1000)
+    kept = []
+    n = len(names)
+    for rec in batches:
+        table.add(rec)
+        if want_clm:
+            ok = (rec[:, 0] != rec[:, 2]) & (rec[:, 0] >= 0) & (rec[:, 2] >= 0) & (rec[:, 0] < n) & (rec[:, 2] < n)
+            kept.append(rec[ok])
+    table.finish()
+    clm_rec = (np.concatenate(kept) if kept else np.zeros((0, 4), np.int32)) if want_clm else None
+    return table, clm_rec
+
+
+def build_clm_dict(clm_rec, names, ctg_len, rank, dist_int_type="int32"):
+    """clm_dict {(ctg_i, ctg_j): array of 4 distances per link} (update_clm_dict, 395-401) in
+    first-seen key order.  Host numpy for now (SURVEY.md f-2 moves it to the GPU)."""
+    from array import array
+    code = "i" if dist_int_type == "int32" else "l"
+    clm = defaultdict(lambda: array(code))
+    if len(clm_rec) == 0:
+        return clm
+    r = clm_rec.astype(np.int64)
+    swap = rank[r[:, 0]] > rank[r[:, 2]]
+    i = np.where(swap, r[:, 2], r[:, 0])
+    j = np.where(swap, r[:, 0], r[:, 2])
+    a0 = np.where(swap, r[:, 3], r[:, 1])
+    b0 = np.where(swap, r[:, 1], r[:, 3])
+    li, lj = ctg_len[i], ctg_len[j]
+    dist = np.stack([li - a0 + b0, li - a0 + lj - b0, a0 + b0, a0 + lj - b0], axis=1)
+    key = i * len(names) + j
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    starts = np.concatenate([[0], np.nonzero(np.diff(ks))[0] + 1])
+    ends = np.concatenate([starts[1:], [len(ks)]])
+    first = order[starts]                         # stable sort: first element of a run = first seen
+    for s in np.argsort(first, kind="stable").tolist():
+        rows = order[starts[s]:ends[s]]
+        k = int(ks[starts[s]])
+        clm[(names[k // len(names)], names[k % len(names)])] = array(code, dist[rows].reshape(-1).tolist())
+    return clm
+
+
+def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_set, pos_int_type, dist_int_type):
+    """Signature and return value of the reference function (1596-1655).  ``alignments`` is an
+    iterable of int32 record batches (hicio.pairs_batches / hicio.bam_batches) or of
+    (ref, mref, pos, mpos) tuples as the reference's generators yield."""
+    logger.info("Parsing input alignments...")
+    if args.remove_allelic_links or args.remove_concentrated_links:
+        raise NotImplementedError("haphic_b200: --remove_allelic_links / --remove_concentrated_links are not supported yet")
+    names = list(fa_dict.keys())
+    ctg_len = np.array([ctg_len_dict[n] for n in names], dtype=np.int64)
+    from .links import link_dicts, name_rank
+    batches = _as_batches(alignments, names)
+    table, clm_rec = count_links(batches, names, ctg_len, Nx_ctg_set, args.flank)
+    full_link_dict, flank_link_dict, HT_link_dict, ctg_link_dict = link_dicts(table, names)
+    clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type)
+    parse_alignments_for_ctgs.last_table = table          # run() keeps using the device table
+    return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, ctg_link_dict, defaultdict(list)
+
+
+def _as_batches(alignments, names, batch=1 << 20):
+    it = iter(alignments)
+    try:
+        first = next(it)
+    except StopIteration:
+        return
+    if isinstance(first, np.ndarray):
+        yield first
+        for rec in it:
+            yield rec
+        return
+    ids = {n: i for i, n in enumerate(names)}
+    buf = []
+
+    def flush():
+        out = np.array(buf, dtype=np.int32).reshape(-1, 4)
+        buf.clear()
+        return out
+
+    def push(t):
+        ref, mref, pos, mpos = t
+        buf.append((ids.get(ref, -1), pos, ids.get(mref, -1), mpos))
+
+    push(first)
+    for t in it:
+        push(t)
+        if len(buf) >= batch:
+            yield flush()
+    if buf:
+        yield flush()
+
+
+# ------------------------------------------------------------------------------------------------
+# writers (376-392, 710-715)
+# ------------------------------------------------------------------------------------------------
+
+def output_pickle(dict_, from_, to):
+    logger.info("Writing {} to {}...".format(from_, to))
+    with open(to, "wb") as f:
+        pickle.dump(dict_, f)
+
+
+def output_clm(clm_dict):
+    """paired_links.clm: contig pairs with >= 2 links, four orientation lines each, every sorted
+    distance printed twice and the count doubled (376-392)."""
+    logger.info("Writing clm_dict to paired_links.clm...")
+    signs = (("+", "+"), ("+", "-"), ("-", "+"), ("-", "-"))
+    with open("paired_links.clm", "w") as fout:
+        for (ci, cj), values in clm_dict.items():
+            if len(values) < 8:
+                continue
+            arr = np.asarray(values).reshape(-1, 4)
+            for k, (si, sj) in enumerate(signs):
+                d = np.sort(arr[:, k]).tolist()
+                fout.write("{}{} {}{}\t{}\t{}\n".format(ci, si, cj, sj, 2 * len(d), " ".join("{0} {0}".format(v) for v in d)))
+
+
+def normalize_by_nlinks(flank_link_dict, frag_link_dict):
+    """links / sqrt(tot_i * tot_j) on the host dict (718-724); the device matrix applies the same
+    formula inside hh_matrix_from_links."""
+    logger.info("Normalizing flank_link_dict by the number of links to other contigs...")
+    for key in flank_link_dict:
+        flank_link_dict[key] /= (frag_link_dict[key[0]] * frag_link_dict[key[1]]) ** 0.5
+
+
+# ------------------------------------------------------------------------------------------------
+# fragment filtering (741-940) -- per-fragment scalars on the host; the rank-sum part works on the
+# dense fragment x fragment matrix (numpy here; SURVEY.md f-1 moves it to the GPU)
+# ------------------------------------------------------------------------------------------------
+
+def check_param(param, string, suffix, true_suffix=""):
+    """'0.2X' -> (0.2, 'X'); '0.3' -> (0.3, '') with range check (2481-2507)."""
+    if len(string) == 0:
+        logger.error("Parameter {} is empty".format(param))
+        raise RuntimeError("Parameter check failed")
+    if len(string) > 1 and suffix and string[-1] in suffix:
+        return check_param(param, string[:-1], None, string[-1])
+    try:
+        num = float(string)
+    except ValueError:
+        num = None
+    if num is None or (not true_suffix and not 0 <= num <= 1):
+        logger.error("Parameter {} {} is illegal".format(param, string + true_suffix))
+        raise RuntimeError("Parameter check failed")
+    return num, true_suffix
+
+
+def _cut_index(sorted_pairs, limit, inclusive):
+    """First position whose value reaches (>=, inclusive) / exceeds (>) ``limit``; len() if none."""
+    for pos, (_f, v) in enumerate(sorted_pairs):
+        if (v >= limit) if inclusive else (v > limit):
+            return pos
+    return len(sorted_pairs)
+
+
+def filter_fragments(Nx_frag_set, RE_site_dict, RE_site_cutoff, frag_link_dict, density_lower, density_upper,
+                     topN, rank_sum_upper, rank_sum_hard_cutoff, flank_link_dict, read_depth_dict, read_depth_upper,
+                     whitelist):
+    """Same decisions and log lines as the reference's filter_fragments (741-940)."""
+    logger.info("Filtering fragments...")
+    if read_depth_dict:
+        raise NotImplementedError("haphic_b200: read-depth filtering (--gfa) is not supported")
+    wl_frags = set()
+    density = []
+    total_links, total_RE = 0, 1
+    for frag in Nx_frag_set:
+        RE_sites = RE_site_dict[frag]
+        if RE_sites > RE_site_cutoff:
+            if frag in frag_link_dict:
+                links = frag_link_dict[frag]
+                total_links += links
+                total_RE += RE_sites - 1
+                density.append((frag, links / RE_sites))
+            else:
+                density.append((frag, 0))
+        if whitelist and frag.rsplit("_bin", 1)[0] in whitelist:
+            wl_frags.add(frag)
+    n_nx = len(Nx_frag_set)
+    logger.info("[Nx filtering] {} fragments kept".format(n_nx))
+    logger.info("[RE sites filtering] {} fragments removed, {} fragments kept".format(n_nx - len(density), len(density)))
+
+    density.sort(key=lambda x: x[1])
+    p_lo = check_param("--density_lower", density_lower, {"X", "x"})
+    p_hi = check_param("--density_upper", density_upper, {"X", "x"})
+    remaining = len(density)
+    avg = total_links / total_RE
+    if p_lo[-1] in {"X", "x"}:
+        lower = _cut_index(density, avg * p_lo[0], True)
+        logger.info('[link density filtering] Parameter --density_lower {} is set to "multiple" mode and equivalent to {} in "fraction" mode'.format(
+            density_lower, lower / remaining))
+    else:
+        lower = int(remaining * float(density_lower))
+        logger.info('[link density filtering] Parameter --density_lower {} is set to "fraction" mode and equivalent to {}X in "multiple" mode'.format(
+            density_lower, density[max(0, lower - 1)][1] / avg))
+    if p_hi[-1] in {"X", "x"}:
+        upper = _cut_index(density, avg * p_hi[0], False)
+        logger.info('[link density filtering] Parameter --density_upper {} is set to "multiple" mode and equivalent to {} in "fraction" mode'.format(
+            density_upper, upper / remaining))
+    else:
+        upper = int(remaining * float(density_upper))
+        logger.info('[link density filtering] Parameter --density_upper {} is set to "fraction" mode and equivalent to {}X in "multiple" mode'.format(
+            density_upper, density[max(0, upper - 1)][1] / avg))
+    filtered = {frag for frag, _ in density[lower:upper]}
+    logger.info("[link density filtering] {} fragments removed, {} fragments kept".format(remaining - len(filtered), len(filtered)))
+    for frag, d in density[:lower] + density[upper:]:
+        logger.debug("[link density filtering] Fragment {} is removed, density={}".format(frag, d))
+    density = density[lower:upper]
+
+    # rank-sum of the topN nearest fragments (864-927)
+    matrix, frag_index = dict_to_matrix(flank_link_dict, filtered)
+    n = matrix.shape[0]
+    index_frag = {i: f for f, i in frag_index.items()}
+    # descending stable sort of every row: ties keep index order, exactly list.sort(reverse=True)
+    order = np.argsort(-matrix, axis=1, kind="stable")
+    rank_of = np.empty((n, n), dtype=np.int32)
+    rows = np.arange(n)[:, None]
+    rank_of[rows, order] = np.arange(n, dtype=np.int32)[None, :]
+    rank_sums = []
+    hard = 0
+    for frag, _ in density:
+        top = order[frag_index[frag], :topN].tolist()
+        rs = 0
+        for a, b in combinations(top, 2):
+            rs += min(int(rank_of[a, b]), int(rank_of[b, a]))
+        if rank_sum_hard_cutoff and rs > rank_sum_hard_cutoff:
+            hard += 1
+            logger.debug("[rank sum filtering] Fragment {} is removed by hard filtering, rank sum={}".format(frag, rs))
+            continue
+        rank_sums.append((frag, rs))
+    rank_sums.sort(key=lambda x: x[1])
+    remaining = len(rank_sums)
+    if rank_sum_hard_cutoff:
+        logger.info("[rank sum filtering] {} fragments removed by hard filtering, {} fragments kept".format(hard, remaining))
+    p_rs = check_param("--rank_sum_upper", rank_sum_upper, {"X", "x"})
+    q1, med, q3 = np.quantile([v for _, v in rank_sums], (0.25, 0.5, 0.75))
+    iqr = q3 - q1
+    logger.info("[rank sum filtering] Q1={}, median={}, Q3={}, IQR=Q3-Q1={}".format(q1, med, q3, iqr))
+    if p_rs[-1]:
+        upper = _cut_index(rank_sums, q3 + p_rs[0] * iqr, False)
+        logger.info('[rank sum filtering] Parameter --rank_sum_upper {} is set to "multiple" mode and equivalent to {} in "fraction" mode'.format(
+            rank_sum_upper, upper / remaining))
+    else:
+        upper = int(remaining * float(rank_sum_upper))
+        logger.info('[rank sum filtering] Parameter --rank_sum_upper {} is set to "fraction" mode and equivalent to {}X in "multiple" mode'.format(
+            rank_sum_upper, (rank_sums[max(0, upper - 1)][1] - q3) / iqr))
+    filtered = {frag for frag, _ in rank_sums[:upper]}
+    logger.info("[rank sum filtering] {} fragments removed, {} fragments kept".format(len(rank_sums) - len(filtered), len(filtered)))
+    for frag, rs in rank_sums[upper:]:
+        logger.debug("[rank sum filtering] Fragment {} is removed, rank sum={}".format(frag, rs))
+    if wl_frags:
+        added = 0
+        for frag in wl_frags:
+            if frag not in filtered:
+                added += 1
+                logger.debug("[rank sum filtering] Fragment {} is added since it is on the whitelist".format(frag))
+                filtered.add(frag)
+        logger.info("[rank sum filtering] {} fragments added, {} fragments are used to perform Markov clustering".format(
+            added, len(filtered)))
+    return filtered
+
+
+def dict_to_matrix(link_dict, frag_set, dense_matrix=True, add_self_loops=False):
+    """Host version with the reference's signature and return (310-373) -- `haphic reassign` imports
+    it (HapHiC_reassign.py:23).  The cluster step itself builds the matrix on the device
+    (hh_matrix_from_links)."""
+    from scipy.sparse import coo_matrix
+    frag_index = dict()
+    rows, cols, vals = [], [], []
+    linked = set()
+    for (fi, fj), links in link_dict.items():
+        if fi not in frag_set or fj not in frag_set:
+            continue
+        linked.add(fi)
+        linked.add(fj)
+        i = frag_index.setdefault(fi, len(frag_index))
+        j = frag_index.setdefault(fj, len(frag_index))
+        rows += (i, j)
+        cols += (j, i)
+        vals += (links, links)
+    for frag in frag_set - linked:
+        frag_index[frag] = len(frag_index)
+    shape = len(frag_set)
+    if add_self_loops:
+        rows += range(shape)
+        cols += range(shape)
+        vals += [1] * shape
+    m = coo_matrix((vals, (rows, cols)), shape=(shape, shape), dtype=np.float32)
+    return (m.toarray() if dense_matrix else m.tocsc()), frag_index
+
+
+# ------------------------------------------------------------------------------------------------
+# Markov clustering (2026-2242): matrix work on the GPU, interpretation / files on the host
+# ------------------------------------------------------------------------------------------------
+
+def interpret_result(result_matrix, dense_matrix=False):
+    from .mcl import interpret_result as _ir
+    return _ir(result_matrix)
+
+
+def get_main_groups(result_clusters, len_ratio):
+    for k in range(len(result_clusters) - 1):
+        if result_clusters[k + 1][1] / result_clusters[k][1] < len_ratio:
+            return k + 1
+    return len(result_clusters)
+
+
+def recommend_inflation(result_stat, nchrs, len_ratio):
+    """Smallest inflation whose main-group count reaches nchrs (2110-2129).  The message format is
+    machine-read by `haphic pipeline`."""
+    ok = sorted(infl for infl, groups in result_stat if groups >= nchrs)
+    if ok:
+        logger.info("You could try inflation from {} (length ratio = {})".format(ok[0], len_ratio))
+        return True
+    if len_ratio > 0.5:
+        logger.info("The length ratio ({}) might be too strict, trying a lower one...".format(len_ratio))
+        return False
+    logger.info("It seems that some chromosomes were grouped together (length ratio = {}) "
+                "You could check whether the parameters used are correct / appropriate and "
+                "then try to tune the parameters for assembly correction, contig / Hi-C link "
+                "filtration, or Markov clustering".format(len_ratio))
+    return True
+
+
+def mcl(engine, expansion, inflation, iters, pruning, dense_matrix=False):
+    """One inflation on the device engine; logs the reference's convergence line (2047-2060)."""
+    st = engine.run(inflation, iters, pruning)
+    if st["converged"]:
+        logger.info("The matrix has converged after {} rounds of iterations "
+                    "(expansion: {}, inflation: {}, maximum iterations: {}, pruning threshold: {})".format(
+                        st["rounds"], expansion, inflation, iters, pruning))
+    else:
+        logger.info("The matrix does not converge after {} rounds of iterations "
+                    "(expansion: {}, inflation: {}, maximum iterations: {}, pruning threshold: {})".format(
+                        st["rounds"], expansion, inflation, iters, pruning))
+    return engine.result()
+
+
+def run_mcl_clustering(link_matrix, bin_set, frag_len_dict, frag_index_dict, expansion, min_inflation,
+                       max_inflation, inflation_step, max_iter, pruning, fa_dict, nchrs, dense_matrix):
+    """run_mcl_clustering (2132-2242).  ``link_matrix`` is a device LinkMatrix (or anything scipy can
+    turn into CSC, which is uploaded).  Writes inflation_*/ files, logs the recommendation."""
+    from .links import LinkMatrix
+    from .mcl import Mcl, inflation_values
+    logger.info("Performing Markov clustering...")
+    if not isinstance(link_matrix, LinkMatrix):
+        link_matrix = LinkMatrix.from_csc(_context(), link_matrix)
+    index_frag = {i: f for f, i in frag_index_dict.items()}
+    engine = Mcl(link_matrix, expansion)          # normalise + pre-expand once for the whole sweep
+    result_clusters_list = []
+    mcl_nrounds = 0
+    for inflation in inflation_values(min_inflation, max_inflation, inflation_step):
+        result = mcl(engine, expansion, float(inflation), max_iter, pruning, dense_matrix)
+        mcl_nrounds += 1
+        clusters = interpret_result(result)
+        if not clusters:
+            logger.info("Some fragments are missing / redundant, result of inflation {} will NOT be output".format(inflation))
+            continue
+        groups = defaultdict(lambda: [[], 0])
+        bin_votes = defaultdict(dict)
+        for gid, members in enumerate(clusters):
+            for i in members:
+                frag = index_frag[i]
+                if frag in bin_set:
+                    ctg = frag.rsplit("_bin", 1)[0]
+                    bin_votes[ctg][gid] = bin_votes[ctg].get(gid, 0) + frag_len_dict[frag]
+                else:
+                    groups[gid][0].append(frag)
+                    groups[gid][1] += fa_dict[frag][1]
+        for ctg, votes in bin_votes.items():
+            best = sorted(votes.keys(), key=lambda g: votes[g], reverse=True)[0]
+            groups[best][0].append(ctg)
+            groups[best][1] += fa_dict[ctg][1]
+        result_clusters = sorted(tuple(groups.values()), key=lambda x: x[1], reverse=True)
+        outdir = "inflation_{}".format(inflation)
+        os.makedirs(outdir, exist_ok=True)
+        with open("{0}/mcl_{0}.clusters.txt".format(outdir), "w") as fout:
+            fout.write("#Group\tnContigs\tContigs\n")
+            for k, (ctgs, glen) in enumerate(result_clusters, 1):
+                ctgs.sort(key=lambda c: fa_dict[c][1], reverse=True)
+                fout.write("group{}_{}bp\t{}\t{}\n".format(k, glen, len(ctgs), " ".join(ctgs)))
+        for k, (ctgs, glen) in enumerate(result_clusters, 1):
+            with open("{}/group{}_{}bp.txt".format(outdir, k, glen), "w") as fout:
+                fout.write("#Contig\tRECounts\tLength\n")
+                for ctg in ctgs:
+                    fout.write("{}\t{}\t{}\n".format(ctg, fa_dict[ctg][2], fa_dict[ctg][1]))
+        result_clusters_list.append((inflation, result_clusters))
+    engine.close()
+
+    max_nclusters = max(len(rc) for _, rc in result_clusters_list)
+    if max_nclusters < nchrs:
+        logger.warning("The maximum number of clusters ({}) is even less than the expected number of "
+                       "chromosomes ({}). You could try higher inflation.".format(max_nclusters, nchrs))
+    else:
+        for len_ratio in (0.75, 0.7, 0.65, 0.6, 0.55, 0.5):
+            stat = [(infl, get_main_groups(rc, len_ratio)) for infl, rc in result_clusters_list]
+            if recommend_inflation(stat, nchrs, len_ratio):
+                break
+    return result_clusters_list, mcl_nrounds
+
+
+# ------------------------------------------------------------------------------------------------
+# statistics for the reassignment step (2245-2478, text files; plots need matplotlib)
+# ------------------------------------------------------------------------------------------------
+
+def add_ungrouped_ctgs(fa_dict, ctg_group_dict):
+    for ctg in fa_dict:
+        ctg_group_dict.setdefault(ctg, "ungrouped")
+
+
+def parse_link_dict(link_dict, ctg_group_dict):
+    out = defaultdict(dict)
+    for (ci, cj), links in link_dict.items():
+        gi, gj = ctg_group_dict[ci], ctg_group_dict[cj]
+        if gj != "ungrouped":
+            out[ci][gj] = out[ci].get(gj, 0) + links
+        if gi != "ungrouped":
+            out[cj][gi] = out[cj].get(gi, 0) + links
+    return out
+
+
+def cal_link_density(max_group, current_group, max_links, group_RE_sites, ctg_RE_sites):
+    if max_group == current_group:
+        return max_links / group_RE_sites
+    return max_links / (group_RE_sites + ctg_RE_sites - 1)
+
+
+def output_statistics(fa_dict, link_dict, result_clusters_list):
+    logger.info("Making some statistics for the next HapHiC reassignment step...")
+    total_n = len(fa_dict)
+    total_len = sum(info[1] for info in fa_dict.values())
+
+    def axes(sorted_list):
+        n_at, len_at = OrderedDict({0: 0}), OrderedDict({0: 0})
+        last = 0
+        for ctg, v in sorted_list:
+            if v in n_at:
+                n_at[v] += 1
+                len_at[v] += fa_dict[ctg][1]
+            else:
+                n_at[v] = n_at[last] + 1
+                len_at[v] = len_at[last] + fa_dict[ctg][1]
+                last = v
+        x = list(n_at.keys())
+        return x, [n_at[k] / total_n * 100 for k in x], [(total_len - len_at[k]) / total_len * 100 for k in x]
+
+    def write(x, y1, y2, title, inflation):
+        with open("inflation_{}/{}_statistics.txt".format(inflation, title), "w") as fout:
+            fout.write("{}\tFiltered_ctg_n\tRest_ctg_len\n".format(title))
+            for k, v in enumerate(x):
+                fout.write(">{}\t{}\t{}\n".format(v, y1[k], y2[k]))
+
+    re_axes = axes(sorted(((c, info[2]) for c, info in fa_dict.items()), key=lambda x: x[1]))
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        have_plt = True
+    except Exception:
+        have_plt = False
+        logger.warning("Module matplotlib is not correctly installed, HapHiC will NOT draw statistical plots")
+
+    for inflation, result_clusters in result_clusters_list:
+        write(*re_axes, "RE_site_threshold", inflation)
+        ctg_group, group_RE = dict(), dict()
+        for gid, (ctgs, _) in enumerate(result_clusters):
+            group_RE[gid] = 1
+            for ctg in ctgs:
+                ctg_group[ctg] = gid
+                group_RE[gid] += fa_dict[ctg][2] - 1
+        add_ungrouped_ctgs(fa_dict, ctg_group)
+        group_links = parse_link_dict(link_dict, ctg_group)
+        best_links, best_density, best_ratio = [], [], []
+        for ctg in fa_dict:
+            if ctg not in group_links:
+                best_links.append((ctg, 0))
+                best_density.append((ctg, 0))
+                best_ratio.append((ctg, 0))
+                continue
+            ranked = sorted(group_links[ctg].items(), key=lambda x: x[1], reverse=True)
+            top_group, top_links = ranked[0]
+            cur = ctg_group[ctg]
+            ctg_RE = fa_dict[ctg][2]
+            dens = cal_link_density(top_group, cur, top_links, group_RE[top_group], ctg_RE)
+            if len(group_RE) > 1:
+                others = sum(cal_link_density(g, cur, l, group_RE[g], ctg_RE) for g, l in ranked[1:]) / (len(group_RE) - 1)
+            else:
+                others = 0
+            best_links.append((ctg, top_links))
+            best_density.append((ctg, dens))
+            best_ratio.append((ctg, dens / others if others else 1000000))
+        curves = {}
+        for title, lst in (("Link_threshold", best_links), ("Link_density_threshold", best_density),
+                           ("Link_density_ratio_threshold", best_ratio)):
+            lst.sort(key=lambda x: x[1])
+            curves[title] = axes(lst)
+            write(*curves[title], title, inflation)
+        if have_plt:
+            fig = plt.figure(figsize=(8, 7))
+            panels = ((221, re_axes, "RE site threshold", "Number of RE sites", [0, 500]),
+                      (222, curves["Link_threshold"], "Hi-C link threshold", "Number of links to the best group", [0, 500]),
+                      (223, curves["Link_density_threshold"], "Link density threshold", "Link density to the best group", [0, 0.001]),
+                      (224, curves["Link_density_ratio_threshold"], "Link density ratio threshold",
+                       "Link density ratio (best/average)", [0, 20]))
+            for pos, (x, y1, y2), title, xlabel, xlim in panels:
+                ax = fig.add_subplot(pos)
+                ax.plot(x, y1, "b")
+                ax.tick_params(axis="y", colors="b")
+                ax.set_xlim(xlim)
+                ax.set_ylim([0, 50])
+                ax.set_ylabel("Number of contigs filtered out (%)", color="b")
+                ax.set_title(title)
+                ax.set_xlabel(xlabel)
+                ax2 = ax.twinx()
+                ax2.plot(x, y2, "r")
+                ax2.tick_params(axis="y", colors="r")
+                ax2.set_ylim([90, 100])
+                ax2.set_ylabel("Length of remaining contigs (%)", color="r")
+            fig.tight_layout(w_pad=1, h_pad=1)
+            plt.savefig("inflation_{}/statistics.pdf".format(inflation))
+            plt.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# command line (2510-2735) and the run driver (2738-2959)
+# ------------------------------------------------------------------------------------------------
+
+def detect_format(args):
+    table = ((".bam", "bam", "BAM"), (".pairs", "pairs", "pairs"), (".pairs.gz", "bgzipped_pairs", "bgzipped pairs"))
+    for suffix, fmt, label in table:
+        if args.alignments.endswith(suffix):
+            args.aln_format = fmt
+            logger.info("The file for Hi-C read alignments is detected as being in {} format".format(label))
+            return
+    raise RuntimeError("Unknown file format for Hi-C read alignments")
+
+
+_FLAGS = (
+    # (group, name, kwargs) -- same names, types and defaults as the reference's parser (2530-2735)
+    ("input", "--aln_format", dict(choices={"bam", "pairs", "bgzipped_pairs", "auto"}, default="auto")),
+    ("input", "--RE", dict(default="GATC")),
+    ("input", "--quick_view", dict(default=False, action="store_true")),
+    ("input", "--gfa", dict(default=None)),
+    ("input", "--ul", dict(default=None)),
+    ("correct", "--correct_nrounds", dict(type=int, default=0)),
+    ("correct", "--correct_resolution", dict(type=int, default=500)),
+    ("correct", "--median_cov_ratio", dict(type=float, default=0.2)),
+    ("correct", "--region_len_ratio", dict(type=float, default=0.1)),
+    ("correct", "--min_region_cutoff", dict(type=int, default=5000)),
+    ("filter", "--Nx", dict(type=int, default=80)),
+    ("filter", "--RE_site_cutoff", dict(type=int, default=5)),
+    ("filter", "--density_lower", dict(default="0.2X")),
+    ("filter", "--density_upper", dict(default="1.9X")),
+    ("filter", "--read_depth_upper", dict(default="1.5X")),
+    ("filter", "--topN", dict(type=int, default=10)),
+    ("filter", "--rank_sum_hard_cutoff", dict(type=int, default=0)),
+    ("filter", "--rank_sum_upper", dict(default="1.5X")),
+    ("filter", "--remove_allelic_links", dict(type=int, default=0)),
+    ("filter", "--concordance_ratio_cutoff", dict(type=float, default=0.2)),
+    ("filter", "--nwindows", dict(type=int, default=50)),
+    ("filter", "--remove_concentrated_links", dict(default=False, action="store_true")),
+    ("filter", "--max_read_pairs", dict(type=int, default=200)),
+    ("filter", "--min_read_pairs", dict(type=int, default=20)),
+    ("filter", "--phasing_weight", dict(type=float, default=1.0)),
+    ("ul", "--min_ul_mapq", dict(type=int, default=30)),
+    ("ul", "--min_ul_alignment_length", dict(type=int, default=10000)),
+    ("ul", "--max_distance_to_end", dict(type=int, default=100)),
+    ("ul", "--max_overlap_ratio", dict(type=float, default=0.5)),
+    ("ul", "--max_gap_len", dict(type=int, default=10000)),
+    ("ul", "--min_ul_support", dict(type=int, default=2)),
+    ("mcl", "--bin_size", dict(type=int, default=-1)),
+    ("mcl", "--flank", dict(type=int, default=500)),
+    ("mcl", "--normalize_by_nlinks", dict(default=False, action="store_true")),
+    ("mcl", "--expansion", dict(type=int, default=2)),
+    ("mcl", "--min_inflation", dict(type=float, default=1.1)),
+    ("mcl", "--max_inflation", dict(type=float, default=3.0)),
+    ("mcl", "--inflation_step", dict(type=float, default=0.1)),
+    ("mcl", "--max_iter", dict(type=int, default=200)),
+    ("mcl", "--pruning", dict(type=float, default=0.0001)),
+    ("mcl", "--skip_clustering", dict(default=False, action="store_true")),
+    ("perf", "--threads", dict(type=int, default=8)),
+    ("perf", "--dense_matrix", dict(default=False, action="store_true")),
+    ("log", "--verbose", dict(default=False, action="store_true")),
+)
+
+_GROUP_TITLES = {
+    "input": ">>> Parameters for parsing input files and pipeline control",
+    "correct": ">>> Parameters for assembly correction",
+    "filter": ">>> Parameters for preprocessing (contig / Hi-C link filtration) before clustering",
+    "ul": ">>> Parameters for parsing ultra-long reads",
+    "mcl": ">>> Parameters for adjacency matrix construction and Markov Clustering",
+    "perf": ">>> Parameters for performance",
+    "log": ">>> Parameters for logging",
+}
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(prog="haphic cluster")
+    groups = {k: parser.add_argument_group(t) for k, t in _GROUP_TITLES.items()}
+    groups["input"].add_argument("fasta", help="draft genome in FASTA format")
+    groups["input"].add_argument("alignments", help="filtered Hi-C read alignments in BAM/pairs format (DO NOT sort it by coordinate)")
+    groups["input"].add_argument("nchrs", type=int, help="expected number of chromosomes")
+    for group, name, kw in _FLAGS:
+        kw = dict(kw)
+        kw.setdefault("help", "same meaning as in `haphic cluster` of HapHiC, default: %(default)s")
+        groups[group].add_argument(name, **kw)
+    return parser
+
+
+def parse_arguments(argv=None):
+    return build_parser().parse_args(argv)
+
+
+def run(args, log_file=None):
+    if log_file:
+        handler = logging.FileHandler(log_file, "w")
+        handler.setFormatter(logging.Formatter(fmt="%(asctime)s <%(filename)s> [%(funcName)s] %(message)s",
+                                               datefmt="%Y-%m-%d %H:%M:%S"))
+        logger.addHandler(handler)
+    start_time = time.time()
+    logger.info("Program started, HapHiC version: {} (update: {})".format(__version__, __update_time__))
+    logger.info("Python version: {}".format(sys.version.replace("\n", "")))
+    logger.info("Command: {}".format(" ".join(sys.argv)))
+    if args.verbose:
+        logger.setLevel(logging.DEBUG)
+    for flag in ("density_lower", "density_upper", "read_depth_upper", "rank_sum_upper"):
+        check_param("--" + flag, getattr(args, flag), {"X", "x"})
+    if args.dense_matrix:
+        logger.warning("--dense_matrix is set: the GPU path stores the pre-expanded matrix densely and every iterate "
+                       "sparsely in either mode, results are identical")
+    if args.aln_format == "auto":
+        detect_format(args)
+    unsupported = [("--correct_nrounds", args.correct_nrounds), ("--ul", args.ul), ("--gfa", args.gfa)]
+    for flag, val in unsupported:
+        if val:
+            raise NotImplementedError("haphic_b200: {} is not supported (out of the hot-path scope)".format(flag))
+    if args.quick_view:
+        args.bin_size = 0
+        args.Nx = 100
+        args.remove_allelic_links = 0
+        args.remove_concentrated_links = False
+
+    fa_dict = parse_fasta(args.fasta, RE=args.RE)
+    pos_int_type, dist_int_type = determine_int_type(fa_dict)
+    read_depth_dict = dict()
+    whitelist = set()
+    args.whitelist = whitelist
+    _, bin_set, bin_size, frag_len_dict, Nx_frag_set, RE_site_dict, split_ctg_set = stat_fragments(
+        fa_dict, args.RE, read_depth_dict, whitelist, nchrs=args.nchrs, flank=args.flank, Nx=args.Nx, bin_size=args.bin_size)
+    if split_ctg_set:
+        raise NotImplementedError(
+            "haphic_b200: {} contig(s) are longer than bin_size ({} bp) and would be split into bins "
+            "(parse_alignments, HapHiC_cluster.py:1658-1752); this path is not on the GPU yet -- rerun with --bin_size 0".format(
+                len(split_ctg_set), bin_size))
+
+    from . import hicio
+    names = list(fa_dict.keys())
+    name_index = hicio.NameIndex(names)
+    if args.aln_format == "bam":
+        alignments = hicio.bam_batches(args.alignments, name_index, inter_only=True, logger=logger)
+    else:
+        alignments = hicio.pairs_batches(args.alignments, args.aln_format, name_index, inter_only=True)
+
+    full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, _coords = parse_alignments_for_ctgs(
+        alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_int_type, dist_int_type)
+    table = parse_alignments_for_ctgs.last_table
+
+    output_pickle(HT_link_dict, "HT_link_dict", "HT_links.pkl")
+    del HT_link_dict
+    if args.quick_view:
+        logger.info("Program finished in {}s".format(time.time() - start_time))
+        return None
+    output_clm(clm_dict)
+    del clm_dict
+
+    if args.normalize_by_nlinks:
+        normalize_by_nlinks(flank_link_dict, frag_link_dict)
+    filtered_frags = filter_fragments(
+        Nx_frag_set, RE_site_dict, args.RE_site_cutoff, frag_link_dict, args.density_lower, args.density_upper,
+        args.topN, args.rank_sum_upper, args.rank_sum_hard_cutoff, flank_link_dict, read_depth_dict,
+        args.read_depth_upper, whitelist)
+    output_pickle(full_link_dict, "full_link_dict", "full_links.pkl")
+
+    # dict_to_matrix on the device: first-seen indices from the table, unlinked fragments appended in
+    # the reference's set-iteration order (355-359)
+    keep = np.fromiter((n in filtered_frags for n in names), dtype=np.uint8, count=len(names))
+    index, n_linked = table.linked_index(keep)
+    order = np.argsort(np.where(index >= 0, index, np.iinfo(np.int32).max), kind="stable")[:n_linked]
+    frags_in_dict = set()
+    for c in order.tolist():                    # same insertion order as 332-333
+        frags_in_dict.add(names[c])
+    ids = {n: i for i, n in enumerate(names)}
+    tail = [ids[f] for f in filtered_frags - frags_in_dict]
+    link_matrix = table.to_matrix(keep, tail, normalize_by_nlinks=args.normalize_by_nlinks)
+    frag_index_dict = {names[c]: int(index[c]) for c in order.tolist()}
+    for k, c in enumerate(tail):
+        frag_index_dict[names[c]] = n_linked + k
+    table.close()
+    matrix_time = time.time()
+    logger.info("Hi-C linking matrix was constructed in {}s".format(matrix_time - start_time))
+
+    if not args.skip_clustering:
+        result_clusters_list, mcl_nrounds = run_mcl_clustering(
+            link_matrix, bin_set, frag_len_dict, frag_index_dict, args.expansion, args.min_inflation, args.max_inflation,
+            args.inflation_step, args.max_iter, args.pruning, fa_dict, args.nchrs, args.dense_matrix)
+        clustering_time = time.time()
+        logger.info("{} round(s) of Markov clustering finished in {}s, average {}s per round".format(
+            mcl_nrounds, clustering_time - matrix_time, (clustering_time - matrix_time) / mcl_nrounds))
+        output_statistics(fa_dict, full_link_dict, result_clusters_list)
+    link_matrix.close()
+    logger.info("Program finished in {}s".format(time.time() - start_time))
+
+
+def main():
+    run(parse_arguments(), "HapHiC_cluster.log")
+
+
+if __name__ == "__main__":
+    main()

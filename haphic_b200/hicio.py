@@ -1,0 +1,223 @@
+"""Alignment readers for the cluster step: .pairs / .pairs.gz text and BAM, yielding int32 record
+batches [m, 4] = (ctg_a, pos_a, ctg_b, pos_b) with 0-based positions -- the tuples the reference's
+generators yield (scripts/HapHiC_cluster.py:1539-1593) after name -> id translation
+(-1 = name not in the FASTA, skipped downstream like HapHiC_cluster.py:1625).
+
+pysam/htslib are not required: BAM is decoded here (BGZF = concatenated gzip members, so the
+standard gzip module inflates it; records are walked with numpy).  A minimal BAM writer is
+included for fixtures and tests.
+"""
+
+from __future__ import annotations
+
+import gzip
+import io
+import struct
+import zlib
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# .pairs
+# ------------------------------------------------------------------------------------------------
+
+def _open_text(path, aln_format):
+    if aln_format == "pairs":
+        return open(path, "rt")
+    if aln_format == "bgzipped_pairs":
+        return gzip.open(path, "rt")
+    raise AssertionError("unknown pairs format {!r}".format(aln_format))
+
+
+def pairs_batches(path, aln_format, name_to_id, bed_path="alignments.bed", batch_lines=2_000_000, inter_only=True):
+    """Yield int32 [m, 4] record batches from a 4DN .pairs file.
+
+    Mirrors pairs_generator / pairs_generator_inter_ctgs (1539-1583): blank lines and lines starting
+    with '#' are skipped; columns are whitespace separated; ``ref, pos, mref, mpos = cols[1],
+    int(cols[2])-1, cols[3], int(cols[4])-1``; two BED lines per pair go to ``alignments.bed``
+    (needed later by `haphic build` for .pairs input); with ``inter_only`` pairs on one contig are
+    dropped (1582).  Tokenising is vectorised with pandas' C parser."""
+    import pandas as pd
+
+    def to_ids(col):
+        return name_to_id.categories.get_indexer(col).astype(np.int32)      # -1 = not in the FASTA
+
+    fbed = open(bed_path, "w") if bed_path else None
+    try:
+        with _open_text(path, aln_format) as f:
+            reader = pd.read_csv(f, sep=r"\s+", header=None, comment=None, usecols=[0, 1, 2, 3, 4], dtype=str,
+                                 chunksize=batch_lines, skip_blank_lines=True, engine="c", na_filter=False,
+                                 names=["rid", "c1", "p1", "c2", "p2"], index_col=False, on_bad_lines="error",
+                                 quoting=3)
+            for chunk in reader:
+                chunk = chunk[~chunk["rid"].str.startswith("#")]
+                if len(chunk) == 0:
+                    continue
+                p1 = chunk["p1"].astype(np.int64).to_numpy() - 1
+                p2 = chunk["p2"].astype(np.int64).to_numpy() - 1
+                if fbed is not None:
+                    a = chunk["c1"] + "\t" + pd.Series(p1, index=chunk.index).astype(str)
+                    b = chunk["c2"] + "\t" + pd.Series(p2, index=chunk.index).astype(str)
+                    l1 = a + "\t" + pd.Series(p1, index=chunk.index).astype(str) + "\t" + chunk["rid"] + "/1\t255\t.\n"
+                    l2 = b + "\t" + pd.Series(p2, index=chunk.index).astype(str) + "\t" + chunk["rid"] + "/2\t255\t.\n"
+                    fbed.write("".join((l1 + l2).tolist()))
+                ia, ib = to_ids(chunk["c1"]), to_ids(chunk["c2"])
+                rec = np.stack([ia, p1.astype(np.int32), ib, p2.astype(np.int32)], axis=1)
+                if inter_only:
+                    rec = rec[chunk["c1"].to_numpy() != chunk["c2"].to_numpy()]
+                if len(rec):
+                    yield np.ascontiguousarray(rec, dtype=np.int32)
+    finally:
+        if fbed is not None:
+            fbed.close()
+
+
+class NameIndex:
+    """name -> dense id with vectorised lookup (pandas Categorical codes; -1 = unknown)."""
+
+    def __init__(self, names):
+        import pandas as pd
+        self.names = list(names)
+        self.categories = pd.Index(self.names)
+        self._d = {n: i for i, n in enumerate(self.names)}
+
+    def __getitem__(self, name):
+        return self._d.get(name, -1)
+
+
+# ------------------------------------------------------------------------------------------------
+# BAM
+# ------------------------------------------------------------------------------------------------
+
+class BamHeader:
+    def __init__(self, text, ref_names, ref_lengths):
+        self.text = text
+        self.ref_names = ref_names
+        self.ref_lengths = ref_lengths
+
+    @property
+    def sort_order(self):
+        for line in self.text.splitlines():
+            if line.startswith("@HD"):
+                for tok in line.split("\t")[1:]:
+                    if tok.startswith("SO:"):
+                        return tok[3:]
+        return None
+
+
+def _read_exact(f, n):
+    b = f.read(n)
+    if len(b) != n:
+        raise EOFError("truncated BAM")
+    return b
+
+
+def read_bam_header(f):
+    if _read_exact(f, 4) != b"BAM\x01":
+        raise RuntimeError("not a BAM file")
+    (l_text,) = struct.unpack("<i", _read_exact(f, 4))
+    text = _read_exact(f, l_text).rstrip(b"\x00").decode()
+    (n_ref,) = struct.unpack("<i", _read_exact(f, 4))
+    names, lens = [], []
+    for _ in range(n_ref):
+        (l_name,) = struct.unpack("<i", _read_exact(f, 4))
+        names.append(_read_exact(f, l_name)[:-1].decode())
+        lens.append(struct.unpack("<i", _read_exact(f, 4))[0])
+    return BamHeader(text, names, lens)
+
+
+def bam_batches(path, name_to_id, inter_only=True, batch_bytes=64 << 20, logger=None):
+    """Yield int32 [m, 4] record batches from a BAM file: one record per read1 alignment
+    (``flag.read1``; plus ``refid != mrefid`` with ``inter_only`` -- the htslib filter strings at
+    HapHiC_cluster.py:2855/2862), fields (reference_name, reference_start, next_reference_name,
+    next_reference_start) as in bam_generator (1586-1593).  Sorting order is checked like
+    check_sorting_order (1347-1359)."""
+    with gzip.open(path, "rb") as f:
+        hdr = read_bam_header(f)
+        so = hdr.sort_order
+        if so in ("unsorted", "queryname"):
+            if logger:
+                logger.info("The sorting order of the BAM file is {}".format(so))
+        elif so == "coordinate":
+            msg = "The sorting order of the BAM file is {}. It should be unsorted or name-sorted".format(so)
+            if logger:
+                logger.error(msg)
+            raise RuntimeError(msg)
+        elif logger:
+            logger.warning("The sorting order of the BAM file is unknown, but the program will continue")
+        ref_to_id = np.array([name_to_id[n] for n in hdr.ref_names] + [-1], dtype=np.int32)   # refID -1 -> last slot
+        carry = b""
+        while True:
+            chunk = f.read(batch_bytes)
+            buf = carry + chunk
+            if not buf:
+                break
+            offs = []
+            p, n = 0, len(buf)
+            unpack = struct.unpack_from
+            while p + 4 <= n:
+                (bs,) = unpack("<i", buf, p)
+                if p + 4 + bs > n:
+                    break
+                offs.append(p + 4)
+                p += 4 + bs
+            carry = buf[p:]
+            if not chunk and carry:
+                raise EOFError("truncated BAM record")
+            if offs:
+                a = np.frombuffer(buf, dtype=np.uint8)
+                o = np.asarray(offs, dtype=np.int64)
+
+                def i32(at):
+                    idx = (o + at)[:, None] + np.arange(4)
+                    return a[idx].copy().view("<i4").ravel()
+
+                def u16(at):
+                    idx = (o + at)[:, None] + np.arange(2)
+                    return a[idx].copy().view("<u2").ravel()
+
+                refid, pos, flag, mrefid, mpos = i32(0), i32(4), u16(14), i32(20), i32(24)
+                sel = (flag & 0x40) != 0
+                if inter_only:
+                    sel &= refid != mrefid
+                if sel.any():
+                    rec = np.stack([ref_to_id[refid[sel]], pos[sel], ref_to_id[mrefid[sel]], mpos[sel]], axis=1)
+                    yield np.ascontiguousarray(rec, dtype=np.int32)
+            if not chunk:
+                break
+
+
+def _bgzf_block(data: bytes) -> bytes:
+    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = comp.compress(data) + comp.flush()
+    bsize = len(body) + 25
+    hdr = struct.pack("<BBBBIBBHBBHH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6, ord("B"), ord("C"), 2, bsize)
+    return hdr + body + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data) & 0xFFFFFFFF)
+
+
+def write_bam(path, ref_names, ref_lengths, records, sort_order="unsorted", read_len=50):
+    """Minimal paired-end BAM writer for fixtures: ``records`` is an int array [P, 4] of
+    (ctg_a, pos_a, ctg_b, pos_b); each pair becomes a read1 and a read2 record with mate fields."""
+    out = io.BytesIO()
+    text = "@HD\tVN:1.6\tSO:{}\n".format(sort_order) + "".join(
+        "@SQ\tSN:{}\tLN:{}\n".format(n, l) for n, l in zip(ref_names, ref_lengths))
+    tb = text.encode()
+    out.write(b"BAM\x01" + struct.pack("<i", len(tb)) + tb + struct.pack("<i", len(ref_names)))
+    for n, l in zip(ref_names, ref_lengths):
+        nb = n.encode() + b"\x00"
+        out.write(struct.pack("<i", len(nb)) + nb + struct.pack("<i", int(l)))
+    seq = bytes([0x11] * ((read_len + 1) // 2))      # 'A' * read_len, 4-bit packed
+    qual = bytes([0xFF] * read_len)
+    cigar = struct.pack("<I", (read_len << 4) | 0)   # read_len M
+    for r, (a, pa, b, pb) in enumerate(np.asarray(records).tolist()):
+        name = "r{}".format(r).encode() + b"\x00"
+        for (rid, pos, mrid, mpos, flag) in ((a, pa, b, pb, 0x1 | 0x40), (b, pb, a, pa, 0x1 | 0x80)):
+            core = struct.pack("<iiBBHHHiiii", rid, pos, len(name), 60, 4680, 1, flag, read_len, mrid, mpos, 0)
+            body = core + name + cigar + seq + qual
+            out.write(struct.pack("<i", len(body)) + body)
+    raw = out.getvalue()
+    with open(path, "wb") as f:
+        for i in range(0, len(raw), 0xFF00):
+            f.write(_bgzf_block(raw[i:i + 0xFF00]))
+        f.write(_bgzf_block(b""))

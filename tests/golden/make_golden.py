@@ -267,9 +267,7 @@ def run_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, seed, **argkw):
             for root, _dirs, fnames in os.walk("."):
                 for fn in fnames:
                     p = os.path.join(root, fn)[2:]
-                    if p.endswith((".clusters.txt", ".txt")) and p.startswith("inflation_"):
-                        if "statistics" in p:
-                            continue
+                    if p.endswith(".txt") and p.startswith("inflation_"):
                         with open(p) as f:
                             files[p] = f.read()
             with open("HapHiC_cluster.log") as f:
@@ -281,6 +279,13 @@ def run_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, seed, **argkw):
                 full = pickle.load(f)
             with open("HT_links.pkl", "rb") as f:
                 HT = pickle.load(f)
+            with open("paired_links.clm") as f:
+                out["clm_text"] = np.array(f.read())
+            with open("alignments.bed") as f:
+                bed = f.read()
+            import hashlib
+            out["bed_sha1"] = np.array(hashlib.sha1(bed.encode()).hexdigest())
+            out["bed_head"] = np.array(bed[:2000])
             out["files_json"] = np.array(json.dumps(files, sort_keys=True))
             out["recommend_lines"] = np.array(rec)
             out["mcl_lines"] = np.array(conv)

@@ -1,0 +1,146 @@
+"""CPU tests of the host-side parts of the drop-in module (haphic_b200/cluster.py, hicio.py):
+FASTA / fragment statistics, filters, dict_to_matrix, readers and writers, against the golden
+fixtures produced by the reference.  PYTHONHASHSEED-dependent orders are not asserted here."""
+
+import argparse
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import csc_from, load_golden
+
+
+def build_dicts(g):
+    names = g["names"].tolist()
+    from collections import defaultdict
+    flank = defaultdict(int)
+    vals = g["flank_norm_vals"] if "flank_norm_vals" in g.files else g["flank_vals"]
+    for (a, b), v in zip(g["flank_keys"].tolist(), vals.tolist()):
+        flank[(names[a], names[b])] = v
+    ctg_links = defaultdict(int)
+    for c, v in zip(g["ctg_link_ids"].tolist(), g["ctg_link_vals"].tolist()):
+        ctg_links[names[c]] = v
+    return names, flank, ctg_links
+
+
+@pytest.mark.parametrize("tag,nchr,n_contigs,mean_len,seed", [("a", 3, 60, 40000, 101), ("b", 4, 120, 60000, 202)])
+def test_fasta_and_fragment_statistics(tmp_path, tag, nchr, n_contigs, mean_len, seed):
+    from haphic_b200 import cluster, synth
+    g = load_golden("links_{}.npz".format(tag))
+    asm = synth.make_assembly(nchr, n_contigs, mean_len, seed=seed)
+    assert asm.names == g["names"].tolist()
+    fasta = str(tmp_path / "asm.fa")
+    synth.write_fasta(asm, fasta, seed=seed + 3)
+    fa = cluster.parse_fasta(fasta)
+    assert list(fa.keys()) == asm.names
+    assert [fa[n][1] for n in asm.names] == g["lengths"].tolist()
+    assert [fa[n][2] for n in asm.names] == g["RE_sites"].tolist()
+    assert cluster.determine_int_type(fa) == ("int32", "int32")
+    out = cluster.stat_fragments(fa, "GATC", dict(), set(), nchrs=nchr, flank=int(g["flank_kb"]), Nx=int(g["Nx"]), bin_size=0)
+    _, bin_set, bin_size, frag_len, nx_set, re_dict, split = out
+    assert not bin_set and not split
+    assert [re_dict[n] for n in asm.names] == g["RE_site_dict"].tolist()
+    assert [int(n in nx_set) for n in asm.names] == g["in_nx"].tolist()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_filter_and_host_dict_to_matrix(tag):
+    from haphic_b200 import cluster
+    g = load_golden("links_{}.npz".format(tag))
+    names, flank, ctg_links = build_dicts(g)
+    nx = {n for n, f in zip(names, g["in_nx"].tolist()) if f}
+    re_dict = dict(zip(names, g["RE_site_dict"].tolist()))
+    kept = cluster.filter_fragments(nx, re_dict, 5, ctg_links, "0.2X", "1.9X", 10, "1.5X", 0, flank, dict(), "1.5X", set())
+    assert [int(n in kept) for n in names] == g["filtered"].tolist()
+    m, index = cluster.dict_to_matrix(flank, kept, dense_matrix=False, add_self_loops=True)
+    ref_index = g["matrix_index"]
+    # linked fragments get first-seen indices (the unlinked tail depends on the hash seed)
+    n_linked = len({a for k in flank for a in k if k[0] in kept and k[1] in kept})
+    assert set(index) == kept
+    for n in kept:
+        i = ref_index[names.index(n)]
+        if 0 <= i < n_linked:
+            assert index[n] == i
+    if n_linked == len(kept):
+        ref = csc_from(g, "link", m.shape[0])
+        m.sort_indices()
+        assert np.array_equal(m.indices, ref.indices) and np.allclose(m.data, ref.data, rtol=1e-7, atol=0)
+
+
+def test_check_param_and_inflation_values():
+    from haphic_b200 import cluster
+    from haphic_b200.mcl import inflation_values
+    assert cluster.check_param("--x", "0.2X", {"X", "x"}) == (0.2, "X")
+    assert cluster.check_param("--x", "1", {"X", "x"}) == (1.0, "")
+    with pytest.raises(RuntimeError):
+        cluster.check_param("--x", "1.5", {"X", "x"})
+    with pytest.raises(RuntimeError):
+        cluster.check_param("--x", "", {"X", "x"})
+    assert [str(v) for v in inflation_values(1.1, 3.0, 0.1)][::19] == ["1.1", "3.0"]
+    assert [str(v) for v in inflation_values(1.2, 2.0, 0.2)] == ["1.2", "1.4", "1.6", "1.8", "2.0"]
+    assert cluster.parse_RE_sites(["GANTC"]) == ["GAATC", "GATTC", "GACTC", "GAGTC"]
+    assert cluster.count_RE_sites("GATCGATCAAGCTT", "GATC,AAGCTT") == 3
+
+
+def test_parser_matches_reference_flags():
+    from haphic_b200 import cluster
+    a = cluster.parse_arguments(["asm.fa", "aln.bam", "12"])
+    want = dict(aln_format="auto", RE="GATC", quick_view=False, gfa=None, ul=None, correct_nrounds=0, correct_resolution=500,
+                median_cov_ratio=0.2, region_len_ratio=0.1, min_region_cutoff=5000, Nx=80, RE_site_cutoff=5,
+                density_lower="0.2X", density_upper="1.9X", read_depth_upper="1.5X", topN=10, rank_sum_hard_cutoff=0,
+                rank_sum_upper="1.5X", remove_allelic_links=0, concordance_ratio_cutoff=0.2, nwindows=50,
+                remove_concentrated_links=False, max_read_pairs=200, min_read_pairs=20, phasing_weight=1.0, min_ul_mapq=30,
+                min_ul_alignment_length=10000, max_distance_to_end=100, max_overlap_ratio=0.5, max_gap_len=10000,
+                min_ul_support=2, bin_size=-1, flank=500, normalize_by_nlinks=False, expansion=2, min_inflation=1.1,
+                max_inflation=3.0, inflation_step=0.1, max_iter=200, pruning=0.0001, skip_clustering=False, threads=8,
+                dense_matrix=False, verbose=False, fasta="asm.fa", alignments="aln.bam", nchrs=12)
+    assert vars(a) == want
+
+
+def test_pairs_and_bam_readers_agree(tmp_path):
+    from haphic_b200 import hicio, synth
+    asm = synth.make_assembly(2, 20, 30000, seed=9)
+    pairs = synth.make_pairs(asm, 5000, seed=10).numpy()
+    names = asm.names + ["not_in_fasta"]
+    pairs[::50, 2] = asm.n              # a reference that the FASTA does not have
+    ext = synth.Assembly(names, None, None, None, None, asm.chrom_len, asm.nchr)
+    ppath, bpath = str(tmp_path / "a.pairs"), str(tmp_path / "a.bam")
+    synth.write_pairs(ext, pairs, ppath)
+    hicio.write_bam(bpath, names, asm.lengths.tolist() + [1000], pairs)
+    idx = hicio.NameIndex(asm.names)
+    want = pairs[pairs[:, 0] != pairs[:, 2]].copy()
+    want[:, 0][want[:, 0] == asm.n] = -1
+    want[:, 2][want[:, 2] == asm.n] = -1
+    got_p = np.concatenate(list(hicio.pairs_batches(ppath, "pairs", idx, bed_path=str(tmp_path / "a.bed"), batch_lines=700)))
+    got_b = np.concatenate(list(hicio.bam_batches(bpath, idx, batch_bytes=20000)))
+    assert np.array_equal(got_p, want) and np.array_equal(got_b, want)
+    with open(tmp_path / "a.bed") as f:
+        bed = f.read().splitlines()
+    assert len(bed) == 2 * len(pairs)
+    a, pa, b, pb = pairs[0].tolist()
+    assert bed[0] == "{}\t{}\t{}\tr0/1\t255\t.".format(names[a], pa, pa)
+    assert bed[1] == "{}\t{}\t{}\tr0/2\t255\t.".format(names[b], pb, pb)
+    # coordinate-sorted BAMs are refused like the reference does
+    hicio.write_bam(bpath, names, asm.lengths.tolist() + [1000], pairs[:10], sort_order="coordinate")
+    with pytest.raises(RuntimeError):
+        list(hicio.bam_batches(bpath, idx))
+
+
+def test_clm_writer_matches_reference(tmp_path, monkeypatch):
+    from haphic_b200 import cluster
+    from haphic_b200.links import name_rank
+    g = load_golden("links_a.npz")
+    names = g["names"].tolist()
+    rec = g["pairs"]
+    n = len(names)
+    ok = (rec[:, 0] != rec[:, 2]) & (rec[:, 0] < n) & (rec[:, 2] < n)
+    clm = cluster.build_clm_dict(rec[ok], names, g["lengths"], name_rank(names))
+    keys = [[names.index(a), names.index(b)] for a, b in clm.keys()]
+    assert keys == g["clm_keys"].tolist()
+    assert sum((list(v) for v in clm.values()), []) == g["clm_vals"].tolist()
+    monkeypatch.chdir(tmp_path)
+    cluster.output_clm(clm)
+    with open("paired_links.clm") as f:
+        assert f.read() == str(g["clm_text"])
