@@ -339,8 +339,8 @@ def run_b200(a):
         mc.close()
         mat.close()
         tab.close()
-    e2e_pairs = P / (sum(e2e_build) / len(e2e_build))
-    e2e_iters = sum(x[1] for x in e2e_mcl) / sum(x[0] for x in e2e_mcl)
+    e2e_pairs = P / (sum(e2e_build) / len(e2e_build)) if e2e_build else None
+    e2e_iters = sum(x[1] for x in e2e_mcl) / sum(x[0] for x in e2e_mcl) if e2e_mcl else None
 
     # ---- CPU baseline on this box's host cores (bounded samples) ------------------------------------
     cpu = None

@@ -54,6 +54,7 @@ struct hh_colargs {
     int inflate_square;
     float inflation, prune;
     int do_conv;
+    int track;                   // product + prune only: keep the dirty-chunk bitmap (sparse columns)
     float* scratch;
     unsigned long long* stats;   // [0] nnz written  [1] products
     int* delta_bits;
@@ -66,7 +67,7 @@ __device__ __forceinline__ uint64_t hh_warp_or64(uint64_t v) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-template <int W, int SRC, int EPI, bool SMEM>
+template <int W, int SRC, int EPI, bool SMEM, bool TRACK>
 __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
     extern __shared__ __align__(16) float hh_dyn_smem[];
     __shared__ double s_d[32];
@@ -107,77 +108,151 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             __syncthreads();
             dirty = ALL;
         } else if (SRC == SRC_DENSE) {
-            const float* __restrict__ col = a.dense_in + (size_t)jj * (size_t)a.ld;
-            for (int r = tile0 + lane; r < tile0 + T; r += 32)
-                if (r < a.n) acc[r] = col[r];
+            // stream the dense column: 128-bit loads, all issued before the first store (rows >= n of
+            // the padded column are zeros written by the pre-expansion)
+            const float4* __restrict__ col4 = reinterpret_cast<const float4*>(a.dense_in + (size_t)jj * (size_t)a.ld);
+            const int ld4 = (int)(a.ld >> 2);
+            const int r4_0 = (tile0 >> 2) + lane, r4_end = (tile0 + T) >> 2;
+            for (int r4 = r4_0; r4 < r4_end; r4 += 128) {
+                float4 x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = r4 + q * 32;
+                    x[q] = (rr < r4_end && rr < ld4) ? hh_ld_stream_f4(col4 + rr) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = r4 + q * 32;
+                    if (rr < r4_end) reinterpret_cast<float4*>(acc)[rr] = x[q];
+                }
+            }
             __syncwarp();
             dirty = ALL;
         } else {
+            // Gustavson expansion restricted to this warp's row block.  The B entries of column j are
+            // taken 32 at a time (one candidate segment of A per lane); the non-empty segments are
+            // compacted and their entries walked as ONE flat list, 32 entries per step, so lanes stay
+            // busy whatever the segment lengths are.  Entries of one segment have distinct rows; entries
+            // of different segments inside a step are applied in segment order (one round per segment),
+            // which keeps every accumulator cell's additions in ascending-i order.
             const int lenB = a.B.len[j];
             const int* __restrict__ Bidx = a.B.idx + (size_t)j * (size_t)a.B.cap;
             const float* __restrict__ Bval = a.B.val + (size_t)j * (size_t)a.B.cap;
             const int* __restrict__ Aidx = a.A.idx;
             const float* __restrict__ Aval = a.A.val;
+            const int* __restrict__ Ablk = a.A.blk;
             const size_t capA = (size_t)a.A.cap;
             unsigned long long warp_prod = 0ull;
+            // software pipeline over batches: B entries two batches ahead, block pointers one batch ahead
+            int i1 = 0, i2 = 0, s1 = 0, e1 = 0;
+            float v1 = 0.f, v2 = 0.f;
+            if (lane < lenB) {
+                i1 = Bidx[lane];
+                v1 = Bval[lane];
+            }
+            if (32 + lane < lenB) {
+                i2 = Bidx[32 + lane];
+                v2 = Bval[32 + lane];
+            }
+            if (lane < lenB) {
+                const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
+                s1 = bp[0];
+                e1 = bp[1];
+            }
             for (int t0 = 0; t0 < lenB; t0 += 32) {
-                const int t = t0 + lane;
-                int il = 0, sl = 0, el = 0;
-                float vl = 0.f;
-                if (t < lenB) {
-                    il = Bidx[t];
-                    vl = Bval[t];
-                    const int* bp = a.A.blk + (size_t)il * (W + 1) + w;
-                    sl = bp[0];
-                    el = bp[1];
+                // ---- current batch header (loaded during the previous trip)
+                const int seg_len = (t0 + lane < lenB) ? (e1 - s1) : 0;
+                const unsigned seg_base = (unsigned)((size_t)i1 * capA + (size_t)s1);
+                const float seg_v = v1;
+                // ---- advance the pipeline: batch +1 gets its block pointers, batch +2 its B entries
+                i1 = i2;
+                v1 = v2;
+                s1 = 0;
+                e1 = 0;
+                if (t0 + 32 + lane < lenB) {
+                    const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
+                    s1 = bp[0];
+                    e1 = bp[1];
                 }
-                const int cnt = min(32, lenB - t0);
-                // two segments in flight: the loads of segment u+1 are issued before segment u is consumed
-                int s_c2 = __shfl_sync(HH_FULL_MASK, sl, 0), e_c2 = __shfl_sync(HH_FULL_MASK, el, 0);
-                float v_c = __shfl_sync(HH_FULL_MASK, vl, 0);
-                size_t base_c = (size_t)__shfl_sync(HH_FULL_MASK, il, 0) * capA;
-                int k_c = 0;
-                float a_c = 0.f;
-                if (s_c2 + lane < e_c2) {
-                    k_c = Aidx[base_c + s_c2 + lane];
-                    a_c = Aval[base_c + s_c2 + lane];
+                if (t0 + 64 + lane < lenB) {
+                    i2 = Bidx[t0 + 64 + lane];
+                    v2 = Bval[t0 + 64 + lane];
                 }
-                for (int u = 0; u < cnt; ++u) {
-                    int s_n = 0, e_n = 0, k_n = 0;
-                    float v_n = 0.f, a_n = 0.f;
-                    size_t base_n = 0;
-                    if (u + 1 < cnt) {
-                        s_n = __shfl_sync(HH_FULL_MASK, sl, u + 1);
-                        e_n = __shfl_sync(HH_FULL_MASK, el, u + 1);
-                        v_n = __shfl_sync(HH_FULL_MASK, vl, u + 1);
-                        base_n = (size_t)__shfl_sync(HH_FULL_MASK, il, u + 1) * capA;
-                        if (s_n + lane < e_n) {
-                            k_n = Aidx[base_n + s_n + lane];
-                            a_n = Aval[base_n + s_n + lane];
+                // ---- compact the non-empty segments to the low lanes
+                const unsigned ne = __ballot_sync(HH_FULL_MASK, seg_len > 0);
+                const int nseg = __popc(ne);
+                if (nseg > 0) {
+                const unsigned src = __fns(ne, 0, lane + 1) & 31u;
+                int c_len = __shfl_sync(HH_FULL_MASK, seg_len, src);
+                const unsigned c_base = __shfl_sync(HH_FULL_MASK, seg_base, src);
+                const float c_v = __shfl_sync(HH_FULL_MASK, seg_v, src);
+                if (lane >= nseg) c_len = 0;
+                int incl = c_len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int tt = __shfl_up_sync(HH_FULL_MASK, incl, o);
+                    if (lane >= o) incl += tt;
+                }
+                const int excl = incl - c_len;
+                const int total = __shfl_sync(HH_FULL_MASK, incl, 31);
+                warp_prod += (unsigned long long)total;
+                // ---- flat walk, two steps in flight
+                int uf = 0;
+                int uf_end = __shfl_sync(HH_FULL_MASK, incl, 0);
+                // step descriptor: (valid, du, nround, v, k, a)
+                bool n_valid = false;
+                int n_du = 0, n_round = 0, n_k = 0;
+                float n_v = 0.f, n_a = 0.f;
+                auto fetch_step = [&](int q0) {
+                    while (uf_end <= q0) {      // warp-uniform
+                        ++uf;
+                        uf_end = __shfl_sync(HH_FULL_MASK, incl, uf);
+                    }
+                    const bool inside = (lane > uf) && (lane < nseg) && (excl > q0) && (excl < q0 + 32);
+                    const unsigned bmask = __reduce_or_sync(HH_FULL_MASK, inside ? (1u << (excl - q0)) : 0u);
+                    const int q = q0 + lane;
+                    n_valid = q < total;
+                    n_du = __popc(bmask & (0xFFFFFFFFu >> (31 - lane)));
+                    n_round = __popc(bmask) + 1;
+                    const int u = (uf + n_du) & 31;
+                    const unsigned b = __shfl_sync(HH_FULL_MASK, c_base, u);
+                    const int o = __shfl_sync(HH_FULL_MASK, excl, u);
+                    n_v = __shfl_sync(HH_FULL_MASK, c_v, u);
+                    if (n_valid) {
+                        const unsigned pidx = b + (unsigned)(q - o);
+                        n_k = Aidx[pidx];
+                        n_a = Aval[pidx];
+                    }
+                };
+                fetch_step(0);
+                for (int q0 = 0; q0 < total; q0 += 32) {
+                    const bool c_valid = n_valid;
+                    const int c_du = n_du, c_round = n_round, c_k = n_k;
+                    const float cv = n_v, ca = n_a;
+                    if (q0 + 32 < total) fetch_step(q0 + 32);
+                    for (int r = 0; r < c_round; ++r) {
+                        if (c_valid && c_du == r) {
+                            acc[c_k] = fmaf(cv, ca, acc[c_k]);
+                            if (TRACK) dirty |= 1ull << ((c_k - tile0) >> ch_shift);
                         }
+                        __syncwarp();
                     }
-                    if (s_c2 + lane < e_c2) {
-                        acc[k_c] = fmaf(v_c, a_c, acc[k_c]);
-                        dirty |= 1ull << ((k_c - tile0) >> ch_shift);
+                }
+                }   // nseg > 0
+                // ---- pull the next batch's segments into L2 (their block pointers arrived long ago)
+                if (e1 > s1) {
+                    const size_t nb = (size_t)i1 * capA;
+                    const char* pi = reinterpret_cast<const char*>(Aidx + nb + s1);
+                    const char* pv = reinterpret_cast<const char*>(Aval + nb + s1);
+                    const int bytes = (e1 - s1) * 4;
+                    for (int o = -(int)((uintptr_t)pi & 127); o < bytes; o += 128) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + o));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + o));
                     }
-                    for (int p = s_c2 + lane + 32; p < e_c2; p += 32) {
-                        const int k = Aidx[base_c + p];
-                        const float av = Aval[base_c + p];
-                        acc[k] = fmaf(v_c, av, acc[k]);
-                        dirty |= 1ull << ((k - tile0) >> ch_shift);
-                    }
-                    warp_prod += (unsigned long long)(e_c2 - s_c2);
-                    __syncwarp();   // the next segment may hit the same rows from other lanes
-                    s_c2 = s_n;
-                    e_c2 = e_n;
-                    v_c = v_n;
-                    base_c = base_n;
-                    k_c = k_n;
-                    a_c = a_n;
                 }
             }
             if (lane == 0) prod_acc += warp_prod;
-            dirty = hh_warp_or64(dirty);
+            dirty = TRACK ? hh_warp_or64(dirty) : ALL;
         }
 
         // ------------------------------------------------------------------ epilogue
@@ -195,7 +270,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
         if (EPI == EPI_DUMP) {
             float* __restrict__ col = a.dense_out + (size_t)jj * (size_t)a.ld;
             for (int r = tile0 + lane; r < tile0 + T; r += 32) {
-                if (r < a.n) {
+                if (r < a.ld) {          // rows in [n, ld) are zero padding (never accumulated)
                     col[r] = acc[r];
                     acc[r] = 0.f;
                 }
@@ -488,6 +563,7 @@ struct hh_mcl {
     float inflation, prune;
     int inflate_square;
     bool begun;
+    int64_t cur_nnz, pending_nnz;   // stored entries of the current / pending iterate (all columns)
     int* d_counter;
     unsigned long long* d_stats;   // [0] nnz [1] products [2] delta bits [3] err
     int64_t nnz_m0, preexp_products;
@@ -505,6 +581,8 @@ static void slot_free(hh_slotmat& s) {
 
 static int slot_alloc(hh_slotmat& s, int n, int cap, int W) {
     memset(&s, 0, sizeof(s));
+    HH_REQUIRE((unsigned long long)n * (unsigned long long)cap <= 0xFFFFFFFFull, HH_ERR_UNSUPPORTED,
+               "hh_mcl: %d columns x %d slot entries exceed the 32-bit entry offsets of the expansion kernel", n, cap);
     s.n = n;
     s.cap = cap;
     s.W = W;
@@ -550,22 +628,29 @@ static hh_geom geom_for(hh_ctx* ctx, int n) {
     return g;
 }
 
-template <int W, int SRC, int EPI>
-static int launch_col_w(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
+template <int W, int SRC, int EPI, bool TRACK>
+static int launch_col_wt(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
     a.scratch = d_scratch;
     int grid = a.ncols < grid_cap ? a.ncols : grid_cap;
     if (grid < 1) return HH_OK;
     HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
     if (g.smem_acc) {
-        auto kern = hh_k_col<W, SRC, EPI, true>;
+        auto kern = hh_k_col<W, SRC, EPI, true, TRACK>;
         HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
         HH_LAUNCH(ctx, kern, grid, W * 32, g.smem_bytes, a);
     } else {
-        auto kern = hh_k_col<W, SRC, EPI, false>;
+        auto kern = hh_k_col<W, SRC, EPI, false, TRACK>;
         HH_CUDA(cudaMemsetAsync(d_scratch, 0, (size_t)grid_cap * (size_t)g.n_pad * sizeof(float), ctx->stream));
         HH_LAUNCH(ctx, kern, grid, W * 32, 0, a);
     }
     return HH_OK;
+}
+
+// dirty-chunk tracking only pays off when a column touches a small part of the accumulator
+template <int W, int SRC, int EPI>
+static int launch_col_w(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
+    if (SRC == SRC_PRODUCT && EPI == EPI_PRUNE && a.track) return launch_col_wt<W, SRC, EPI, true>(ctx, g, d_scratch, grid_cap, a);
+    return launch_col_wt<W, SRC, EPI, false>(ctx, g, d_scratch, grid_cap, a);
 }
 
 template <int SRC, int EPI>
@@ -586,21 +671,21 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
         // every instantiation has the same footprint; query the heaviest (product + prune)
         switch (g.W) {
             case 8:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true>, 256,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true>, 256,
                                                                      g.smem_bytes));
                 break;
             case 16:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true>, 512,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true>, 512,
                                                                      g.smem_bytes));
                 break;
             default:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true>, 1024,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true>, 1024,
                                                                      g.smem_bytes));
                 break;
         }
@@ -901,6 +986,9 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
         a.A = mc->it[mc->cur];
         a.B = mc->it[mc->cur];
         a.do_conv = 1;
+        // expected products per column ~ (nnz/n)^2; track dirty chunks when that is well below n
+        const double dcol = (double)mc->cur_nnz / (double)mc->n;
+        a.track = (dcol * dcol * 4.0 < (double)mc->n) ? 1 : 0;
         HH_CHECK((launch_col<SRC_PRODUCT, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
     }
     HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
@@ -909,6 +997,7 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
     if (kernel_ms) HH_CUDA(cudaEventElapsedTime(kernel_ms, mc->ev0, mc->ev1));
     HH_REQUIRE((int)(st[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY,
                "hh_mcl_step: a pruned column exceeded its slot (%d entries); pruning threshold too small for this layout", mc->it_cap);
+    mc->pending_nnz = (int64_t)st[0] * (int64_t)mc->n / (int64_t)(mc->col_hi - mc->col_lo);   // owned block scaled to n
     if (nnz_owned) *nnz_owned = (int64_t)st[0];
     if (products) *products = (int64_t)st[1];
     if (delta) {
@@ -975,6 +1064,7 @@ extern "C" int hh_mcl_commit(hh_mcl* mc) {
     HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_commit: NULL handle");
     HH_REQUIRE(mc->have_pending, HH_ERR_STATE, "hh_mcl_commit: nothing to commit");
     mc->cur = mc->pending;
+    mc->cur_nnz = mc->pending_nnz;
     mc->have_pending = false;
     return HH_OK;
 }

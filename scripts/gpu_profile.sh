@@ -6,7 +6,7 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 ARGS="${BENCH_ARGS:---steps 1 --warmup 0 --no-cpu-baseline --e2e-steps 0}"
 echo "== launch list"
-timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:hh_ -c 600 --csv --log-file gpurun_out/launches.csv \
     python bench.py $ARGS > gpurun_out/launches_bench.log 2>&1
 tail -3 gpurun_out/launches_bench.log
 echo "== full capture: MCL column kernel: pre-expansion, dense iteration 0, first sparse expansion"
