@@ -59,12 +59,25 @@ struct hh_ctx {
     uint64_t* d_scratch;    // device, 64 x u64
 };
 
-// RAII-less device buffer helper (explicit free keeps destruction order obvious)
+// Every ABI entry point opens an hh_scope: device selected, and device buffers come from the
+// stream-ordered memory pool of the context's stream (cudaMallocAsync / cudaFreeAsync; the pool keeps
+// freed blocks, so the multi-GB tables of one pass are reused by the next without cudaMalloc cost).
+extern thread_local hh_ctx* hh_tls_ctx;
+struct hh_scope {
+    hh_ctx* prev;
+    explicit hh_scope(hh_ctx* c) : prev(hh_tls_ctx) {
+        hh_tls_ctx = c;
+        if (c) cudaSetDevice(c->device);
+    }
+    ~hh_scope() { hh_tls_ctx = prev; }
+};
+
 template <typename T>
 static inline int hh_dmalloc(T** p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    cudaError_t e = hh_tls_ctx ? cudaMallocAsync((void**)p, count * sizeof(T), hh_tls_ctx->stream)
+                               : cudaMalloc((void**)p, count * sizeof(T));
     if (e != cudaSuccess) {
         hh_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
         cudaGetLastError();
@@ -74,7 +87,10 @@ static inline int hh_dmalloc(T** p, size_t count) {
 }
 template <typename T>
 static inline void hh_dfree(T*& p) {
-    if (p) cudaFree((void*)p);
+    if (p) {
+        if (hh_tls_ctx) cudaFreeAsync((void*)p, hh_tls_ctx->stream);
+        else cudaFree((void*)p);
+    }
     p = nullptr;
 }
 

@@ -2,6 +2,7 @@
 #include "hh_common.cuh"
 
 static thread_local char g_err[1024] = "";
+thread_local hh_ctx* hh_tls_ctx = nullptr;
 
 void hh_set_error(const char* fmt, ...) {
     va_list ap;
@@ -42,6 +43,12 @@ extern "C" int hh_ctx_create(int device, hh_ctx** out) {
     c->h_scratch = nullptr;
     c->d_scratch = nullptr;
     HH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // keep freed device memory in the pool: a pass re-allocates the same multi-GB buffers
+        cudaMemPool_t pool;
+        HH_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        HH_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     HH_CUDA(cudaMallocHost((void**)&c->h_scratch, 64 * sizeof(uint64_t)));
     HH_CUDA(cudaMalloc((void**)&c->d_scratch, 64 * sizeof(uint64_t)));
     *out = c;

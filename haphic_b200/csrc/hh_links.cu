@@ -420,6 +420,7 @@ extern "C" int hh_links_create(hh_ctx* ctx, int32_t n_ctg, const int64_t* ctg_le
     HH_REQUIRE(ctx && out && ctg_len && name_rank && in_nx, HH_ERR_ARG, "hh_links_create: NULL argument");
     HH_REQUIRE(n_ctg > 0, HH_ERR_ARG, "hh_links_create: n_ctg must be positive");
     HH_REQUIRE(flank_bp >= 0, HH_ERR_ARG, "hh_links_create: flank_bp must be >= 0");
+    hh_scope _scope(ctx);
     *out = nullptr;
     HH_CUDA(cudaSetDevice(ctx->device));
     std::vector<int32_t> len32(n_ctg);
@@ -487,6 +488,7 @@ static int links_launch_insert(hh_links* lk, const int4* d_rec, int64_t n_rec, i
 
 extern "C" int hh_links_add_async(hh_links* lk, const int32_t* rec_dev, int64_t n_rec, int64_t stream_offset) {
     HH_REQUIRE(lk && (rec_dev || n_rec == 0), HH_ERR_ARG, "hh_links_add_async: NULL argument");
+    hh_scope _scope(lk->ctx);
     HH_REQUIRE(!lk->finished, HH_ERR_STATE, "hh_links_add_async: stream already finished");
     HH_REQUIRE(n_rec >= 0 && stream_offset >= 0 && stream_offset + n_rec <= 0xFFFFFFFELL, HH_ERR_UNSUPPORTED,
                "hh_links_add: stream indices must fit 32 bits (offset %lld + %lld records)", (long long)stream_offset,
@@ -503,6 +505,7 @@ extern "C" int hh_links_add_async(hh_links* lk, const int32_t* rec_dev, int64_t 
 
 extern "C" int hh_links_add(hh_links* lk, const int32_t* rec, int64_t n_rec, int64_t stream_offset, int mem) {
     HH_REQUIRE(lk && (rec || n_rec == 0), HH_ERR_ARG, "hh_links_add: NULL argument");
+    hh_scope _scope(lk->ctx);
     HH_REQUIRE(!lk->finished, HH_ERR_STATE, "hh_links_add: stream already finished");
     HH_REQUIRE(mem == HH_MEM_HOST || mem == HH_MEM_DEVICE, HH_ERR_ARG, "hh_links_add: bad mem flag %d", mem);
     HH_REQUIRE(n_rec >= 0 && stream_offset >= 0 && stream_offset + n_rec <= 0xFFFFFFFELL, HH_ERR_UNSUPPORTED,
@@ -523,8 +526,8 @@ extern "C" int hh_links_add(hh_links* lk, const int32_t* rec, int64_t n_rec, int
     } else {
         if (!lk->d_stage[0]) {
             lk->stage_records = CH;
-            HH_CHECK(hh_dmalloc(&lk->d_stage[0], (size_t)CH));
-            HH_CHECK(hh_dmalloc(&lk->d_stage[1], (size_t)CH));
+            HH_CUDA(cudaMalloc((void**)&lk->d_stage[0], (size_t)CH * sizeof(int4)));   // plain cudaMalloc: also used by copy_stream
+            HH_CUDA(cudaMalloc((void**)&lk->d_stage[1], (size_t)CH * sizeof(int4)));
         }
         int buf = 0;
         for (int64_t off = 0; off < n_rec; off += CH, buf ^= 1) {
@@ -548,6 +551,7 @@ extern "C" int hh_links_add(hh_links* lk, const int32_t* rec, int64_t n_rec, int
 
 extern "C" int hh_links_finish(hh_links* lk, hh_links_info* info) {
     HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_finish: NULL handle");
+    hh_scope _scope(lk->ctx);
     hh_ctx* ctx = lk->ctx;
     HH_CUDA(cudaSetDevice(ctx->device));
     if (!lk->finished) {
@@ -606,31 +610,52 @@ extern "C" int hh_links_finish(hh_links* lk, hh_links_info* info) {
     return HH_OK;
 }
 
+// AoS compact entries -> the 7 output arrays (SoA), so each goes to the host with one plain copy
+__global__ void hh_k_links_split(const uint32_t* __restrict__ compact, int64_t nnz, uint32_t* __restrict__ soa, int64_t ht_off) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        const uint32_t* p = compact + e * 9;
+        soa[0 * nnz + e] = p[0];
+        soa[1 * nnz + e] = p[1];
+        soa[2 * nnz + e] = p[2];
+        soa[3 * nnz + e] = p[3];
+        soa[4 * nnz + e] = p[4];
+        soa[5 * nnz + e] = p[5];
+        uint4 h;
+        h.y = p[6];
+        h.z = p[7];
+        h.w = p[8];
+        h.x = p[2] - p[6] - p[7] - p[8];          // HH = full - HT - TH - TT
+        reinterpret_cast<uint4*>(soa + ht_off)[e] = h;
+    }
+}
+
 extern "C" int hh_links_fetch(hh_links* lk, int32_t* key_i, int32_t* key_j, uint32_t* full, uint32_t* flank,
                               uint32_t* first_full, uint32_t* first_flank, uint32_t* ht) {
     HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_fetch: NULL handle");
+    hh_scope _scope(lk->ctx);
     HH_REQUIRE(lk->finished, HH_ERR_STATE, "hh_links_fetch: call hh_links_finish first");
     if (lk->nnz == 0) return HH_OK;
-    HH_CUDA(cudaSetDevice(lk->ctx->device));
-    std::vector<uint32_t> h((size_t)lk->nnz * 9);
-    HH_CUDA(cudaMemcpyAsync(h.data(), lk->d_compact, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, lk->ctx->stream));
-    HH_CUDA(cudaStreamSynchronize(lk->ctx->stream));
-    for (int64_t e = 0; e < lk->nnz; ++e) {
-        const uint32_t* p = h.data() + e * 9;
-        if (key_i) key_i[e] = (int32_t)p[0];
-        if (key_j) key_j[e] = (int32_t)p[1];
-        if (full) full[e] = p[2];
-        if (flank) flank[e] = p[3];
-        if (first_full) first_full[e] = p[4];
-        if (first_flank) first_flank[e] = p[5];
-        if (ht) {
-            ht[4 * e + 1] = p[6];
-            ht[4 * e + 2] = p[7];
-            ht[4 * e + 3] = p[8];
-            ht[4 * e + 0] = p[2] - p[6] - p[7] - p[8];
-        }
-    }
-    return HH_OK;
+    hh_ctx* ctx = lk->ctx;
+    const int64_t nnz = lk->nnz;
+    uint32_t* d_soa = nullptr;
+    HH_CHECK(hh_dmalloc(&d_soa, (size_t)nnz * 10 + 4));
+    int rc = [&]() -> int {
+        uint32_t* base = d_soa;
+        const int64_t ht_off = (6 * nnz + 3) & ~3ll;      // the 4-wide HT block is written with 16-byte stores
+        int64_t blocks = (nnz + 255) / 256;
+        int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
+        HH_LAUNCH(ctx, hh_k_links_split, grid, 256, 0, lk->d_compact, nnz, base, ht_off);
+        void* dst[6] = {key_i, key_j, full, flank, first_full, first_flank};
+        for (int k = 0; k < 6; ++k)
+            if (dst[k])
+                HH_CUDA(cudaMemcpyAsync(dst[k], base + (size_t)k * nnz, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ht) HH_CUDA(cudaMemcpyAsync(ht, base + ht_off, (size_t)nnz * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        return HH_OK;
+    }();
+    hh_dfree(d_soa);
+    return rc;
 }
 
 extern "C" int hh_links_fetch_ctg(hh_links* lk, int64_t* ctg_links) {
@@ -658,6 +683,7 @@ extern "C" int hh_links_export(hh_links* lk, uint32_t* entries_dev, int64_t* ctg
 extern "C" int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t n_entries, const int64_t* ctg_links_dev,
                               int64_t n_records, int64_t n_used) {
     HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_merge: NULL handle");
+    hh_scope _scope(lk->ctx);
     lk->finished = false;   // a finished table is re-opened: the next hh_links_finish rebuilds the ordered view
     HH_REQUIRE(n_entries >= 0 && (entries_dev || n_entries == 0), HH_ERR_ARG, "hh_links_merge: bad entries");
     hh_ctx* ctx = lk->ctx;
@@ -679,6 +705,7 @@ extern "C" int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t
 
 extern "C" int hh_links_linked_index(hh_links* lk, const uint8_t* keep, int32_t* index, int32_t* n_linked) {
     HH_REQUIRE(lk && keep, HH_ERR_ARG, "hh_links_linked_index: NULL argument");
+    hh_scope _scope(lk->ctx);
     HH_REQUIRE(lk->finished, HH_ERR_STATE, "hh_links_linked_index: call hh_links_finish first");
     hh_ctx* ctx = lk->ctx;
     HH_CUDA(cudaSetDevice(ctx->device));
@@ -710,6 +737,7 @@ extern "C" int hh_links_linked_index(hh_links* lk, const uint8_t* keep, int32_t*
 
 extern "C" int hh_links_destroy(hh_links* lk) {
     if (!lk) return HH_OK;
+    hh_scope _scope(lk->ctx);
     cudaSetDevice(lk->ctx->device);
     cudaStreamSynchronize(lk->ctx->stream);
     if (lk->copy_stream) {
@@ -719,7 +747,7 @@ extern "C" int hh_links_destroy(hh_links* lk) {
     for (int k = 0; k < 2; ++k) {
         if (lk->ev_copied[k]) cudaEventDestroy(lk->ev_copied[k]);
         if (lk->ev_consumed[k]) cudaEventDestroy(lk->ev_consumed[k]);
-        hh_dfree(lk->d_stage[k]);
+        if (lk->d_stage[k]) cudaFree(lk->d_stage[k]);
     }
     hh_dfree(lk->d_len);
     hh_dfree(lk->d_rank);

@@ -98,6 +98,7 @@ static int matrix_alloc(hh_ctx* ctx, int32_t n, int64_t nnz, hh_matrix** out) {
 extern "C" int hh_matrix_from_links(hh_links* lk, const uint8_t* keep, const int32_t* tail, int32_t n_tail,
                                     int normalize_by_nlinks, hh_matrix** out) {
     HH_REQUIRE(lk && keep && out, HH_ERR_ARG, "hh_matrix_from_links: NULL argument");
+    hh_scope _scope(hh_links_ctx(lk));
     HH_REQUIRE(n_tail >= 0 && (tail || n_tail == 0), HH_ERR_ARG, "hh_matrix_from_links: bad tail");
     HH_REQUIRE(hh_links_finished(lk), HH_ERR_STATE, "hh_matrix_from_links: call hh_links_finish first");
     *out = nullptr;
@@ -173,6 +174,7 @@ extern "C" int hh_matrix_from_links(hh_links* lk, const uint8_t* keep, const int
 extern "C" int hh_matrix_from_csc(hh_ctx* ctx, int32_t n, const int64_t* indptr, const int32_t* indices, const float* data,
                                   hh_matrix** out) {
     HH_REQUIRE(ctx && indptr && out, HH_ERR_ARG, "hh_matrix_from_csc: NULL argument");
+    hh_scope _scope(ctx);
     HH_REQUIRE(n > 0, HH_ERR_ARG, "hh_matrix_from_csc: n must be positive");
     *out = nullptr;
     HH_REQUIRE(indptr[0] == 0, HH_ERR_ARG, "hh_matrix_from_csc: indptr[0] must be 0");
@@ -213,6 +215,7 @@ extern "C" int hh_matrix_info(hh_matrix* m, int32_t* n, int64_t* nnz) {
 
 extern "C" int hh_matrix_destroy(hh_matrix* m) {
     if (!m) return HH_OK;
+    hh_scope _scope(m->ctx);
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     hh_dfree(m->d_colptr);

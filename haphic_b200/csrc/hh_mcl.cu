@@ -25,6 +25,7 @@
 #include "hh_common.cuh"
 #include "hh_internal.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 struct hh_slotmat {
     int n;       // rows == columns
@@ -55,6 +56,8 @@ struct hh_colargs {
     float inflation, prune;
     int do_conv;
     int track;                   // product + prune only: keep the dirty-chunk bitmap (sparse columns)
+    int flat;                    // expansion inner loop: 1 = flat 32-entry walk, 0 = one segment at a time
+    int l2pf;                    // expansion: prefetch the next batch's segments into L2
     float* scratch;
     unsigned long long* stats;   // [0] nnz written  [1] products
     int* delta_bits;
@@ -67,7 +70,7 @@ __device__ __forceinline__ uint64_t hh_warp_or64(uint64_t v) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-template <int W, int SRC, int EPI, bool SMEM, bool TRACK>
+template <int W, int SRC, int EPI, bool SMEM, bool TRACK, bool FLAT>
 __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
     extern __shared__ __align__(16) float hh_dyn_smem[];
     __shared__ double s_d[32];
@@ -178,9 +181,72 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     i2 = Bidx[t0 + 64 + lane];
                     v2 = Bval[t0 + 64 + lane];
                 }
-                // ---- compact the non-empty segments to the low lanes
                 const unsigned ne = __ballot_sync(HH_FULL_MASK, seg_len > 0);
-                const int nseg = __popc(ne);
+                if (!FLAT) {
+                    // ---- one segment at a time, two 32-entry chunks per trip; the first two chunks of the
+                    // next segment are loaded before the current one is applied
+                    unsigned rem = ne;
+                    int nL = 0, nk0 = 0, nk1 = 0;
+                    unsigned nb = 0;
+                    float nv = 0.f, na0 = 0.f, na1 = 0.f;
+                    auto preload = [&]() {
+                        const int u = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        nL = __shfl_sync(HH_FULL_MASK, seg_len, u);
+                        nb = __shfl_sync(HH_FULL_MASK, seg_base, u);
+                        nv = __shfl_sync(HH_FULL_MASK, seg_v, u);
+                        if (lane < nL) {
+                            nk0 = Aidx[nb + lane];
+                            na0 = Aval[nb + lane];
+                        }
+                        if (lane + 32 < nL) {
+                            nk1 = Aidx[nb + lane + 32];
+                            na1 = Aval[nb + lane + 32];
+                        }
+                    };
+                    if (rem) preload();
+                    bool have = ne != 0;
+                    while (have) {
+                        const int cL = nL, ck0 = nk0, ck1 = nk1;
+                        const unsigned cb = nb;
+                        const float cv = nv, ca0 = na0, ca1 = na1;
+                        have = rem != 0;
+                        if (have) preload();
+                        warp_prod += (unsigned long long)cL;
+                        if (lane < cL) {
+                            acc[ck0] = fmaf(cv, ca0, acc[ck0]);
+                            if (TRACK) dirty |= 1ull << ((ck0 - tile0) >> ch_shift);
+                        }
+                        if (lane + 32 < cL) {
+                            acc[ck1] = fmaf(cv, ca1, acc[ck1]);
+                            if (TRACK) dirty |= 1ull << ((ck1 - tile0) >> ch_shift);
+                        }
+                        for (int c = 64; c < cL; c += 64) {
+                            const int p0 = c + lane, p1 = c + 32 + lane;
+                            int k0 = 0, k1 = 0;
+                            float a0 = 0.f, a1 = 0.f;
+                            if (p0 < cL) {
+                                k0 = Aidx[cb + p0];
+                                a0 = Aval[cb + p0];
+                            }
+                            if (p1 < cL) {
+                                k1 = Aidx[cb + p1];
+                                a1 = Aval[cb + p1];
+                            }
+                            if (p0 < cL) {
+                                acc[k0] = fmaf(cv, a0, acc[k0]);
+                                if (TRACK) dirty |= 1ull << ((k0 - tile0) >> ch_shift);
+                            }
+                            if (p1 < cL) {
+                                acc[k1] = fmaf(cv, a1, acc[k1]);
+                                if (TRACK) dirty |= 1ull << ((k1 - tile0) >> ch_shift);
+                            }
+                        }
+                        __syncwarp();   // the next segment may hit the same rows from other lanes
+                    }
+                }
+                // ---- compact the non-empty segments to the low lanes
+                const int nseg = FLAT ? __popc(ne) : 0;
                 if (nseg > 0) {
                 const unsigned src = __fns(ne, 0, lane + 1) & 31u;
                 int c_len = __shfl_sync(HH_FULL_MASK, seg_len, src);
@@ -240,7 +306,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 }
                 }   // nseg > 0
                 // ---- pull the next batch's segments into L2 (their block pointers arrived long ago)
-                if (e1 > s1) {
+                if (a.l2pf && e1 > s1) {
                     const size_t nb = (size_t)i1 * capA;
                     const char* pi = reinterpret_cast<const char*>(Aidx + nb + s1);
                     const char* pv = reinterpret_cast<const char*>(Aval + nb + s1);
@@ -567,6 +633,7 @@ struct hh_mcl {
     int* d_counter;
     unsigned long long* d_stats;   // [0] nnz [1] products [2] delta bits [3] err
     int64_t nnz_m0, preexp_products;
+    int flat, l2pf;                // expansion inner-loop variant / L2 prefetch (HH_MCL_FLAT, HH_MCL_L2PF)
     cudaEvent_t ev0, ev1;
     float create_ms[2];            // device time of the normalisation / pre-expansion kernels
 };
@@ -601,9 +668,16 @@ struct hh_geom {
     size_t smem_bytes;
 };
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 static hh_geom geom_for(hh_ctx* ctx, int n) {
     hh_geom g;
     g.W = (n <= 12288) ? 8 : (n <= 28672 ? 16 : 32);
+    const int wo = env_int("HH_MCL_W", 0);       // tuning override: row blocks per column = warps per CTA
+    if (wo == 8 || wo == 16 || wo == 32) g.W = wo;
     int T = (n + g.W - 1) / g.W;
     T = (T + 31) & ~31;
     g.T = T;
@@ -628,18 +702,18 @@ static hh_geom geom_for(hh_ctx* ctx, int n) {
     return g;
 }
 
-template <int W, int SRC, int EPI, bool TRACK>
-static int launch_col_wt(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
+template <int W, int SRC, int EPI, bool TRACK, bool FLAT>
+static int launch_col_wtf(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
     a.scratch = d_scratch;
     int grid = a.ncols < grid_cap ? a.ncols : grid_cap;
     if (grid < 1) return HH_OK;
     HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
     if (g.smem_acc) {
-        auto kern = hh_k_col<W, SRC, EPI, true, TRACK>;
+        auto kern = hh_k_col<W, SRC, EPI, true, TRACK, FLAT>;
         HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
         HH_LAUNCH(ctx, kern, grid, W * 32, g.smem_bytes, a);
     } else {
-        auto kern = hh_k_col<W, SRC, EPI, false, TRACK>;
+        auto kern = hh_k_col<W, SRC, EPI, false, TRACK, FLAT>;
         HH_CUDA(cudaMemsetAsync(d_scratch, 0, (size_t)grid_cap * (size_t)g.n_pad * sizeof(float), ctx->stream));
         HH_LAUNCH(ctx, kern, grid, W * 32, 0, a);
     }
@@ -649,8 +723,16 @@ static int launch_col_wt(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int gr
 // dirty-chunk tracking only pays off when a column touches a small part of the accumulator
 template <int W, int SRC, int EPI>
 static int launch_col_w(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
-    if (SRC == SRC_PRODUCT && EPI == EPI_PRUNE && a.track) return launch_col_wt<W, SRC, EPI, true>(ctx, g, d_scratch, grid_cap, a);
-    return launch_col_wt<W, SRC, EPI, false>(ctx, g, d_scratch, grid_cap, a);
+    if (SRC == SRC_PRODUCT) {
+        const bool track = (EPI == EPI_PRUNE) && a.track;
+        if (a.flat) {
+            if (track) return launch_col_wtf<W, SRC, EPI, true, true>(ctx, g, d_scratch, grid_cap, a);
+            return launch_col_wtf<W, SRC, EPI, false, true>(ctx, g, d_scratch, grid_cap, a);
+        }
+        if (track) return launch_col_wtf<W, SRC, EPI, true, false>(ctx, g, d_scratch, grid_cap, a);
+        return launch_col_wtf<W, SRC, EPI, false, false>(ctx, g, d_scratch, grid_cap, a);
+    }
+    return launch_col_wtf<W, SRC, EPI, false, false>(ctx, g, d_scratch, grid_cap, a);
 }
 
 template <int SRC, int EPI>
@@ -671,21 +753,21 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
         // every instantiation has the same footprint; query the heaviest (product + prune)
         switch (g.W) {
             case 8:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true>, 256,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 256,
                                                                      g.smem_bytes));
                 break;
             case 16:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true>, 512,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 512,
                                                                      g.smem_bytes));
                 break;
             default:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true>, 1024,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 1024,
                                                                      g.smem_bytes));
                 break;
         }
@@ -768,6 +850,7 @@ static int read_stats(hh_ctx* ctx, unsigned long long* d_stats, unsigned long lo
 
 extern "C" int hh_matrix_fetch_csc(hh_matrix* m, int64_t* indptr, int32_t* indices, float* data) {
     HH_REQUIRE(m != nullptr, HH_ERR_ARG, "hh_matrix_fetch_csc: NULL handle");
+    hh_scope _scope(m->ctx);
     hh_ctx* ctx = m->ctx;
     HH_CUDA(cudaSetDevice(ctx->device));
     const hh_geom g = geom_for(ctx, m->n);
@@ -800,6 +883,7 @@ extern "C" int hh_matrix_fetch_csc(hh_matrix* m, int64_t* indptr, int32_t* indic
 
 extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     if (!mc) return HH_OK;
+    hh_scope _scope(mc->ctx);
     cudaSetDevice(mc->ctx->device);
     cudaStreamSynchronize(mc->ctx->stream);
     slot_free(mc->m0);
@@ -836,10 +920,13 @@ static void mcl_base_args(hh_mcl* mc, hh_colargs& a) {
     a.stats = mc->d_stats;
     a.delta_bits = reinterpret_cast<int*>(mc->d_stats + 2);
     a.err = reinterpret_cast<int*>(mc->d_stats + 3);
+    a.flat = mc->flat;
+    a.l2pf = mc->l2pf;
 }
 
 extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, hh_mcl** out) {
     HH_REQUIRE(m && out, HH_ERR_ARG, "hh_mcl_create: NULL argument");
+    hh_scope _scope(m->ctx);
     *out = nullptr;
     HH_REQUIRE(expansion == 2, HH_ERR_UNSUPPORTED,
                "hh_mcl_create: expansion %d is not supported yet (only the default --expansion 2)", expansion);
@@ -856,6 +943,8 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
     mc->col_hi = col_hi;
     mc->expansion = expansion;
     mc->cur = -1;
+    mc->flat = env_int("HH_MCL_FLAT", 0);
+    mc->l2pf = env_int("HH_MCL_L2PF", 1);
     const hh_geom g = geom_for(ctx, m->n);
     mc->W = g.W;
     mc->T = g.T;
@@ -922,6 +1011,7 @@ extern "C" int hh_mcl_info(hh_mcl* mc, int32_t* n, int64_t* nnz_m0, int64_t* pre
 
 extern "C" int hh_mcl_fetch_m0(hh_mcl* mc, int64_t* indptr, int32_t* indices, float* data) {
     HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_fetch_m0: NULL handle");
+    hh_scope _scope(mc->ctx);
     HH_CUDA(cudaSetDevice(mc->ctx->device));
     return slot_fetch_csc(mc->ctx, mc->m0, 0, mc->n, indptr, indices, data);
 }
@@ -938,6 +1028,7 @@ extern "C" int hh_mcl_fetch_m1(hh_mcl* mc, float* dense) {
 
 extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
     HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_begin: NULL handle");
+    hh_scope _scope(mc->ctx);
     HH_REQUIRE(inflation > 0.0, HH_ERR_ARG, "hh_mcl_begin: inflation must be positive");
     HH_CUDA(cudaSetDevice(mc->ctx->device));
     // a column that sums to 1 holds at most 1/pruning entries >= pruning (+ slack for fp32 rounding)
@@ -963,6 +1054,7 @@ extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
 
 extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* products, float* delta, float* kernel_ms) {
     HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_step: NULL handle");
+    hh_scope _scope(mc->ctx);
     HH_REQUIRE(mc->begun, HH_ERR_STATE, "hh_mcl_step: call hh_mcl_begin first");
     HH_REQUIRE(!mc->have_pending, HH_ERR_STATE, "hh_mcl_step: previous step not committed");
     HH_REQUIRE((it == 0) == (mc->cur < 0), HH_ERR_STATE, "hh_mcl_step: iteration %d out of sequence", it);
@@ -1013,6 +1105,7 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
 
 extern "C" int hh_mcl_pack(hh_mcl* mc, int32_t* len_dev, int32_t* idx_dev, float* val_dev) {
     HH_REQUIRE(mc && len_dev, HH_ERR_ARG, "hh_mcl_pack: NULL argument");
+    hh_scope _scope(mc->ctx);
     HH_REQUIRE(mc->have_pending, HH_ERR_STATE, "hh_mcl_pack: nothing to pack (call hh_mcl_step first)");
     hh_ctx* ctx = mc->ctx;
     HH_CUDA(cudaSetDevice(ctx->device));
@@ -1035,6 +1128,7 @@ extern "C" int hh_mcl_pack(hh_mcl* mc, int32_t* len_dev, int32_t* idx_dev, float
 extern "C" int hh_mcl_unpack(hh_mcl* mc, int32_t col_lo, int32_t col_hi, const int32_t* len_dev, const int32_t* idx_dev,
                              const float* val_dev, int64_t nnz_block) {
     HH_REQUIRE(mc && len_dev, HH_ERR_ARG, "hh_mcl_unpack: NULL argument");
+    hh_scope _scope(mc->ctx);
     HH_REQUIRE(mc->have_pending, HH_ERR_STATE, "hh_mcl_unpack: no pending iterate (call hh_mcl_step first)");
     HH_REQUIRE(0 <= col_lo && col_lo < col_hi && col_hi <= mc->n, HH_ERR_ARG, "hh_mcl_unpack: bad column block");
     HH_REQUIRE(col_hi <= mc->col_lo || col_lo >= mc->col_hi, HH_ERR_ARG, "hh_mcl_unpack: block overlaps the owned columns");
@@ -1106,6 +1200,7 @@ extern "C" int hh_mcl_run(hh_mcl* mc, double inflation, int max_iter, double pru
 
 extern "C" int hh_mcl_fetch_result(hh_mcl* mc, int64_t* indptr, int32_t* indices, float* data) {
     HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_fetch_result: NULL handle");
+    hh_scope _scope(mc->ctx);
     HH_REQUIRE(mc->cur >= 0 && !mc->have_pending, HH_ERR_STATE, "hh_mcl_fetch_result: no committed iterate");
     HH_CUDA(cudaSetDevice(mc->ctx->device));
     return slot_fetch_csc(mc->ctx, mc->it[mc->cur], 0, mc->n, indptr, indices, data);
