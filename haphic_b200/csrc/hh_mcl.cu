@@ -56,6 +56,8 @@ struct hh_colargs {
     float inflation, prune;
     int do_conv;
     int track;                   // product + prune only: keep the dirty-chunk bitmap (sparse columns)
+    const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
+    int* attr_out;               // EPI_PRUNE: strongest row of every produced column
     int flat;                    // expansion inner loop: 1 = flat 32-entry walk, 0 = one segment at a time
     int l2pf;                    // expansion: prefetch the next batch's segments into L2
     float* scratch;
@@ -101,7 +103,8 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
         __syncthreads();
         const int jj = s_col;
         if (jj >= a.ncols) break;
-        const int j = a.col_lo + jj;
+        const int j = a.order ? a.order[jj] : (a.col_lo + jj);
+        const int jloc = j - a.col_lo;          // position inside the owned (dense) column block
         uint64_t dirty = 0ull;
 
         // ------------------------------------------------------------------ source
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
         } else if (SRC == SRC_DENSE) {
             // stream the dense column: 128-bit loads, all issued before the first store (rows >= n of
             // the padded column are zeros written by the pre-expansion)
-            const float4* __restrict__ col4 = reinterpret_cast<const float4*>(a.dense_in + (size_t)jj * (size_t)a.ld);
+            const float4* __restrict__ col4 = reinterpret_cast<const float4*>(a.dense_in + (size_t)jloc * (size_t)a.ld);
             const int ld4 = (int)(a.ld >> 2);
             const int r4_0 = (tile0 >> 2) + lane, r4_end = (tile0 + T) >> 2;
             for (int r4 = r4_0; r4 < r4_end; r4 += 128) {
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
     }
 
         if (EPI == EPI_DUMP) {
-            float* __restrict__ col = a.dense_out + (size_t)jj * (size_t)a.ld;
+            float* __restrict__ col = a.dense_out + (size_t)jloc * (size_t)a.ld;
             for (int r = tile0 + lane; r < tile0 + T; r += 32) {
                 if (r < a.ld) {          // rows in [n, ld) are zero padding (never accumulated)
                     col[r] = acc[r];
@@ -508,6 +511,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 a.out.len[j] = min(total, a.out.cap);
                 if (total > a.out.cap) atomicExch(a.err, 1);
                 nnz_acc += (unsigned long long)total;
+                if (a.attr_out) a.attr_out[j] = (vmax > 0.f) ? kmax : j;   // strongest row: groups columns of one cluster
             }
             if (SRC == SRC_PRODUCT && conv) {
                 // E4: entries of the previous iterate L = B[:, j]  ->  |M - L| - 1e-5|L|  (fp32, 2045)
@@ -546,6 +550,29 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
         if (prod_acc) atomicAdd(a.stats + 1, prod_acc);
     }
     if (threadIdx.x == 0 && nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cluster-sorted processing order: columns whose strongest rows chain to the same root are handed to
+// the CTAs back to back, so the operand columns they gather are still in L2
+// ---------------------------------------------------------------------------------------------
+__global__ void hh_k_order_roots(const int* __restrict__ attr, int n, int col_lo, int ncols, int jumps, int* __restrict__ root,
+                                 int* __restrict__ count) {
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj >= ncols) return;
+    int r = attr[col_lo + jj];
+    for (int t = 0; t < jumps; ++t) r = attr[r];
+    if (r < 0 || r >= n) r = 0;
+    root[jj] = r;
+    atomicAdd(count + r, 1);
+}
+
+__global__ void hh_k_order_scatter(const int* __restrict__ root, int col_lo, int ncols, const int64_t* __restrict__ start,
+                                   int* __restrict__ cursor, int* __restrict__ order) {
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj >= ncols) return;
+    const int r = root[jj];
+    order[start[r] + atomicAdd(cursor + r, 1)] = col_lo + jj;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -634,6 +661,13 @@ struct hh_mcl {
     unsigned long long* d_stats;   // [0] nnz [1] products [2] delta bits [3] err
     int64_t nnz_m0, preexp_products;
     int flat, l2pf;                // expansion inner-loop variant / L2 prefetch (HH_MCL_FLAT, HH_MCL_L2PF)
+    int use_order;                 // cluster-sorted column processing (HH_MCL_ORDER)
+    int* d_attr;                   // [n] strongest row per column of the current iterate
+    int* d_order;                  // [ncols] processing order for the next expansion
+    int* d_root;                   // [ncols]
+    int* d_cnt;                    // [2n] histogram + cursors
+    int64_t* d_start;              // [n+1]
+    bool order_valid;
     cudaEvent_t ev0, ev1;
     float create_ms[2];            // device time of the normalisation / pre-expansion kernels
 };
@@ -893,6 +927,11 @@ extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     hh_dfree(mc->d_scratch);
     hh_dfree(mc->d_counter);
     hh_dfree(mc->d_stats);
+    hh_dfree(mc->d_attr);
+    hh_dfree(mc->d_order);
+    hh_dfree(mc->d_root);
+    hh_dfree(mc->d_cnt);
+    hh_dfree(mc->d_start);
     if (mc->ev0) cudaEventDestroy(mc->ev0);
     if (mc->ev1) cudaEventDestroy(mc->ev1);
     delete mc;
@@ -920,8 +959,16 @@ static void mcl_base_args(hh_mcl* mc, hh_colargs& a) {
     a.stats = mc->d_stats;
     a.delta_bits = reinterpret_cast<int*>(mc->d_stats + 2);
     a.err = reinterpret_cast<int*>(mc->d_stats + 3);
-    a.flat = mc->flat;
-    a.l2pf = mc->l2pf;
+    a.flat = mc->flat > 0 ? 1 : 0;
+    a.l2pf = mc->l2pf > 0 ? 1 : 0;
+}
+
+// mean entries per (column, row block) segment below which the flat walk beats the segment-wise one
+// (measured on B200, 50k contigs: 32 -> segment-wise 180 ms vs flat 267 ms; 12 -> 71 ms vs 61 ms)
+static int choose_flat(const hh_mcl* mc, double nnz_operand) {
+    if (mc->flat >= 0) return mc->flat > 0;
+    const double seg = nnz_operand / (double)mc->n / (double)mc->W;
+    return seg < 16.0 ? 1 : 0;
 }
 
 extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, hh_mcl** out) {
@@ -943,8 +990,9 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
     mc->col_hi = col_hi;
     mc->expansion = expansion;
     mc->cur = -1;
-    mc->flat = env_int("HH_MCL_FLAT", 0);
-    mc->l2pf = env_int("HH_MCL_L2PF", 1);
+    mc->use_order = env_int("HH_MCL_ORDER", 0);   // measured on B200 (50k contigs): no gain, the gathers are latency- not L2-bound
+    mc->flat = env_int("HH_MCL_FLAT", -1);      // -1 = choose per launch from the mean segment length
+    mc->l2pf = env_int("HH_MCL_L2PF", -1);       // -1 = prefetch in segment-wise mode only (long segments)
     const hh_geom g = geom_for(ctx, m->n);
     mc->W = g.W;
     mc->T = g.T;
@@ -960,6 +1008,11 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         if (!g.smem_acc) HH_CHECK(hh_dmalloc(&mc->d_scratch, (size_t)mc->grid_cap * (size_t)g.n_pad));
         HH_CHECK(hh_dmalloc(&mc->d_counter, 1));
         HH_CHECK(hh_dmalloc(&mc->d_stats, 4));
+        HH_CHECK(hh_dmalloc(&mc->d_attr, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_order, (size_t)(col_hi - col_lo)));
+        HH_CHECK(hh_dmalloc(&mc->d_root, (size_t)(col_hi - col_lo)));
+        HH_CHECK(hh_dmalloc(&mc->d_cnt, (size_t)m->n * 2));
+        HH_CHECK(hh_dmalloc(&mc->d_start, (size_t)m->n + 1));
         HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
         // 1) M0 = normalize(link_matrix, 'l1', axis=0)   (2144)
         int cap0 = 0;
@@ -982,6 +1035,8 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         a.A = mc->m0;
         a.B = mc->m0;
         a.dense_out = mc->d_m1;
+        a.flat = choose_flat(mc, (double)mc->nnz_m0);
+        a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
         HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
         HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
         HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
@@ -1048,6 +1103,7 @@ extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
     mc->prune = (float)pruning;   // `matrix >= pruning` compares in fp32
     mc->cur = -1;
     mc->have_pending = false;
+    mc->order_valid = false;
     mc->begun = true;
     return HH_OK;
 }
@@ -1069,6 +1125,7 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
     a.prune = mc->prune;
     const int dst = (mc->cur < 0) ? 0 : (mc->cur ^ 1);
     a.out = mc->it[dst];
+    a.attr_out = mc->d_attr;
     HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
     if (it == 0) {
         a.dense_in = mc->d_m1;
@@ -1078,9 +1135,23 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
         a.A = mc->it[mc->cur];
         a.B = mc->it[mc->cur];
         a.do_conv = 1;
+        // cluster-sorted processing order while the iterate is big enough for operand reuse to matter
+        if (mc->use_order && mc->order_valid && mc->cur_nnz > 8ll * mc->n) {
+            const int ncols = mc->col_hi - mc->col_lo;
+            const bool whole = (ncols == mc->n);     // attr of foreign columns is not exchanged between shards
+            HH_CUDA(cudaMemsetAsync(mc->d_cnt, 0, (size_t)mc->n * 2 * sizeof(int), ctx->stream));
+            HH_LAUNCH(ctx, hh_k_order_roots, (ncols + 255) / 256, 256, 0, mc->d_attr, mc->n, mc->col_lo, ncols, whole ? 3 : 0,
+                      mc->d_root, mc->d_cnt);
+            HH_CHECK(hh_exclusive_scan_i32(ctx, mc->d_cnt, mc->d_start, mc->n));
+            HH_LAUNCH(ctx, hh_k_order_scatter, (ncols + 255) / 256, 256, 0, mc->d_root, mc->col_lo, ncols, mc->d_start,
+                      mc->d_cnt + mc->n, mc->d_order);
+            a.order = mc->d_order;
+        }
         // expected products per column ~ (nnz/n)^2; track dirty chunks when that is well below n
         const double dcol = (double)mc->cur_nnz / (double)mc->n;
         a.track = (dcol * dcol * 4.0 < (double)mc->n) ? 1 : 0;
+        a.flat = choose_flat(mc, (double)mc->cur_nnz);
+        a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
         HH_CHECK((launch_col<SRC_PRODUCT, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
     }
     HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
@@ -1100,6 +1171,7 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
     }
     mc->pending = dst;
     mc->have_pending = true;
+    mc->order_valid = true;       // d_attr now describes the pending iterate (owned columns)
     return HH_OK;
 }
 
