@@ -44,6 +44,8 @@ _SIGNATURES = {
     "hh_ctx_sm_count": (C.c_int, [_P]),
     "hh_ctx_launches": (C.c_int64, [_P]),
     "hh_links_create": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    "hh_links_create_frags": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64,
+                                        C.POINTER(_P)]),
     "hh_links_add": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int]),
     "hh_links_add_async": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
     "hh_links_finish": (C.c_int, [_P, C.POINTER(LinksInfo)]),

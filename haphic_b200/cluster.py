@@ -10,8 +10,7 @@ unchanged.  The per-read-pair link counting, dict_to_matrix and the Markov-clust
 libhaphic_b200.so on the GPU; file parsing, fragment statistics, filters on per-fragment scalars,
 result interpretation and the writers are host Python, as in the reference.
 
-Not supported yet (raise, never silently degrade): contigs split into bins (``--bin_size`` other
-than 0 when a contig is longer than the bin size), ``--correct_nrounds``, ``--ul``, ``--gfa``,
+Not supported yet (raise, never silently degrade): ``--correct_nrounds``, ``--ul``, ``--gfa``,
 ``--remove_allelic_links``, ``--remove_concentrated_links``.
 
 Reference line numbers below refer to scripts/HapHiC_cluster.py (v1.0.7).
@@ -196,9 +195,10 @@ def _context():
     return _CTX
 
 
-def count_links(batches, names, ctg_len, Nx_ctg_set, flank_kb, want_clm=True):
-    """Stream record batches through the GPU link table.  Returns (table, clm_records) where
-    clm_records is the concatenation of the usable records (for the CLM writer) or None."""
+def count_links(batches, names, ctg_len, Nx_ctg_set, flank_kb, want_clm=True, frag_table=None):
+    """Stream record batches through the GPU link table(s).  Returns (table, clm_records) where
+    clm_records is the concatenation of the usable inter-contig records (for the CLM writer) or None.
+    ``frag_table`` (fragment mode) receives every batch as well."""
     from .links import LinkTable, name_rank
     ctx = _context()
     in_nx = np.fromiter((n in Nx_ctg_set for n in names), dtype=np.uint8, count=len(names))
@@ -207,12 +207,59 @@ def count_links(batches, names, ctg_len, Nx_ctg_set, flank_kb, want_clm=True):
     n = len(names)
     for rec in batches:
         table.add(rec)
+        if frag_table is not None:
+            frag_table.add(rec)
         if want_clm:
             ok = (rec[:, 0] != rec[:, 2]) & (rec[:, 0] >= 0) & (rec[:, 2] >= 0) & (rec[:, 0] < n) & (rec[:, 2] < n)
             kept.append(rec[ok])
     table.finish()
+    if frag_table is not None:
+        frag_table.finish()
     clm_rec = (np.concatenate(kept) if kept else np.zeros((0, 4), np.int32)) if want_clm else None
     return table, clm_rec
+
+
+def fragment_layout(fa_dict, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set):
+    """Fragment ids for fragment mode: contig c (FASTA order) owns ids [frag_base[c], frag_base[c+1]); a split
+    contig's bins are '{ctg}_bin{k}' (stat_fragments, 229-248)."""
+    from .links import name_rank
+    frag_names, frag_base = [], [0]
+    for ctg, info in fa_dict.items():
+        if ctg in split_ctg_set:
+            nbins = ceil(info[1] / bin_size)
+            frag_names += ["{}_bin{}".format(ctg, k + 1) for k in range(nbins)]
+        else:
+            frag_names.append(ctg)
+        frag_base.append(len(frag_names))
+    frag_len = np.array([frag_len_dict[f] for f in frag_names], dtype=np.int64)
+    in_nx = np.fromiter((f in Nx_frag_set for f in frag_names), dtype=np.uint8, count=len(frag_names))
+    return frag_names, np.asarray(frag_base, np.int32), frag_len, name_rank(frag_names), in_nx
+
+
+def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type):
+    """Signature and return value of the reference function for the case that some contigs are split into
+    bins (1658-1752): flank links and per-fragment totals are keyed by FRAGMENTS (second device table in
+    fragment mode), full / HT / clm stay contig-level."""
+    logger.info("Parsing input alignments...")
+    if args.remove_allelic_links or args.remove_concentrated_links:
+        raise NotImplementedError("haphic_b200: --remove_allelic_links / --remove_concentrated_links are not supported yet")
+    from .links import LinkTable, link_dicts, name_rank
+    names = list(fa_dict.keys())
+    ctg_len = np.array([fa_dict[n][1] for n in names], dtype=np.int64)
+    frag_names, frag_base, frag_len, frag_rank, frag_nx = fragment_layout(fa_dict, bin_size, frag_len_dict, Nx_frag_set,
+                                                                          split_ctg_set)
+    ftab = LinkTable(_context(), frag_len, frag_rank, frag_nx, args.flank * 1000,
+                     frags=dict(ctg_rank=name_rank(names), frag_base=frag_base, bin_size=int(bin_size)))
+    batches = _as_batches(alignments, names)
+    # contig-level table: Nx membership is irrelevant there (flank links are counted per fragment)
+    table, clm_rec = count_links(batches, names, ctg_len, set(), args.flank, frag_table=ftab)
+    full_link_dict, _unused_flank, HT_link_dict, _unused_tot = link_dicts(table, names)
+    table.close()
+    _unused_full, flank_link_dict, _unused_ht, frag_link_dict = link_dicts(ftab, frag_names)
+    clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type)
+    parse_alignments.last_table = ftab
+    parse_alignments.frag_names = frag_names
+    return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, defaultdict(list), defaultdict(set)
 
 
 def build_clm_dict(clm_rec, names, ctg_len, rank, dist_int_type="int32"):
@@ -850,23 +897,24 @@ def run(args, log_file=None):
     args.whitelist = whitelist
     _, bin_set, bin_size, frag_len_dict, Nx_frag_set, RE_site_dict, split_ctg_set = stat_fragments(
         fa_dict, args.RE, read_depth_dict, whitelist, nchrs=args.nchrs, flank=args.flank, Nx=args.Nx, bin_size=args.bin_size)
-    if split_ctg_set:
-        raise NotImplementedError(
-            "haphic_b200: {} contig(s) are longer than bin_size ({} bp) and would be split into bins "
-            "(parse_alignments, HapHiC_cluster.py:1658-1752); this path is not on the GPU yet -- rerun with --bin_size 0".format(
-                len(split_ctg_set), bin_size))
-
     from . import hicio
     names = list(fa_dict.keys())
     name_index = hicio.NameIndex(names)
+    inter_only = not split_ctg_set          # bins need the intra-contig pairs too (2849-2856)
     if args.aln_format == "bam":
-        alignments = hicio.bam_batches(args.alignments, name_index, inter_only=True, logger=logger)
+        alignments = hicio.bam_batches(args.alignments, name_index, inter_only=inter_only, logger=logger)
     else:
-        alignments = hicio.pairs_batches(args.alignments, args.aln_format, name_index, inter_only=True)
+        alignments = hicio.pairs_batches(args.alignments, args.aln_format, name_index, inter_only=inter_only)
 
-    full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, _coords = parse_alignments_for_ctgs(
-        alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_int_type, dist_int_type)
-    table = parse_alignments_for_ctgs.last_table
+    if split_ctg_set:
+        full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, _coords, _c2f = parse_alignments(
+            alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type)
+        table = parse_alignments.last_table
+        names = parse_alignments.frag_names         # the matrix lives in fragment space from here on
+    else:
+        full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, _coords = parse_alignments_for_ctgs(
+            alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_int_type, dist_int_type)
+        table = parse_alignments_for_ctgs.last_table
 
     output_pickle(HT_link_dict, "HT_link_dict", "HT_links.pkl")
     del HT_link_dict

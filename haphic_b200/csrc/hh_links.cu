@@ -25,11 +25,16 @@ struct __align__(32) hh_slot {
 
 struct hh_links {
     hh_ctx* ctx;
-    int32_t n_ctg;
+    int32_t n_ctg;                   // key space: contigs, or fragments (contigs / bins) in fragment mode
     int64_t flank_bp;
-    int32_t* d_len;
-    int32_t* d_rank;
+    int32_t* d_len;                  // [n_ctg] lengths of the key-space objects
+    int32_t* d_rank;                 // [n_ctg] name rank of the key-space objects
     uint8_t* d_nx;
+    // fragment mode (parse_alignments, HapHiC_cluster.py:1658-1752): records name SOURCE contigs, keys are fragments
+    int32_t n_src;                   // number of source contigs (= n_ctg in contig mode)
+    int32_t* d_src_rank;             // [n_src] name rank of the source contigs
+    int32_t* d_fbase;                // [n_src + 1] first fragment id of every contig (more than one fragment = split into bins)
+    int64_t bin_size;
     unsigned long long* d_ctg;       // [n_ctg] per-fragment flank-link totals
     uint64_t* d_keys;                // [cap]
     hh_slot* d_vals;                 // [cap]
@@ -99,7 +104,8 @@ hh_k_links_insert(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_o
                   const int32_t* __restrict__ ctg_len, const int32_t* __restrict__ name_rank,
                   const uint8_t* __restrict__ in_nx, int64_t flank_bp, uint64_t* __restrict__ keys,
                   hh_slot* __restrict__ vals, uint64_t cap, unsigned long long* __restrict__ ctg_links,
-                  unsigned long long* __restrict__ counters) {
+                  unsigned long long* __restrict__ counters, const int32_t* __restrict__ src_rank,
+                  const int32_t* __restrict__ fbase, int64_t bin_size, int32_t n_src) {
     __shared__ unsigned int s_new, s_used, s_over;
     if (threadIdx.x == 0) {
         s_new = 0;
@@ -116,16 +122,54 @@ hh_k_links_insert(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_o
         bool ok = i < n_rec;
         int4 r = make_int4(-1, 0, -1, 0);
         if (ok) r = hh_ld_stream(rec + i);
-        ok = ok && (r.x != r.z) && ((unsigned)r.x < (unsigned)n_ctg) && ((unsigned)r.z < (unsigned)n_ctg);
         uint64_t key = HH_EMPTY_KEY - 1 - (uint64_t)lane;   // unique per lane: never groups, never a real key
         int ci = 0, cj = 0;
         bool fl = false, ti = false, tj = false;
-        if (ok) {
-            int a = r.x, b = r.z, pa = r.y, pb = r.w;
-            if (name_rank[a] > name_rank[b]) {            // sorted(((ref,pos+1),(mref,mpos+1))), 1629
+        int a = r.x, b = r.z, pa = r.y, pb = r.w;
+        if (fbase == nullptr) {
+            ok = ok && (a != b) && ((unsigned)a < (unsigned)n_ctg) && ((unsigned)b < (unsigned)n_ctg);
+            if (ok && name_rank[a] > name_rank[b]) {      // sorted(((ref,pos+1),(mref,mpos+1))), 1629
                 int t = a; a = b; b = t;
                 t = pa; pa = pb; pb = t;
             }
+        } else {
+            // fragment mode (1696-1720): records name source contigs; a contig with several fragments is split
+            // into bins of bin_size bp.  n_ctg is the number of fragments here; ids are checked against fbase.
+            ok = ok && ((unsigned)a < (unsigned)n_src) && ((unsigned)b < (unsigned)n_src);
+            if (ok) {
+                const bool split_a = fbase[a + 1] - fbase[a] > 1;
+                ok = (a != b) || split_a;                  // intra-contig pairs only matter for split contigs (1699)
+            }
+            if (ok) {
+                // sorted(((ref, pos+1), (mref, mpos+1))): by contig name, then by coordinate (1707)
+                const int ra = src_rank[a], rb = src_rank[b];
+                if (ra > rb || (a == b && pa > pb)) {
+                    int t = a; a = b; b = t;
+                    t = pa; pa = pb; pb = t;
+                }
+                // convert_frags (1662-1670)
+                int fa = fbase[a], fb = fbase[b];
+                const bool sa = fbase[a + 1] - fa > 1, sb = fbase[b + 1] - fb > 1;
+                if (sa) {
+                    const int64_t nb = ((int64_t)pa + 1 + bin_size - 1) / bin_size;
+                    fa += (int)(nb - 1);
+                    pa = (int)((int64_t)pa - (nb - 1) * bin_size);
+                }
+                if (sb) {
+                    const int64_t nb = ((int64_t)pb + 1 + bin_size - 1) / bin_size;
+                    fb += (int)(nb - 1);
+                    pb = (int)((int64_t)pb - (nb - 1) * bin_size);
+                }
+                ok = fa != fb;                             // intra-bin links are not considered (1715)
+                a = fa;
+                b = fb;
+                if (ok && (sa || sb) && name_rank[a] > name_rank[b]) {   // sort by bin name (1719-1720)
+                    int t = a; a = b; b = t;
+                    t = pa; pa = pb; pb = t;
+                }
+            }
+        }
+        if (ok) {
             ci = a;
             cj = b;
             const int64_t coord_i = (int64_t)pa + 1, coord_j = (int64_t)pb + 1;   // 1-based
@@ -415,49 +459,55 @@ static int links_ensure_capacity(hh_links* lk, int64_t incoming) {
     return HH_OK;
 }
 
-extern "C" int hh_links_create(hh_ctx* ctx, int32_t n_ctg, const int64_t* ctg_len, const int32_t* name_rank,
-                               const uint8_t* in_nx, int64_t flank_bp, int64_t capacity_hint, hh_links** out) {
-    HH_REQUIRE(ctx && out && ctg_len && name_rank && in_nx, HH_ERR_ARG, "hh_links_create: NULL argument");
-    HH_REQUIRE(n_ctg > 0, HH_ERR_ARG, "hh_links_create: n_ctg must be positive");
-    HH_REQUIRE(flank_bp >= 0, HH_ERR_ARG, "hh_links_create: flank_bp must be >= 0");
-    hh_scope _scope(ctx);
+static int links_create_common(hh_ctx* ctx, int32_t n_key, const int64_t* key_len, const int32_t* key_rank, const uint8_t* in_nx,
+                               int64_t flank_bp, int64_t capacity_hint, int32_t n_src, const int32_t* src_rank,
+                               const int32_t* frag_base, int64_t bin_size, hh_links** out) {
     *out = nullptr;
-    HH_CUDA(cudaSetDevice(ctx->device));
-    std::vector<int32_t> len32(n_ctg);
-    for (int32_t c = 0; c < n_ctg; ++c) {
-        HH_REQUIRE(ctg_len[c] > 0 && ctg_len[c] <= 0x7fffffffLL, HH_ERR_UNSUPPORTED,
-                   "hh_links_create: contig %d has length %lld; records carry int32 positions (pos_int_type int32, "
-                   "HapHiC_cluster.py:116-147)", c, (long long)ctg_len[c]);
-        HH_REQUIRE(name_rank[c] >= 0 && name_rank[c] < n_ctg, HH_ERR_ARG, "hh_links_create: name_rank[%d] out of range", c);
-        len32[c] = (int32_t)ctg_len[c];
+    std::vector<int32_t> len32(n_key);
+    for (int32_t c = 0; c < n_key; ++c) {
+        HH_REQUIRE(key_len[c] > 0 && key_len[c] <= 0x7fffffffLL, HH_ERR_UNSUPPORTED,
+                   "hh_links_create: object %d has length %lld; records carry int32 positions (pos_int_type int32, "
+                   "HapHiC_cluster.py:116-147)", c, (long long)key_len[c]);
+        HH_REQUIRE(key_rank[c] >= 0 && key_rank[c] < n_key, HH_ERR_ARG, "hh_links_create: name_rank[%d] out of range", c);
+        len32[c] = (int32_t)key_len[c];
     }
     hh_links* lk = new (std::nothrow) hh_links();
     HH_REQUIRE(lk != nullptr, HH_ERR_NOMEM, "hh_links_create: out of host memory");
     memset(lk, 0, sizeof(*lk));
     lk->ctx = ctx;
-    lk->n_ctg = n_ctg;
+    lk->n_ctg = n_key;
+    lk->n_src = frag_base ? n_src : n_key;
+    lk->bin_size = bin_size;
     lk->flank_bp = flank_bp;
     int rc = HH_OK;
     do {
-        if ((rc = hh_dmalloc(&lk->d_len, n_ctg)) != HH_OK) break;
-        if ((rc = hh_dmalloc(&lk->d_rank, n_ctg)) != HH_OK) break;
-        if ((rc = hh_dmalloc(&lk->d_nx, n_ctg)) != HH_OK) break;
-        if ((rc = hh_dmalloc(&lk->d_ctg, n_ctg)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_len, n_key)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_rank, n_key)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_nx, n_key)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_ctg, n_key)) != HH_OK) break;
         if ((rc = hh_dmalloc(&lk->d_counters, 8)) != HH_OK) break;
-        if ((rc = hh_dmalloc(&lk->d_index, n_ctg)) != HH_OK) break;
-        if ((rc = hh_dmalloc(&lk->d_keep, n_ctg)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_index, n_key)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&lk->d_keep, n_key)) != HH_OK) break;
+        if (frag_base) {
+            if ((rc = hh_dmalloc(&lk->d_src_rank, n_src)) != HH_OK) break;
+            if ((rc = hh_dmalloc(&lk->d_fbase, (size_t)n_src + 1)) != HH_OK) break;
+        }
     } while (0);
     if (rc != HH_OK) {
         hh_links_destroy(lk);
         return rc;
     }
     cudaStream_t st = ctx->stream;
-    HH_CUDA(cudaMemcpyAsync(lk->d_len, len32.data(), n_ctg * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    HH_CUDA(cudaMemcpyAsync(lk->d_rank, name_rank, n_ctg * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    HH_CUDA(cudaMemcpyAsync(lk->d_nx, in_nx, n_ctg * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
-    HH_CUDA(cudaMemsetAsync(lk->d_ctg, 0, n_ctg * sizeof(unsigned long long), st));
+    HH_CUDA(cudaMemcpyAsync(lk->d_len, len32.data(), n_key * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    HH_CUDA(cudaMemcpyAsync(lk->d_rank, key_rank, n_key * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    HH_CUDA(cudaMemcpyAsync(lk->d_nx, in_nx, n_key * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
+    HH_CUDA(cudaMemsetAsync(lk->d_ctg, 0, n_key * sizeof(unsigned long long), st));
     HH_CUDA(cudaMemsetAsync(lk->d_counters, 0, 8 * sizeof(unsigned long long), st));
-    HH_CUDA(cudaStreamSynchronize(st));   // len32 goes out of scope
+    if (frag_base) {
+        HH_CUDA(cudaMemcpyAsync(lk->d_src_rank, src_rank, (size_t)n_src * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        HH_CUDA(cudaMemcpyAsync(lk->d_fbase, frag_base, ((size_t)n_src + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    HH_CUDA(cudaStreamSynchronize(st));   // host temporaries go out of scope
     uint64_t cap = 1ull << 16;
     const double want = capacity_hint > 0 ? (double)capacity_hint / 0.5 : 0.0;
     while ((double)cap < want) cap <<= 1;
@@ -476,13 +526,40 @@ extern "C" int hh_links_create(hh_ctx* ctx, int32_t n_ctg, const int64_t* ctg_le
     return HH_OK;
 }
 
+extern "C" int hh_links_create(hh_ctx* ctx, int32_t n_ctg, const int64_t* ctg_len, const int32_t* name_rank,
+                               const uint8_t* in_nx, int64_t flank_bp, int64_t capacity_hint, hh_links** out) {
+    HH_REQUIRE(ctx && out && ctg_len && name_rank && in_nx, HH_ERR_ARG, "hh_links_create: NULL argument");
+    HH_REQUIRE(n_ctg > 0, HH_ERR_ARG, "hh_links_create: n_ctg must be positive");
+    HH_REQUIRE(flank_bp >= 0, HH_ERR_ARG, "hh_links_create: flank_bp must be >= 0");
+    hh_scope _scope(ctx);
+    return links_create_common(ctx, n_ctg, ctg_len, name_rank, in_nx, flank_bp, capacity_hint, n_ctg, nullptr, nullptr, 0, out);
+}
+
+extern "C" int hh_links_create_frags(hh_ctx* ctx, int32_t n_ctg, const int32_t* ctg_rank, const int32_t* frag_base,
+                                     int32_t n_frag, const int64_t* frag_len, const int32_t* frag_rank, const uint8_t* frag_in_nx,
+                                     int64_t bin_size, int64_t flank_bp, int64_t capacity_hint, hh_links** out) {
+    HH_REQUIRE(ctx && out && ctg_rank && frag_base && frag_len && frag_rank && frag_in_nx, HH_ERR_ARG,
+               "hh_links_create_frags: NULL argument");
+    HH_REQUIRE(n_ctg > 0 && n_frag >= n_ctg, HH_ERR_ARG, "hh_links_create_frags: need n_frag >= n_ctg > 0");
+    HH_REQUIRE(flank_bp >= 0 && bin_size > 0, HH_ERR_ARG, "hh_links_create_frags: flank_bp >= 0 and bin_size > 0 required");
+    HH_REQUIRE(frag_base[0] == 0 && frag_base[n_ctg] == n_frag, HH_ERR_ARG, "hh_links_create_frags: frag_base must span [0, n_frag]");
+    for (int32_t c = 0; c < n_ctg; ++c) {
+        HH_REQUIRE(frag_base[c + 1] > frag_base[c], HH_ERR_ARG, "hh_links_create_frags: contig %d has no fragment", c);
+        HH_REQUIRE(ctg_rank[c] >= 0 && ctg_rank[c] < n_ctg, HH_ERR_ARG, "hh_links_create_frags: ctg_rank[%d] out of range", c);
+    }
+    hh_scope _scope(ctx);
+    return links_create_common(ctx, n_frag, frag_len, frag_rank, frag_in_nx, flank_bp, capacity_hint, n_ctg, ctg_rank, frag_base,
+                               bin_size, out);
+}
+
 static int links_launch_insert(hh_links* lk, const int4* d_rec, int64_t n_rec, int64_t stream_offset) {
     hh_ctx* ctx = lk->ctx;
     int64_t blocks = (n_rec + 255) / 256;
     int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
     if (grid < 1) grid = 1;
     HH_LAUNCH(ctx, hh_k_links_insert, grid, 256, 0, d_rec, n_rec, (uint32_t)stream_offset, lk->n_ctg, lk->d_len, lk->d_rank,
-              lk->d_nx, lk->flank_bp, lk->d_keys, lk->d_vals, lk->cap, lk->d_ctg, lk->d_counters);
+              lk->d_nx, lk->flank_bp, lk->d_keys, lk->d_vals, lk->cap, lk->d_ctg, lk->d_counters, lk->d_src_rank, lk->d_fbase,
+              lk->bin_size, lk->n_src);
     return HH_OK;
 }
 
@@ -749,6 +826,8 @@ extern "C" int hh_links_destroy(hh_links* lk) {
         if (lk->ev_consumed[k]) cudaEventDestroy(lk->ev_consumed[k]);
         if (lk->d_stage[k]) cudaFree(lk->d_stage[k]);
     }
+    hh_dfree(lk->d_src_rank);
+    hh_dfree(lk->d_fbase);
     hh_dfree(lk->d_len);
     hh_dfree(lk->d_rank);
     hh_dfree(lk->d_nx);

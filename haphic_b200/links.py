@@ -30,7 +30,10 @@ def name_rank(names) -> np.ndarray:
 class LinkTable:
     """Device-resident link counters of one run (full / flank / HT / per-fragment totals)."""
 
-    def __init__(self, ctx: Context, ctg_len, rank, in_nx, flank_bp: int, capacity_hint: int = 0):
+    def __init__(self, ctx: Context, ctg_len, rank, in_nx, flank_bp: int, capacity_hint: int = 0, frags=None):
+        """``frags`` switches to fragment mode (parse_alignments, 1658-1752): a dict with
+        ``ctg_rank`` [n_src], ``frag_base`` [n_src+1] and ``bin_size``; then ctg_len / rank / in_nx describe
+        the FRAGMENTS (contigs or bins) and every result of this table is in fragment ids."""
         self.ctx = ctx
         self.n_ctg = len(ctg_len)
         self._len = np.ascontiguousarray(ctg_len, dtype=np.int64)
@@ -39,8 +42,15 @@ class LinkTable:
         if not (len(self._rank) == self.n_ctg == len(self._nx)):
             raise ValueError("ctg_len, rank and in_nx must have one entry per contig")
         self._h = C.c_void_p()
-        check(load().hh_links_create(ctx.handle, self.n_ctg, ptr(self._len), ptr(self._rank), ptr(self._nx),
-                                     int(flank_bp), int(capacity_hint), C.byref(self._h)))
+        if frags is None:
+            check(load().hh_links_create(ctx.handle, self.n_ctg, ptr(self._len), ptr(self._rank), ptr(self._nx),
+                                         int(flank_bp), int(capacity_hint), C.byref(self._h)))
+        else:
+            self._src_rank = np.ascontiguousarray(frags["ctg_rank"], dtype=np.int32)
+            self._fbase = np.ascontiguousarray(frags["frag_base"], dtype=np.int32)
+            check(load().hh_links_create_frags(ctx.handle, len(self._src_rank), ptr(self._src_rank), ptr(self._fbase),
+                                               self.n_ctg, ptr(self._len), ptr(self._rank), ptr(self._nx),
+                                               int(frags["bin_size"]), int(flank_bp), int(capacity_hint), C.byref(self._h)))
         self._stream_pos = 0
         self.info = None
 

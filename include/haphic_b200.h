@@ -77,6 +77,19 @@ int64_t hh_ctx_launches(hh_ctx* ctx);
  */
 int hh_links_create(hh_ctx* ctx, int32_t n_ctg, const int64_t* ctg_len, const int32_t* name_rank,
                     const uint8_t* in_nx, int64_t flank_bp, int64_t capacity_hint, hh_links** out);
+/* Fragment mode -- parse_alignments, HapHiC_cluster.py:1658-1752 (some contig longer than bin_size): records
+ * still name CONTIGS, the table is keyed by FRAGMENT pairs.  Contig c owns the fragment ids
+ * [frag_base[c], frag_base[c+1]); more than one fragment means the contig is split into bins of `bin_size` bp
+ * (bin = ceil(coord / bin_size), convert_frags 1662-1670).  Pairs inside one unsplit contig or one bin are
+ * dropped (1699, 1715); ends are ordered by contig name then coordinate (1707) and, when a bin is involved,
+ * re-ordered by fragment name rank (1719-1720).  Counts the flank links between fragments and the
+ * per-fragment totals (1723-1726); its full/HT counters refer to fragment pairs and have no counterpart in the
+ * reference -- full_link_dict / HT_link_dict / clm of that run come from a second, contig-level table fed
+ * with the same records (hh_links_create with in_nx = 0). */
+int hh_links_create_frags(hh_ctx* ctx, int32_t n_ctg, const int32_t* ctg_rank, const int32_t* frag_base,
+                          int32_t n_frag, const int64_t* frag_len, const int32_t* frag_rank,
+                          const uint8_t* frag_in_nx, int64_t bin_size, int64_t flank_bp, int64_t capacity_hint,
+                          hh_links** out);
 /* stream `n_rec` more records; `stream_offset` is the index of rec[0] in the whole read stream
  * (first-seen order of dict keys is reproduced from it; use the running total on one GPU, the
  * shard offset when the stream is split over ranks).  May be called repeatedly. */

@@ -170,6 +170,70 @@ def link_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, flank, Nx, seed, nor
     return matrix
 
 
+def link_case_bins(ref, tag, nchr, n_contigs, mean_len, n_pairs, flank, Nx, bin_kb, seed):
+    """Golden for parse_alignments (a4): contigs longer than bin_size are split into bins."""
+    from haphic_b200 import synth
+    asm = synth.make_assembly(nchr, n_contigs, mean_len, seed=seed)
+    pairs = synth.make_pairs(asm, n_pairs, seed=seed + 1).numpy()
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            fasta = os.path.join(tmp, "asm.fa")
+            pfile = os.path.join(tmp, "aln.pairs")
+            synth.write_fasta(asm, fasta, seed=seed + 3)
+            synth.write_pairs(asm, pairs, pfile)
+            args = make_args(fasta=fasta, alignments=pfile, nchrs=nchr, flank=flank, Nx=Nx, bin_size=bin_kb, aln_format="pairs")
+            fa_dict = ref.parse_fasta(fasta, RE=args.RE)
+            pos_t, dist_t = ref.determine_int_type(fa_dict)
+            _, bin_set, bin_size, frag_len_dict, Nx_frag_set, RE_site_dict, split_ctg_set = ref.stat_fragments(
+                fa_dict, args.RE, dict(), set(), nchrs=nchr, flank=flank, Nx=Nx, bin_size=bin_kb)
+            assert split_ctg_set
+            alignments = ref.pairs_generator(pfile, "pairs")
+            full, flank_d, HT, clm, frag_links, _coord, _c2f = ref.parse_alignments(
+                alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_t, dist_t)
+            # fragment ids: FASTA order, bins of a split contig in bin order
+            frag_names = []
+            frag_base = [0]
+            import math
+            for ctg, info in fa_dict.items():
+                if ctg in split_ctg_set:
+                    frag_names += ["{}_bin{}".format(ctg, k + 1) for k in range(math.ceil(info[1] / bin_size))]
+                else:
+                    frag_names.append(ctg)
+                frag_base.append(len(frag_names))
+            fid = {n: i for i, n in enumerate(frag_names)}
+            cid = {n: i for i, n in enumerate(asm.names)}
+            out["names"] = np.array(asm.names)
+            out["lengths"] = asm.lengths
+            out["pairs"] = pairs.astype(np.int32)
+            out["flank_kb"] = np.int64(flank)
+            out["Nx"] = np.int64(Nx)
+            out["bin_kb"] = np.int64(bin_kb)
+            out["bin_size"] = np.int64(bin_size)
+            out["frag_names"] = np.array(frag_names)
+            out["frag_base"] = np.array(frag_base, dtype=np.int32)
+            out["frag_len"] = np.array([frag_len_dict[f] for f in frag_names], dtype=np.int64)
+            out["frag_in_nx"] = np.array([f in Nx_frag_set for f in frag_names], dtype=np.uint8)
+            out["frag_RE"] = np.array([RE_site_dict[f] for f in frag_names], dtype=np.int64)
+            out["full_keys"], out["full_vals"] = dict_pairs_to_arrays(full, cid, np.int64)
+            out["flank_keys"], out["flank_vals"] = dict_pairs_to_arrays(flank_d, fid, np.int64)
+            hk = [(cid[a[:-2]], int(a.endswith("_T")), cid[b[:-2]], int(b.endswith("_T"))) for (a, b) in HT.keys()]
+            out["HT_keys"] = np.array(hk, dtype=np.int32).reshape(-1, 4)
+            out["HT_vals"] = np.array(list(HT.values()), dtype=np.int64)
+            out["frag_link_ids"] = np.array([fid[k] for k in frag_links.keys()], dtype=np.int32)
+            out["frag_link_vals"] = np.array(list(frag_links.values()), dtype=np.int64)
+            ref.output_clm(clm)
+            with open("paired_links.clm") as f:
+                out["clm_text"] = np.array(f.read())
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "links_{}.npz".format(tag)), **out)
+    print("links_{}: n_ctg={} n_frag={} P={} nnz_full={} nnz_flank={}".format(
+        tag, asm.n, len(frag_names), n_pairs, len(out["full_vals"]), len(out["flank_vals"])))
+
+
 def mcl_case(ref, tag, link_matrix, inflations, pruning=1e-4, expansion=2, max_iter=200, keep_iters=4):
     """Golden for MCL (a11-a15): first normalisation, pre-expansion, per-iteration matrices, clusters."""
     from sklearn.preprocessing import normalize
@@ -311,6 +375,9 @@ def main():
     run_case(ref, "c1", nchr=4, n_contigs=200, mean_len=40000, n_pairs=150000, seed=303, Nx=100, bin_size=0)
     run_case(ref, "c1_nx80", nchr=4, n_contigs=200, mean_len=40000, n_pairs=150000, seed=303, Nx=80, bin_size=0,
              min_inflation=1.2, max_inflation=2.0, inflation_step=0.2)
+    link_case_bins(ref, "bins", nchr=3, n_contigs=45, mean_len=300000, n_pairs=60000, flank=40, Nx=90, bin_kb=100, seed=404)
+    run_case(ref, "bins", nchr=3, n_contigs=60, mean_len=350000, n_pairs=120000, seed=505, Nx=100, bin_size=120, flank=60,
+             min_inflation=1.4, max_inflation=2.2, inflation_step=0.4)
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "sklearn": sklearn.__version__,
             "python": sys.version.split()[0], "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED"),
             "reference": "zengxiaofei/HapHiC scripts/HapHiC_cluster.py (v1.0.7, commit 1f29080), imported unmodified",

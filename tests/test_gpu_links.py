@@ -199,3 +199,39 @@ def test_matrix_from_links_matches_reference_golden(ctx, tag):
         assert np.array_equal(got.data, ref.data)
     mat.close()
     tab.close()
+
+
+def test_fragment_mode_matches_reference_golden(ctx):
+    """parse_alignments (contigs split into bins): flank links and per-fragment totals are keyed by fragments
+    (second table in fragment mode); full / HT stay contig-level."""
+    from haphic_b200.links import LinkTable, name_rank
+    g = load_golden("links_bins.npz")
+    names = g["names"].tolist()
+    frag_names = g["frag_names"].tolist()
+    flank_bp = int(g["flank_kb"]) * 1000
+    pairs = g["pairs"]
+    ftab = LinkTable(ctx, g["frag_len"], name_rank(frag_names), g["frag_in_nx"], flank_bp,
+                     frags=dict(ctg_rank=name_rank(names), frag_base=g["frag_base"], bin_size=int(g["bin_size"])))
+    ctab = LinkTable(ctx, g["lengths"], name_rank(names), np.zeros(len(names), np.uint8), flank_bp)
+    for lo in range(0, len(pairs), 17000):
+        ftab.add(pairs[lo:lo + 17000])
+        ctab.add(pairs[lo:lo + 17000])
+    ftab.finish()
+    ctab.finish()
+    f = ftab.fetch()
+    sel = np.nonzero(f["flank"] > 0)[0]
+    sel = sel[np.argsort(f["first_flank"][sel], kind="stable")]
+    assert np.array_equal(np.stack([f["key_i"][sel], f["key_j"][sel]], 1), g["flank_keys"])
+    assert np.array_equal(f["flank"][sel].astype(np.int64), g["flank_vals"])
+    tot = ftab.fetch_ctg()
+    want = np.zeros(len(frag_names), np.int64)
+    want[g["frag_link_ids"]] = g["frag_link_vals"]
+    assert np.array_equal(tot, want)
+    c = ctab.fetch()
+    assert np.array_equal(np.stack([c["key_i"], c["key_j"]], 1), g["full_keys"])
+    assert np.array_equal(c["full"].astype(np.int64), g["full_vals"])
+    assert int(c["flank"].sum()) == 0
+    got_ht = ht_dict(c["key_i"], c["key_j"], c["ht"])
+    assert got_ht == {tuple(k): int(v) for k, v in zip(g["HT_keys"].tolist(), g["HT_vals"].tolist())}
+    ftab.close()
+    ctab.close()

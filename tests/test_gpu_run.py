@@ -49,7 +49,7 @@ def run_case(tmp_path, g, bam):
     return r
 
 
-@pytest.mark.parametrize("tag,bam", [("c1", False), ("c1_nx80", False), ("c1_nx80", True)])
+@pytest.mark.parametrize("tag,bam", [("c1", False), ("c1_nx80", False), ("c1_nx80", True), ("bins", False), ("bins", True)])
 def test_cluster_run_matches_reference_files(tmp_path, tag, bam):
     g = load_golden("run_{}.npz".format(tag))
     run_case(tmp_path, g, bam)
