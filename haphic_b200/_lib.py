@@ -55,7 +55,8 @@ _SIGNATURES = {
     "hh_links_merge": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64]),
     "hh_links_destroy": (C.c_int, [_P]),
     "hh_links_linked_index": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32)]),
-    "hh_matrix_from_links": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
+    "hh_matrix_from_links": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, C.c_int, C.POINTER(_P)]),
+    "hh_matrix_rank_sums": (C.c_int, [_P, C.c_int, _P]),
     "hh_matrix_from_csc": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.POINTER(_P)]),
     "hh_matrix_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "hh_matrix_fetch_csc": (C.c_int, [_P, _P, _P, _P]),

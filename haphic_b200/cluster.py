@@ -404,10 +404,29 @@ def _cut_index(sorted_pairs, limit, inclusive):
     return len(sorted_pairs)
 
 
+def device_matrix(table, names, frag_set, normalize_by_nlinks=False, add_self_loops=True):
+    """dict_to_matrix (310-373) on the device table: (LinkMatrix, frag_index_dict).  Linked fragments get their
+    first-seen index on the GPU; kept-but-unlinked ones follow in the reference's set-iteration order (355-359)."""
+    keep = np.fromiter((n in frag_set for n in names), dtype=np.uint8, count=len(names))
+    index, n_linked = table.linked_index(keep)
+    order = np.argsort(np.where(index >= 0, index, np.iinfo(np.int32).max), kind="stable")[:n_linked]
+    frags_in_dict = set()
+    for c in order.tolist():                    # same insertion order as 332-333
+        frags_in_dict.add(names[c])
+    ids = {n: i for i, n in enumerate(names)}
+    tail = [ids[f] for f in frag_set - frags_in_dict]
+    matrix = table.to_matrix(keep, tail, normalize_by_nlinks=normalize_by_nlinks, add_self_loops=add_self_loops)
+    frag_index = {names[c]: int(index[c]) for c in order.tolist()}
+    for k, c in enumerate(tail):
+        frag_index[names[c]] = n_linked + k
+    return matrix, frag_index
+
+
 def filter_fragments(Nx_frag_set, RE_site_dict, RE_site_cutoff, frag_link_dict, density_lower, density_upper,
                      topN, rank_sum_upper, rank_sum_hard_cutoff, flank_link_dict, read_depth_dict, read_depth_upper,
-                     whitelist):
-    """Same decisions and log lines as the reference's filter_fragments (741-940)."""
+                     whitelist, device_table=None, device_names=None, normalized=False):
+    """Same decisions and log lines as the reference's filter_fragments (741-940).  With ``device_table`` the
+    O(n^2 log n) rank-sum part (864-892) runs on the GPU (hh_matrix_rank_sums); otherwise on the host."""
     logger.info("Filtering fragments...")
     if read_depth_dict:
         raise NotImplementedError("haphic_b200: read-depth filtering (--gfa) is not supported")
@@ -458,21 +477,29 @@ def filter_fragments(Nx_frag_set, RE_site_dict, RE_site_cutoff, frag_link_dict, 
     density = density[lower:upper]
 
     # rank-sum of the topN nearest fragments (864-927)
-    matrix, frag_index = dict_to_matrix(flank_link_dict, filtered)
-    n = matrix.shape[0]
-    index_frag = {i: f for f, i in frag_index.items()}
-    # descending stable sort of every row: ties keep index order, exactly list.sort(reverse=True)
-    order = np.argsort(-matrix, axis=1, kind="stable")
-    rank_of = np.empty((n, n), dtype=np.int32)
-    rows = np.arange(n)[:, None]
-    rank_of[rows, order] = np.arange(n, dtype=np.int32)[None, :]
+    if device_table is not None:
+        dmat, frag_index = device_matrix(device_table, device_names, filtered, normalize_by_nlinks=normalized,
+                                         add_self_loops=False)
+        device_rs = dmat.rank_sums(topN)
+        dmat.close()
+    else:
+        matrix, frag_index = dict_to_matrix(flank_link_dict, filtered)
+        n = matrix.shape[0]
+        # descending stable sort of every row: ties keep index order, exactly list.sort(reverse=True)
+        order = np.argsort(-matrix, axis=1, kind="stable")
+        rank_of = np.empty((n, n), dtype=np.int32)
+        rows = np.arange(n)[:, None]
+        rank_of[rows, order] = np.arange(n, dtype=np.int32)[None, :]
     rank_sums = []
     hard = 0
     for frag, _ in density:
-        top = order[frag_index[frag], :topN].tolist()
-        rs = 0
-        for a, b in combinations(top, 2):
-            rs += min(int(rank_of[a, b]), int(rank_of[b, a]))
+        if device_table is not None:
+            rs = int(device_rs[frag_index[frag]])
+        else:
+            top = order[frag_index[frag], :topN].tolist()
+            rs = 0
+            for a, b in combinations(top, 2):
+                rs += min(int(rank_of[a, b]), int(rank_of[b, a]))
         if rank_sum_hard_cutoff and rs > rank_sum_hard_cutoff:
             hard += 1
             logger.debug("[rank sum filtering] Fragment {} is removed by hard filtering, rank sum={}".format(frag, rs))
@@ -929,23 +956,13 @@ def run(args, log_file=None):
     filtered_frags = filter_fragments(
         Nx_frag_set, RE_site_dict, args.RE_site_cutoff, frag_link_dict, args.density_lower, args.density_upper,
         args.topN, args.rank_sum_upper, args.rank_sum_hard_cutoff, flank_link_dict, read_depth_dict,
-        args.read_depth_upper, whitelist)
+        args.read_depth_upper, whitelist, device_table=table, device_names=names, normalized=args.normalize_by_nlinks)
     output_pickle(full_link_dict, "full_link_dict", "full_links.pkl")
 
     # dict_to_matrix on the device: first-seen indices from the table, unlinked fragments appended in
     # the reference's set-iteration order (355-359)
-    keep = np.fromiter((n in filtered_frags for n in names), dtype=np.uint8, count=len(names))
-    index, n_linked = table.linked_index(keep)
-    order = np.argsort(np.where(index >= 0, index, np.iinfo(np.int32).max), kind="stable")[:n_linked]
-    frags_in_dict = set()
-    for c in order.tolist():                    # same insertion order as 332-333
-        frags_in_dict.add(names[c])
-    ids = {n: i for i, n in enumerate(names)}
-    tail = [ids[f] for f in filtered_frags - frags_in_dict]
-    link_matrix = table.to_matrix(keep, tail, normalize_by_nlinks=args.normalize_by_nlinks)
-    frag_index_dict = {names[c]: int(index[c]) for c in order.tolist()}
-    for k, c in enumerate(tail):
-        frag_index_dict[names[c]] = n_linked + k
+    link_matrix, frag_index_dict = device_matrix(table, names, filtered_frags, normalize_by_nlinks=args.normalize_by_nlinks,
+                                                 add_self_loops=True)
     table.close()
     matrix_time = time.time()
     logger.info("Hi-C linking matrix was constructed in {}s".format(matrix_time - start_time))

@@ -96,7 +96,7 @@ static int matrix_alloc(hh_ctx* ctx, int32_t n, int64_t nnz, hh_matrix** out) {
 }
 
 extern "C" int hh_matrix_from_links(hh_links* lk, const uint8_t* keep, const int32_t* tail, int32_t n_tail,
-                                    int normalize_by_nlinks, hh_matrix** out) {
+                                    int normalize_by_nlinks, int add_self_loops, hh_matrix** out) {
     HH_REQUIRE(lk && keep && out, HH_ERR_ARG, "hh_matrix_from_links: NULL argument");
     hh_scope _scope(hh_links_ctx(lk));
     HH_REQUIRE(n_tail >= 0 && (tail || n_tail == 0), HH_ERR_ARG, "hh_matrix_from_links: bad tail");
@@ -127,7 +127,7 @@ extern "C" int hh_matrix_from_links(hh_links* lk, const uint8_t* keep, const int
         HH_LAUNCH(ctx, hh_k_check_index, (n_ctg + 255) / 256, 256, 0, d_index, d_keep, n_ctg, n, d_err);
         HH_CHECK(hh_dmalloc(&d_cnt, (size_t)n));
         HH_CHECK(hh_dmalloc(&d_cursor, (size_t)n));
-        HH_LAUNCH(ctx, hh_k_fill_i32, (n + 255) / 256, 256, 0, d_cnt, 1, n);     // the self loop
+        HH_LAUNCH(ctx, hh_k_fill_i32, (n + 255) / 256, 256, 0, d_cnt, add_self_loops ? 1 : 0, n);     // the self loop
         HH_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)n * sizeof(int), ctx->stream));
         int64_t nnz_c = 0;
         const uint32_t* compact = hh_links_compact(lk, &nnz_c);
@@ -150,7 +150,7 @@ extern "C" int hh_matrix_from_links(hh_links* lk, const uint8_t* keep, const int
             if (nnz_c)
                 HH_LAUNCH(ctx, hh_k_mat_scatter, gridc, 256, 0, compact, nnz_c, d_index, hh_links_ctg_totals(lk), normalize_by_nlinks,
                           m->d_colptr, d_cursor, m->d_row, m->d_val);
-            HH_LAUNCH(ctx, hh_k_mat_diag, (n + 255) / 256, 256, 0, n, m->d_colptr, d_cursor, m->d_row, m->d_val);
+            if (add_self_loops) HH_LAUNCH(ctx, hh_k_mat_diag, (n + 255) / 256, 256, 0, n, m->d_colptr, d_cursor, m->d_row, m->d_val);
             HH_CHECK(hh_dmalloc(&m->d_index, (size_t)n_ctg));
             m->n_index = n_ctg;
             HH_CUDA(cudaMemcpyAsync(m->d_index, d_index, (size_t)n_ctg * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));

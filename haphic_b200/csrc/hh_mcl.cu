@@ -576,6 +576,133 @@ __global__ void hh_k_order_scatter(const int* __restrict__ root, int col_lo, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// rank-sum statistic of filter_fragments (HapHiC_cluster.py:864-892) on the sorted slotted matrix
+// (symmetric, so row a == column a).  Order of a row: links descending, ties by matrix index.
+// ---------------------------------------------------------------------------------------------
+#define HH_TOPN_MAX 32
+
+// warp per fragment: the first topN columns of its sorted row
+__global__ void hh_k_topn(const hh_slotmat m, int topN, int* __restrict__ top) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < m.n; a += warps) {
+        const int L = m.len[a];
+        const int* idx = m.idx + (size_t)a * (size_t)m.cap;
+        const float* val = m.val + (size_t)a * (size_t)m.cap;
+        float last_v = INFINITY;
+        int last_i = -1;
+        int zero_c = -1, zero_p = 0;        // cursor over the zero-valued columns (ascending index)
+        for (int t = 0; t < topN; ++t) {
+            // best stored entry strictly after (last_v, last_i) in (value desc, index asc) order
+            float bv = -1.f;
+            int bi = 0x7fffffff;
+            for (int p = lane; p < L; p += 32) {
+                const float v = val[p];
+                const int i = idx[p];
+                if (v <= 0.f) continue;
+                const bool after = (v < last_v) || (v == last_v && i > last_i);
+                if (after && (v > bv || (v == bv && i < bi))) {
+                    bv = v;
+                    bi = i;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(HH_FULL_MASK, bv, o);
+                const int oi = __shfl_xor_sync(HH_FULL_MASK, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) {
+                    bv = ov;
+                    bi = oi;
+                }
+            }
+            int pick;
+            if (bv > 0.f) {
+                pick = bi;
+                last_v = bv;
+                last_i = bi;
+            } else {
+                // no positive entry left: zero-valued columns in ascending index (the fragment itself included)
+                last_v = 0.f;
+                int c = zero_c + 1;
+                if (lane == 0) {
+                    for (;;) {
+                        if (c >= m.n) break;
+                        while (zero_p < L && idx[zero_p] < c) zero_p++;
+                        if (zero_p < L && idx[zero_p] == c && val[zero_p] > 0.f) {
+                            c++;            // a positive entry: not a zero column
+                            continue;
+                        }
+                        break;
+                    }
+                }
+                c = __shfl_sync(HH_FULL_MASK, c, 0);
+                zero_p = __shfl_sync(HH_FULL_MASK, zero_p, 0);
+                zero_c = c;
+                pick = (c < m.n) ? c : -1;
+            }
+            if (lane == 0) top[(size_t)a * topN + t] = pick;
+        }
+    }
+}
+
+// position of column b in the sorted row of fragment a
+__device__ __forceinline__ int hh_rank_of(const hh_slotmat& m, int a, int b) {
+    const int L = m.len[a];
+    const int* idx = m.idx + (size_t)a * (size_t)m.cap;
+    const float* val = m.val + (size_t)a * (size_t)m.cap;
+    int lo = 0, hi = L;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (idx[mid] < b) lo = mid + 1;
+        else hi = mid;
+    }
+    const bool found = lo < L && idx[lo] == b && val[lo] > 0.f;
+    int npos = 0, before = 0;           // positive entries in the row / positive entries left of b
+    if (!found) {
+        for (int p = 0; p < L; ++p) {
+            const bool pos = val[p] > 0.f;
+            npos += pos;
+            before += pos && idx[p] < b;
+        }
+        return npos + (b - before);     // all positive entries first, then the zero columns by index
+    }
+    const float v = val[lo];
+    int r = 0;
+    for (int p = 0; p < L; ++p) {
+        const float x = val[p];
+        r += (x > v) || (x == v && idx[p] < b);
+    }
+    return r;
+}
+
+// warp per fragment x: sum over the pairs of its top list of min(rank_a(b), rank_b(a))
+__global__ void hh_k_rank_sum(const hh_slotmat m, int topN, const int* __restrict__ top, long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int npairs = topN * (topN - 1) / 2;
+    for (int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; x < m.n; x += warps) {
+        const int* tx = top + (size_t)x * topN;
+        long long s = 0;
+        for (int p = lane; p < npairs; p += 32) {
+            // unrank pair p -> (u < v) in combinations order
+            int u = 0, rem = p;
+            while (rem >= topN - 1 - u) {
+                rem -= topN - 1 - u;
+                u++;
+            }
+            const int v = u + 1 + rem;
+            const int a = tx[u], b = tx[v];
+            if (a < 0 || b < 0) continue;
+            const int r1 = hh_rank_of(m, a, b), r2 = hh_rank_of(m, b, a);
+            s += (r1 < r2) ? r1 : r2;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(HH_FULL_MASK, s, o);
+        if (lane == 0) out[x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // pack / unpack of column blocks (canonical CSC export, multi-GPU exchange)
 // ---------------------------------------------------------------------------------------------
 __global__ void hh_k_pack(const hh_slotmat m, int col_lo, int ncols, const int64_t* __restrict__ off, int* __restrict__ len_out,
@@ -911,6 +1038,51 @@ extern "C" int hh_matrix_fetch_csc(hh_matrix* m, int64_t* indptr, int32_t* indic
     hh_dfree(d_scratch);
     hh_dfree(d_counter);
     hh_dfree(d_stats);
+    slot_free(s);
+    return rc;
+}
+
+extern "C" int hh_matrix_rank_sums(hh_matrix* m, int topN, int64_t* rank_sum) {
+    HH_REQUIRE(m && rank_sum, HH_ERR_ARG, "hh_matrix_rank_sums: NULL argument");
+    hh_scope _scope(m->ctx);
+    HH_REQUIRE(topN >= 2 && topN <= HH_TOPN_MAX, HH_ERR_UNSUPPORTED, "hh_matrix_rank_sums: topN must be in [2, %d]", HH_TOPN_MAX);
+    HH_REQUIRE(topN <= m->n, HH_ERR_ARG, "hh_matrix_rank_sums: topN exceeds the number of fragments");
+    hh_ctx* ctx = m->ctx;
+    const hh_geom g = geom_for(ctx, m->n);
+    int grid_cap = 0;
+    HH_CHECK(grid_cap_for(ctx, g, &grid_cap));
+    int cap = 0;
+    HH_CHECK(max_col_len(ctx, m, &cap));
+    hh_slotmat s;
+    HH_CHECK(slot_alloc(s, m->n, cap, g.W));
+    float* d_scratch = nullptr;
+    int* d_counter = nullptr;
+    unsigned long long* d_stats = nullptr;
+    int* d_top = nullptr;
+    long long* d_out = nullptr;
+    int rc = [&]() -> int {
+        if (!g.smem_acc) HH_CHECK(hh_dmalloc(&d_scratch, (size_t)grid_cap * (size_t)g.n_pad));
+        HH_CHECK(hh_dmalloc(&d_counter, 1));
+        HH_CHECK(hh_dmalloc(&d_stats, 4));
+        HH_CHECK(hh_dmalloc(&d_top, (size_t)m->n * topN));
+        HH_CHECK(hh_dmalloc(&d_out, (size_t)m->n));
+        HH_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        HH_CHECK(slot_from_csc(ctx, g, d_scratch, grid_cap, d_counter, d_stats, m, 1, s));     // rows sorted, raw values
+        int grid = (m->n + 7) / 8;
+        if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+        HH_LAUNCH(ctx, hh_k_topn, grid, 256, 0, s, topN, d_top);
+        HH_LAUNCH(ctx, hh_k_rank_sum, grid, 256, 0, s, topN, d_top, d_out);
+        HH_CUDA(cudaMemcpyAsync(rank_sum, d_out, (size_t)m->n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long st[4];
+        HH_CHECK(read_stats(ctx, d_stats, st));
+        HH_REQUIRE((int)st[3] == 0, HH_ERR_CAPACITY, "hh_matrix_rank_sums: column slot overflow");
+        return HH_OK;
+    }();
+    hh_dfree(d_scratch);
+    hh_dfree(d_counter);
+    hh_dfree(d_stats);
+    hh_dfree(d_top);
+    hh_dfree(d_out);
     slot_free(s);
     return rc;
 }

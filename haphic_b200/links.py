@@ -117,14 +117,14 @@ class LinkTable:
         check(load().hh_links_linked_index(self._h, ptr(keep), ptr(index), C.byref(n_linked)))
         return index, int(n_linked.value)
 
-    def to_matrix(self, keep, tail=None, normalize_by_nlinks: bool = False) -> "LinkMatrix":
+    def to_matrix(self, keep, tail=None, normalize_by_nlinks: bool = False, add_self_loops: bool = True) -> "LinkMatrix":
         if self.info is None:
             self.finish()
         keep = np.ascontiguousarray(keep, dtype=np.uint8)
         tail = np.ascontiguousarray(tail if tail is not None else [], dtype=np.int32)
         h = C.c_void_p()
         check(load().hh_matrix_from_links(self._h, ptr(keep), ptr(tail) if len(tail) else None, len(tail),
-                                          int(bool(normalize_by_nlinks)), C.byref(h)))
+                                          int(bool(normalize_by_nlinks)), int(bool(add_self_loops)), C.byref(h)))
         return LinkMatrix(self.ctx, h)
 
     # -- multi-GPU -------------------------------------------------------------------------
@@ -180,6 +180,12 @@ class LinkMatrix:
         h = C.c_void_p()
         check(load().hh_matrix_from_csc(ctx.handle, m.shape[0], ptr(indptr), ptr(indices), ptr(data), C.byref(h)))
         return cls(ctx, h)
+
+    def rank_sums(self, topN: int = 10) -> np.ndarray:
+        """rank-sum statistic of filter_fragments (864-892) per matrix index (matrix built without self loops)."""
+        out = np.empty(self.n, np.int64)
+        check(load().hh_matrix_rank_sums(self._h, int(topN), ptr(out)))
+        return out
 
     def to_scipy(self):
         """Canonical (row-sorted, duplicates summed) CSC on the host."""

@@ -131,13 +131,18 @@ int hh_links_destroy(hh_links* lk);
  * (355-359), which only the host can reproduce:
  *   hh_links_linked_index: first-seen index of every fragment that occurs in flank_link_dict
  *     restricted to `keep` (327-349); index[c] = -1 otherwise; *n_linked = len(frags_in_dict).
- *   hh_matrix_from_links: builds the symmetric fp32 matrix with self loops = 1 (351-364);
+ *   hh_matrix_from_links: builds the symmetric fp32 matrix, with self loops = 1 when add_self_loops (351-364);
  *     `tail[n_tail]` lists the kept-but-unlinked contig ids in the order they get the following
  *     indices.  normalize_by_nlinks != 0 applies links / sqrt(tot_i * tot_j) first (718-724).
  */
 int hh_links_linked_index(hh_links* lk, const uint8_t* keep, int32_t* index, int32_t* n_linked);
 int hh_matrix_from_links(hh_links* lk, const uint8_t* keep, const int32_t* tail, int32_t n_tail,
-                         int normalize_by_nlinks, hh_matrix** out);
+                         int normalize_by_nlinks, int add_self_loops, hh_matrix** out);
+/* rank-sum statistic of filter_fragments, HapHiC_cluster.py:864-892, on a matrix WITHOUT self loops: for every
+ * fragment, sort its row by links descending (ties by matrix index, a stable list.sort(reverse=True)), take
+ * the first topN fragments and sum min(rank_a(b), rank_b(a)) over their pairs.  rank_sum[n] (host) is
+ * indexed by matrix index.  topN <= 32. */
+int hh_matrix_rank_sums(hh_matrix* m, int topN, int64_t* rank_sum);
 /* the same matrix from a host CSC (symmetric, self loops included) -- the entry point when host
  * code edited the link dict (allele-aware removal, UL boosts, phasing weights: 2911-2928) */
 int hh_matrix_from_csc(hh_ctx* ctx, int32_t n, const int64_t* indptr, const int32_t* indices,

@@ -192,3 +192,27 @@ def test_mcl_rejects_unsupported(ctx):
     with pytest.raises(HHError):
         Mcl(mat, expansion=3)
     mat.close()
+
+
+@pytest.mark.parametrize("n,density,topN", [(400, 0.05, 10), (300, 0.004, 10), (64, 0.5, 5)])
+def test_rank_sums_match_host(ctx, n, density, topN):
+    """filter_fragments' rank-sum statistic (864-892): GPU == the dense host computation, including ties
+    (integer link counts), fragments with fewer than topN linked neighbours and empty rows."""
+    from itertools import combinations
+    from haphic_b200.links import LinkMatrix
+    rng = np.random.default_rng(n)
+    a = np.triu((rng.random((n, n)) < density) * rng.integers(1, 6, size=(n, n)), 1).astype(np.float32)
+    a = a + a.T
+    a[7, :] = 0
+    a[:, 7] = 0                      # an unlinked fragment
+    mat = LinkMatrix.from_csc(ctx, sp.csc_matrix(a))
+    got = mat.rank_sums(topN)
+    mat.close()
+    order = np.argsort(-a, axis=1, kind="stable")
+    rank_of = np.empty((n, n), np.int64)
+    rank_of[np.arange(n)[:, None], order] = np.arange(n)[None, :]
+    want = np.zeros(n, np.int64)
+    for x in range(n):
+        top = order[x, :topN].tolist()
+        want[x] = sum(min(rank_of[p, q], rank_of[q, p]) for p, q in combinations(top, 2))
+    assert np.array_equal(got, want)
