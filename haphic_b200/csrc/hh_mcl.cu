@@ -33,8 +33,7 @@ struct hh_slotmat {
     int W;       // row blocks per column
     int* len;    // [n]
     int* blk;    // [n * (W+1)]
-    int* idx;    // [n * cap]
-    float* val;  // [n * cap]
+    uint2* ent;  // [n * cap]  {row index, fp32 value bits}: one 64-bit load per entry
 };
 
 enum { SRC_CSC = 0, SRC_PRODUCT = 1, SRC_DENSE = 2 };
@@ -142,10 +141,8 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             // of different segments inside a step are applied in segment order (one round per segment),
             // which keeps every accumulator cell's additions in ascending-i order.
             const int lenB = a.B.len[j];
-            const int* __restrict__ Bidx = a.B.idx + (size_t)j * (size_t)a.B.cap;
-            const float* __restrict__ Bval = a.B.val + (size_t)j * (size_t)a.B.cap;
-            const int* __restrict__ Aidx = a.A.idx;
-            const float* __restrict__ Aval = a.A.val;
+            const uint2* __restrict__ Bent = a.B.ent + (size_t)j * (size_t)a.B.cap;
+            const uint2* __restrict__ Aent = a.A.ent;
             const int* __restrict__ Ablk = a.A.blk;
             const size_t capA = (size_t)a.A.cap;
             unsigned long long warp_prod = 0ull;
@@ -153,12 +150,14 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             int i1 = 0, i2 = 0, s1 = 0, e1 = 0;
             float v1 = 0.f, v2 = 0.f;
             if (lane < lenB) {
-                i1 = Bidx[lane];
-                v1 = Bval[lane];
+                const uint2 be = Bent[lane];
+                i1 = (int)be.x;
+                v1 = __uint_as_float(be.y);
             }
             if (32 + lane < lenB) {
-                i2 = Bidx[32 + lane];
-                v2 = Bval[32 + lane];
+                const uint2 be = Bent[32 + lane];
+                i2 = (int)be.x;
+                v2 = __uint_as_float(be.y);
             }
             if (lane < lenB) {
                 const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
@@ -181,8 +180,9 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     e1 = bp[1];
                 }
                 if (t0 + 64 + lane < lenB) {
-                    i2 = Bidx[t0 + 64 + lane];
-                    v2 = Bval[t0 + 64 + lane];
+                    const uint2 be = Bent[t0 + 64 + lane];
+                    i2 = (int)be.x;
+                    v2 = __uint_as_float(be.y);
                 }
                 const unsigned ne = __ballot_sync(HH_FULL_MASK, seg_len > 0);
                 if (!FLAT) {
@@ -199,12 +199,14 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                         nb = __shfl_sync(HH_FULL_MASK, seg_base, u);
                         nv = __shfl_sync(HH_FULL_MASK, seg_v, u);
                         if (lane < nL) {
-                            nk0 = Aidx[nb + lane];
-                            na0 = Aval[nb + lane];
+                            const uint2 e0 = Aent[nb + lane];
+                            nk0 = (int)e0.x;
+                            na0 = __uint_as_float(e0.y);
                         }
                         if (lane + 32 < nL) {
-                            nk1 = Aidx[nb + lane + 32];
-                            na1 = Aval[nb + lane + 32];
+                            const uint2 e1x = Aent[nb + lane + 32];
+                            nk1 = (int)e1x.x;
+                            na1 = __uint_as_float(e1x.y);
                         }
                     };
                     if (rem) preload();
@@ -229,12 +231,14 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                             int k0 = 0, k1 = 0;
                             float a0 = 0.f, a1 = 0.f;
                             if (p0 < cL) {
-                                k0 = Aidx[cb + p0];
-                                a0 = Aval[cb + p0];
+                                const uint2 e0 = Aent[cb + p0];
+                                k0 = (int)e0.x;
+                                a0 = __uint_as_float(e0.y);
                             }
                             if (p1 < cL) {
-                                k1 = Aidx[cb + p1];
-                                a1 = Aval[cb + p1];
+                                const uint2 e1x = Aent[cb + p1];
+                                k1 = (int)e1x.x;
+                                a1 = __uint_as_float(e1x.y);
                             }
                             if (p0 < cL) {
                                 acc[k0] = fmaf(cv, a0, acc[k0]);
@@ -289,8 +293,9 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     n_v = __shfl_sync(HH_FULL_MASK, c_v, u);
                     if (n_valid) {
                         const unsigned pidx = b + (unsigned)(q - o);
-                        n_k = Aidx[pidx];
-                        n_a = Aval[pidx];
+                        const uint2 e0 = Aent[pidx];
+                        n_k = (int)e0.x;
+                        n_a = __uint_as_float(e0.y);
                     }
                 };
                 fetch_step(0);
@@ -311,13 +316,9 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 // ---- pull the next batch's segments into L2 (their block pointers arrived long ago)
                 if (a.l2pf && e1 > s1) {
                     const size_t nb = (size_t)i1 * capA;
-                    const char* pi = reinterpret_cast<const char*>(Aidx + nb + s1);
-                    const char* pv = reinterpret_cast<const char*>(Aval + nb + s1);
-                    const int bytes = (e1 - s1) * 4;
-                    for (int o = -(int)((uintptr_t)pi & 127); o < bytes; o += 128) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + o));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + o));
-                    }
+                    const char* pi = reinterpret_cast<const char*>(Aent + nb + s1);
+                    const int bytes = (e1 - s1) * 8;
+                    for (int o = -(int)((uintptr_t)pi & 127); o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + o));
                 }
             }
             if (lane == 0) prod_acc += warp_prod;
@@ -373,8 +374,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             const int base = __shfl_sync(HH_FULL_MASK, incl - cv, w);
             const int total = __shfl_sync(HH_FULL_MASK, incl, 31);
             int off = base;
-            int* __restrict__ oidx = a.out.idx + (size_t)j * (size_t)a.out.cap;
-            float* __restrict__ oval = a.out.val + (size_t)j * (size_t)a.out.cap;
+            uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
             HH_FOR_DIRTY_ROWS({
                 const float x = acc[k];
                 const bool f = (x != 0.f);
@@ -382,8 +382,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 if (f) {
                     const int pos = off + __popc(bal & lt_mask);
                     if (pos < a.out.cap) {
-                        oidx[pos] = k;
-                        oval[pos] = (a.raw || S == 0.0) ? x : (float)((double)x / S);
+                        oent[pos] = make_uint2((unsigned)k, __float_as_uint((a.raw || S == 0.0) ? x : (float)((double)x / S)));
                     }
                     acc[k] = 0.f;
                 }
@@ -485,8 +484,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             }
             // E3: compact the survivors in row order, second normalisation (2014)
             int off = base;
-            int* __restrict__ oidx = a.out.idx + (size_t)j * (size_t)a.out.cap;
-            float* __restrict__ oval = a.out.val + (size_t)j * (size_t)a.out.cap;
+            uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
             const bool conv = a.do_conv != 0;
             HH_FOR_DIRTY_ROWS({
                 const float x1 = acc[k];
@@ -497,8 +495,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     const int pos = off + __popc(bal & lt_mask);
                     const float x2 = (float)((double)x1 / S2);
                     if (pos < a.out.cap) {
-                        oidx[pos] = k;
-                        oval[pos] = x2;
+                        oent[pos] = make_uint2((unsigned)k, __float_as_uint(x2));
                     }
                     keepv = x2;
                 }
@@ -518,11 +515,11 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 __syncwarp();
                 const int* bp = a.B.blk + (size_t)j * (W + 1) + w;
                 const int ps = bp[0], pe = bp[1];
-                const int* __restrict__ Lidx = a.B.idx + (size_t)j * (size_t)a.B.cap;
-                const float* __restrict__ Lval = a.B.val + (size_t)j * (size_t)a.B.cap;
+                const uint2* __restrict__ Lent = a.B.ent + (size_t)j * (size_t)a.B.cap;
                 for (int p = ps + lane; p < pe; p += 32) {
-                    const int k = Lidx[p];
-                    const float l = Lval[p];
+                    const uint2 le = Lent[p];
+                    const int k = (int)le.x;
+                    const float l = __uint_as_float(le.y);
                     const float m = acc[k];
                     const float d = __fsub_rn(fabsf(__fsub_rn(m, l)), __fmul_rn(1e-5f, fabsf(l)));
                     dmax = fmaxf(dmax, d);
@@ -587,8 +584,7 @@ __global__ void hh_k_topn(const hh_slotmat m, int topN, int* __restrict__ top) {
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < m.n; a += warps) {
         const int L = m.len[a];
-        const int* idx = m.idx + (size_t)a * (size_t)m.cap;
-        const float* val = m.val + (size_t)a * (size_t)m.cap;
+        const uint2* ent = m.ent + (size_t)a * (size_t)m.cap;
         float last_v = INFINITY;
         int last_i = -1;
         int zero_c = -1, zero_p = 0;        // cursor over the zero-valued columns (ascending index)
@@ -597,8 +593,8 @@ __global__ void hh_k_topn(const hh_slotmat m, int topN, int* __restrict__ top) {
             float bv = -1.f;
             int bi = 0x7fffffff;
             for (int p = lane; p < L; p += 32) {
-                const float v = val[p];
-                const int i = idx[p];
+                const float v = __uint_as_float(ent[p].y);
+                const int i = (int)ent[p].x;
                 if (v <= 0.f) continue;
                 const bool after = (v < last_v) || (v == last_v && i > last_i);
                 if (after && (v > bv || (v == bv && i < bi))) {
@@ -627,8 +623,8 @@ __global__ void hh_k_topn(const hh_slotmat m, int topN, int* __restrict__ top) {
                 if (lane == 0) {
                     for (;;) {
                         if (c >= m.n) break;
-                        while (zero_p < L && idx[zero_p] < c) zero_p++;
-                        if (zero_p < L && idx[zero_p] == c && val[zero_p] > 0.f) {
+                        while (zero_p < L && (int)ent[zero_p].x < c) zero_p++;
+                        if (zero_p < L && (int)ent[zero_p].x == c && __uint_as_float(ent[zero_p].y) > 0.f) {
                             c++;            // a positive entry: not a zero column
                             continue;
                         }
@@ -648,29 +644,30 @@ __global__ void hh_k_topn(const hh_slotmat m, int topN, int* __restrict__ top) {
 // position of column b in the sorted row of fragment a
 __device__ __forceinline__ int hh_rank_of(const hh_slotmat& m, int a, int b) {
     const int L = m.len[a];
-    const int* idx = m.idx + (size_t)a * (size_t)m.cap;
-    const float* val = m.val + (size_t)a * (size_t)m.cap;
+    const uint2* ent = m.ent + (size_t)a * (size_t)m.cap;
     int lo = 0, hi = L;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (idx[mid] < b) lo = mid + 1;
+        if ((int)ent[mid].x < b) lo = mid + 1;
         else hi = mid;
     }
-    const bool found = lo < L && idx[lo] == b && val[lo] > 0.f;
+    const bool found = lo < L && (int)ent[lo].x == b && __uint_as_float(ent[lo].y) > 0.f;
     int npos = 0, before = 0;           // positive entries in the row / positive entries left of b
     if (!found) {
         for (int p = 0; p < L; ++p) {
-            const bool pos = val[p] > 0.f;
+            const uint2 e = ent[p];
+            const bool pos = __uint_as_float(e.y) > 0.f;
             npos += pos;
-            before += pos && idx[p] < b;
+            before += pos && (int)e.x < b;
         }
         return npos + (b - before);     // all positive entries first, then the zero columns by index
     }
-    const float v = val[lo];
+    const float v = __uint_as_float(ent[lo].y);
     int r = 0;
     for (int p = 0; p < L; ++p) {
-        const float x = val[p];
-        r += (x > v) || (x == v && idx[p] < b);
+        const uint2 e = ent[p];
+        const float x = __uint_as_float(e.y);
+        r += (x > v) || (x == v && (int)e.x < b);
     }
     return r;
 }
@@ -713,12 +710,12 @@ __global__ void hh_k_pack(const hh_slotmat m, int col_lo, int ncols, const int64
         const int c = col_lo + jj;
         const int L = m.len[c];
         if (lane == 0 && len_out) len_out[jj] = L;
-        const int* si = m.idx + (size_t)c * (size_t)m.cap;
-        const float* sv = m.val + (size_t)c * (size_t)m.cap;
+        const uint2* se = m.ent + (size_t)c * (size_t)m.cap;
         const int64_t o = off[jj];
         for (int p = lane; p < L; p += 32) {
-            idx_out[o + p] = si[p];
-            val_out[o + p] = sv[p];
+            const uint2 e = se[p];
+            idx_out[o + p] = (int)e.x;
+            val_out[o + p] = __uint_as_float(e.y);
         }
     }
 }
@@ -737,12 +734,8 @@ __global__ void hh_k_unpack(const hh_slotmat m, int T, int col_lo, int ncols, co
             L = 0;
         }
         const int64_t o = off[jj];
-        int* di = m.idx + (size_t)c * (size_t)m.cap;
-        float* dv = m.val + (size_t)c * (size_t)m.cap;
-        for (int p = lane; p < L; p += 32) {
-            di[p] = idx_in[o + p];
-            dv[p] = val_in[o + p];
-        }
+        uint2* de = m.ent + (size_t)c * (size_t)m.cap;
+        for (int p = lane; p < L; p += 32) de[p] = make_uint2((unsigned)idx_in[o + p], __float_as_uint(val_in[o + p]));
         if (lane < W) {   // first entry with row >= lane*T
             const int target = lane * T;
             int lo = 0, hi = L;
@@ -802,8 +795,7 @@ struct hh_mcl {
 static void slot_free(hh_slotmat& s) {
     hh_dfree(s.len);
     hh_dfree(s.blk);
-    hh_dfree(s.idx);
-    hh_dfree(s.val);
+    hh_dfree(s.ent);
     s.cap = 0;
 }
 
@@ -816,7 +808,7 @@ static int slot_alloc(hh_slotmat& s, int n, int cap, int W) {
     s.W = W;
     int rc;
     if ((rc = hh_dmalloc(&s.len, (size_t)n)) != HH_OK || (rc = hh_dmalloc(&s.blk, (size_t)n * (W + 1))) != HH_OK ||
-        (rc = hh_dmalloc(&s.idx, (size_t)n * (size_t)cap)) != HH_OK || (rc = hh_dmalloc(&s.val, (size_t)n * (size_t)cap)) != HH_OK) {
+        (rc = hh_dmalloc(&s.ent, (size_t)n * (size_t)cap)) != HH_OK) {
         slot_free(s);
         return rc;
     }

@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""Turn the ncu artefacts in gpurun_out/ into the tracked summaries under profiles/.
+
+    python scripts/summarize_profiles.py <tag> [--launches gpurun_out/launches.csv] [--rep gpurun_out/prof.ncu-rep ...]
+"""
+import argparse
+import collections
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_shared_mem", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def ms(value, unit):
+    t = float(value.replace(",", ""))
+    return {"ns": t / 1e6, "us": t / 1e3, "usecond": t / 1e3, "ms": t, "msecond": t, "s": t * 1e3, "second": t * 1e3}.get(unit, t)
+
+
+def launches(path, out):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    agg = collections.OrderedDict()
+    for r in rows:
+        name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ms(r["Metric Value"], r["Metric Unit"])
+    tot = sum(v[1] for v in agg.values())
+    with open(out, "w") as f:
+        f.write("# per-kernel device time of ONE bench step under `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:hh_`\n")
+        f.write("# (serialised, cold caches: compare SHARES, not absolutes)\n")
+        f.write("kernel,launches,total_ms,share_pct\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("{},{},{:.3f},{:.1f}\n".format(k, v[0], v[1], 100 * v[1] / tot))
+        f.write("TOTAL,{},{:.3f},100.0\n".format(sum(v[0] for v in agg.values()), tot))
+    print("wrote", out)
+
+
+def report(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    stall = [h for h in hdr if "issue_stalled" in h and "per_warp_active" in h]
+    with open(out, "w") as f:
+        f.write("# `ncu --set full --clock-control none --import-source on` summary of {}\n".format(os.path.basename(rep)))
+        for r in rows[2:]:
+            f.write("\n## {}\n".format(r[idx["Kernel Name"]]))
+            for m in METRICS:
+                if m in idx and r[idx[m]] not in ("", "nan", "-nan"):
+                    f.write("{:78s} {} {}\n".format(m, r[idx[m]], units[idx[m]]))
+            st = []
+            for h in stall:
+                try:
+                    st.append((float(r[idx[h]]), h))
+                except ValueError:
+                    pass
+            for v, h in sorted(st, reverse=True)[:6]:
+                f.write("stall {:72s} {:.1f} %\n".format(h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", ""), v))
+    print("wrote", out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("tag")
+    ap.add_argument("--launches")
+    ap.add_argument("--rep", nargs="*", default=[])
+    a = ap.parse_args()
+    os.makedirs("profiles", exist_ok=True)
+    if a.launches:
+        launches(a.launches, "profiles/{}_launches.csv".format(a.tag))
+    for rep in a.rep:
+        base = os.path.splitext(os.path.basename(rep))[0]
+        report(rep, "profiles/{}_{}.txt".format(a.tag, base))
+
+
+if __name__ == "__main__":
+    main()

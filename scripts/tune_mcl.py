@@ -32,8 +32,7 @@ def main():
     mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))
     tab.close()
     del rec
-    configs = [dict(W=32, FLAT=-1, L2PF=1, ORDER=0), dict(W=32, FLAT=-1, L2PF=1, ORDER=1),
-               dict(W=32, FLAT=0, L2PF=1, ORDER=1), dict(W=32, FLAT=-1, L2PF=0, ORDER=1)]
+    configs = [dict(W=32, FLAT=-1, L2PF=-1, ORDER=0), dict(W=32, FLAT=0, L2PF=1, ORDER=0), dict(W=32, FLAT=1, L2PF=0, ORDER=0)]
     sel = os.environ.get("TUNE_CONFIGS")
     if sel:
         configs = [configs[int(k)] for k in sel.split(",")]
