@@ -55,6 +55,7 @@ struct hh_colargs {
     float inflation, prune;
     int do_conv;
     int track;                   // product + prune only: keep the dirty-chunk bitmap (sparse columns)
+    const int* ncols_ptr;        // optional: number of columns to process is read from device memory (overflow list)
     const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
     int* attr_out;               // EPI_PRUNE: strongest row of every produced column
     int flat;                    // expansion inner loop: 1 = flat 32-entry walk, 0 = one segment at a time
@@ -96,12 +97,13 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
 
     float dmax = 0.f;
     unsigned long long prod_acc = 0ull, nnz_acc = 0ull;
+    const int ncols_run = a.ncols_ptr ? *a.ncols_ptr : a.ncols;
 
     for (;;) {
         if (threadIdx.x == 0) s_col = atomicAdd(a.counter, 1);
         __syncthreads();
         const int jj = s_col;
-        if (jj >= a.ncols) break;
+        if (jj >= ncols_run) break;
         const int j = a.order ? a.order[jj] : (a.col_lo + jj);
         const int jloc = j - a.col_lo;          // position inside the owned (dense) column block
         uint64_t dirty = 0ull;
@@ -573,6 +575,215 @@ __global__ void hh_k_order_scatter(const int* __restrict__ root, int col_lo, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// nearly converged iterates: a column has a handful of entries, and the CTA-per-column kernel is bound
+// by its per-column latency chain (one column in flight per SM).  Here ONE WARP expands a column by a
+// 32-way merge of the operand columns (rows come out ascending, contributions are fused in ascending-i
+// order exactly like the accumulator kernel), prunes it in shared memory and writes its slot.  Columns
+// that do not fit (more than 32 entries, long operand columns, more than HH_SMALL_CAP result rows) are
+// appended to an overflow list and handled by the accumulator kernel afterwards.
+// ---------------------------------------------------------------------------------------------
+#define HH_SMALL_CAP 256
+#define HH_SMALL_MAXPROD 4096
+
+__global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W, int* __restrict__ biglist, int* __restrict__ bigcount) {
+    __shared__ int s_k[8][HH_SMALL_CAP];
+    __shared__ float s_v[8][HH_SMALL_CAP];
+    __shared__ int s_ok[8][32];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint2* __restrict__ Aent = a.A.ent;
+    const size_t capA = (size_t)a.A.cap;
+    const float p32 = a.prune, rf = a.inflation;
+    const bool sq = a.inflate_square != 0;
+    int* sk = s_k[wq];
+    float* sv = s_v[wq];
+    int* sok = s_ok[wq];
+    float dmax = 0.f;
+    unsigned long long prod_acc = 0ull, nnz_acc = 0ull;
+    for (int jj = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jj < a.ncols; jj += nwarps) {
+        const int j = a.col_lo + jj;
+        const int L = a.B.len[j];
+        bool big = L > 32;
+        int il = 0x7fffffff, lenl = 0;
+        float vl = 0.f;
+        size_t basel = 0;
+        if (!big && lane < L) {
+            const uint2 be = a.B.ent[(size_t)j * (size_t)a.B.cap + lane];
+            il = (int)be.x;
+            vl = __uint_as_float(be.y);
+            lenl = a.A.len[il];
+            basel = (size_t)il * capA;
+        }
+        const int tot = hh_warp_sum(lenl);
+        if (tot > HH_SMALL_MAXPROD) big = true;
+        int nout = 0;
+        if (!big) {
+            // ---- 32-way merge: every round emits the smallest pending row
+            int h = 0x7fffffff, c = 0;
+            float av = 0.f;
+            if (lenl > 0) {
+                const uint2 e = Aent[basel];
+                h = (int)e.x;
+                av = __uint_as_float(e.y);
+            }
+            for (;;) {
+                const int kmin = __reduce_min_sync(HH_FULL_MASK, h);
+                if (kmin == 0x7fffffff) break;
+                const bool mine = (h == kmin);
+                const unsigned part = __ballot_sync(HH_FULL_MASK, mine);
+                float accv = 0.f;
+                for (unsigned mm = part; mm; mm &= mm - 1u) {          // ascending lane == ascending i
+                    const int b = __ffs(mm) - 1;
+                    accv = fmaf(__shfl_sync(HH_FULL_MASK, vl, b), __shfl_sync(HH_FULL_MASK, av, b), accv);
+                }
+                if (lane == 0 && nout < HH_SMALL_CAP) {
+                    sk[nout] = kmin;
+                    sv[nout] = accv;
+                }
+                nout++;
+                if (mine) {
+                    c++;
+                    if (c < lenl) {
+                        const uint2 e = Aent[basel + c];
+                        h = (int)e.x;
+                        av = __uint_as_float(e.y);
+                    } else {
+                        h = 0x7fffffff;
+                    }
+                }
+            }
+            if (nout > HH_SMALL_CAP) big = true;
+        }
+        if (big) {
+            if (lane == 0) biglist[atomicAdd(bigcount, 1)] = j;
+            continue;
+        }
+        if (lane == 0) prod_acc += (unsigned long long)tot;
+        __syncwarp();
+        // ---- E1: inflate + first column sum
+        double s1 = 0.0;
+        for (int p = lane; p < nout; p += 32) {
+            const float x = sv[p];
+            if (x != 0.f) {
+                const float y = sq ? (x * x) : powf(x, rf);
+                sv[p] = y;
+                s1 += (double)y;
+            }
+        }
+        const double S1 = hh_warp_sum(s1);
+        __syncwarp();
+        // ---- E2: normalise, threshold statistics, first maximum
+        double s2 = 0.0;
+        int cnt = 0, kmax = 0x7fffffff;
+        float vmax = 0.f;
+        for (int p = lane; p < nout; p += 32) {
+            const float y = sv[p];
+            if (y != 0.f) {
+                const float x1 = (S1 != 0.0) ? (float)((double)y / S1) : y;
+                sv[p] = x1;
+                if (x1 >= p32 && x1 > 0.f) {
+                    cnt++;
+                    s2 += (double)x1;
+                }
+                if (x1 > vmax) {
+                    vmax = x1;
+                    kmax = sk[p];
+                }
+            }
+        }
+        double S2 = hh_warp_sum(s2);
+        cnt = hh_warp_sum(cnt);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(HH_FULL_MASK, vmax, o);
+            const int ok = __shfl_xor_sync(HH_FULL_MASK, kmax, o);
+            if (ov > vmax || (ov == vmax && ok < kmax)) {
+                vmax = ov;
+                kmax = ok;
+            }
+        }
+        const bool need_max = (cnt == 0) && (vmax > 0.f);
+        int total = cnt;
+        if (need_max) {
+            total = 1;
+            S2 = (double)vmax;
+        }
+        __syncwarp();
+        // ---- E3: ordered compaction (in place in shared memory) + slot write
+        uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
+        int off = 0;
+        for (int p0 = 0; p0 < nout; p0 += 32) {
+            const int p = p0 + lane;
+            const float x1 = (p < nout) ? sv[p] : 0.f;
+            const int k = (p < nout) ? sk[p] : 0;
+            const bool f = (p < nout) && (need_max ? (k == kmax && x1 > 0.f) : (x1 >= p32 && x1 > 0.f));
+            const unsigned bal = __ballot_sync(HH_FULL_MASK, f);
+            __syncwarp();
+            if (f) {
+                const int pos = off + __popc(bal & lt_mask);
+                const float x2 = (float)((double)x1 / S2);
+                if (pos < a.out.cap) oent[pos] = make_uint2((unsigned)k, __float_as_uint(x2));
+                sk[pos] = k;
+                sv[pos] = x2;
+            }
+            off += __popc(bal);
+            __syncwarp();
+        }
+        // row-block pointers of the new column
+        if (lane < W) {
+            const int target = lane * a.T;
+            int lo = 0, hi = total;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (sk[mid] < target) lo = mid + 1;
+                else hi = mid;
+            }
+            a.out.blk[(size_t)j * (W + 1) + lane] = lo;
+        }
+        if (lane == 0) {
+            a.out.blk[(size_t)j * (W + 1) + W] = min(total, a.out.cap);
+            a.out.len[j] = min(total, a.out.cap);
+            if (total > a.out.cap) atomicExch(a.err, 1);
+            nnz_acc += (unsigned long long)total;
+            if (a.attr_out) a.attr_out[j] = (vmax > 0.f) ? kmax : j;
+        }
+        // ---- convergence term against the previous iterate L = B[:, j] (its entries sit in the lanes)
+        if (a.do_conv) {
+            sok[lane] = il;                    // old rows, ascending; 0x7fffffff beyond L
+            __syncwarp();
+            if (lane < L) {
+                int lo = 0, hi = total;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sk[mid] < il) lo = mid + 1;
+                    else hi = mid;
+                }
+                const float m = (lo < total && sk[lo] == il) ? sv[lo] : 0.f;
+                dmax = fmaxf(dmax, __fsub_rn(fabsf(__fsub_rn(m, vl)), __fmul_rn(1e-5f, fabsf(vl))));
+            }
+            for (int p = lane; p < total; p += 32) {
+                const int k = sk[p];
+                int lo = 0, hi = L;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sok[mid] < k) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (!(lo < L && sok[lo] == k)) dmax = fmaxf(dmax, sv[p]);
+            }
+        }
+        __syncwarp();
+    }
+    dmax = hh_warp_max(dmax);
+    if (lane == 0) {
+        if (dmax > 0.f) atomicMax(a.delta_bits, __float_as_int(dmax));
+        if (prod_acc) atomicAdd(a.stats + 1, prod_acc);
+        if (nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // rank-sum statistic of filter_fragments (HapHiC_cluster.py:864-892) on the sorted slotted matrix
 // (symmetric, so row a == column a).  Order of a row: links descending, ties by matrix index.
 // ---------------------------------------------------------------------------------------------
@@ -788,6 +999,8 @@ struct hh_mcl {
     int* d_cnt;                    // [2n] histogram + cursors
     int64_t* d_start;              // [n+1]
     bool order_valid;
+    int use_small;                 // warp-per-column kernel for nearly converged iterates (HH_MCL_SMALL)
+    int* d_bigcount;
     cudaEvent_t ev0, ev1;
     float create_ms[2];            // device time of the normalisation / pre-expansion kernels
 };
@@ -1096,6 +1309,7 @@ extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     hh_dfree(mc->d_root);
     hh_dfree(mc->d_cnt);
     hh_dfree(mc->d_start);
+    hh_dfree(mc->d_bigcount);
     if (mc->ev0) cudaEventDestroy(mc->ev0);
     if (mc->ev1) cudaEventDestroy(mc->ev1);
     delete mc;
@@ -1154,6 +1368,7 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
     mc->col_hi = col_hi;
     mc->expansion = expansion;
     mc->cur = -1;
+    mc->use_small = env_int("HH_MCL_SMALL", 1);
     mc->use_order = env_int("HH_MCL_ORDER", 0);   // measured on B200 (50k contigs): no gain, the gathers are latency- not L2-bound
     mc->flat = env_int("HH_MCL_FLAT", -1);      // -1 = choose per launch from the mean segment length
     mc->l2pf = env_int("HH_MCL_L2PF", -1);       // -1 = prefetch in segment-wise mode only (long segments)
@@ -1177,6 +1392,7 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         HH_CHECK(hh_dmalloc(&mc->d_root, (size_t)(col_hi - col_lo)));
         HH_CHECK(hh_dmalloc(&mc->d_cnt, (size_t)m->n * 2));
         HH_CHECK(hh_dmalloc(&mc->d_start, (size_t)m->n + 1));
+        HH_CHECK(hh_dmalloc(&mc->d_bigcount, 1));
         HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
         // 1) M0 = normalize(link_matrix, 'l1', axis=0)   (2144)
         int cap0 = 0;
@@ -1316,6 +1532,17 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
         a.track = (dcol * dcol * 4.0 < (double)mc->n) ? 1 : 0;
         a.flat = choose_flat(mc, (double)mc->cur_nnz);
         a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
+        if (mc->use_small && !a.order && mc->cur_nnz <= 8ll * mc->n) {
+            // nearly converged: one warp per column; what does not fit goes to the accumulator kernel
+            const int ncols = mc->col_hi - mc->col_lo;
+            HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, sizeof(int), ctx->stream));
+            a.T = g.T;
+            int grid = (ncols + 7) / 8;
+            if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+            HH_LAUNCH(ctx, hh_k_col_small, grid, 256, 0, a, g.W, mc->d_order, mc->d_bigcount);
+            a.order = mc->d_order;
+            a.ncols_ptr = mc->d_bigcount;
+        }
         HH_CHECK((launch_col<SRC_PRODUCT, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
     }
     HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));

@@ -32,7 +32,7 @@ def main():
     mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))
     tab.close()
     del rec
-    configs = [dict(W=32, FLAT=-1, L2PF=-1, ORDER=0), dict(W=32, FLAT=0, L2PF=1, ORDER=0), dict(W=32, FLAT=1, L2PF=0, ORDER=0)]
+    configs = [dict(W=32, FLAT=-1, L2PF=-1, ORDER=0, SMALL=0), dict(W=32, FLAT=-1, L2PF=-1, ORDER=0, SMALL=1)]
     sel = os.environ.get("TUNE_CONFIGS")
     if sel:
         configs = [configs[int(k)] for k in sel.split(",")]
@@ -43,10 +43,12 @@ def main():
         t0 = time.perf_counter()
         mc = Mcl(mat)
         out = {"cfg": cfg, "preexp_ms": round(mc.preexp_ms, 1), "norm_ms": round(mc.normalize_ms, 2)}
-        for r, iters in ((1.5, 8), (2.0, 6)):
+        for r, iters in ((1.5, 200), (2.0, 200), (3.0, 200)):
             st = mc.run(r, iters, 1e-4)
-            out["r{}".format(r)] = [round(float(x), 2) for x in st["iter_ms"]]
-            out["nnz{}".format(r)] = st["iter_nnz"].tolist()
+            out["r{}".format(r)] = [round(float(x), 2) for x in st["iter_ms"]][:40:3]
+            out["tot{}".format(r)] = round(float(st["iter_ms"].sum()), 1)
+            out["rounds{}".format(r)] = st["rounds"]
+            out["nnz{}".format(r)] = st["iter_nnz"].tolist()[-3:]
         fin = mc.result()
         h = hashlib.sha1(fin.indptr.tobytes() + fin.indices.tobytes() + fin.data.tobytes()).hexdigest()[:12]
         out["hash"] = h
