@@ -55,6 +55,11 @@ struct hh_colargs {
     float inflation, prune;
     int do_conv;
     int track;                   // product + prune only: keep the dirty-chunk bitmap (sparse columns)
+    const unsigned* A16;         // optional compressed operand for the pre-expansion: (count << 16) | row-in-block, same
+    const float* rinv16;         //   offsets as A; value of an entry = count * rinv16[column]
+    unsigned* out16;             // EPI_NORM: also emit that compressed form (+ rinv_out per column, bad16 flag)
+    float* rinv_out;
+    int* bad16;
     const int* ncols_ptr;        // optional: number of columns to process is read from device memory (overflow list)
     const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
     int* attr_out;               // EPI_PRUNE: strongest row of every produced column
@@ -72,7 +77,7 @@ __device__ __forceinline__ uint64_t hh_warp_or64(uint64_t v) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-template <int W, int SRC, int EPI, bool SMEM, bool TRACK, bool FLAT>
+template <int W, int SRC, int EPI, bool SMEM, bool TRACK, bool FLAT, bool A16>
 __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
     extern __shared__ __align__(16) float hh_dyn_smem[];
     __shared__ double s_d[32];
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             unsigned long long warp_prod = 0ull;
             // software pipeline over batches: B entries two batches ahead, block pointers one batch ahead
             int i1 = 0, i2 = 0, s1 = 0, e1 = 0;
-            float v1 = 0.f, v2 = 0.f;
+            float v1 = 0.f, v2 = 0.f, r1 = 0.f;
             if (lane < lenB) {
                 const uint2 be = Bent[lane];
                 i1 = (int)be.x;
@@ -165,12 +170,14 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
                 s1 = bp[0];
                 e1 = bp[1];
+                if (A16) r1 = a.rinv16[i1];
             }
             for (int t0 = 0; t0 < lenB; t0 += 32) {
                 // ---- current batch header (loaded during the previous trip)
                 const int seg_len = (t0 + lane < lenB) ? (e1 - s1) : 0;
                 const unsigned seg_base = (unsigned)((size_t)i1 * capA + (size_t)s1);
                 const float seg_v = v1;
+                const float seg_r = r1;
                 // ---- advance the pipeline: batch +1 gets its block pointers, batch +2 its B entries
                 i1 = i2;
                 v1 = v2;
@@ -180,6 +187,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
                     s1 = bp[0];
                     e1 = bp[1];
+                    if (A16) r1 = a.rinv16[i1];
                 }
                 if (t0 + 64 + lane < lenB) {
                     const uint2 be = Bent[t0 + 64 + lane];
@@ -193,22 +201,36 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     unsigned rem = ne;
                     int nL = 0, nk0 = 0, nk1 = 0;
                     unsigned nb = 0;
-                    float nv = 0.f, na0 = 0.f, na1 = 0.f;
+                    float nv = 0.f, na0 = 0.f, na1 = 0.f, nr = 0.f;
                     auto preload = [&]() {
                         const int u = __ffs(rem) - 1;
                         rem &= rem - 1;
                         nL = __shfl_sync(HH_FULL_MASK, seg_len, u);
                         nb = __shfl_sync(HH_FULL_MASK, seg_base, u);
                         nv = __shfl_sync(HH_FULL_MASK, seg_v, u);
-                        if (lane < nL) {
-                            const uint2 e0 = Aent[nb + lane];
-                            nk0 = (int)e0.x;
-                            na0 = __uint_as_float(e0.y);
-                        }
-                        if (lane + 32 < nL) {
-                            const uint2 e1x = Aent[nb + lane + 32];
-                            nk1 = (int)e1x.x;
-                            na1 = __uint_as_float(e1x.y);
+                        if (A16) {
+                            nr = __shfl_sync(HH_FULL_MASK, seg_r, u);
+                            if (lane < nL) {
+                                const unsigned e0 = a.A16[nb + lane];
+                                nk0 = tile0 + (int)(e0 & 0xFFFFu);
+                                na0 = __fmul_rn((float)(e0 >> 16), nr);
+                            }
+                            if (lane + 32 < nL) {
+                                const unsigned e1x = a.A16[nb + lane + 32];
+                                nk1 = tile0 + (int)(e1x & 0xFFFFu);
+                                na1 = __fmul_rn((float)(e1x >> 16), nr);
+                            }
+                        } else {
+                            if (lane < nL) {
+                                const uint2 e0 = Aent[nb + lane];
+                                nk0 = (int)e0.x;
+                                na0 = __uint_as_float(e0.y);
+                            }
+                            if (lane + 32 < nL) {
+                                const uint2 e1x = Aent[nb + lane + 32];
+                                nk1 = (int)e1x.x;
+                                na1 = __uint_as_float(e1x.y);
+                            }
                         }
                     };
                     if (rem) preload();
@@ -216,7 +238,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     while (have) {
                         const int cL = nL, ck0 = nk0, ck1 = nk1;
                         const unsigned cb = nb;
-                        const float cv = nv, ca0 = na0, ca1 = na1;
+                        const float cv = nv, ca0 = na0, ca1 = na1, cr = nr;
                         have = rem != 0;
                         if (have) preload();
                         warp_prod += (unsigned long long)cL;
@@ -232,15 +254,28 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                             const int p0 = c + lane, p1 = c + 32 + lane;
                             int k0 = 0, k1 = 0;
                             float a0 = 0.f, a1 = 0.f;
-                            if (p0 < cL) {
-                                const uint2 e0 = Aent[cb + p0];
-                                k0 = (int)e0.x;
-                                a0 = __uint_as_float(e0.y);
-                            }
-                            if (p1 < cL) {
-                                const uint2 e1x = Aent[cb + p1];
-                                k1 = (int)e1x.x;
-                                a1 = __uint_as_float(e1x.y);
+                            if (A16) {
+                                if (p0 < cL) {
+                                    const unsigned e0 = a.A16[cb + p0];
+                                    k0 = tile0 + (int)(e0 & 0xFFFFu);
+                                    a0 = __fmul_rn((float)(e0 >> 16), cr);
+                                }
+                                if (p1 < cL) {
+                                    const unsigned e1x = a.A16[cb + p1];
+                                    k1 = tile0 + (int)(e1x & 0xFFFFu);
+                                    a1 = __fmul_rn((float)(e1x >> 16), cr);
+                                }
+                            } else {
+                                if (p0 < cL) {
+                                    const uint2 e0 = Aent[cb + p0];
+                                    k0 = (int)e0.x;
+                                    a0 = __uint_as_float(e0.y);
+                                }
+                                if (p1 < cL) {
+                                    const uint2 e1x = Aent[cb + p1];
+                                    k1 = (int)e1x.x;
+                                    a1 = __uint_as_float(e1x.y);
+                                }
                             }
                             if (p0 < cL) {
                                 acc[k0] = fmaf(cv, a0, acc[k0]);
@@ -318,8 +353,8 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 // ---- pull the next batch's segments into L2 (their block pointers arrived long ago)
                 if (a.l2pf && e1 > s1) {
                     const size_t nb = (size_t)i1 * capA;
-                    const char* pi = reinterpret_cast<const char*>(Aent + nb + s1);
-                    const int bytes = (e1 - s1) * 8;
+                    const char* pi = A16 ? reinterpret_cast<const char*>(a.A16 + nb + s1) : reinterpret_cast<const char*>(Aent + nb + s1);
+                    const int bytes = (e1 - s1) * (A16 ? 4 : 8);
                     for (int o = -(int)((uintptr_t)pi & 127); o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + o));
                 }
             }
@@ -385,6 +420,10 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     const int pos = off + __popc(bal & lt_mask);
                     if (pos < a.out.cap) {
                         oent[pos] = make_uint2((unsigned)k, __float_as_uint((a.raw || S == 0.0) ? x : (float)((double)x / S)));
+                        if (a.out16) {
+                            a.out16[(size_t)j * (size_t)a.out.cap + pos] = ((unsigned)x << 16) | (unsigned)(k - tile0);
+                            if (!(x >= 1.f && x <= 65535.f && x == floorf(x))) atomicExch(a.bad16, 1);
+                        }
                     }
                     acc[k] = 0.f;
                 }
@@ -396,6 +435,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 a.out.len[j] = min(total, a.out.cap);
                 if (total > a.out.cap) atomicExch(a.err, 1);
                 nnz_acc += (unsigned long long)total;
+                if (a.rinv_out) a.rinv_out[j] = (S != 0.0) ? (float)(1.0 / S) : 0.f;
             }
         } else {
             // E1: inflate (matrix.power(r), fp32) and first column sum (fp64)
@@ -999,6 +1039,9 @@ struct hh_mcl {
     int* d_cnt;                    // [2n] histogram + cursors
     int64_t* d_start;              // [n+1]
     bool order_valid;
+    int use_a16;                   // compressed operand for the pre-expansion (HH_MCL_A16)
+    unsigned* d_m0c;               // [n * cap0] (count << 16) | row-in-block
+    float* d_rinv;                 // [n] 1 / column sum
     int use_small;                 // warp-per-column kernel for nearly converged iterates (HH_MCL_SMALL)
     int* d_bigcount;
     cudaEvent_t ev0, ev1;
@@ -1068,18 +1111,18 @@ static hh_geom geom_for(hh_ctx* ctx, int n) {
     return g;
 }
 
-template <int W, int SRC, int EPI, bool TRACK, bool FLAT>
+template <int W, int SRC, int EPI, bool TRACK, bool FLAT, bool A16 = false>
 static int launch_col_wtf(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
     a.scratch = d_scratch;
     int grid = a.ncols < grid_cap ? a.ncols : grid_cap;
     if (grid < 1) return HH_OK;
     HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
     if (g.smem_acc) {
-        auto kern = hh_k_col<W, SRC, EPI, true, TRACK, FLAT>;
+        auto kern = hh_k_col<W, SRC, EPI, true, TRACK, FLAT, A16>;
         HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
         HH_LAUNCH(ctx, kern, grid, W * 32, g.smem_bytes, a);
     } else {
-        auto kern = hh_k_col<W, SRC, EPI, false, TRACK, FLAT>;
+        auto kern = hh_k_col<W, SRC, EPI, false, TRACK, FLAT, A16>;
         HH_CUDA(cudaMemsetAsync(d_scratch, 0, (size_t)grid_cap * (size_t)g.n_pad * sizeof(float), ctx->stream));
         HH_LAUNCH(ctx, kern, grid, W * 32, 0, a);
     }
@@ -1089,6 +1132,8 @@ static int launch_col_wtf(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int g
 // dirty-chunk tracking only pays off when a column touches a small part of the accumulator
 template <int W, int SRC, int EPI>
 static int launch_col_w(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
+    if (SRC == SRC_PRODUCT && EPI == EPI_DUMP && a.A16 && !a.flat)
+        return launch_col_wtf<W, SRC_PRODUCT, EPI_DUMP, false, false, true>(ctx, g, d_scratch, grid_cap, a);
     if (SRC == SRC_PRODUCT) {
         const bool track = (EPI == EPI_PRUNE) && a.track;
         if (a.flat) {
@@ -1119,21 +1164,21 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
         // every instantiation has the same footprint; query the heaviest (product + prune)
         switch (g.W) {
             case 8:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 256,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, 256,
                                                                      g.smem_bytes));
                 break;
             case 16:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 512,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, 512,
                                                                      g.smem_bytes));
                 break;
             default:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 1024,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, 1024,
                                                                      g.smem_bytes));
                 break;
         }
@@ -1147,7 +1192,8 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
 
 // unsorted CSC -> slotted (raw or column-normalised); cap must be >= the longest column
 static int slot_from_csc(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, int* d_counter, unsigned long long* d_stats,
-                         const hh_matrix* m, int raw, hh_slotmat& out) {
+                         const hh_matrix* m, int raw, hh_slotmat& out, unsigned* out16 = nullptr, float* rinv_out = nullptr,
+                         int* bad16 = nullptr) {
     hh_colargs a;
     memset(&a, 0, sizeof(a));
     a.n = m->n;
@@ -1159,6 +1205,9 @@ static int slot_from_csc(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int gr
     a.csc_val = m->d_val;
     a.out = out;
     a.raw = raw;
+    a.out16 = out16;
+    a.rinv_out = rinv_out;
+    a.bad16 = bad16;
     a.stats = d_stats;
     a.delta_bits = reinterpret_cast<int*>(d_stats + 2);
     a.err = reinterpret_cast<int*>(d_stats + 3);
@@ -1310,6 +1359,8 @@ extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     hh_dfree(mc->d_cnt);
     hh_dfree(mc->d_start);
     hh_dfree(mc->d_bigcount);
+    hh_dfree(mc->d_m0c);
+    hh_dfree(mc->d_rinv);
     if (mc->ev0) cudaEventDestroy(mc->ev0);
     if (mc->ev1) cudaEventDestroy(mc->ev1);
     delete mc;
@@ -1368,6 +1419,7 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
     mc->col_hi = col_hi;
     mc->expansion = expansion;
     mc->cur = -1;
+    mc->use_a16 = env_int("HH_MCL_A16", 1);
     mc->use_small = env_int("HH_MCL_SMALL", 1);
     mc->use_order = env_int("HH_MCL_ORDER", 0);   // measured on B200 (50k contigs): no gain, the gathers are latency- not L2-bound
     mc->flat = env_int("HH_MCL_FLAT", -1);      // -1 = choose per launch from the mean segment length
@@ -1399,7 +1451,16 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         HH_CHECK(max_col_len(ctx, m, &cap0));
         HH_CHECK(slot_alloc(mc->m0, m->n, cap0, g.W));
         HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
-        HH_CHECK(slot_from_csc(ctx, g, mc->d_scratch, mc->grid_cap, mc->d_counter, mc->d_stats, m, 0, mc->m0));
+        // with integer link counts <= 65535 and row blocks <= 65536 rows the pre-expansion reads a 4-byte
+        // (count, row-in-block) operand instead of the 8-byte (row, value) one
+        const bool try16 = mc->use_a16 && g.T <= 65536;
+        if (try16) {
+            HH_CHECK(hh_dmalloc(&mc->d_m0c, (size_t)m->n * (size_t)cap0));
+            HH_CHECK(hh_dmalloc(&mc->d_rinv, (size_t)m->n));
+            HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, sizeof(int), ctx->stream));
+        }
+        HH_CHECK(slot_from_csc(ctx, g, mc->d_scratch, mc->grid_cap, mc->d_counter, mc->d_stats, m, 0, mc->m0,
+                               try16 ? mc->d_m0c : nullptr, try16 ? mc->d_rinv : nullptr, try16 ? mc->d_bigcount : nullptr));
         HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
         unsigned long long st[4];
         HH_CHECK(read_stats(ctx, mc->d_stats, st));
@@ -1416,6 +1477,15 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         a.B = mc->m0;
         a.dense_out = mc->d_m1;
         a.flat = choose_flat(mc, (double)mc->nnz_m0);
+        if (try16) {
+            int bad = 0;
+            HH_CUDA(cudaMemcpyAsync(&bad, mc->d_bigcount, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            HH_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (!bad) {
+                a.A16 = mc->d_m0c;
+                a.rinv16 = mc->d_rinv;
+            }
+        }
         a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
         HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
         HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
