@@ -196,97 +196,90 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 }
                 const unsigned ne = __ballot_sync(HH_FULL_MASK, seg_len > 0);
                 if (!FLAT) {
-                    // ---- one segment at a time, two 32-entry chunks per trip; the first two chunks of the
-                    // next segment are loaded before the current one is applied
+                    // ---- segment-wise walk.  A work item is up to 128 consecutive entries of one segment, fetched
+                    // with two 128-bit loads per lane (entry pairs at even offsets; a pair straddling the segment
+                    // boundary is masked), and the next item is in flight while the current one is applied.
                     unsigned rem = ne;
-                    int nL = 0, nk0 = 0, nk1 = 0;
-                    unsigned nb = 0;
-                    float nv = 0.f, na0 = 0.f, na1 = 0.f, nr = 0.f;
-                    auto preload = [&]() {
-                        const int u = __ffs(rem) - 1;
-                        rem &= rem - 1;
-                        nL = __shfl_sync(HH_FULL_MASK, seg_len, u);
-                        nb = __shfl_sync(HH_FULL_MASK, seg_base, u);
-                        nv = __shfl_sync(HH_FULL_MASK, seg_v, u);
+                    // uniform state of the item being fetched (absolute entry positions inside the A arrays)
+                    unsigned fpos = 0, fhi = 0;   // next item starts at fpos; the segment ends at fhi
+                    float fv = 0.f, fr = 0.f;
+                    // fetched registers
+                    int nk[4] = {0, 0, 0, 0};
+                    float na[4] = {0.f, 0.f, 0.f, 0.f};
+                    unsigned nm = 0;           // validity bits of the four entries
+                    bool nsync = false;        // item is the last one of its segment -> sync before the next segment
+                    auto fetch = [&]() -> bool {
+                        if (fpos >= fhi) {
+                            if (!rem) return false;
+                            const int u = __ffs(rem) - 1;
+                            rem &= rem - 1;
+                            const int L = __shfl_sync(HH_FULL_MASK, seg_len, u);
+                            fpos = __shfl_sync(HH_FULL_MASK, seg_base, u);
+                            fhi = fpos + (unsigned)L;
+                            fv = __shfl_sync(HH_FULL_MASK, seg_v, u);
+                            if (A16) fr = __shfl_sync(HH_FULL_MASK, seg_r, u);
+                            warp_prod += (unsigned long long)L;
+                        }
+                        const unsigned lo = fpos;
+                        const unsigned al = lo & ~1u;                 // items end on even positions: 128-bit pair loads
+                        const unsigned end = (al + 128u < fhi) ? (al + 128u) : fhi;
+                        fpos = end;
+                        nsync = end >= fhi;
+                        nm = 0;
                         if (A16) {
-                            nr = __shfl_sync(HH_FULL_MASK, seg_r, u);
-                            if (lane < nL) {
-                                const unsigned e0 = a.A16[nb + lane];
-                                nk0 = tile0 + (int)(e0 & 0xFFFFu);
-                                na0 = __fmul_rn((float)(e0 >> 16), nr);
-                            }
-                            if (lane + 32 < nL) {
-                                const unsigned e1x = a.A16[nb + lane + 32];
-                                nk1 = tile0 + (int)(e1x & 0xFFFFu);
-                                na1 = __fmul_rn((float)(e1x >> 16), nr);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const unsigned pq = al + (unsigned)lane + 32u * (unsigned)q;
+                                if (pq >= lo && pq < end) {
+                                    const unsigned e = a.A16[pq];
+                                    nk[q] = tile0 + (int)(e & 0xFFFFu);
+                                    na[q] = __fmul_rn((float)(e >> 16), fr);
+                                    nm |= 1u << q;
+                                }
                             }
                         } else {
-                            if (lane < nL) {
-                                const uint2 e0 = Aent[nb + lane];
-                                nk0 = (int)e0.x;
-                                na0 = __uint_as_float(e0.y);
-                            }
-                            if (lane + 32 < nL) {
-                                const uint2 e1x = Aent[nb + lane + 32];
-                                nk1 = (int)e1x.x;
-                                na1 = __uint_as_float(e1x.y);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const unsigned pp = al + 2u * (unsigned)lane + 64u * (unsigned)h;
+                                if (pp < end && pp + 1u >= lo) {
+                                    const uint4 qd = *reinterpret_cast<const uint4*>(Aent + pp);
+                                    if (pp >= lo) {
+                                        nk[2 * h] = (int)qd.x;
+                                        na[2 * h] = __uint_as_float(qd.y);
+                                        nm |= 1u << (2 * h);
+                                    }
+                                    if (pp + 1u < end) {
+                                        nk[2 * h + 1] = (int)qd.z;
+                                        na[2 * h + 1] = __uint_as_float(qd.w);
+                                        nm |= 1u << (2 * h + 1);
+                                    }
+                                }
                             }
                         }
+                        return true;
                     };
-                    if (rem) preload();
-                    bool have = ne != 0;
+                    bool have = fetch();
                     while (have) {
-                        const int cL = nL, ck0 = nk0, ck1 = nk1;
-                        const unsigned cb = nb;
-                        const float cv = nv, ca0 = na0, ca1 = na1, cr = nr;
-                        have = rem != 0;
-                        if (have) preload();
-                        warp_prod += (unsigned long long)cL;
-                        if (lane < cL) {
-                            acc[ck0] = fmaf(cv, ca0, acc[ck0]);
-                            if (TRACK) dirty |= 1ull << ((ck0 - tile0) >> ch_shift);
+                        int ck[4];
+                        float ca[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            ck[q] = nk[q];
+                            ca[q] = na[q];
                         }
-                        if (lane + 32 < cL) {
-                            acc[ck1] = fmaf(cv, ca1, acc[ck1]);
-                            if (TRACK) dirty |= 1ull << ((ck1 - tile0) >> ch_shift);
-                        }
-                        for (int c = 64; c < cL; c += 64) {
-                            const int p0 = c + lane, p1 = c + 32 + lane;
-                            int k0 = 0, k1 = 0;
-                            float a0 = 0.f, a1 = 0.f;
-                            if (A16) {
-                                if (p0 < cL) {
-                                    const unsigned e0 = a.A16[cb + p0];
-                                    k0 = tile0 + (int)(e0 & 0xFFFFu);
-                                    a0 = __fmul_rn((float)(e0 >> 16), cr);
-                                }
-                                if (p1 < cL) {
-                                    const unsigned e1x = a.A16[cb + p1];
-                                    k1 = tile0 + (int)(e1x & 0xFFFFu);
-                                    a1 = __fmul_rn((float)(e1x >> 16), cr);
-                                }
-                            } else {
-                                if (p0 < cL) {
-                                    const uint2 e0 = Aent[cb + p0];
-                                    k0 = (int)e0.x;
-                                    a0 = __uint_as_float(e0.y);
-                                }
-                                if (p1 < cL) {
-                                    const uint2 e1x = Aent[cb + p1];
-                                    k1 = (int)e1x.x;
-                                    a1 = __uint_as_float(e1x.y);
-                                }
-                            }
-                            if (p0 < cL) {
-                                acc[k0] = fmaf(cv, a0, acc[k0]);
-                                if (TRACK) dirty |= 1ull << ((k0 - tile0) >> ch_shift);
-                            }
-                            if (p1 < cL) {
-                                acc[k1] = fmaf(cv, a1, acc[k1]);
-                                if (TRACK) dirty |= 1ull << ((k1 - tile0) >> ch_shift);
+                        const unsigned cm = nm;
+                        const float cv = fv;
+                        const bool csync = nsync;
+                        // NOTE: fv belongs to the item just fetched; keep the current item's multiplier before fetching
+                        have = fetch();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (cm & (1u << q)) {
+                                acc[ck[q]] = fmaf(cv, ca[q], acc[ck[q]]);
+                                if (TRACK) dirty |= 1ull << ((ck[q] - tile0) >> ch_shift);
                             }
                         }
-                        __syncwarp();   // the next segment may hit the same rows from other lanes
+                        if (csync) __syncwarp();   // the next segment may hit the same rows from other lanes
                     }
                 }
                 // ---- compact the non-empty segments to the low lanes
@@ -1057,6 +1050,7 @@ static void slot_free(hh_slotmat& s) {
 
 static int slot_alloc(hh_slotmat& s, int n, int cap, int W) {
     memset(&s, 0, sizeof(s));
+    cap = (cap + 1) & ~1;      // even: every column slot starts on a 16-byte boundary (128-bit entry-pair loads)
     HH_REQUIRE((unsigned long long)n * (unsigned long long)cap <= 0xFFFFFFFFull, HH_ERR_UNSUPPORTED,
                "hh_mcl: %d columns x %d slot entries exceed the 32-bit entry offsets of the expansion kernel", n, cap);
     s.n = n;
@@ -1064,7 +1058,7 @@ static int slot_alloc(hh_slotmat& s, int n, int cap, int W) {
     s.W = W;
     int rc;
     if ((rc = hh_dmalloc(&s.len, (size_t)n)) != HH_OK || (rc = hh_dmalloc(&s.blk, (size_t)n * (W + 1))) != HH_OK ||
-        (rc = hh_dmalloc(&s.ent, (size_t)n * (size_t)cap)) != HH_OK) {
+        (rc = hh_dmalloc(&s.ent, (size_t)n * (size_t)cap + 2)) != HH_OK) {      // +2: a masked pair load may touch one entry past the last slot
         slot_free(s);
         return rc;
     }
@@ -1455,7 +1449,7 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         // (count, row-in-block) operand instead of the 8-byte (row, value) one
         const bool try16 = mc->use_a16 && g.T <= 65536;
         if (try16) {
-            HH_CHECK(hh_dmalloc(&mc->d_m0c, (size_t)m->n * (size_t)cap0));
+            HH_CHECK(hh_dmalloc(&mc->d_m0c, (size_t)m->n * (size_t)(cap0 + 1) + 4));   // slot stride is cap0 rounded up to even
             HH_CHECK(hh_dmalloc(&mc->d_rinv, (size_t)m->n));
             HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, sizeof(int), ctx->stream));
         }
