@@ -55,11 +55,6 @@ struct hh_colargs {
     float inflation, prune;
     int do_conv;
     int track;                   // product + prune only: keep the dirty-chunk bitmap (sparse columns)
-    const unsigned* A16;         // optional compressed operand for the pre-expansion: (count << 16) | row-in-block, same
-    const float* rinv16;         //   offsets as A; value of an entry = count * rinv16[column]
-    unsigned* out16;             // EPI_NORM: also emit that compressed form (+ rinv_out per column, bad16 flag)
-    float* rinv_out;
-    int* bad16;
     const int* ncols_ptr;        // optional: number of columns to process is read from device memory (overflow list)
     const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
     int* attr_out;               // EPI_PRUNE: strongest row of every produced column
@@ -77,7 +72,7 @@ __device__ __forceinline__ uint64_t hh_warp_or64(uint64_t v) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-template <int W, int SRC, int EPI, bool SMEM, bool TRACK, bool FLAT, bool A16>
+template <int W, int SRC, int EPI, bool SMEM, bool TRACK, bool FLAT>
 __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
     extern __shared__ __align__(16) float hh_dyn_smem[];
     __shared__ double s_d[32];
@@ -155,7 +150,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             unsigned long long warp_prod = 0ull;
             // software pipeline over batches: B entries two batches ahead, block pointers one batch ahead
             int i1 = 0, i2 = 0, s1 = 0, e1 = 0;
-            float v1 = 0.f, v2 = 0.f, r1 = 0.f;
+            float v1 = 0.f, v2 = 0.f;
             if (lane < lenB) {
                 const uint2 be = Bent[lane];
                 i1 = (int)be.x;
@@ -170,14 +165,12 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
                 s1 = bp[0];
                 e1 = bp[1];
-                if (A16) r1 = a.rinv16[i1];
             }
             for (int t0 = 0; t0 < lenB; t0 += 32) {
                 // ---- current batch header (loaded during the previous trip)
                 const int seg_len = (t0 + lane < lenB) ? (e1 - s1) : 0;
                 const unsigned seg_base = (unsigned)((size_t)i1 * capA + (size_t)s1);
                 const float seg_v = v1;
-                const float seg_r = r1;
                 // ---- advance the pipeline: batch +1 gets its block pointers, batch +2 its B entries
                 i1 = i2;
                 v1 = v2;
@@ -187,7 +180,6 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
                     s1 = bp[0];
                     e1 = bp[1];
-                    if (A16) r1 = a.rinv16[i1];
                 }
                 if (t0 + 64 + lane < lenB) {
                     const uint2 be = Bent[t0 + 64 + lane];
@@ -196,90 +188,70 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 }
                 const unsigned ne = __ballot_sync(HH_FULL_MASK, seg_len > 0);
                 if (!FLAT) {
-                    // ---- segment-wise walk.  A work item is up to 128 consecutive entries of one segment, fetched
-                    // with two 128-bit loads per lane (entry pairs at even offsets; a pair straddling the segment
-                    // boundary is masked), and the next item is in flight while the current one is applied.
+                    // ---- one segment at a time, two 32-entry chunks per trip; the first two chunks of the
+                    // next segment are loaded before the current one is applied
                     unsigned rem = ne;
-                    // uniform state of the item being fetched (absolute entry positions inside the A arrays)
-                    unsigned fpos = 0, fhi = 0;   // next item starts at fpos; the segment ends at fhi
-                    float fv = 0.f, fr = 0.f;
-                    // fetched registers
-                    int nk[4] = {0, 0, 0, 0};
-                    float na[4] = {0.f, 0.f, 0.f, 0.f};
-                    unsigned nm = 0;           // validity bits of the four entries
-                    bool nsync = false;        // item is the last one of its segment -> sync before the next segment
-                    auto fetch = [&]() -> bool {
-                        if (fpos >= fhi) {
-                            if (!rem) return false;
-                            const int u = __ffs(rem) - 1;
-                            rem &= rem - 1;
-                            const int L = __shfl_sync(HH_FULL_MASK, seg_len, u);
-                            fpos = __shfl_sync(HH_FULL_MASK, seg_base, u);
-                            fhi = fpos + (unsigned)L;
-                            fv = __shfl_sync(HH_FULL_MASK, seg_v, u);
-                            if (A16) fr = __shfl_sync(HH_FULL_MASK, seg_r, u);
-                            warp_prod += (unsigned long long)L;
+                    int nL = 0, nk0 = 0, nk1 = 0;
+                    unsigned nb = 0;
+                    float nv = 0.f, na0 = 0.f, na1 = 0.f;
+                    auto preload = [&]() {
+                        const int u = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        nL = __shfl_sync(HH_FULL_MASK, seg_len, u);
+                        nb = __shfl_sync(HH_FULL_MASK, seg_base, u);
+                        nv = __shfl_sync(HH_FULL_MASK, seg_v, u);
+                        if (lane < nL) {
+                            const uint2 e0 = Aent[nb + lane];
+                            nk0 = (int)e0.x;
+                            na0 = __uint_as_float(e0.y);
                         }
-                        const unsigned lo = fpos;
-                        const unsigned al = lo & ~1u;                 // items end on even positions: 128-bit pair loads
-                        const unsigned end = (al + 128u < fhi) ? (al + 128u) : fhi;
-                        fpos = end;
-                        nsync = end >= fhi;
-                        nm = 0;
-                        if (A16) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const unsigned pq = al + (unsigned)lane + 32u * (unsigned)q;
-                                if (pq >= lo && pq < end) {
-                                    const unsigned e = a.A16[pq];
-                                    nk[q] = tile0 + (int)(e & 0xFFFFu);
-                                    na[q] = __fmul_rn((float)(e >> 16), fr);
-                                    nm |= 1u << q;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const unsigned pp = al + 2u * (unsigned)lane + 64u * (unsigned)h;
-                                if (pp < end && pp + 1u >= lo) {
-                                    const uint4 qd = *reinterpret_cast<const uint4*>(Aent + pp);
-                                    if (pp >= lo) {
-                                        nk[2 * h] = (int)qd.x;
-                                        na[2 * h] = __uint_as_float(qd.y);
-                                        nm |= 1u << (2 * h);
-                                    }
-                                    if (pp + 1u < end) {
-                                        nk[2 * h + 1] = (int)qd.z;
-                                        na[2 * h + 1] = __uint_as_float(qd.w);
-                                        nm |= 1u << (2 * h + 1);
-                                    }
-                                }
-                            }
+                        if (lane + 32 < nL) {
+                            const uint2 e1x = Aent[nb + lane + 32];
+                            nk1 = (int)e1x.x;
+                            na1 = __uint_as_float(e1x.y);
                         }
-                        return true;
                     };
-                    bool have = fetch();
+                    if (rem) preload();
+                    bool have = ne != 0;
                     while (have) {
-                        int ck[4];
-                        float ca[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            ck[q] = nk[q];
-                            ca[q] = na[q];
+                        const int cL = nL, ck0 = nk0, ck1 = nk1;
+                        const unsigned cb = nb;
+                        const float cv = nv, ca0 = na0, ca1 = na1;
+                        have = rem != 0;
+                        if (have) preload();
+                        warp_prod += (unsigned long long)cL;
+                        if (lane < cL) {
+                            acc[ck0] = fmaf(cv, ca0, acc[ck0]);
+                            if (TRACK) dirty |= 1ull << ((ck0 - tile0) >> ch_shift);
                         }
-                        const unsigned cm = nm;
-                        const float cv = fv;
-                        const bool csync = nsync;
-                        // NOTE: fv belongs to the item just fetched; keep the current item's multiplier before fetching
-                        have = fetch();
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (cm & (1u << q)) {
-                                acc[ck[q]] = fmaf(cv, ca[q], acc[ck[q]]);
-                                if (TRACK) dirty |= 1ull << ((ck[q] - tile0) >> ch_shift);
+                        if (lane + 32 < cL) {
+                            acc[ck1] = fmaf(cv, ca1, acc[ck1]);
+                            if (TRACK) dirty |= 1ull << ((ck1 - tile0) >> ch_shift);
+                        }
+                        for (int c = 64; c < cL; c += 64) {
+                            const int p0 = c + lane, p1 = c + 32 + lane;
+                            int k0 = 0, k1 = 0;
+                            float a0 = 0.f, a1 = 0.f;
+                            if (p0 < cL) {
+                                const uint2 e0 = Aent[cb + p0];
+                                k0 = (int)e0.x;
+                                a0 = __uint_as_float(e0.y);
+                            }
+                            if (p1 < cL) {
+                                const uint2 e1x = Aent[cb + p1];
+                                k1 = (int)e1x.x;
+                                a1 = __uint_as_float(e1x.y);
+                            }
+                            if (p0 < cL) {
+                                acc[k0] = fmaf(cv, a0, acc[k0]);
+                                if (TRACK) dirty |= 1ull << ((k0 - tile0) >> ch_shift);
+                            }
+                            if (p1 < cL) {
+                                acc[k1] = fmaf(cv, a1, acc[k1]);
+                                if (TRACK) dirty |= 1ull << ((k1 - tile0) >> ch_shift);
                             }
                         }
-                        if (csync) __syncwarp();   // the next segment may hit the same rows from other lanes
+                        __syncwarp();   // the next segment may hit the same rows from other lanes
                     }
                 }
                 // ---- compact the non-empty segments to the low lanes
@@ -346,8 +318,8 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 // ---- pull the next batch's segments into L2 (their block pointers arrived long ago)
                 if (a.l2pf && e1 > s1) {
                     const size_t nb = (size_t)i1 * capA;
-                    const char* pi = A16 ? reinterpret_cast<const char*>(a.A16 + nb + s1) : reinterpret_cast<const char*>(Aent + nb + s1);
-                    const int bytes = (e1 - s1) * (A16 ? 4 : 8);
+                    const char* pi = reinterpret_cast<const char*>(Aent + nb + s1);
+                    const int bytes = (e1 - s1) * 8;
                     for (int o = -(int)((uintptr_t)pi & 127); o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + o));
                 }
             }
@@ -413,10 +385,6 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     const int pos = off + __popc(bal & lt_mask);
                     if (pos < a.out.cap) {
                         oent[pos] = make_uint2((unsigned)k, __float_as_uint((a.raw || S == 0.0) ? x : (float)((double)x / S)));
-                        if (a.out16) {
-                            a.out16[(size_t)j * (size_t)a.out.cap + pos] = ((unsigned)x << 16) | (unsigned)(k - tile0);
-                            if (!(x >= 1.f && x <= 65535.f && x == floorf(x))) atomicExch(a.bad16, 1);
-                        }
                     }
                     acc[k] = 0.f;
                 }
@@ -428,7 +396,6 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 a.out.len[j] = min(total, a.out.cap);
                 if (total > a.out.cap) atomicExch(a.err, 1);
                 nnz_acc += (unsigned long long)total;
-                if (a.rinv_out) a.rinv_out[j] = (S != 0.0) ? (float)(1.0 / S) : 0.f;
             }
         } else {
             // E1: inflate (matrix.power(r), fp32) and first column sum (fp64)
@@ -1032,9 +999,6 @@ struct hh_mcl {
     int* d_cnt;                    // [2n] histogram + cursors
     int64_t* d_start;              // [n+1]
     bool order_valid;
-    int use_a16;                   // compressed operand for the pre-expansion (HH_MCL_A16)
-    unsigned* d_m0c;               // [n * cap0] (count << 16) | row-in-block
-    float* d_rinv;                 // [n] 1 / column sum
     int use_small;                 // warp-per-column kernel for nearly converged iterates (HH_MCL_SMALL)
     int* d_bigcount;
     cudaEvent_t ev0, ev1;
@@ -1050,7 +1014,6 @@ static void slot_free(hh_slotmat& s) {
 
 static int slot_alloc(hh_slotmat& s, int n, int cap, int W) {
     memset(&s, 0, sizeof(s));
-    cap = (cap + 1) & ~1;      // even: every column slot starts on a 16-byte boundary (128-bit entry-pair loads)
     HH_REQUIRE((unsigned long long)n * (unsigned long long)cap <= 0xFFFFFFFFull, HH_ERR_UNSUPPORTED,
                "hh_mcl: %d columns x %d slot entries exceed the 32-bit entry offsets of the expansion kernel", n, cap);
     s.n = n;
@@ -1058,7 +1021,7 @@ static int slot_alloc(hh_slotmat& s, int n, int cap, int W) {
     s.W = W;
     int rc;
     if ((rc = hh_dmalloc(&s.len, (size_t)n)) != HH_OK || (rc = hh_dmalloc(&s.blk, (size_t)n * (W + 1))) != HH_OK ||
-        (rc = hh_dmalloc(&s.ent, (size_t)n * (size_t)cap + 2)) != HH_OK) {      // +2: a masked pair load may touch one entry past the last slot
+        (rc = hh_dmalloc(&s.ent, (size_t)n * (size_t)cap)) != HH_OK) {
         slot_free(s);
         return rc;
     }
@@ -1105,18 +1068,18 @@ static hh_geom geom_for(hh_ctx* ctx, int n) {
     return g;
 }
 
-template <int W, int SRC, int EPI, bool TRACK, bool FLAT, bool A16 = false>
+template <int W, int SRC, int EPI, bool TRACK, bool FLAT>
 static int launch_col_wtf(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
     a.scratch = d_scratch;
     int grid = a.ncols < grid_cap ? a.ncols : grid_cap;
     if (grid < 1) return HH_OK;
     HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
     if (g.smem_acc) {
-        auto kern = hh_k_col<W, SRC, EPI, true, TRACK, FLAT, A16>;
+        auto kern = hh_k_col<W, SRC, EPI, true, TRACK, FLAT>;
         HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
         HH_LAUNCH(ctx, kern, grid, W * 32, g.smem_bytes, a);
     } else {
-        auto kern = hh_k_col<W, SRC, EPI, false, TRACK, FLAT, A16>;
+        auto kern = hh_k_col<W, SRC, EPI, false, TRACK, FLAT>;
         HH_CUDA(cudaMemsetAsync(d_scratch, 0, (size_t)grid_cap * (size_t)g.n_pad * sizeof(float), ctx->stream));
         HH_LAUNCH(ctx, kern, grid, W * 32, 0, a);
     }
@@ -1126,8 +1089,6 @@ static int launch_col_wtf(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int g
 // dirty-chunk tracking only pays off when a column touches a small part of the accumulator
 template <int W, int SRC, int EPI>
 static int launch_col_w(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, hh_colargs& a) {
-    if (SRC == SRC_PRODUCT && EPI == EPI_DUMP && a.A16 && !a.flat)
-        return launch_col_wtf<W, SRC_PRODUCT, EPI_DUMP, false, false, true>(ctx, g, d_scratch, grid_cap, a);
     if (SRC == SRC_PRODUCT) {
         const bool track = (EPI == EPI_PRUNE) && a.track;
         if (a.flat) {
@@ -1158,21 +1119,21 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
         // every instantiation has the same footprint; query the heaviest (product + prune)
         switch (g.W) {
             case 8:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, 256,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<8, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 256,
                                                                      g.smem_bytes));
                 break;
             case 16:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, 512,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<16, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 512,
                                                                      g.smem_bytes));
                 break;
             default:
-                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                HH_CUDA(cudaFuncSetAttribute(hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)g.smem_bytes));
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true, false>, 1024,
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hh_k_col<32, SRC_PRODUCT, EPI_PRUNE, true, true, true>, 1024,
                                                                      g.smem_bytes));
                 break;
         }
@@ -1186,8 +1147,7 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
 
 // unsorted CSC -> slotted (raw or column-normalised); cap must be >= the longest column
 static int slot_from_csc(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, int* d_counter, unsigned long long* d_stats,
-                         const hh_matrix* m, int raw, hh_slotmat& out, unsigned* out16 = nullptr, float* rinv_out = nullptr,
-                         int* bad16 = nullptr) {
+                         const hh_matrix* m, int raw, hh_slotmat& out) {
     hh_colargs a;
     memset(&a, 0, sizeof(a));
     a.n = m->n;
@@ -1199,9 +1159,6 @@ static int slot_from_csc(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int gr
     a.csc_val = m->d_val;
     a.out = out;
     a.raw = raw;
-    a.out16 = out16;
-    a.rinv_out = rinv_out;
-    a.bad16 = bad16;
     a.stats = d_stats;
     a.delta_bits = reinterpret_cast<int*>(d_stats + 2);
     a.err = reinterpret_cast<int*>(d_stats + 3);
@@ -1353,8 +1310,6 @@ extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     hh_dfree(mc->d_cnt);
     hh_dfree(mc->d_start);
     hh_dfree(mc->d_bigcount);
-    hh_dfree(mc->d_m0c);
-    hh_dfree(mc->d_rinv);
     if (mc->ev0) cudaEventDestroy(mc->ev0);
     if (mc->ev1) cudaEventDestroy(mc->ev1);
     delete mc;
@@ -1413,7 +1368,6 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
     mc->col_hi = col_hi;
     mc->expansion = expansion;
     mc->cur = -1;
-    mc->use_a16 = env_int("HH_MCL_A16", 1);
     mc->use_small = env_int("HH_MCL_SMALL", 1);
     mc->use_order = env_int("HH_MCL_ORDER", 0);   // measured on B200 (50k contigs): no gain, the gathers are latency- not L2-bound
     mc->flat = env_int("HH_MCL_FLAT", -1);      // -1 = choose per launch from the mean segment length
@@ -1445,16 +1399,7 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         HH_CHECK(max_col_len(ctx, m, &cap0));
         HH_CHECK(slot_alloc(mc->m0, m->n, cap0, g.W));
         HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
-        // with integer link counts <= 65535 and row blocks <= 65536 rows the pre-expansion reads a 4-byte
-        // (count, row-in-block) operand instead of the 8-byte (row, value) one
-        const bool try16 = mc->use_a16 && g.T <= 65536;
-        if (try16) {
-            HH_CHECK(hh_dmalloc(&mc->d_m0c, (size_t)m->n * (size_t)(cap0 + 1) + 4));   // slot stride is cap0 rounded up to even
-            HH_CHECK(hh_dmalloc(&mc->d_rinv, (size_t)m->n));
-            HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, sizeof(int), ctx->stream));
-        }
-        HH_CHECK(slot_from_csc(ctx, g, mc->d_scratch, mc->grid_cap, mc->d_counter, mc->d_stats, m, 0, mc->m0,
-                               try16 ? mc->d_m0c : nullptr, try16 ? mc->d_rinv : nullptr, try16 ? mc->d_bigcount : nullptr));
+        HH_CHECK(slot_from_csc(ctx, g, mc->d_scratch, mc->grid_cap, mc->d_counter, mc->d_stats, m, 0, mc->m0));
         HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
         unsigned long long st[4];
         HH_CHECK(read_stats(ctx, mc->d_stats, st));
@@ -1471,15 +1416,6 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         a.B = mc->m0;
         a.dense_out = mc->d_m1;
         a.flat = choose_flat(mc, (double)mc->nnz_m0);
-        if (try16) {
-            int bad = 0;
-            HH_CUDA(cudaMemcpyAsync(&bad, mc->d_bigcount, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            HH_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (!bad) {
-                a.A16 = mc->d_m0c;
-                a.rinv16 = mc->d_rinv;
-            }
-        }
         a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
         HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
         HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
