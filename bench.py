@@ -235,7 +235,7 @@ def run_b200(a):
     keep = np.ones(n, np.uint8)
     ctx = Context(0)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    hint = int(min(P, n * (n - 1) // 2) * (0.45 if P > 4_000_000 else 1.0))
+    hint = int(min(P, n * (n - 1) // 2) * (0.45 if P > 4_000_000 else 1.0))     # distinct contig pairs the table is sized for
     torch.cuda.synchronize()
 
     def ev():
