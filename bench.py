@@ -315,7 +315,7 @@ def run_b200(a):
         tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
         tab.add(rec_host)                                   # H2D inside, double-buffered
         info = tab.finish()
-        table = tab.fetch()                                 # D2H: the link dicts' arrays
+        table = tab.fetch(pinned=True)                                 # D2H: the link dicts' arrays
         tot = tab.fetch_ctg()
         index, n_linked = tab.linked_index(keep)
         tail = np.nonzero(index < 0)[0].astype(np.int32)

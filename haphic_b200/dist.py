@@ -219,7 +219,7 @@ def bench_multi(a, world: int, rank_id: int, local: int):
         merge_link_tables(tab)
         tab.finish()
         if rank_id == 0:
-            table = tab.fetch()
+            table = tab.fetch(pinned=True)
             tot = tab.fetch_ctg()
         index, n_linked = tab.linked_index(keep)
         mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))

@@ -17,6 +17,28 @@ from ._lib import Context, HHError, LinksInfo, check, load, ptr
 
 NONE32 = 0xFFFFFFFF
 
+_PINNED = {}
+
+
+def _host_buffer(tag, shape, dtype):
+    """numpy array for D2H results.  Backed by page-locked memory (cached per tag and size, because
+    cudaHostAlloc of gigabytes costs more than the copy) when torch is importable: pageable targets
+    limit cudaMemcpy to a fraction of the PCIe rate."""
+    n = int(np.prod(shape))
+    if n * np.dtype(dtype).itemsize < (1 << 20):
+        return np.empty(shape, dtype)
+    try:
+        import torch
+        key = (tag, np.dtype(dtype).str)
+        buf = _PINNED.get(key)
+        nbytes = n * np.dtype(dtype).itemsize
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, pin_memory=True)
+            _PINNED[key] = buf
+        return buf[:nbytes].numpy().view(dtype).reshape(shape)
+    except Exception:
+        return np.empty(shape, dtype)
+
 
 def name_rank(names) -> np.ndarray:
     """Rank of every contig under Python ``str`` ordering of the names (the order
@@ -86,16 +108,18 @@ class LinkTable:
         return info
 
     # -- results ---------------------------------------------------------------------------
-    def fetch(self) -> dict:
-        """Arrays of nnz_full entries in full_link_dict insertion order."""
+    def fetch(self, pinned: bool = False) -> dict:
+        """Arrays of nnz_full entries in full_link_dict insertion order.  ``pinned=True`` returns views of
+        cached page-locked buffers (full PCIe rate) that the next pinned fetch overwrites."""
         if self.info is None:
             self.finish()
         nnz = int(self.info.nnz_full)
+        hb = _host_buffer if pinned else (lambda _tag, shape, dtype: np.empty(shape, dtype))
         out = {
-            "key_i": np.empty(nnz, np.int32), "key_j": np.empty(nnz, np.int32),
-            "full": np.empty(nnz, np.uint32), "flank": np.empty(nnz, np.uint32),
-            "first_full": np.empty(nnz, np.uint32), "first_flank": np.empty(nnz, np.uint32),
-            "ht": np.empty((nnz, 4), np.uint32),
+            "key_i": hb("key_i", (nnz,), np.int32), "key_j": hb("key_j", (nnz,), np.int32),
+            "full": hb("full", (nnz,), np.uint32), "flank": hb("flank", (nnz,), np.uint32),
+            "first_full": hb("first_full", (nnz,), np.uint32), "first_flank": hb("first_flank", (nnz,), np.uint32),
+            "ht": hb("ht", (nnz, 4), np.uint32),
         }
         check(load().hh_links_fetch(self._h, ptr(out["key_i"]), ptr(out["key_j"]), ptr(out["full"]), ptr(out["flank"]),
                                     ptr(out["first_full"]), ptr(out["first_flank"]), ptr(out["ht"])))
