@@ -27,7 +27,7 @@ def _nvcc() -> str:
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def needs_build() -> bool:
@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in sources():
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(objdir, os.path.splitext(os.path.basename(src))[0] + ".o")
         objs.append(obj)
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: {}\n{}".format(" ".join(cmd), out))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lz"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: {}\n{}".format(" ".join(cmd), r.stdout))

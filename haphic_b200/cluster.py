@@ -262,14 +262,13 @@ def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag
     return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, defaultdict(list), defaultdict(set)
 
 
-def build_clm_dict(clm_rec, names, ctg_len, rank, dist_int_type="int32"):
-    """clm_dict {(ctg_i, ctg_j): array of 4 distances per link} (update_clm_dict, 395-401) in
-    first-seen key order.  Host numpy for now (SURVEY.md f-2 moves it to the GPU)."""
-    from array import array
-    code = "i" if dist_int_type == "int32" else "l"
-    clm = defaultdict(lambda: array(code))
+def clm_arrays(clm_rec, n_names, ctg_len, rank, sort_within=True):
+    """(key_i, key_j, offsets, dist[4, total]) of update_clm_dict (395-401): contig pairs in first-seen order;
+    every pair's four distance rows sorted ascending (output_clm sorts them, 388).  Vectorised numpy for now
+    (SURVEY.md f-2 moves the distances and the segmented sort to the GPU)."""
     if len(clm_rec) == 0:
-        return clm
+        z = np.zeros(0, np.int32)
+        return z, z, np.zeros(1, np.int64), np.zeros((4, 0), np.int64)
     r = clm_rec.astype(np.int64)
     swap = rank[r[:, 0]] > rank[r[:, 2]]
     i = np.where(swap, r[:, 2], r[:, 0])
@@ -277,18 +276,54 @@ def build_clm_dict(clm_rec, names, ctg_len, rank, dist_int_type="int32"):
     a0 = np.where(swap, r[:, 3], r[:, 1])
     b0 = np.where(swap, r[:, 1], r[:, 3])
     li, lj = ctg_len[i], ctg_len[j]
-    dist = np.stack([li - a0 + b0, li - a0 + lj - b0, a0 + b0, a0 + lj - b0], axis=1)
-    key = i * len(names) + j
+    key = i * n_names + j
     order = np.argsort(key, kind="stable")
     ks = key[order]
     starts = np.concatenate([[0], np.nonzero(np.diff(ks))[0] + 1])
-    ends = np.concatenate([starts[1:], [len(ks)]])
-    first = order[starts]                         # stable sort: first element of a run = first seen
-    for s in np.argsort(first, kind="stable").tolist():
-        rows = order[starts[s]:ends[s]]
-        k = int(ks[starts[s]])
-        clm[(names[k // len(names)], names[k % len(names)])] = array(code, dist[rows].reshape(-1).tolist())
+    lens = np.diff(np.concatenate([starts, [len(ks)]]))
+    first = order[starts]                          # stable sort: first element of a run = first seen
+    seg_order = np.argsort(first, kind="stable")
+    offsets = np.concatenate([[0], np.cumsum(lens[seg_order])]).astype(np.int64)
+    # position of every sorted element in the output: segments re-ordered by first appearance
+    new_start = np.empty(len(starts), np.int64)
+    new_start[seg_order] = offsets[:-1]
+    seg_id = np.repeat(np.arange(len(starts)), lens)
+    dest = new_start[seg_id] + (np.arange(len(ks)) - starts[seg_id])
+    dist = np.empty((4, len(ks)), np.int64)
+    rows = (li - a0 + b0, li - a0 + lj - b0, a0 + b0, a0 + lj - b0)
+    for k in range(4):
+        dk = rows[k][order]
+        if sort_within:
+            dk = dk[np.lexsort((dk, seg_id))]       # ascending inside every segment
+        dist[k, dest] = dk                          # else: stream order inside the segment (stable key sort)
+    uk = ks[starts][seg_order]
+    return (uk // n_names).astype(np.int32), (uk % n_names).astype(np.int32), offsets, dist
+
+
+def build_clm_dict(clm_rec, names, ctg_len, rank, dist_int_type="int32"):
+    """clm_dict {(ctg_i, ctg_j): array of 4 distances per link} as the reference returns it (395-401), in
+    first-seen key order, distances in stream order."""
+    from array import array
+    code = "i" if dist_int_type == "int32" else "l"
+    clm = defaultdict(lambda: array(code))
+    ki, kj, off, dist = clm_arrays(clm_rec, len(names), ctg_len, rank, sort_within=False)
+    for e in range(len(ki)):
+        s, t = int(off[e]), int(off[e + 1])
+        clm[(names[ki[e]], names[kj[e]])] = array(code, dist[:, s:t].T.reshape(-1).tolist())
     return clm
+
+
+def write_clm(clm_rec, names, ctg_len, rank, path="paired_links.clm"):
+    """paired_links.clm straight from the records with the native writer (hh_clm_write)."""
+    import ctypes as C
+    from . import hicio
+    from ._lib import check, load, ptr
+    logger.info("Writing clm_dict to paired_links.clm...")
+    ki, kj, off, dist = clm_arrays(clm_rec, len(names), ctg_len, rank)
+    dist = np.ascontiguousarray(dist)
+    check(load().hh_clm_write(os.fsencode(path), hicio.names_blob(names), len(names), ptr(np.ascontiguousarray(ki)),
+                              ptr(np.ascontiguousarray(kj)), len(ki), ptr(np.ascontiguousarray(off)), ptr(dist),
+                              dist.shape[1]))
 
 
 def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_set, pos_int_type, dist_int_type):

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import gzip
 import io
+import os
 import struct
 import zlib
 
@@ -30,47 +31,40 @@ def _open_text(path, aln_format):
     raise AssertionError("unknown pairs format {!r}".format(aln_format))
 
 
-def pairs_batches(path, aln_format, name_to_id, bed_path="alignments.bed", batch_lines=2_000_000, inter_only=True):
-    """Yield int32 [m, 4] record batches from a 4DN .pairs file.
+def names_blob(names):
+    """NUL-terminated concatenation of names for the C ABI."""
+    return b"".join(n.encode() + b"\x00" for n in names)
+
+
+def pairs_batches(path, aln_format, name_to_id, bed_path="alignments.bed", batch_lines=4_000_000, inter_only=True):
+    """Yield int32 [m, 4] record batches from a 4DN .pairs / .pairs.gz file.
 
     Mirrors pairs_generator / pairs_generator_inter_ctgs (1539-1583): blank lines and lines starting
     with '#' are skipped; columns are whitespace separated; ``ref, pos, mref, mpos = cols[1],
     int(cols[2])-1, cols[3], int(cols[4])-1``; two BED lines per pair go to ``alignments.bed``
     (needed later by `haphic build` for .pairs input); with ``inter_only`` pairs on one contig are
-    dropped (1582).  Tokenising is vectorised with pandas' C parser."""
-    import pandas as pd
-
-    def to_ids(col):
-        return name_to_id.categories.get_indexer(col).astype(np.int32)      # -1 = not in the FASTA
-
-    fbed = open(bed_path, "w") if bed_path else None
+    dropped (1582).  Tokenising, name lookup and the BED writer are native (hh_pairs_* in
+    libhaphic_b200.so)."""
+    import ctypes as C
+    from ._lib import check, load
+    assert aln_format in ("pairs", "bgzipped_pairs"), aln_format
+    names = name_to_id.names
+    blob = names_blob(names)
+    h = C.c_void_p()
+    lib = load()
+    check(lib.hh_pairs_open(os.fsencode(path), blob, len(names), os.fsencode(bed_path) if bed_path else None,
+                            int(bool(inter_only)), C.byref(h)))
     try:
-        with _open_text(path, aln_format) as f:
-            reader = pd.read_csv(f, sep=r"\s+", header=None, comment=None, usecols=[0, 1, 2, 3, 4], dtype=str,
-                                 chunksize=batch_lines, skip_blank_lines=True, engine="c", na_filter=False,
-                                 names=["rid", "c1", "p1", "c2", "p2"], index_col=False, on_bad_lines="error",
-                                 quoting=3)
-            for chunk in reader:
-                chunk = chunk[~chunk["rid"].str.startswith("#")]
-                if len(chunk) == 0:
-                    continue
-                p1 = chunk["p1"].astype(np.int64).to_numpy() - 1
-                p2 = chunk["p2"].astype(np.int64).to_numpy() - 1
-                if fbed is not None:
-                    a = chunk["c1"] + "\t" + pd.Series(p1, index=chunk.index).astype(str)
-                    b = chunk["c2"] + "\t" + pd.Series(p2, index=chunk.index).astype(str)
-                    l1 = a + "\t" + pd.Series(p1, index=chunk.index).astype(str) + "\t" + chunk["rid"] + "/1\t255\t.\n"
-                    l2 = b + "\t" + pd.Series(p2, index=chunk.index).astype(str) + "\t" + chunk["rid"] + "/2\t255\t.\n"
-                    fbed.write("".join((l1 + l2).tolist()))
-                ia, ib = to_ids(chunk["c1"]), to_ids(chunk["c2"])
-                rec = np.stack([ia, p1.astype(np.int32), ib, p2.astype(np.int32)], axis=1)
-                if inter_only:
-                    rec = rec[chunk["c1"].to_numpy() != chunk["c2"].to_numpy()]
-                if len(rec):
-                    yield np.ascontiguousarray(rec, dtype=np.int32)
+        n_out = C.c_int64()
+        while True:
+            rec = np.empty((batch_lines, 4), np.int32)
+            check(lib.hh_pairs_next(h, rec.ctypes.data_as(C.c_void_p), batch_lines, C.byref(n_out)))
+            m = int(n_out.value)
+            if m == 0:
+                break
+            yield rec[:m]
     finally:
-        if fbed is not None:
-            fbed.close()
+        lib.hh_pairs_close(h)
 
 
 class NameIndex:

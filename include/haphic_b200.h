@@ -196,6 +196,22 @@ int hh_mcl_unpack(hh_mcl* mc, int32_t col_lo, int32_t col_hi, const int32_t* len
 int hh_mcl_commit(hh_mcl* mc);
 int hh_mcl_destroy(hh_mcl* mc);
 
+/* ---- host-side I/O around the path (native, no CUDA) ------------------------------------------------
+ * .pairs / .pairs.gz reader: pairs_generator / pairs_generator_inter_ctgs, HapHiC_cluster.py:1539-1583.  Skips blank
+ * and '#' lines, takes `cols[1], int(cols[2])-1, cols[3], int(cols[4])-1`, writes the two BED lines per pair
+ * to `bed_path` (may be NULL) and returns int32 records {id_a, pos_a, id_b, pos_b} (id -1 = name not in the table);
+ * with inter_only pairs whose two names are equal are dropped (1582).  names_blob = n_names NUL-terminated names. */
+typedef struct hh_pairs_reader hh_pairs_reader;
+int hh_pairs_open(const char* path, const char* names_blob, int32_t n_names, const char* bed_path, int inter_only,
+                  hh_pairs_reader** out);
+int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_records, int64_t* n_out);   /* *n_out == 0: end of file */
+int hh_pairs_close(hh_pairs_reader* r);
+/* paired_links.clm writer: output_clm, HapHiC_cluster.py:376-392.  Pair e links contigs key_i[e], key_j[e]; its
+ * links occupy [offsets[e], offsets[e+1]) of each of the four orientation rows of dist[4][total_links], already
+ * sorted ascending; pairs with fewer than 2 links are skipped, every distance is printed twice. */
+int hh_clm_write(const char* path, const char* names_blob, int32_t n_names, const int32_t* key_i, const int32_t* key_j,
+                 int64_t n_pairs, const int64_t* offsets, const int64_t* dist, int64_t total_links);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,3 +144,39 @@ def test_clm_writer_matches_reference(tmp_path, monkeypatch):
     cluster.output_clm(clm)
     with open("paired_links.clm") as f:
         assert f.read() == str(g["clm_text"])
+
+
+def test_native_clm_writer_matches_reference(tmp_path):
+    from haphic_b200 import cluster
+    from haphic_b200.links import name_rank
+    g = load_golden("links_a.npz")
+    names = g["names"].tolist()
+    rec = g["pairs"]
+    n = len(names)
+    ok = (rec[:, 0] != rec[:, 2]) & (rec[:, 0] < n) & (rec[:, 2] < n)
+    out = str(tmp_path / "paired_links.clm")
+    cluster.write_clm(rec[ok], names, g["lengths"], name_rank(names), out)
+    with open(out) as f:
+        assert f.read() == str(g["clm_text"])
+
+
+def test_native_pairs_reader_gz_and_comments(tmp_path):
+    import gzip
+    from haphic_b200 import hicio
+    names = ["ctgA", "ctgB", "c"]
+    text = ("## pairs format v1.0\n#columns: readID chr1 pos1 chr2 pos2 strand1 strand2\n"
+            "r1\tctgA\t10\tctgB\t20\t+\t-\n\n   \n"
+            "r2 ctgB  5   ctgB 9 + +\n"
+            "r3\tnope\t7\tc\t1\t-\t-\n"
+            "r4\tc\t3\tctgA\t4")                      # last line without newline
+    p = tmp_path / "a.pairs.gz"
+    with gzip.open(p, "wt") as f:
+        f.write(text)
+    idx = hicio.NameIndex(names)
+    got = np.concatenate(list(hicio.pairs_batches(str(p), "bgzipped_pairs", idx, bed_path=str(tmp_path / "a.bed"), batch_lines=2)))
+    assert got.tolist() == [[0, 9, 1, 19], [-1, 6, 2, 0], [2, 2, 0, 3]]
+    bed = (tmp_path / "a.bed").read_text().splitlines()
+    assert bed == ["ctgA\t9\t9\tr1/1\t255\t.", "ctgB\t19\t19\tr1/2\t255\t.", "ctgB\t4\t4\tr2/1\t255\t.", "ctgB\t8\t8\tr2/2\t255\t.",
+                   "nope\t6\t6\tr3/1\t255\t.", "c\t0\t0\tr3/2\t255\t.", "c\t2\t2\tr4/1\t255\t.", "ctgA\t3\t3\tr4/2\t255\t."]
+    all_pairs = np.concatenate(list(hicio.pairs_batches(str(p), "bgzipped_pairs", idx, bed_path=None, inter_only=False)))
+    assert all_pairs.tolist() == [[0, 9, 1, 19], [1, 4, 1, 8], [-1, 6, 2, 0], [2, 2, 0, 3]]
