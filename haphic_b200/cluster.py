@@ -236,7 +236,8 @@ def fragment_layout(fa_dict, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set
     return frag_names, np.asarray(frag_base, np.int32), frag_len, name_rank(frag_names), in_nx
 
 
-def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type):
+def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type,
+                     build_clm=True):
     """Signature and return value of the reference function for the case that some contigs are split into
     bins (1658-1752): flank links and per-fragment totals are keyed by FRAGMENTS (second device table in
     fragment mode), full / HT / clm stay contig-level."""
@@ -256,7 +257,8 @@ def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag
     full_link_dict, _unused_flank, HT_link_dict, _unused_tot = link_dicts(table, names)
     table.close()
     _unused_full, flank_link_dict, _unused_ht, frag_link_dict = link_dicts(ftab, frag_names)
-    clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type)
+    clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type) if build_clm else defaultdict(list)
+    parse_alignments.last_clm = (clm_rec, names, ctg_len, name_rank(names))
     parse_alignments.last_table = ftab
     parse_alignments.frag_names = frag_names
     return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, defaultdict(list), defaultdict(set)
@@ -326,10 +328,12 @@ def write_clm(clm_rec, names, ctg_len, rank, path="paired_links.clm"):
                               dist.shape[1]))
 
 
-def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_set, pos_int_type, dist_int_type):
+def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_set, pos_int_type, dist_int_type,
+                              build_clm=True):
     """Signature and return value of the reference function (1596-1655).  ``alignments`` is an
     iterable of int32 record batches (hicio.pairs_batches / hicio.bam_batches) or of
-    (ref, mref, pos, mpos) tuples as the reference's generators yield."""
+    (ref, mref, pos, mpos) tuples as the reference's generators yield.  ``build_clm=False`` (used by run())
+    leaves clm_dict empty and keeps the usable records in ``.last_clm`` for the native CLM writer."""
     logger.info("Parsing input alignments...")
     if args.remove_allelic_links or args.remove_concentrated_links:
         raise NotImplementedError("haphic_b200: --remove_allelic_links / --remove_concentrated_links are not supported yet")
@@ -339,8 +343,9 @@ def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_se
     batches = _as_batches(alignments, names)
     table, clm_rec = count_links(batches, names, ctg_len, Nx_ctg_set, args.flank)
     full_link_dict, flank_link_dict, HT_link_dict, ctg_link_dict = link_dicts(table, names)
-    clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type)
+    clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type) if build_clm else defaultdict(list)
     parse_alignments_for_ctgs.last_table = table          # run() keeps using the device table
+    parse_alignments_for_ctgs.last_clm = (clm_rec, names, ctg_len, name_rank(names))
     return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, ctg_link_dict, defaultdict(list)
 
 
@@ -970,21 +975,24 @@ def run(args, log_file=None):
 
     if split_ctg_set:
         full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, _coords, _c2f = parse_alignments(
-            alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type)
+            alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type,
+            build_clm=False)
         table = parse_alignments.last_table
+        clm_src = parse_alignments.last_clm
         names = parse_alignments.frag_names         # the matrix lives in fragment space from here on
     else:
         full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, _coords = parse_alignments_for_ctgs(
-            alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_int_type, dist_int_type)
+            alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_int_type, dist_int_type, build_clm=False)
         table = parse_alignments_for_ctgs.last_table
+        clm_src = parse_alignments_for_ctgs.last_clm
 
     output_pickle(HT_link_dict, "HT_link_dict", "HT_links.pkl")
     del HT_link_dict
     if args.quick_view:
         logger.info("Program finished in {}s".format(time.time() - start_time))
         return None
-    output_clm(clm_dict)
-    del clm_dict
+    write_clm(*clm_src)          # same file as output_clm(clm_dict), from the records, native formatter
+    del clm_dict, clm_src
 
     if args.normalize_by_nlinks:
         normalize_by_nlinks(flank_link_dict, frag_link_dict)
