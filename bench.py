@@ -160,7 +160,7 @@ def make_inputs(a, device, rank_id=0, world=1):
     per = a.pairs // world
     lo = rank_id * per
     hi = a.pairs if rank_id == world - 1 else lo + per
-    rec = synth.make_pairs(asm, hi - lo, seed=a.seed + 1 + rank_id, device=device)
+    rec = synth.make_pairs_range(asm, lo, hi, seed=a.seed + 1, device=device)      # same stream for any world size
     return asm, rank, in_nx, rec, lo
 
 
@@ -176,7 +176,7 @@ def run_reference(a):
     asm = synth.make_assembly(a.nchr, a.contigs, a.mean_len, seed=a.seed)
     rank = name_rank(asm.names)
     in_nx = np.ones(asm.n, np.uint8)
-    sample = synth.make_pairs(asm, a.cpu_sample_pairs, seed=a.seed + 1, device="cpu").numpy()
+    sample = synth.make_pairs_range(asm, 0, a.cpu_sample_pairs, seed=a.seed + 1, device="cpu").numpy()
     times = []
     for s in range(a.warmup + a.steps):
         v, dt = cpu_pairs_per_sec(asm, rank, in_nx, sample)

@@ -80,6 +80,22 @@ def make_assembly(nchr: int, n_contigs: int, mean_len: int, seed: int = 12345,
                     np.asarray(start, np.int64), np.asarray(ori, np.int8), int(chrom_len), nchr)
 
 
+def make_pairs_range(asm: Assembly, lo: int, hi: int, seed: int = 12345, cis_frac: float = 0.85,
+                     device: str | torch.device = "cpu", block: int = 1 << 22) -> torch.Tensor:
+    """Records [lo, hi) of the (conceptually infinite) pair stream of ``seed``.  The stream is generated in
+    independently seeded blocks, so any slicing -- one GPU taking everything, or N ranks taking contiguous
+    shards -- sees exactly the same records."""
+    parts = []
+    b0, b1 = lo // block, (hi + block - 1) // block
+    for b in range(b0, b1):
+        blk = make_pairs(asm, block, seed=seed * 1000003 + b, cis_frac=cis_frac, device=device, chunk=block)
+        s, e = max(lo, b * block) - b * block, min(hi, (b + 1) * block) - b * block
+        parts.append(blk[s:e])
+    if not parts:
+        return torch.empty((0, 4), dtype=torch.int32, device=torch.device(device))
+    return torch.cat(parts) if len(parts) > 1 else parts[0].contiguous()
+
+
 def make_pairs(asm: Assembly, n_pairs: int, seed: int = 12345, cis_frac: float = 0.85,
                device: str | torch.device = "cpu", chunk: int = 1 << 24) -> torch.Tensor:
     """Return an int32 tensor [n_pairs, 4] of (ctg_a, pos_a, ctg_b, pos_b)."""
