@@ -26,6 +26,8 @@
 #include "hh_internal.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <utility>
 
 struct hh_slotmat {
     int n;       // rows == columns
@@ -55,6 +57,10 @@ struct hh_colargs {
     float inflation, prune;
     int do_conv;
     int track;                   // product + prune only: keep the dirty-chunk bitmap (sparse columns)
+    // cluster-contiguous relabelling ("perm space"): new index = perm[original index], orig = inverse
+    const int* perm;             // SRC_DENSE / SRC_CSC(slot source): scatter rows through perm
+    const int* orig;             // original index of every (new) row: tie-break of the first maximum; source column lookup
+    int slot_src;                // SRC_CSC: read the column from slotted matrix B (column orig[j] when orig != NULL) instead of a CSC
     const int* ncols_ptr;        // optional: number of columns to process is read from device memory (overflow list)
     const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
     int* attr_out;               // EPI_PRUNE: strongest row of every produced column
@@ -79,6 +85,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
     __shared__ float s_f[32];
     __shared__ int s_k[32];
     __shared__ int s_c[32];
+    __shared__ int s_o[32];
     __shared__ int s_col;
 
     float* __restrict__ acc = SMEM ? hh_dyn_smem : (a.scratch + (size_t)blockIdx.x * a.n_pad);
@@ -105,13 +112,24 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
         const int jj = s_col;
         if (jj >= ncols_run) break;
         const int j = a.order ? a.order[jj] : (a.col_lo + jj);
-        const int jloc = j - a.col_lo;          // position inside the owned (dense) column block
+        const int jsrc = (a.orig && (SRC == SRC_DENSE || (SRC == SRC_CSC && a.slot_src))) ? a.orig[j] : j;   // source column
+        const int jloc = jsrc - a.col_lo;       // position inside the owned (dense) column block
         uint64_t dirty = 0ull;
 
         // ------------------------------------------------------------------ source
         if (SRC == SRC_CSC) {
-            const int64_t p0 = a.csc_ptr[j], p1 = a.csc_ptr[j + 1];
-            for (int64_t p = p0 + threadIdx.x; p < p1; p += W * 32) atomicAdd(&acc[a.csc_row[p]], a.csc_val[p]);
+            if (a.slot_src) {
+                // relabelling pass: column jsrc of the slotted matrix B, rows sent through perm
+                const int L = a.B.len[jsrc];
+                const uint2* __restrict__ se = a.B.ent + (size_t)jsrc * (size_t)a.B.cap;
+                for (int p = threadIdx.x; p < L; p += W * 32) {
+                    const uint2 e = se[p];
+                    acc[a.perm ? a.perm[e.x] : (int)e.x] = __uint_as_float(e.y);
+                }
+            } else {
+                const int64_t p0 = a.csc_ptr[j], p1 = a.csc_ptr[j + 1];
+                for (int64_t p = p0 + threadIdx.x; p < p1; p += W * 32) atomicAdd(&acc[a.csc_row[p]], a.csc_val[p]);
+            }
             __syncthreads();
             dirty = ALL;
         } else if (SRC == SRC_DENSE) {
@@ -119,6 +137,19 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             // the padded column are zeros written by the pre-expansion)
             const float4* __restrict__ col4 = reinterpret_cast<const float4*>(a.dense_in + (size_t)jloc * (size_t)a.ld);
             const int ld4 = (int)(a.ld >> 2);
+            if (a.perm) {
+                // perm space: source row r lands in accumulator row perm[r] (any warp's tile) -> block-wide load
+                const int n4 = (a.n + 3) >> 2;
+                for (int r4 = threadIdx.x; r4 < n4; r4 += W * 32) {
+                    const float4 x = hh_ld_stream_f4(col4 + r4);
+                    const int r = r4 << 2;
+                    if (r < a.n) acc[a.perm[r]] = x.x;
+                    if (r + 1 < a.n) acc[a.perm[r + 1]] = x.y;
+                    if (r + 2 < a.n) acc[a.perm[r + 2]] = x.z;
+                    if (r + 3 < a.n) acc[a.perm[r + 3]] = x.w;
+                }
+                __syncthreads();
+            } else {
             const int r4_0 = (tile0 >> 2) + lane, r4_end = (tile0 + T) >> 2;
             for (int r4 = r4_0; r4 < r4_end; r4 += 128) {
                 float4 x[4];
@@ -132,6 +163,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     const int rr = r4 + q * 32;
                     if (rr < r4_end) reinterpret_cast<float4*>(acc)[rr] = x[q];
                 }
+            }
             }
             __syncwarp();
             dirty = ALL;
@@ -420,7 +452,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             double s2 = 0.0;
             int cnt = 0;
             float vbest = 0.f;
-            int kbest = 0x7fffffff;
+            int kbest = 0x7fffffff, obest = 0x7fffffff;     // obest: ORIGINAL row index of kbest (first maximum = lowest original row)
             HH_FOR_DIRTY_ROWS({
                 const float y = acc[k];
                 if (y != 0.f) {
@@ -430,9 +462,16 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                         cnt++;
                         s2 += (double)x1;
                     }
-                    if (x1 > vbest) {   // rows ascend inside a lane: strict > keeps the first maximum
+                    if (x1 > vbest) {
                         vbest = x1;
                         kbest = k;
+                        obest = a.orig ? a.orig[k] : k;
+                    } else if (x1 == vbest && a.orig) {
+                        const int o = a.orig[k];
+                        if (o < obest) {
+                            kbest = k;
+                            obest = o;
+                        }
                     }
                 }
             })
@@ -442,9 +481,11 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(HH_FULL_MASK, vbest, o);
                 const int ok = __shfl_xor_sync(HH_FULL_MASK, kbest, o);
-                if (ov > vbest || (ov == vbest && ok < kbest)) {
+                const int oo = __shfl_xor_sync(HH_FULL_MASK, obest, o);
+                if (ov > vbest || (ov == vbest && oo < obest)) {
                     vbest = ov;
                     kbest = ok;
+                    obest = oo;
                 }
             }
             if (lane == 0) {
@@ -452,20 +493,24 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 s_c[w] = cnt;
                 s_f[w] = vbest;
                 s_k[w] = kbest;
+                s_o[w] = obest;
             }
             __syncthreads();
             const double sv = (lane < W) ? s_d[lane] : 0.0;
             const int cv = (lane < W) ? s_c[lane] : 0;
             float vmax = (lane < W) ? s_f[lane] : 0.f;
             int kmax = (lane < W) ? s_k[lane] : 0x7fffffff;
+            int omax = (lane < W) ? s_o[lane] : 0x7fffffff;
             double S2 = hh_warp_sum(sv);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(HH_FULL_MASK, vmax, o);
                 const int ok = __shfl_xor_sync(HH_FULL_MASK, kmax, o);
-                if (ov > vmax || (ov == vmax && ok < kmax)) {
+                const int oo = __shfl_xor_sync(HH_FULL_MASK, omax, o);
+                if (ov > vmax || (ov == vmax && oo < omax)) {
                     vmax = ov;
                     kmax = ok;
+                    omax = oo;
                 }
             }
             int incl = cv;
@@ -575,6 +620,337 @@ __global__ void hh_k_order_scatter(const int* __restrict__ root, int col_lo, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cluster-contiguous relabelling.  Markov clustering never creates an entry between two connected
+// components of the iterate's pattern, so once the vertices of a component are contiguous every later
+// column lives in a window of rows = its component.  Components are found on the first pruned iterate by
+// min-label hooking + pointer jumping; new index = rank of (component label, original index).
+// ---------------------------------------------------------------------------------------------
+__global__ void hh_k_cc_init(int* __restrict__ label, int n) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) label[v] = v;
+}
+
+__global__ void hh_k_cc_hook(const hh_slotmat m, int* __restrict__ label, int* __restrict__ changed) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < m.n; j += warps) {
+        const int L = m.len[j];
+        const uint2* e = m.ent + (size_t)j * (size_t)m.cap;
+        int lj = label[j];
+        int mn = lj;
+        for (int p = lane; p < L; p += 32) mn = min(mn, label[e[p].x]);
+        mn = __reduce_min_sync(HH_FULL_MASK, mn);
+        bool ch = false;
+        if (mn < lj) {
+            if (lane == 0) atomicMin(label + j, mn);
+            ch = true;
+        }
+        for (int p = lane; p < L; p += 32) {
+            const int k = (int)e[p].x;
+            if (label[k] > mn) {
+                atomicMin(label + k, mn);
+                ch = true;
+            }
+        }
+        if (ch) *changed = 1;
+    }
+}
+
+__global__ void hh_k_cc_jump(int* __restrict__ label, int n) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    int l = label[v];
+    for (int t = 0; t < 8; ++t) {
+        const int l2 = label[l];
+        if (l2 == l) break;
+        l = l2;
+    }
+    label[v] = l;
+}
+
+// perm[v] = number of vertices with a smaller (label, v) key; also component sizes
+__global__ void __launch_bounds__(256) hh_k_cc_rank(const int* __restrict__ label, int n, int* __restrict__ perm,
+                                                    int* __restrict__ inv, int* __restrict__ comp_size) {
+    __shared__ unsigned long long tile[1024];
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long mine = (v < n) ? (((unsigned long long)(unsigned)label[v] << 32) | (unsigned)v) : ~0ull;
+    int rank = 0;
+    for (int base = 0; base < n; base += 1024) {
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x)
+            tile[k] = (base + k < n) ? (((unsigned long long)(unsigned)label[base + k] << 32) | (unsigned)(base + k)) : ~0ull;
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 1024; ++k) rank += (tile[k] < mine) ? 1 : 0;
+        __syncthreads();
+    }
+    if (v < n) {
+        perm[v] = rank;
+        inv[rank] = v;
+        atomicAdd(comp_size + label[v], 1);
+    }
+}
+
+// per NEW index: the row window of its component
+__global__ void hh_k_cc_ranges(const int* __restrict__ label, const int* __restrict__ perm, const int* __restrict__ comp_size, int n,
+                               int* __restrict__ comp_lo, int* __restrict__ comp_hi) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int root = label[v];                 // the smallest original index of the component = its first new index
+    const int lo = perm[root];
+    comp_lo[perm[v]] = lo;
+    comp_hi[perm[v]] = lo + comp_size[root];
+}
+
+// split the owned columns (new indices perm[col_lo + jj]) into window-eligible and the rest
+__global__ void hh_k_cc_lists(const int* __restrict__ perm, int col_lo, int ncols, const int* __restrict__ comp_lo,
+                              const int* __restrict__ comp_hi, int wmax, int* __restrict__ owned, int* __restrict__ win_list,
+                              int* __restrict__ big_list, int* __restrict__ counts) {
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj >= ncols) return;
+    const int j = perm[col_lo + jj];
+    owned[jj] = j;
+    if (comp_hi[j] - comp_lo[j] <= wmax) win_list[atomicAdd(counts + 0, 1)] = j;
+    else big_list[atomicAdd(counts + 1, 1)] = j;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Windowed expansion (perm space): a CTA of NW warps per column; every warp owns a PRIVATE accumulator of
+// the column's row window and expands a contiguous share of the column's entries by streaming whole operand
+// columns (long coalesced reads, no per-row-block bookkeeping).  The partial accumulators are added in warp
+// order, then the usual epilogue runs over the window only.
+// ---------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) hh_k_col_win(const hh_colargs a, int W, const int* __restrict__ list, int nlist,
+                                                        const int* __restrict__ comp_lo, const int* __restrict__ comp_hi, int wmax) {
+    extern __shared__ __align__(16) float hh_win_smem[];
+    __shared__ double s_d[NW];
+    __shared__ float s_f[NW];
+    __shared__ int s_k[NW], s_o[NW], s_c[NW];
+    __shared__ int s_col;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float* __restrict__ accw = hh_win_smem + (size_t)w * wmax;      // this warp's private accumulator
+    float* __restrict__ acc0 = hh_win_smem;                         // merged column after the reduction
+    int* __restrict__ rows = reinterpret_cast<int*>(hh_win_smem + wmax);   // compacted rows (NW >= 2)
+    const uint2* __restrict__ Aent = a.A.ent;
+    const size_t capA = (size_t)a.A.cap;
+    const float p32 = a.prune, rf = a.inflation;
+    const bool sq = a.inflate_square != 0;
+    const bool conv = a.do_conv != 0;
+    for (int k = threadIdx.x; k < NW * wmax; k += NW * 32) hh_win_smem[k] = 0.f;
+    __syncthreads();
+    float dmax = 0.f;
+    unsigned long long prod_acc = 0ull, nnz_acc = 0ull;
+    for (;;) {
+        if (threadIdx.x == 0) s_col = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int jj = s_col;
+        if (jj >= nlist) break;
+        const int j = list[jj];
+        const int lo = comp_lo[j], width = comp_hi[j] - lo;
+        const int lenB = a.B.len[j];
+        const uint2* __restrict__ Bent = a.B.ent + (size_t)j * (size_t)a.B.cap;
+        // ---- expansion: this warp's contiguous share of the column's entries
+        const int t_beg = (int)(((long long)lenB * w) / NW), t_end = (int)(((long long)lenB * (w + 1)) / NW);
+        unsigned long long warp_prod = 0ull;
+        for (int t0 = t_beg; t0 < t_end; t0 += 32) {
+            const int t = t0 + lane;
+            int il = 0, Ll = 0;
+            float vl = 0.f;
+            if (t < t_end) {
+                const uint2 be = Bent[t];
+                il = (int)be.x;
+                vl = __uint_as_float(be.y);
+                Ll = a.A.len[il];
+            }
+            const int cnt = min(32, t_end - t0);
+            for (int u = 0; u < cnt; ++u) {
+                const int L = __shfl_sync(HH_FULL_MASK, Ll, u);
+                const float v = __shfl_sync(HH_FULL_MASK, vl, u);
+                const uint2* __restrict__ col = Aent + (size_t)__shfl_sync(HH_FULL_MASK, il, u) * capA;
+                warp_prod += (unsigned long long)L;
+                for (int p = lane; p < L; p += 128) {
+                    uint2 e[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) e[q] = (p + 32 * q < L) ? col[p + 32 * q] : make_uint2(0xFFFFFFFFu, 0u);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (e[q].x != 0xFFFFFFFFu) {
+                            const unsigned r = e[q].x - (unsigned)lo;
+                            if (r < (unsigned)width) accw[r] = fmaf(v, __uint_as_float(e[q].y), accw[r]);
+                            else atomicExch(a.err, 2);             // a row outside the component window: never silently dropped
+                        }
+                    }
+                }
+                __syncwarp();      // the next operand column may hit the same rows from other lanes
+            }
+        }
+        if (lane == 0) prod_acc += warp_prod;
+        __syncthreads();
+        // ---- merge the private accumulators (warp order) + E1 inflate + first column sum
+        const int Tw = (((width + NW - 1) / NW) + 31) & ~31;
+        const int r_beg = w * Tw, r_end = min(width, (w + 1) * Tw);
+        double s1 = 0.0;
+        for (int r = r_beg + lane; r < r_end; r += 32) {
+            float x = acc0[r];
+#pragma unroll
+            for (int q = 1; q < NW; ++q) {
+                x += hh_win_smem[(size_t)q * wmax + r];
+                hh_win_smem[(size_t)q * wmax + r] = 0.f;
+            }
+            float y = 0.f;
+            if (x != 0.f) {
+                y = sq ? (x * x) : powf(x, rf);
+                s1 += (double)y;
+            }
+            acc0[r] = y;
+        }
+        s1 = hh_warp_sum(s1);
+        if (lane == 0) s_d[w] = s1;
+        __syncthreads();
+        double S1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) S1 += s_d[q];
+        __syncthreads();
+        // ---- E2: normalise, threshold statistics, first maximum (lowest ORIGINAL row among ties)
+        double s2 = 0.0;
+        int cnt = 0, kbest = 0x7fffffff, obest = 0x7fffffff;
+        float vbest = 0.f;
+        for (int r = r_beg + lane; r < r_end; r += 32) {
+            const float y = acc0[r];
+            if (y != 0.f) {
+                const float x1 = (S1 != 0.0) ? (float)((double)y / S1) : y;
+                acc0[r] = x1;
+                if (x1 >= p32 && x1 > 0.f) {
+                    cnt++;
+                    s2 += (double)x1;
+                }
+                if (x1 > vbest || (x1 == vbest && x1 > 0.f)) {
+                    const int o = a.orig ? a.orig[lo + r] : (lo + r);
+                    if (x1 > vbest || o < obest) {
+                        vbest = x1;
+                        kbest = lo + r;
+                        obest = o;
+                    }
+                }
+            }
+        }
+        s2 = hh_warp_sum(s2);
+        cnt = hh_warp_sum(cnt);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(HH_FULL_MASK, vbest, o);
+            const int ok = __shfl_xor_sync(HH_FULL_MASK, kbest, o);
+            const int oo = __shfl_xor_sync(HH_FULL_MASK, obest, o);
+            if (ov > vbest || (ov == vbest && oo < obest)) {
+                vbest = ov;
+                kbest = ok;
+                obest = oo;
+            }
+        }
+        if (lane == 0) {
+            s_d[w] = s2;
+            s_c[w] = cnt;
+            s_f[w] = vbest;
+            s_k[w] = kbest;
+            s_o[w] = obest;
+        }
+        __syncthreads();
+        double S2 = 0.0;
+        int total = 0, base = 0, kmax = 0x7fffffff, omax = 0x7fffffff;
+        float vmax = 0.f;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            S2 += s_d[q];
+            if (q < w) base += s_c[q];
+            total += s_c[q];
+            if (s_f[q] > vmax || (s_f[q] == vmax && s_o[q] < omax)) {
+                vmax = s_f[q];
+                kmax = s_k[q];
+                omax = s_o[q];
+            }
+        }
+        const bool need_max = (total == 0) && (vmax > 0.f);
+        if (need_max) {
+            const int wk = (kmax - lo) / Tw;
+            base = (w > wk) ? 1 : 0;
+            total = 1;
+            S2 = (double)vmax;
+        }
+        // ---- E3: ordered compaction into the slot; rows kept in shared memory for the row-block pointers
+        uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
+        int off = base;
+        for (int r0 = r_beg; r0 < r_end; r0 += 32) {
+            const int r = r0 + lane;
+            const float x1 = (r < r_end) ? acc0[r] : 0.f;
+            const bool f = (r < r_end) && (need_max ? (lo + r == kmax) : (x1 >= p32 && x1 > 0.f));
+            const unsigned bal = __ballot_sync(HH_FULL_MASK, f);
+            float keepv = 0.f;
+            if (f) {
+                const int pos = off + __popc(bal & lt_mask);
+                const float x2 = (float)((double)x1 / S2);
+                if (pos < a.out.cap) oent[pos] = make_uint2((unsigned)(lo + r), __float_as_uint(x2));
+                if (pos < wmax) rows[pos] = lo + r;
+                keepv = x2;
+            }
+            if (r < r_end) acc0[r] = conv ? keepv : 0.f;
+            off += __popc(bal);
+        }
+        __syncthreads();
+        // row-block pointers of the new column
+        if (threadIdx.x <= W) {
+            int bp = total;
+            if (threadIdx.x < W) {
+                const int target = threadIdx.x * a.T;
+                int lo2 = 0, hi2 = min(total, wmax);
+                while (lo2 < hi2) {
+                    const int mid = (lo2 + hi2) >> 1;
+                    if (rows[mid] < target) lo2 = mid + 1;
+                    else hi2 = mid;
+                }
+                bp = lo2;
+            }
+            a.out.blk[(size_t)j * (W + 1) + threadIdx.x] = min(bp, a.out.cap);
+        }
+        if (threadIdx.x == 0) {
+            a.out.len[j] = min(total, a.out.cap);
+            if (total > a.out.cap || total > wmax) atomicExch(a.err, 1);
+            nnz_acc += (unsigned long long)total;
+            if (a.attr_out) a.attr_out[j] = (vmax > 0.f) ? kmax : j;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < min(total, wmax); p += NW * 32) rows[p] = 0;     // it aliases warp 1's accumulator
+        if (conv) {
+            // E4: entries of the previous iterate L = B[:, j]
+            for (int p = threadIdx.x; p < lenB; p += NW * 32) {
+                const uint2 le = Bent[p];
+                const unsigned r = le.x - (unsigned)lo;
+                const float l = __uint_as_float(le.y);
+                const float m = (r < (unsigned)width) ? acc0[r] : 0.f;
+                dmax = fmaxf(dmax, __fsub_rn(fabsf(__fsub_rn(m, l)), __fmul_rn(1e-5f, fabsf(l))));
+                if (r < (unsigned)width) acc0[r] = 0.f;
+            }
+            __syncthreads();
+            // E5: entries only in M + accumulator reset
+            for (int r = r_beg + lane; r < r_end; r += 32) {
+                const float m = acc0[r];
+                if (m != 0.f) {
+                    dmax = fmaxf(dmax, m);
+                    acc0[r] = 0.f;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    dmax = hh_warp_max(dmax);
+    if (lane == 0) {
+        if (dmax > 0.f) atomicMax(a.delta_bits, __float_as_int(dmax));
+        if (prod_acc) atomicAdd(a.stats + 1, prod_acc);
+    }
+    if (threadIdx.x == 0 && nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
+}
+
+// ---------------------------------------------------------------------------------------------
 // nearly converged iterates: a column has a handful of entries, and the CTA-per-column kernel is bound
 // by its per-column latency chain (one column in flight per SM).  Here ONE WARP expands a column by a
 // 32-way merge of the operand columns (rows come out ascending, contributions are fused in ascending-i
@@ -585,7 +961,8 @@ __global__ void hh_k_order_scatter(const int* __restrict__ root, int col_lo, int
 #define HH_SMALL_CAP 256
 #define HH_SMALL_MAXPROD 4096
 
-__global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W, int* __restrict__ biglist, int* __restrict__ bigcount) {
+__global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W, int* __restrict__ biglist, int* __restrict__ bigcount,
+                                                      const int* __restrict__ list) {
     __shared__ int s_k[8][HH_SMALL_CAP];
     __shared__ float s_v[8][HH_SMALL_CAP];
     __shared__ int s_ok[8][32];
@@ -602,7 +979,7 @@ __global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W,
     float dmax = 0.f;
     unsigned long long prod_acc = 0ull, nnz_acc = 0ull;
     for (int jj = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jj < a.ncols; jj += nwarps) {
-        const int j = a.col_lo + jj;
+        const int j = list ? list[jj] : (a.col_lo + jj);
         const int L = a.B.len[j];
         bool big = L > 32;
         int il = 0x7fffffff, lenl = 0;
@@ -675,7 +1052,7 @@ __global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W,
         __syncwarp();
         // ---- E2: normalise, threshold statistics, first maximum
         double s2 = 0.0;
-        int cnt = 0, kmax = 0x7fffffff;
+        int cnt = 0, kmax = 0x7fffffff, omax = 0x7fffffff;
         float vmax = 0.f;
         for (int p = lane; p < nout; p += 32) {
             const float y = sv[p];
@@ -686,9 +1063,13 @@ __global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W,
                     cnt++;
                     s2 += (double)x1;
                 }
-                if (x1 > vmax) {
-                    vmax = x1;
-                    kmax = sk[p];
+                if (x1 > vmax || (x1 == vmax && x1 > 0.f)) {
+                    const int o = a.orig ? a.orig[sk[p]] : sk[p];      // first maximum = lowest ORIGINAL row
+                    if (x1 > vmax || o < omax) {
+                        vmax = x1;
+                        kmax = sk[p];
+                        omax = o;
+                    }
                 }
             }
         }
@@ -698,9 +1079,11 @@ __global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W,
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(HH_FULL_MASK, vmax, o);
             const int ok = __shfl_xor_sync(HH_FULL_MASK, kmax, o);
-            if (ov > vmax || (ov == vmax && ok < kmax)) {
+            const int oo = __shfl_xor_sync(HH_FULL_MASK, omax, o);
+            if (ov > vmax || (ov == vmax && oo < omax)) {
                 vmax = ov;
                 kmax = ok;
+                omax = oo;
             }
         }
         const bool need_max = (cnt == 0) && (vmax > 0.f);
@@ -914,11 +1297,11 @@ __global__ void hh_k_rank_sum(const hh_slotmat m, int topN, const int* __restric
 // pack / unpack of column blocks (canonical CSC export, multi-GPU exchange)
 // ---------------------------------------------------------------------------------------------
 __global__ void hh_k_pack(const hh_slotmat m, int col_lo, int ncols, const int64_t* __restrict__ off, int* __restrict__ len_out,
-                          int* __restrict__ idx_out, float* __restrict__ val_out) {
+                          int* __restrict__ idx_out, float* __restrict__ val_out, const int* __restrict__ colmap) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int jj = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jj < ncols; jj += warps) {
-        const int c = col_lo + jj;
+        const int c = colmap ? colmap[col_lo + jj] : (col_lo + jj);
         const int L = m.len[c];
         if (lane == 0 && len_out) len_out[jj] = L;
         const uint2* se = m.ent + (size_t)c * (size_t)m.cap;
@@ -933,12 +1316,12 @@ __global__ void hh_k_pack(const hh_slotmat m, int col_lo, int ncols, const int64
 
 __global__ void hh_k_unpack(const hh_slotmat m, int T, int col_lo, int ncols, const int* __restrict__ len_in,
                             const int64_t* __restrict__ off, const int* __restrict__ idx_in, const float* __restrict__ val_in,
-                            int* __restrict__ err) {
+                            int* __restrict__ err, const int* __restrict__ colmap) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int W = m.W;
     for (int jj = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jj < ncols; jj += warps) {
-        const int c = col_lo + jj;
+        const int c = colmap ? colmap[col_lo + jj] : (col_lo + jj);
         int L = len_in[jj];
         if (L > m.cap || L < 0) {
             if (lane == 0) atomicExch(err, 1);
@@ -962,6 +1345,11 @@ __global__ void hh_k_unpack(const hh_slotmat m, int T, int col_lo, int ncols, co
             m.len[c] = L;
         }
     }
+}
+
+__global__ void hh_k_gather_len(const int* __restrict__ len, const int* __restrict__ colmap, int col_lo, int ncols, int* __restrict__ out) {
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj < ncols) out[jj] = len[colmap ? colmap[col_lo + jj] : (col_lo + jj)];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1001,6 +1389,21 @@ struct hh_mcl {
     bool order_valid;
     int use_small;                 // warp-per-column kernel for nearly converged iterates (HH_MCL_SMALL)
     int* d_bigcount;
+    // cluster-contiguous relabelling + windowed expansion (HH_MCL_WINDOW)
+    int use_window;
+    bool perm_valid;               // perm / lists below are built (once per hh_mcl, from the first pruned iterate)
+    bool perm_space;               // the iterates it[] are stored in new (perm) indices
+    int last_step_it;              // iteration number of the pending / last committed step
+    int* d_perm;                   // [n] original -> new
+    int* d_inv;                    // [n] new -> original
+    int* d_comp_lo;                // [n] per new index: first row of its component
+    int* d_comp_hi;                // [n]
+    int* d_owned;                  // [ncols] new indices of the owned columns
+    int* d_win_list;               // owned columns whose component fits the window kernel
+    int* d_big_list;               // the rest
+    int* d_overflow;               // [ncols] overflow list of the small kernel
+    int n_win, n_big, wmax;
+    std::vector<int>* h_inv;       // host copy of d_inv (result export)
     cudaEvent_t ev0, ev1;
     float create_ms[2];            // device time of the normalisation / pre-expansion kernels
 };
@@ -1179,13 +1582,17 @@ static int max_col_len(hh_ctx* ctx, const hh_matrix* m, int* out) {
 }
 
 // slotted -> canonical CSC on the host
-static int slot_fetch_csc(hh_ctx* ctx, const hh_slotmat& s, int col_lo, int ncols, int64_t* indptr, int32_t* indices, float* data) {
+static int slot_fetch_csc(hh_ctx* ctx, const hh_slotmat& s, int col_lo, int ncols, int64_t* indptr, int32_t* indices, float* data,
+                          const int* d_colmap = nullptr, const std::vector<int>* h_rowinv = nullptr) {
     int64_t* d_off = nullptr;
     int* d_idx = nullptr;
     float* d_val = nullptr;
+    int* d_len = nullptr;
     HH_CHECK(hh_dmalloc(&d_off, (size_t)ncols + 1));
     int rc = [&]() -> int {
-        HH_CHECK(hh_exclusive_scan_i32(ctx, s.len + col_lo, d_off, ncols));
+        HH_CHECK(hh_dmalloc(&d_len, (size_t)ncols));
+        HH_LAUNCH(ctx, hh_k_gather_len, (ncols + 255) / 256, 256, 0, s.len, d_colmap, col_lo, ncols, d_len);
+        HH_CHECK(hh_exclusive_scan_i32(ctx, d_len, d_off, ncols));
         if (indptr) HH_CUDA(cudaMemcpyAsync(indptr, d_off, ((size_t)ncols + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         HH_CUDA(cudaMemcpyAsync(ctx->h_scratch, d_off + ncols, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1195,15 +1602,30 @@ static int slot_fetch_csc(hh_ctx* ctx, const hh_slotmat& s, int col_lo, int ncol
         HH_CHECK(hh_dmalloc(&d_val, (size_t)nnz));
         int grid = (ncols + 7) / 8;
         if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-        HH_LAUNCH(ctx, hh_k_pack, grid, 256, 0, s, col_lo, ncols, d_off, (int*)nullptr, d_idx, d_val);
+        HH_LAUNCH(ctx, hh_k_pack, grid, 256, 0, s, col_lo, ncols, d_off, (int*)nullptr, d_idx, d_val, d_colmap);
         if (indices) HH_CUDA(cudaMemcpyAsync(indices, d_idx, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (data) HH_CUDA(cudaMemcpyAsync(data, d_val, (size_t)nnz * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h_rowinv && indices && data && indptr) {
+            // rows are new indices: translate to original ones and restore ascending order inside every column
+            std::vector<std::pair<int32_t, float>> tmp;
+            for (int c = 0; c < ncols; ++c) {
+                const int64_t b = indptr[c], e = indptr[c + 1];
+                tmp.resize((size_t)(e - b));
+                for (int64_t q = b; q < e; ++q) tmp[(size_t)(q - b)] = std::make_pair((int32_t)(*h_rowinv)[(size_t)indices[q]], data[q]);
+                std::sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, float>& x, const std::pair<int32_t, float>& y) { return x.first < y.first; });
+                for (int64_t q = b; q < e; ++q) {
+                    indices[q] = tmp[(size_t)(q - b)].first;
+                    data[q] = tmp[(size_t)(q - b)].second;
+                }
+            }
+        }
         return HH_OK;
     }();
     hh_dfree(d_off);
     hh_dfree(d_idx);
     hh_dfree(d_val);
+    hh_dfree(d_len);
     return rc;
 }
 
@@ -1310,6 +1732,15 @@ extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     hh_dfree(mc->d_cnt);
     hh_dfree(mc->d_start);
     hh_dfree(mc->d_bigcount);
+    hh_dfree(mc->d_perm);
+    hh_dfree(mc->d_inv);
+    hh_dfree(mc->d_comp_lo);
+    hh_dfree(mc->d_comp_hi);
+    hh_dfree(mc->d_owned);
+    hh_dfree(mc->d_win_list);
+    hh_dfree(mc->d_big_list);
+    hh_dfree(mc->d_overflow);
+    delete mc->h_inv;
     if (mc->ev0) cudaEventDestroy(mc->ev0);
     if (mc->ev1) cudaEventDestroy(mc->ev1);
     delete mc;
@@ -1369,6 +1800,7 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
     mc->expansion = expansion;
     mc->cur = -1;
     mc->use_small = env_int("HH_MCL_SMALL", 1);
+    mc->use_window = env_int("HH_MCL_WINDOW", 1);
     mc->use_order = env_int("HH_MCL_ORDER", 0);   // measured on B200 (50k contigs): no gain, the gathers are latency- not L2-bound
     mc->flat = env_int("HH_MCL_FLAT", -1);      // -1 = choose per launch from the mean segment length
     mc->l2pf = env_int("HH_MCL_L2PF", -1);       // -1 = prefetch in segment-wise mode only (long segments)
@@ -1392,7 +1824,15 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         HH_CHECK(hh_dmalloc(&mc->d_root, (size_t)(col_hi - col_lo)));
         HH_CHECK(hh_dmalloc(&mc->d_cnt, (size_t)m->n * 2));
         HH_CHECK(hh_dmalloc(&mc->d_start, (size_t)m->n + 1));
-        HH_CHECK(hh_dmalloc(&mc->d_bigcount, 1));
+        HH_CHECK(hh_dmalloc(&mc->d_bigcount, 4));
+        HH_CHECK(hh_dmalloc(&mc->d_perm, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_inv, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_comp_lo, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_comp_hi, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_owned, (size_t)(col_hi - col_lo)));
+        HH_CHECK(hh_dmalloc(&mc->d_win_list, (size_t)(col_hi - col_lo)));
+        HH_CHECK(hh_dmalloc(&mc->d_big_list, (size_t)(col_hi - col_lo)));
+        HH_CHECK(hh_dmalloc(&mc->d_overflow, (size_t)(col_hi - col_lo)));
         HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
         // 1) M0 = normalize(link_matrix, 'l1', axis=0)   (2144)
         int cap0 = 0;
@@ -1461,6 +1901,79 @@ extern "C" int hh_mcl_fetch_m1(hh_mcl* mc, float* dense) {
     return HH_OK;
 }
 
+// components of the committed iterate's pattern -> perm / inv / component windows / column lists, then the
+// iterate itself is rewritten in new indices (one pass of the column kernel)
+static int mcl_build_perm(hh_mcl* mc) {
+    hh_ctx* ctx = mc->ctx;
+    const int n = mc->n;
+    const hh_geom g = mcl_geom(mc);
+    const hh_slotmat& M = mc->it[mc->cur];
+    int* d_label = mc->d_root;            // scratch
+    int* d_csize = mc->d_cnt;             // [n] component sizes (+ [n..2n) unused)
+    int* d_flag = mc->d_bigcount + 2;
+    const int ncols = mc->col_hi - mc->col_lo;
+    int* d_lab = nullptr;
+    HH_CHECK(hh_dmalloc(&d_lab, (size_t)n));
+    (void)d_label;
+    int rc = [&]() -> int {
+        HH_LAUNCH(ctx, hh_k_cc_init, (n + 255) / 256, 256, 0, d_lab, n);
+        int grid = (n + 7) / 8;
+        if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+        for (int round = 0; round < 64; ++round) {
+            HH_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+            HH_LAUNCH(ctx, hh_k_cc_hook, grid, 256, 0, M, d_lab, d_flag);
+            HH_LAUNCH(ctx, hh_k_cc_jump, (n + 255) / 256, 256, 0, d_lab, n);
+            int changed = 0;
+            HH_CUDA(cudaMemcpyAsync(&changed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            HH_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (!changed) break;
+        }
+        HH_CUDA(cudaMemsetAsync(d_csize, 0, (size_t)n * sizeof(int), ctx->stream));
+        HH_LAUNCH(ctx, hh_k_cc_rank, (n + 255) / 256, 256, 0, d_lab, n, mc->d_perm, mc->d_inv, d_csize);
+        HH_LAUNCH(ctx, hh_k_cc_ranges, (n + 255) / 256, 256, 0, d_lab, mc->d_perm, d_csize, n, mc->d_comp_lo, mc->d_comp_hi);
+        // window size: the largest component that still fits (4 private accumulators of wmax floats, several CTAs per SM)
+        const int wlimit = env_int("HH_MCL_WMAX", 4096);
+        HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, 2 * sizeof(int), ctx->stream));
+        HH_LAUNCH(ctx, hh_k_cc_lists, (ncols + 255) / 256, 256, 0, mc->d_perm, mc->col_lo, ncols, mc->d_comp_lo, mc->d_comp_hi, wlimit,
+                  mc->d_owned, mc->d_win_list, mc->d_big_list, mc->d_bigcount);
+        int counts[2] = {0, 0};
+        HH_CUDA(cudaMemcpyAsync(counts, mc->d_bigcount, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (!mc->h_inv) mc->h_inv = new std::vector<int>((size_t)n);
+        HH_CUDA(cudaMemcpyAsync(mc->h_inv->data(), mc->d_inv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<int> csz((size_t)n);
+        HH_CUDA(cudaMemcpyAsync(csz.data(), d_csize, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        mc->n_win = counts[0];
+        mc->n_big = counts[1];
+        int wmax = 32;
+        for (int v = 0; v < n; ++v)
+            if (csz[(size_t)v] <= wlimit && csz[(size_t)v] > wmax) wmax = csz[(size_t)v];
+        mc->wmax = (wmax + 31) & ~31;
+        // rewrite the iterate in new indices: column j' <- column inv[j'], rows through perm, rows re-sorted
+        hh_colargs a;
+        mcl_base_args(mc, a);
+        a.col_lo = 0;
+        a.ncols = n;
+        a.B = M;
+        a.slot_src = 1;
+        a.perm = mc->d_perm;
+        a.orig = mc->d_inv;
+        a.out = mc->it[mc->cur ^ 1];
+        a.raw = 1;
+        HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        HH_CHECK((launch_col<SRC_CSC, EPI_NORM>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+        unsigned long long st[4];
+        HH_CHECK(read_stats(ctx, mc->d_stats, st));
+        HH_REQUIRE((int)(st[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY, "hh_mcl: slot overflow while relabelling");
+        mc->cur ^= 1;
+        mc->perm_valid = true;
+        mc->perm_space = true;
+        return HH_OK;
+    }();
+    hh_dfree(d_lab);
+    return rc;
+}
+
 extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
     HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_begin: NULL handle");
     hh_scope _scope(mc->ctx);
@@ -1484,6 +1997,10 @@ extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
     mc->cur = -1;
     mc->have_pending = false;
     mc->order_valid = false;
+    // the relabelling is rebuilt from this inflation's own first pruned iterate: its components bound every later
+    // iterate of the same mcl() call, which is what makes the row windows safe
+    mc->perm_valid = false;
+    mc->perm_space = false;
     mc->begun = true;
     return HH_OK;
 }
@@ -1507,10 +2024,54 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
     a.out = mc->it[dst];
     a.attr_out = mc->d_attr;
     HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
+    const int ncols_owned = mc->col_hi - mc->col_lo;
     if (it == 0) {
         a.dense_in = mc->d_m1;
         a.do_conv = 0;
+        if (mc->perm_space) {              // new indices: source column inv[j'], rows scattered through perm
+            a.perm = mc->d_perm;
+            a.orig = mc->d_inv;
+            a.order = mc->d_owned;
+        }
         HH_CHECK((launch_col<SRC_DENSE, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+    } else if (mc->perm_space) {
+        a.A = mc->it[mc->cur];
+        a.B = mc->it[mc->cur];
+        a.do_conv = 1;
+        a.orig = mc->d_inv;
+        const double dcol = (double)mc->cur_nnz / (double)mc->n;
+        a.track = (dcol * dcol * 4.0 < (double)mc->n) ? 1 : 0;
+        a.flat = choose_flat(mc, (double)mc->cur_nnz);
+        a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
+        a.T = g.T;
+        if (mc->use_small && mc->cur_nnz <= 8ll * mc->n) {
+            HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, sizeof(int), ctx->stream));
+            a.ncols = ncols_owned;
+            int grid = (ncols_owned + 7) / 8;
+            if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+            HH_LAUNCH(ctx, hh_k_col_small, grid, 256, 0, a, g.W, mc->d_overflow, mc->d_bigcount, mc->d_owned);
+            a.order = mc->d_overflow;
+            a.ncols_ptr = mc->d_bigcount;
+            HH_CHECK((launch_col<SRC_PRODUCT, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+        } else {
+            if (mc->n_win > 0) {
+                const size_t smem = (size_t)4 * (size_t)mc->wmax * sizeof(float);
+                auto kern = hh_k_col_win<4>;
+                HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 0;
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+                int grid = per_sm * ctx->sm_count;
+                if (grid > mc->n_win) grid = mc->n_win;
+                if (grid < 1) grid = 1;
+                HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
+                HH_LAUNCH(ctx, kern, grid, 128, smem, a, g.W, mc->d_win_list, mc->n_win, mc->d_comp_lo, mc->d_comp_hi, mc->wmax);
+            }
+            if (mc->n_big > 0) {
+                a.order = mc->d_big_list;
+                a.ncols = mc->n_big;
+                HH_CHECK((launch_col<SRC_PRODUCT, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+            }
+        }
     } else {
         a.A = mc->it[mc->cur];
         a.B = mc->it[mc->cur];
@@ -1539,7 +2100,7 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
             a.T = g.T;
             int grid = (ncols + 7) / 8;
             if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-            HH_LAUNCH(ctx, hh_k_col_small, grid, 256, 0, a, g.W, mc->d_order, mc->d_bigcount);
+            HH_LAUNCH(ctx, hh_k_col_small, grid, 256, 0, a, g.W, mc->d_order, mc->d_bigcount, (const int*)nullptr);
             a.order = mc->d_order;
             a.ncols_ptr = mc->d_bigcount;
         }
@@ -1562,6 +2123,7 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
     }
     mc->pending = dst;
     mc->have_pending = true;
+    mc->last_step_it = it;
     mc->order_valid = true;       // d_attr now describes the pending iterate (owned columns)
     return HH_OK;
 }
@@ -1577,10 +2139,12 @@ extern "C" int hh_mcl_pack(hh_mcl* mc, int32_t* len_dev, int32_t* idx_dev, float
     HH_CHECK(hh_dmalloc(&d_off, (size_t)ncols + 1));
     int rc = [&]() -> int {
         const hh_slotmat& s = mc->it[mc->pending];
-        HH_CHECK(hh_exclusive_scan_i32(ctx, s.len + mc->col_lo, d_off, ncols));
+        const int* colmap = mc->perm_space ? mc->d_perm : nullptr;        // owned ORIGINAL columns live at perm[c]
+        HH_LAUNCH(ctx, hh_k_gather_len, (ncols + 255) / 256, 256, 0, s.len, colmap, mc->col_lo, ncols, len_dev);
+        HH_CHECK(hh_exclusive_scan_i32(ctx, len_dev, d_off, ncols));
         int grid = (ncols + 7) / 8;
         if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-        HH_LAUNCH(ctx, hh_k_pack, grid, 256, 0, s, mc->col_lo, ncols, d_off, len_dev, idx_dev, val_dev);
+        HH_LAUNCH(ctx, hh_k_pack, grid, 256, 0, s, mc->col_lo, ncols, d_off, len_dev, idx_dev, val_dev, colmap);
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
         return HH_OK;
     }();
@@ -1607,7 +2171,7 @@ extern "C" int hh_mcl_unpack(hh_mcl* mc, int32_t col_lo, int32_t col_hi, const i
         int grid = (ncols + 7) / 8;
         if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
         HH_LAUNCH(ctx, hh_k_unpack, grid, 256, 0, mc->it[mc->pending], mc->T, col_lo, ncols, len_dev, d_off, idx_dev, val_dev,
-                  reinterpret_cast<int*>(mc->d_stats + 3));
+                  reinterpret_cast<int*>(mc->d_stats + 3), mc->perm_space ? mc->d_perm : nullptr);
         unsigned long long st[4];
         HH_CHECK(read_stats(ctx, mc->d_stats, st));
         HH_REQUIRE((int)(st[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY, "hh_mcl_unpack: a peer column exceeds the slot capacity");
@@ -1623,6 +2187,10 @@ extern "C" int hh_mcl_commit(hh_mcl* mc) {
     mc->cur = mc->pending;
     mc->cur_nnz = mc->pending_nnz;
     mc->have_pending = false;
+    if (mc->use_window && !mc->perm_valid && mc->last_step_it == 0) {
+        hh_scope _scope(mc->ctx);
+        HH_CHECK(mcl_build_perm(mc));
+    }
     return HH_OK;
 }
 
@@ -1666,5 +2234,6 @@ extern "C" int hh_mcl_fetch_result(hh_mcl* mc, int64_t* indptr, int32_t* indices
     hh_scope _scope(mc->ctx);
     HH_REQUIRE(mc->cur >= 0 && !mc->have_pending, HH_ERR_STATE, "hh_mcl_fetch_result: no committed iterate");
     HH_CUDA(cudaSetDevice(mc->ctx->device));
+    if (mc->perm_space) return slot_fetch_csc(mc->ctx, mc->it[mc->cur], 0, mc->n, indptr, indices, data, mc->d_perm, mc->h_inv);
     return slot_fetch_csc(mc->ctx, mc->it[mc->cur], 0, mc->n, indptr, indices, data);
 }

@@ -32,7 +32,7 @@ def main():
     mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))
     tab.close()
     del rec
-    configs = [dict(W=32, FLAT=-1, L2PF=-1, SMALL=1, A16=0), dict(W=32, FLAT=-1, L2PF=-1, SMALL=1, A16=1)]
+    configs = [dict(W=32, SMALL=1, WINDOW=0), dict(W=32, SMALL=1, WINDOW=1)]
     sel = os.environ.get("TUNE_CONFIGS")
     if sel:
         configs = [configs[int(k)] for k in sel.split(",")]
