@@ -714,61 +714,55 @@ __global__ void hh_k_cc_lists(const int* __restrict__ perm, int col_lo, int ncol
 }
 
 // ---------------------------------------------------------------------------------------------
-// Windowed expansion (perm space): a CTA of NW warps per column; every warp owns a PRIVATE accumulator of
-// the column's row window and expands a contiguous share of the column's entries by streaming whole operand
-// columns (long coalesced reads, no per-row-block bookkeeping).  The partial accumulators are added in warp
-// order, then the usual epilogue runs over the window only.
+// Windowed expansion (perm space): ONE WARP per column with a private accumulator of the column's row
+// window (its component).  The warp walks the column's entries in order and streams every operand column
+// whole (long coalesced 64-bit loads, four in flight per lane), so each accumulator cell receives its
+// additions in ascending i exactly like the accumulator kernel and like SciPy's SpGEMM -- the results are
+// bit-identical to the un-windowed path.  The epilogue runs over the window only.  Dozens of such
+// single-warp CTAs share an SM, and consecutive columns of the list belong to the same component, so the
+// operand columns they re-read stay in L2.
 // ---------------------------------------------------------------------------------------------
-template <int NW>
-__global__ void __launch_bounds__(NW * 32) hh_k_col_win(const hh_colargs a, int W, const int* __restrict__ list, int nlist,
-                                                        const int* __restrict__ comp_lo, const int* __restrict__ comp_hi, int wmax) {
-    extern __shared__ __align__(16) float hh_win_smem[];
-    __shared__ double s_d[NW];
-    __shared__ float s_f[NW];
-    __shared__ int s_k[NW], s_o[NW], s_c[NW];
-    __shared__ int s_col;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+__global__ void __launch_bounds__(32) hh_k_col_win(const hh_colargs a, int W, const int* __restrict__ list, int nlist,
+                                                   const int* __restrict__ comp_lo, const int* __restrict__ comp_hi, int wmax) {
+    extern __shared__ __align__(16) float acc[];      // wmax floats, zero between columns
+    const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
-    float* __restrict__ accw = hh_win_smem + (size_t)w * wmax;      // this warp's private accumulator
-    float* __restrict__ acc0 = hh_win_smem;                         // merged column after the reduction
-    int* __restrict__ rows = reinterpret_cast<int*>(hh_win_smem + wmax);   // compacted rows (NW >= 2)
     const uint2* __restrict__ Aent = a.A.ent;
     const size_t capA = (size_t)a.A.cap;
     const float p32 = a.prune, rf = a.inflation;
     const bool sq = a.inflate_square != 0;
     const bool conv = a.do_conv != 0;
-    for (int k = threadIdx.x; k < NW * wmax; k += NW * 32) hh_win_smem[k] = 0.f;
-    __syncthreads();
+    const int T = a.T;
+    for (int k = lane; k < wmax; k += 32) acc[k] = 0.f;
+    __syncwarp();
     float dmax = 0.f;
     unsigned long long prod_acc = 0ull, nnz_acc = 0ull;
     for (;;) {
-        if (threadIdx.x == 0) s_col = atomicAdd(a.counter, 1);
-        __syncthreads();
-        const int jj = s_col;
+        int jj = 0;
+        if (lane == 0) jj = atomicAdd(a.counter, 1);
+        jj = __shfl_sync(HH_FULL_MASK, jj, 0);
         if (jj >= nlist) break;
         const int j = list[jj];
         const int lo = comp_lo[j], width = comp_hi[j] - lo;
         const int lenB = a.B.len[j];
         const uint2* __restrict__ Bent = a.B.ent + (size_t)j * (size_t)a.B.cap;
-        // ---- expansion: this warp's contiguous share of the column's entries
-        const int t_beg = (int)(((long long)lenB * w) / NW), t_end = (int)(((long long)lenB * (w + 1)) / NW);
-        unsigned long long warp_prod = 0ull;
-        for (int t0 = t_beg; t0 < t_end; t0 += 32) {
+        // ---- expansion
+        for (int t0 = 0; t0 < lenB; t0 += 32) {
             const int t = t0 + lane;
             int il = 0, Ll = 0;
             float vl = 0.f;
-            if (t < t_end) {
+            if (t < lenB) {
                 const uint2 be = Bent[t];
                 il = (int)be.x;
                 vl = __uint_as_float(be.y);
                 Ll = a.A.len[il];
             }
-            const int cnt = min(32, t_end - t0);
+            const int cnt = min(32, lenB - t0);
             for (int u = 0; u < cnt; ++u) {
                 const int L = __shfl_sync(HH_FULL_MASK, Ll, u);
                 const float v = __shfl_sync(HH_FULL_MASK, vl, u);
                 const uint2* __restrict__ col = Aent + (size_t)__shfl_sync(HH_FULL_MASK, il, u) * capA;
-                warp_prod += (unsigned long long)L;
+                prod_acc += (unsigned long long)L;
                 for (int p = lane; p < L; p += 128) {
                     uint2 e[4];
 #pragma unroll
@@ -777,7 +771,7 @@ __global__ void __launch_bounds__(NW * 32) hh_k_col_win(const hh_colargs a, int 
                     for (int q = 0; q < 4; ++q) {
                         if (e[q].x != 0xFFFFFFFFu) {
                             const unsigned r = e[q].x - (unsigned)lo;
-                            if (r < (unsigned)width) accw[r] = fmaf(v, __uint_as_float(e[q].y), accw[r]);
+                            if (r < (unsigned)width) acc[r] = fmaf(v, __uint_as_float(e[q].y), acc[r]);
                             else atomicExch(a.err, 2);             // a row outside the component window: never silently dropped
                         }
                     }
@@ -785,169 +779,126 @@ __global__ void __launch_bounds__(NW * 32) hh_k_col_win(const hh_colargs a, int 
                 __syncwarp();      // the next operand column may hit the same rows from other lanes
             }
         }
-        if (lane == 0) prod_acc += warp_prod;
-        __syncthreads();
-        // ---- merge the private accumulators (warp order) + E1 inflate + first column sum
-        const int Tw = (((width + NW - 1) / NW) + 31) & ~31;
-        const int r_beg = w * Tw, r_end = min(width, (w + 1) * Tw);
+        // ---- E1: inflate + first column sum
         double s1 = 0.0;
-        for (int r = r_beg + lane; r < r_end; r += 32) {
-            float x = acc0[r];
-#pragma unroll
-            for (int q = 1; q < NW; ++q) {
-                x += hh_win_smem[(size_t)q * wmax + r];
-                hh_win_smem[(size_t)q * wmax + r] = 0.f;
-            }
-            float y = 0.f;
+        for (int r = lane; r < width; r += 32) {
+            const float x = acc[r];
             if (x != 0.f) {
-                y = sq ? (x * x) : powf(x, rf);
+                const float y = sq ? (x * x) : powf(x, rf);
+                acc[r] = y;
                 s1 += (double)y;
             }
-            acc0[r] = y;
         }
-        s1 = hh_warp_sum(s1);
-        if (lane == 0) s_d[w] = s1;
-        __syncthreads();
-        double S1 = 0.0;
-#pragma unroll
-        for (int q = 0; q < NW; ++q) S1 += s_d[q];
-        __syncthreads();
+        const double S1 = hh_warp_sum(s1);
+        __syncwarp();
         // ---- E2: normalise, threshold statistics, first maximum (lowest ORIGINAL row among ties)
         double s2 = 0.0;
-        int cnt = 0, kbest = 0x7fffffff, obest = 0x7fffffff;
-        float vbest = 0.f;
-        for (int r = r_beg + lane; r < r_end; r += 32) {
-            const float y = acc0[r];
+        int cnt = 0, kmax = 0x7fffffff, omax = 0x7fffffff;
+        float vmax = 0.f;
+        for (int r = lane; r < width; r += 32) {
+            const float y = acc[r];
             if (y != 0.f) {
                 const float x1 = (S1 != 0.0) ? (float)((double)y / S1) : y;
-                acc0[r] = x1;
+                acc[r] = x1;
                 if (x1 >= p32 && x1 > 0.f) {
                     cnt++;
                     s2 += (double)x1;
                 }
-                if (x1 > vbest || (x1 == vbest && x1 > 0.f)) {
+                if (x1 > vmax || (x1 == vmax && x1 > 0.f)) {
                     const int o = a.orig ? a.orig[lo + r] : (lo + r);
-                    if (x1 > vbest || o < obest) {
-                        vbest = x1;
-                        kbest = lo + r;
-                        obest = o;
+                    if (x1 > vmax || o < omax) {
+                        vmax = x1;
+                        kmax = lo + r;
+                        omax = o;
                     }
                 }
             }
         }
-        s2 = hh_warp_sum(s2);
+        double S2 = hh_warp_sum(s2);
         cnt = hh_warp_sum(cnt);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(HH_FULL_MASK, vbest, o);
-            const int ok = __shfl_xor_sync(HH_FULL_MASK, kbest, o);
-            const int oo = __shfl_xor_sync(HH_FULL_MASK, obest, o);
-            if (ov > vbest || (ov == vbest && oo < obest)) {
-                vbest = ov;
-                kbest = ok;
-                obest = oo;
+            const float ov = __shfl_xor_sync(HH_FULL_MASK, vmax, o);
+            const int ok = __shfl_xor_sync(HH_FULL_MASK, kmax, o);
+            const int oo = __shfl_xor_sync(HH_FULL_MASK, omax, o);
+            if (ov > vmax || (ov == vmax && oo < omax)) {
+                vmax = ov;
+                kmax = ok;
+                omax = oo;
             }
         }
-        if (lane == 0) {
-            s_d[w] = s2;
-            s_c[w] = cnt;
-            s_f[w] = vbest;
-            s_k[w] = kbest;
-            s_o[w] = obest;
-        }
-        __syncthreads();
-        double S2 = 0.0;
-        int total = 0, base = 0, kmax = 0x7fffffff, omax = 0x7fffffff;
-        float vmax = 0.f;
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            S2 += s_d[q];
-            if (q < w) base += s_c[q];
-            total += s_c[q];
-            if (s_f[q] > vmax || (s_f[q] == vmax && s_o[q] < omax)) {
-                vmax = s_f[q];
-                kmax = s_k[q];
-                omax = s_o[q];
-            }
-        }
-        const bool need_max = (total == 0) && (vmax > 0.f);
+        const bool need_max = (cnt == 0) && (vmax > 0.f);
+        int total = cnt;
         if (need_max) {
-            const int wk = (kmax - lo) / Tw;
-            base = (w > wk) ? 1 : 0;
             total = 1;
             S2 = (double)vmax;
         }
-        // ---- E3: ordered compaction into the slot; rows kept in shared memory for the row-block pointers
+        __syncwarp();
+        // ---- E3: ordered compaction into the slot; row-block pointers on the fly (rows ascend)
         uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
-        int off = base;
-        for (int r0 = r_beg; r0 < r_end; r0 += 32) {
+        int* __restrict__ oblk = a.out.blk + (size_t)j * (W + 1);
+        int bnext = 0;                       // next row-block boundary (row bnext*T) whose pointer is still unset
+        int off = 0;
+        for (int r0 = 0; r0 < width; r0 += 32) {
             const int r = r0 + lane;
-            const float x1 = (r < r_end) ? acc0[r] : 0.f;
-            const bool f = (r < r_end) && (need_max ? (lo + r == kmax) : (x1 >= p32 && x1 > 0.f));
+            const float x1 = (r < width) ? acc[r] : 0.f;
+            const bool f = (r < width) && (need_max ? (lo + r == kmax) : (x1 >= p32 && x1 > 0.f));
             const unsigned bal = __ballot_sync(HH_FULL_MASK, f);
+            // boundaries that fall at or before the end of this 32-row step
+            while (bnext <= W && (long long)bnext * T <= (long long)(lo + r0 + 31)) {
+                const long long brow = (long long)bnext * T;
+                // survivors of this step with row < brow
+                const int nlt = (brow <= lo + r0) ? 0 : (int)(brow - (lo + r0));     // lanes [0, nlt) have row < brow
+                const unsigned below = (nlt >= 32) ? 0xFFFFFFFFu : ((1u << nlt) - 1u);
+                if (lane == 0) oblk[bnext] = min(off + __popc(bal & below), a.out.cap);
+                bnext++;
+            }
             float keepv = 0.f;
             if (f) {
                 const int pos = off + __popc(bal & lt_mask);
                 const float x2 = (float)((double)x1 / S2);
                 if (pos < a.out.cap) oent[pos] = make_uint2((unsigned)(lo + r), __float_as_uint(x2));
-                if (pos < wmax) rows[pos] = lo + r;
                 keepv = x2;
             }
-            if (r < r_end) acc0[r] = conv ? keepv : 0.f;
+            if (r < width) acc[r] = conv ? keepv : 0.f;
             off += __popc(bal);
         }
-        __syncthreads();
-        // row-block pointers of the new column
-        if (threadIdx.x <= W) {
-            int bp = total;
-            if (threadIdx.x < W) {
-                const int target = threadIdx.x * a.T;
-                int lo2 = 0, hi2 = min(total, wmax);
-                while (lo2 < hi2) {
-                    const int mid = (lo2 + hi2) >> 1;
-                    if (rows[mid] < target) lo2 = mid + 1;
-                    else hi2 = mid;
-                }
-                bp = lo2;
-            }
-            a.out.blk[(size_t)j * (W + 1) + threadIdx.x] = min(bp, a.out.cap);
-        }
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
+            for (; bnext <= W; ++bnext) oblk[bnext] = min(total, a.out.cap);   // boundaries beyond the window
             a.out.len[j] = min(total, a.out.cap);
-            if (total > a.out.cap || total > wmax) atomicExch(a.err, 1);
+            if (total > a.out.cap) atomicExch(a.err, 1);
             nnz_acc += (unsigned long long)total;
             if (a.attr_out) a.attr_out[j] = (vmax > 0.f) ? kmax : j;
         }
-        __syncthreads();
-        for (int p = threadIdx.x; p < min(total, wmax); p += NW * 32) rows[p] = 0;     // it aliases warp 1's accumulator
+        __syncwarp();
         if (conv) {
             // E4: entries of the previous iterate L = B[:, j]
-            for (int p = threadIdx.x; p < lenB; p += NW * 32) {
+            for (int p = lane; p < lenB; p += 32) {
                 const uint2 le = Bent[p];
                 const unsigned r = le.x - (unsigned)lo;
                 const float l = __uint_as_float(le.y);
-                const float m = (r < (unsigned)width) ? acc0[r] : 0.f;
+                const float m = (r < (unsigned)width) ? acc[r] : 0.f;
                 dmax = fmaxf(dmax, __fsub_rn(fabsf(__fsub_rn(m, l)), __fmul_rn(1e-5f, fabsf(l))));
-                if (r < (unsigned)width) acc0[r] = 0.f;
+                if (r < (unsigned)width) acc[r] = 0.f;
             }
-            __syncthreads();
+            __syncwarp();
             // E5: entries only in M + accumulator reset
-            for (int r = r_beg + lane; r < r_end; r += 32) {
-                const float m = acc0[r];
+            for (int r = lane; r < width; r += 32) {
+                const float m = acc[r];
                 if (m != 0.f) {
                     dmax = fmaxf(dmax, m);
-                    acc0[r] = 0.f;
+                    acc[r] = 0.f;
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     dmax = hh_warp_max(dmax);
     if (lane == 0) {
         if (dmax > 0.f) atomicMax(a.delta_bits, __float_as_int(dmax));
         if (prod_acc) atomicAdd(a.stats + 1, prod_acc);
+        if (nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
     }
-    if (threadIdx.x == 0 && nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2055,16 +2006,16 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
             HH_CHECK((launch_col<SRC_PRODUCT, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
         } else {
             if (mc->n_win > 0) {
-                const size_t smem = (size_t)4 * (size_t)mc->wmax * sizeof(float);
-                auto kern = hh_k_col_win<4>;
+                const size_t smem = (size_t)mc->wmax * sizeof(float);
+                auto kern = hh_k_col_win;
                 HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int per_sm = 0;
-                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+                HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
                 int grid = per_sm * ctx->sm_count;
                 if (grid > mc->n_win) grid = mc->n_win;
                 if (grid < 1) grid = 1;
                 HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
-                HH_LAUNCH(ctx, kern, grid, 128, smem, a, g.W, mc->d_win_list, mc->n_win, mc->d_comp_lo, mc->d_comp_hi, mc->wmax);
+                HH_LAUNCH(ctx, kern, grid, 32, smem, a, g.W, mc->d_win_list, mc->n_win, mc->d_comp_lo, mc->d_comp_hi, mc->wmax);
             }
             if (mc->n_big > 0) {
                 a.order = mc->d_big_list;
