@@ -656,6 +656,36 @@ __global__ void hh_k_cc_hook(const hh_slotmat m, int* __restrict__ label, int* _
     }
 }
 
+// same on the raw link matrix (unsorted CSC), strong links only: components of the counts >= thr graph order the
+// columns of the pre-expansion so that CTAs working side by side gather the same operand columns (L2 reuse)
+__global__ void hh_k_cc_hook_csc(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row, const float* __restrict__ val,
+                                 int n, float thr, int* __restrict__ label, int* __restrict__ changed) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
+        const int64_t p0 = colptr[j], p1 = colptr[j + 1];
+        const int lj = label[j];
+        int mn = lj;
+        for (int64_t p = p0 + lane; p < p1; p += 32)
+            if (val[p] >= thr) mn = min(mn, label[row[p]]);
+        mn = __reduce_min_sync(HH_FULL_MASK, mn);
+        bool ch = false;
+        if (mn < lj) {
+            if (lane == 0) atomicMin(label + j, mn);
+            ch = true;
+        }
+        for (int64_t p = p0 + lane; p < p1; p += 32) {
+            if (val[p] < thr) continue;
+            const int k = row[p];
+            if (label[k] > mn) {
+                atomicMin(label + k, mn);
+                ch = true;
+            }
+        }
+        if (ch) *changed = 1;
+    }
+}
+
 __global__ void hh_k_cc_jump(int* __restrict__ label, int n) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
@@ -1807,6 +1837,27 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         a.B = mc->m0;
         a.dense_out = mc->d_m1;
         a.flat = choose_flat(mc, (double)mc->nnz_m0);
+        const float pre_thr = (float)env_int("HH_MCL_PREORDER", 10);     // 0 = off; else link count that makes an edge "strong"
+        if (pre_thr > 0.f && col_lo == 0 && col_hi == m->n) {
+            const int n = m->n;
+            int* d_lab = mc->d_root;
+            int* d_flag = mc->d_bigcount + 2;
+            HH_LAUNCH(ctx, hh_k_cc_init, (n + 255) / 256, 256, 0, d_lab, n);
+            int gridc = (n + 7) / 8;
+            if (gridc > ctx->sm_count * 16) gridc = ctx->sm_count * 16;
+            for (int round = 0; round < 64; ++round) {
+                HH_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+                HH_LAUNCH(ctx, hh_k_cc_hook_csc, gridc, 256, 0, m->d_colptr, m->d_row, m->d_val, n, pre_thr, d_lab, d_flag);
+                HH_LAUNCH(ctx, hh_k_cc_jump, (n + 255) / 256, 256, 0, d_lab, n);
+                int changed = 0;
+                HH_CUDA(cudaMemcpyAsync(&changed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                HH_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (!changed) break;
+            }
+            HH_CUDA(cudaMemsetAsync(mc->d_cnt, 0, (size_t)n * sizeof(int), ctx->stream));
+            HH_LAUNCH(ctx, hh_k_cc_rank, (n + 255) / 256, 256, 0, d_lab, n, mc->d_perm, mc->d_inv, mc->d_cnt);
+            a.order = mc->d_inv;              // columns sorted by (component, index)
+        }
         a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
         HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
         HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
