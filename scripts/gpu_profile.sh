@@ -9,15 +9,12 @@ echo "== launch list"
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:hh_ -c 800 --csv --log-file gpurun_out/launches.csv \
     python bench.py $ARGS > gpurun_out/launches_bench.log 2>&1
 tail -1 gpurun_out/launches_bench.log | cut -c1-200
-echo "== full capture: column kernel -- pre-expansion, dense iteration 0, first two sparse expansions"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:hh_k_col -s 1 -c 4 -f -o gpurun_out/prof_col \
+echo "== full capture: column kernels -- pre-expansion, dense iteration 0, then the first window / big-list expansions"
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:hh_k_col -c 6 -f -o gpurun_out/prof_col \
     python bench.py $ARGS > gpurun_out/prof_col.log 2>&1
 tail -1 gpurun_out/prof_col.log | cut -c1-200
 echo "== full capture: link insert kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hh_k_links_insert -c 1 -f -o gpurun_out/prof_links \
     python bench.py $ARGS > gpurun_out/prof_links.log 2>&1
 tail -1 gpurun_out/prof_links.log | cut -c1-200
-echo "== full capture: small-column kernel (first launch)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:hh_k_col_small -c 1 -f -o gpurun_out/prof_small \
-    python bench.py $ARGS > gpurun_out/prof_small.log 2>&1
 ls -la gpurun_out/ | grep ncu-rep

@@ -52,7 +52,7 @@ def report(rep, out):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    stall = [h for h in hdr if "issue_stalled" in h and "per_warp_active" in h]
+    stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
     with open(out, "w") as f:
         f.write("# `ncu --set full --clock-control none --import-source on` summary of {}\n".format(os.path.basename(rep)))
         for r in rows[2:]:
@@ -63,11 +63,13 @@ def report(rep, out):
             st = []
             for h in stall:
                 try:
-                    st.append((float(r[idx[h]]), h))
+                    if float(r[idx[h]]) == float(r[idx[h]]):
+                        st.append((float(r[idx[h]]), h))
                 except ValueError:
                     pass
             for v, h in sorted(st, reverse=True)[:6]:
-                f.write("stall {:72s} {:.1f} %\n".format(h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", ""), v))
+                f.write("stall {:40s} {:.2f} warps per issue\n".format(
+                    h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
     print("wrote", out)
 
 
