@@ -47,7 +47,7 @@ def parse_args():
     p.add_argument("--pruning", type=float, default=1e-4)
     p.add_argument("--seed", type=int, default=12345)
     p.add_argument("--e2e-steps", type=int, default=1)
-    p.add_argument("--cpu-sample-pairs", type=int, default=400_000)
+    p.add_argument("--cpu-sample-pairs", type=int, default=4_000_000)
     p.add_argument("--cpu-sample-cols", type=int, default=24)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--verbose", action="store_true")
@@ -135,9 +135,9 @@ def cpu_mcl_iter_per_sec(m_csc, n_cols, inflation, pruning, seed=0):
     from oracle import haphic_oracle as orc
     n = m_csc.shape[0]
     rng = np.random.default_rng(seed)
-    # size the sample for ~2e8 Gustavson products (a few seconds of scipy SpGEMM)
+    # size the sample for ~4e9 Gustavson products (about ten seconds of scipy SpGEMM)
     per_col = max(1.0, (m_csc.nnz / n) ** 2)
-    n_cols = int(min(n, max(n_cols, 2e8 / per_col)))
+    n_cols = int(min(n, max(n_cols, 4e9 / per_col)))
     cols = np.sort(rng.choice(n, size=min(n_cols, n), replace=False))
     sub = m_csc[:, cols]
     t0 = time.perf_counter()
@@ -209,6 +209,18 @@ def run_reference(a):
                 "host_cores": os.cpu_count()},
     }
     print(json.dumps(line))
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json); only valid for the workload it
+    was captured on."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+    except OSError:
+        return {}
+    return t if t.get("workload") == workload else {}
 
 
 def run_b200(a):
@@ -299,9 +311,16 @@ def run_b200(a):
     pairs_per_s = P / ((build_ms + matrix_ms) / 1000.0)
     iters_per_s = s0["iters"] / (mcl_ms / 1000.0)
     peak, peak_src = measured_peaks()
-    # dominant kernel: the per-column MCL kernel (hh_k_col); algorithmic bytes per SURVEY.md 8(d)
-    mcl_bytes = s0["alg_bytes"] + 8 * s0["nnz_m0"] + 4 * s0["n_matrix"] ** 2
+    # dominant kernel launch: the pre-expansion pass of the MCL column kernel (hh_k_col<SRC_PRODUCT,EPI_DUMP>), one
+    # launch per step; algorithmic bytes per SURVEY.md 8(d): read the sparse operand once, write dense M1 once
+    pre_bytes = 8 * s0["nnz_m0"] + 4 * s0["n_matrix"] ** 2
+    pre_achieved = pre_bytes / (s0["preexp_ms"] / 1000.0) / 1e9
+    # all launches of the column kernels of the sweep (pre-expansion + every iteration), same definition
+    mcl_bytes = s0["alg_bytes"] + pre_bytes
     mcl_achieved = mcl_bytes / (s0["kernel_ms"] / 1000.0) / 1e9
+    # what a column-at-a-time Gustavson expansion has to gather: one 8-byte operand entry per product
+    gather_achieved = 8.0 * s0["preexp_products"] / (s0["preexp_ms"] / 1000.0) / 1e9
+    traffic = ncu_traffic(workload_name(a))
     build_bytes = 16 * P + 12 * s0["nnz_full"] + 12 * s0["nnz_flank"] + 4 * n
     build_achieved = build_bytes / (build_ms / 1000.0) / 1e9
 
@@ -386,11 +405,18 @@ def run_b200(a):
         "e2e": {"value": e2e_pairs, "unit": "pairs/s", "h2d_bytes_per_step": 16 * P + 13 * n, "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "hh_k_col (MCL column kernel: expansion + inflate/normalise/prune)", "bound": "hbm",
-                     "achieved": mcl_achieved, "peak": peak, "unit": "GB/s", "frac": mcl_achieved / peak, "traffic": None,
-                     "peak_source": peak_src},
+        "roofline": {"kernel": "hh_k_col<SRC_PRODUCT,EPI_DUMP> (pre-expansion M0*M0 -> dense M1, one launch per step)",
+                     "bound": "hbm", "achieved": pre_achieved, "peak": peak, "unit": "GB/s", "frac": pre_achieved / peak,
+                     "traffic": traffic.get("hh_k_col_preexpansion"), "algorithmic_bytes": pre_bytes,
+                     "launch_ms": s0["preexp_ms"], "peak_source": peak_src},
+        "roofline_mcl": {"kernel": "all hh_k_col / hh_k_col_win / hh_k_col_small launches of the sweep", "bound": "hbm",
+                         "achieved": mcl_achieved, "peak": peak, "unit": "GB/s", "frac": mcl_achieved / peak,
+                         "algorithmic_bytes": mcl_bytes, "kernel_ms": s0["kernel_ms"]},
+        "roofline_gather": {"kernel": "pre-expansion, against the operand bytes a column-wise SpGEMM gathers (8 B/product)",
+                            "achieved": gather_achieved, "peak": peak, "unit": "GB/s", "frac": gather_achieved / peak,
+                            "products": s0["preexp_products"]},
         "roofline_build": {"kernel": "hh_k_links_insert + finish", "bound": "hbm", "achieved": build_achieved, "peak": peak,
-                           "unit": "GB/s", "frac": build_achieved / peak, "traffic": None},
+                           "unit": "GB/s", "frac": build_achieved / peak, "traffic": traffic.get("hh_k_links_insert")},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
