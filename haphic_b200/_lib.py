@@ -53,6 +53,10 @@ _SIGNATURES = {
     "hh_links_fetch_ctg": (C.c_int, [_P, _P]),
     "hh_links_export": (C.c_int, [_P, _P, _P]),
     "hh_links_merge": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64]),
+    "hh_links_route": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P]),
+    "hh_links_add_routed": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "hh_links_finish_partition": (C.c_int, [_P, _P]),
+    "hh_links_adopt": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64]),
     "hh_links_destroy": (C.c_int, [_P]),
     "hh_links_linked_index": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32)]),
     "hh_matrix_from_links": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, C.c_int, C.POINTER(_P)]),

@@ -44,6 +44,7 @@ struct hh_links {
     int64_t n_records, stream_end;
     int64_t known_unique, since_known;   // growth bookkeeping (see ensure_capacity)
     bool finished;
+    bool ordered;                    // d_compact is in dict insertion order (false after hh_links_finish_partition / hh_links_adopt)
     int64_t nnz, nnz_flank, n_used;
     int64_t peer_used;               // records counted by merged peers
     uint32_t* d_compact;             // [nnz][9]  {i, j, full, flank, first_full, first_flank, HT, TH, TT}
@@ -105,7 +106,7 @@ hh_k_links_insert(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_o
                   const uint8_t* __restrict__ in_nx, int64_t flank_bp, uint64_t* __restrict__ keys,
                   hh_slot* __restrict__ vals, uint64_t cap, unsigned long long* __restrict__ ctg_links,
                   unsigned long long* __restrict__ counters, const int32_t* __restrict__ src_rank,
-                  const int32_t* __restrict__ fbase, int64_t bin_size, int32_t n_src) {
+                  const int32_t* __restrict__ fbase, int64_t bin_size, int32_t n_src, const uint32_t* __restrict__ pos) {
     __shared__ unsigned int s_new, s_used, s_over;
     if (threadIdx.x == 0) {
         s_new = 0;
@@ -183,6 +184,13 @@ hh_k_links_insert(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_o
             my_used++;
         }
         const unsigned peers = __match_any_sync(HH_FULL_MASK, key);
+        // stream position of the record: implicit (contiguous shard) or carried along (routed records, any order)
+        uint32_t first_all = stream_off + (uint32_t)i, first_fl = HH_NONE32;
+        if (pos != nullptr) {
+            const uint32_t mine = ok ? pos[i] : HH_NONE32;
+            first_all = __reduce_min_sync(peers, mine);
+            first_fl = __reduce_min_sync(peers, (ok && fl) ? mine : HH_NONE32);
+        }
         const unsigned b_fl = __ballot_sync(HH_FULL_MASK, ok && fl);
         const unsigned b_ht = __ballot_sync(HH_FULL_MASK, ok && !ti && tj);
         const unsigned b_th = __ballot_sync(HH_FULL_MASK, ok && ti && !tj);
@@ -199,10 +207,10 @@ hh_k_links_insert(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_o
                 const unsigned m_fl = peers & b_fl;
                 const unsigned c_fl = __popc(m_fl);
                 atomicAdd(&v->full, c_full);
-                atomicMin(&v->first_full, stream_off + (uint32_t)i);      // leader = lowest lane = earliest record
+                atomicMin(&v->first_full, first_all);                     // leader = lowest lane = earliest record
                 if (c_fl) {
                     atomicAdd(&v->flank, c_fl);
-                    atomicMin(&v->first_flank, stream_off + (uint32_t)(i0 + (__ffs(m_fl) - 1)));
+                    atomicMin(&v->first_flank, pos ? first_fl : stream_off + (uint32_t)(i0 + (__ffs(m_fl) - 1)));
                     atomicAdd(ctg_links + ci, (unsigned long long)c_fl);
                     atomicAdd(ctg_links + cj, (unsigned long long)c_fl);
                 }
@@ -284,6 +292,98 @@ __global__ void hh_k_add_u64(unsigned long long* __restrict__ dst, const int64_t
     if (i < n) dst[i] += (unsigned long long)src[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU routing: every contig pair has ONE owner rank, so the partition tables are disjoint and no
+// counter is ever reduced across ranks
+// ---------------------------------------------------------------------------------------------
+#define HH_MAX_WORLD 64
+
+__device__ __forceinline__ int hh_owner(int a, int b, int world) {
+    const uint32_t lo = (uint32_t)min(a, b), hi = (uint32_t)max(a, b);
+    return (int)(hh_mix64(((uint64_t)lo << 32) | (uint64_t)hi) % (uint64_t)world);
+}
+
+// destination of a record, -1 = can never be used (same contig in contig mode, ids outside the FASTA)
+__device__ __forceinline__ int hh_route_dest(const int4 r, int n_src, bool contig_mode, int world) {
+    if ((unsigned)r.x >= (unsigned)n_src || (unsigned)r.z >= (unsigned)n_src) return -1;
+    if (contig_mode && r.x == r.z) return -1;
+    return hh_owner(r.x, r.z, world);
+}
+
+__global__ void __launch_bounds__(256)
+hh_k_route_count(const int4* __restrict__ rec, int64_t n_rec, int n_src, int contig_mode, int world,
+                 unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_cnt[HH_MAX_WORLD];
+    if (threadIdx.x < HH_MAX_WORLD) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += stride) {
+        const int d = hh_route_dest(hh_ld_stream(rec + i), n_src, contig_mode != 0, world);
+        if (d >= 0) atomicAdd(&s_cnt[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// scatter into the destination groups; cursor[d] starts at the group's base.  One tile of 256 records per trip:
+// shared-memory ranks inside the tile, one global atomic per destination and tile.
+__global__ void __launch_bounds__(256)
+hh_k_route_scatter(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_off, int n_src, int contig_mode, int world,
+                   unsigned long long* __restrict__ cursor, int4* __restrict__ rec_out, uint32_t* __restrict__ pos_out) {
+    __shared__ unsigned int s_cnt[HH_MAX_WORLD];
+    __shared__ unsigned long long s_base[HH_MAX_WORLD];
+    const int64_t tiles = (n_rec + 255) / 256;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        if (threadIdx.x < HH_MAX_WORLD) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t i = t * 256 + threadIdx.x;
+        int4 r = make_int4(-1, 0, -1, 0);
+        int d = -1;
+        unsigned int my = 0;
+        if (i < n_rec) {
+            r = hh_ld_stream(rec + i);
+            d = hh_route_dest(r, n_src, contig_mode != 0, world);
+            if (d >= 0) my = atomicAdd(&s_cnt[d], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < world && s_cnt[threadIdx.x])
+            s_base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+        if (d >= 0) {
+            const unsigned long long q = s_base[d] + my;
+            rec_out[q] = r;
+            pos_out[q] = stream_off + (uint32_t)i;
+        }
+        __syncthreads();
+    }
+}
+
+// order[s] = s for live slots (unordered compaction of a partition table re-uses the compaction kernels)
+__global__ void hh_k_links_mark_slots(const uint64_t* __restrict__ keys, uint64_t cap, uint32_t* __restrict__ order) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += stride)
+        order[s] = (keys[s] == HH_EMPTY_KEY) ? HH_NONE32 : (uint32_t)s;
+}
+
+// adopted (unordered) entry list -> order[first_full] = entry index; and the flank count
+__global__ void hh_k_list_scatter_order(const uint32_t* __restrict__ ent, int64_t nnz, uint32_t* __restrict__ order, int64_t stream_end,
+                                        unsigned long long* __restrict__ counters) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        const uint32_t f = ent[e * 9 + 4];
+        if ((int64_t)f < stream_end) order[f] = (uint32_t)e;
+        else atomicExch(counters + 2, 2ull);
+    }
+}
+
+__global__ void hh_k_list_count_flank(const uint32_t* __restrict__ ent, int64_t nnz, unsigned long long* __restrict__ counters) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int c = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) c += ent[e * 9 + 3] ? 1u : 0u;
+    c = hh_warp_sum((int)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(counters + 3, (unsigned long long)c);
+}
+
 // order[first_full] = slot
 __global__ void hh_k_links_scatter_order(const uint64_t* __restrict__ keys, const hh_slot* __restrict__ vals, uint64_t cap,
                                          uint32_t* __restrict__ order, int64_t stream_end,
@@ -349,6 +449,15 @@ hh_k_compact_gather(const uint32_t* __restrict__ order, int64_t n, const int64_t
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (slot[k] == HH_NONE32) continue;
+        if (keys == nullptr) {
+            // source is an entry list (hh_links_adopt): plain copy of the 9 words
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(vals) + (size_t)slot[k] * 9;
+            uint32_t* o = compact + q * 9;
+#pragma unroll
+            for (int w = 0; w < 9; ++w) o[w] = src[w];
+            q++;
+            continue;
+        }
         const uint64_t key = keys[slot[k]];
         const uint4* v = reinterpret_cast<const uint4*>(vals + slot[k]);
         const uint4 v0 = v[0], v1 = v[1];   // {first_full, first_flank, full, flank} {ht, th, tt, pad}
@@ -552,14 +661,15 @@ extern "C" int hh_links_create_frags(hh_ctx* ctx, int32_t n_ctg, const int32_t* 
                                bin_size, out);
 }
 
-static int links_launch_insert(hh_links* lk, const int4* d_rec, int64_t n_rec, int64_t stream_offset) {
+static int links_launch_insert(hh_links* lk, const int4* d_rec, int64_t n_rec, int64_t stream_offset,
+                               const uint32_t* d_pos = nullptr) {
     hh_ctx* ctx = lk->ctx;
     int64_t blocks = (n_rec + 255) / 256;
     int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
     if (grid < 1) grid = 1;
     HH_LAUNCH(ctx, hh_k_links_insert, grid, 256, 0, d_rec, n_rec, (uint32_t)stream_offset, lk->n_ctg, lk->d_len, lk->d_rank,
               lk->d_nx, lk->flank_bp, lk->d_keys, lk->d_vals, lk->cap, lk->d_ctg, lk->d_counters, lk->d_src_rank, lk->d_fbase,
-              lk->bin_size, lk->n_src);
+              lk->bin_size, lk->n_src, d_pos);
     return HH_OK;
 }
 
@@ -676,6 +786,7 @@ extern "C" int hh_links_finish(hh_links* lk, hh_links_info* info) {
             lk->nnz_flank = (int64_t)c[3];
         }
         lk->finished = true;
+        lk->ordered = true;
     }
     if (info) {
         info->n_records = lk->n_records;
@@ -707,6 +818,224 @@ __global__ void hh_k_links_split(const uint32_t* __restrict__ compact, int64_t n
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// routed multi-GPU counting: route -> [all-to-all] -> add_routed -> finish_partition ->
+// export -> [all-gather] -> adopt
+// ---------------------------------------------------------------------------------------------
+extern "C" int hh_links_route(hh_links* lk, const int32_t* rec_dev, int64_t n_rec, int64_t stream_offset, int world,
+                              int32_t* rec_out_dev, uint32_t* pos_out_dev, int64_t* counts) {
+    HH_REQUIRE(lk && counts && (n_rec == 0 || (rec_dev && rec_out_dev && pos_out_dev)), HH_ERR_ARG, "hh_links_route: NULL argument");
+    HH_REQUIRE(world >= 1 && world <= HH_MAX_WORLD, HH_ERR_ARG, "hh_links_route: world must be in [1, %d]", HH_MAX_WORLD);
+    HH_REQUIRE(n_rec >= 0 && stream_offset >= 0 && stream_offset + n_rec <= 0xFFFFFFFELL, HH_ERR_UNSUPPORTED,
+               "hh_links_route: stream indices must fit 32 bits (offset %lld + %lld records)", (long long)stream_offset,
+               (long long)n_rec);
+    HH_REQUIRE((((uintptr_t)rec_dev | (uintptr_t)rec_out_dev) & 15) == 0, HH_ERR_ARG, "hh_links_route: records must be 16-byte aligned");
+    hh_scope _scope(lk->ctx);
+    hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    for (int d = 0; d < world; ++d) counts[d] = 0;
+    if (n_rec == 0) return HH_OK;
+    unsigned long long* d_cnt = nullptr;
+    HH_CHECK(hh_dmalloc(&d_cnt, 2 * HH_MAX_WORLD));
+    int rc = [&]() -> int {
+        HH_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * HH_MAX_WORLD * sizeof(unsigned long long), ctx->stream));
+        const int contig_mode = lk->d_fbase == nullptr;
+        int64_t blocks = (n_rec + 255) / 256;
+        int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
+        const int4* rec4 = reinterpret_cast<const int4*>(rec_dev);
+        HH_LAUNCH(ctx, hh_k_route_count, grid, 256, 0, rec4, n_rec, lk->n_src, contig_mode, world, d_cnt);
+        unsigned long long h[HH_MAX_WORLD];
+        HH_CUDA(cudaMemcpyAsync(h, d_cnt, (size_t)world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        unsigned long long base[HH_MAX_WORLD], acc = 0;
+        for (int d = 0; d < world; ++d) {
+            counts[d] = (int64_t)h[d];
+            base[d] = acc;
+            acc += h[d];
+        }
+        HH_CUDA(cudaMemcpyAsync(d_cnt + HH_MAX_WORLD, base, (size_t)world * sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                                ctx->stream));
+        HH_LAUNCH(ctx, hh_k_route_scatter, grid, 256, 0, rec4, n_rec, (uint32_t)stream_offset, lk->n_src, contig_mode, world,
+                  d_cnt + HH_MAX_WORLD, reinterpret_cast<int4*>(rec_out_dev), pos_out_dev);
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));      // `base` is a host temporary; the caller hands the buffers to NCCL next
+        return HH_OK;
+    }();
+    hh_dfree(d_cnt);
+    HH_CHECK(rc);
+    lk->n_records += n_rec;          // records this rank read from the stream (used or not)
+    if (stream_offset + n_rec > lk->stream_end) lk->stream_end = stream_offset + n_rec;
+    return HH_OK;
+}
+
+extern "C" int hh_links_add_routed(hh_links* lk, const int32_t* rec_dev, const uint32_t* pos_dev, int64_t n_rec) {
+    HH_REQUIRE(lk && (n_rec == 0 || (rec_dev && pos_dev)), HH_ERR_ARG, "hh_links_add_routed: NULL argument");
+    hh_scope _scope(lk->ctx);
+    HH_REQUIRE(!lk->finished, HH_ERR_STATE, "hh_links_add_routed: stream already finished");
+    HH_REQUIRE(n_rec >= 0, HH_ERR_ARG, "hh_links_add_routed: negative record count");
+    HH_REQUIRE(((uintptr_t)rec_dev & 15) == 0, HH_ERR_ARG, "hh_links_add_routed: records must be 16-byte aligned");
+    if (n_rec == 0) return HH_OK;
+    HH_CUDA(cudaSetDevice(lk->ctx->device));
+    const int64_t CH = 1ll << 23;
+    for (int64_t off = 0; off < n_rec; off += CH) {
+        const int64_t m = (n_rec - off < CH) ? (n_rec - off) : CH;
+        HH_CHECK(links_ensure_capacity(lk, m));
+        HH_CHECK(links_launch_insert(lk, reinterpret_cast<const int4*>(rec_dev) + off, m, 0, pos_dev + off));
+        lk->since_known += m;
+    }
+    return HH_OK;
+}
+
+// compact list of a partition table in slot order (no first-seen ordering: the union is ordered lazily by hh_links_fetch)
+extern "C" int hh_links_finish_partition(hh_links* lk, hh_links_info* info) {
+    HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_finish_partition: NULL handle");
+    hh_scope _scope(lk->ctx);
+    hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    if (!lk->finished) {
+        unsigned long long c[8];
+        HH_CHECK(links_read_counters(lk, c));
+        HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY, "hh_links_finish_partition: hash table overflow (capacity %llu slots)",
+                   (unsigned long long)lk->cap);
+        lk->nnz = (int64_t)c[0];
+        lk->n_used = lk->peer_used + (int64_t)c[1];
+        HH_CUDA(cudaMemsetAsync(lk->d_counters + 3, 0, sizeof(unsigned long long), ctx->stream));
+        hh_dfree(lk->d_compact);
+        HH_CHECK(hh_dmalloc(&lk->d_compact, (size_t)(lk->nnz > 0 ? lk->nnz : 1) * 9));
+        if (lk->nnz > 0) {
+            HH_REQUIRE(lk->cap <= 0xFFFFFFFFull, HH_ERR_UNSUPPORTED, "hh_links_finish_partition: table too large");
+            const int64_t S = (int64_t)lk->cap;
+            uint32_t* d_order = nullptr;
+            int* d_bcnt = nullptr;
+            int64_t* d_boff = nullptr;
+            const int64_t nb = (S + HH_CMP_TILE - 1) / HH_CMP_TILE;
+            int rc = HH_OK;
+            do {
+                if ((rc = hh_dmalloc(&d_order, (size_t)S)) != HH_OK) break;
+                if ((rc = hh_dmalloc(&d_bcnt, (size_t)nb)) != HH_OK) break;
+                if ((rc = hh_dmalloc(&d_boff, (size_t)nb + 1)) != HH_OK) break;
+            } while (0);
+            if (rc == HH_OK) {
+                rc = [&]() -> int {
+                    HH_LAUNCH(ctx, hh_k_links_mark_slots, hh_grid(ctx, 8), 256, 0, lk->d_keys, lk->cap, d_order);
+                    HH_LAUNCH(ctx, hh_k_compact_count, (unsigned)nb, 256, 0, d_order, S, d_bcnt);
+                    HH_CHECK(hh_exclusive_scan_i32(ctx, d_bcnt, d_boff, (int)nb));
+                    HH_LAUNCH(ctx, hh_k_compact_gather, (unsigned)nb, 256, 0, d_order, S, d_boff, lk->d_keys, lk->d_vals,
+                              lk->d_compact, lk->d_counters);
+                    HH_CHECK(links_read_counters(lk, c));
+                    return HH_OK;
+                }();
+            }
+            hh_dfree(d_order);
+            hh_dfree(d_bcnt);
+            hh_dfree(d_boff);
+            HH_CHECK(rc);
+            lk->nnz_flank = (int64_t)c[3];
+        }
+        lk->finished = true;
+        lk->ordered = false;
+    }
+    if (info) {
+        info->n_records = lk->n_records;
+        info->n_used = lk->n_used;
+        info->nnz_full = lk->nnz;
+        info->nnz_flank = lk->nnz_flank;
+        info->table_slots = (int64_t)lk->cap;
+    }
+    return HH_OK;
+}
+
+// the table becomes the union of disjoint partitions: `entries_dev` is the concatenation of every rank's export,
+// `ctg_links_dev` / n_records / n_used the sums over ranks, stream_end the length of the whole stream
+extern "C" int hh_links_adopt(hh_links* lk, const uint32_t* entries_dev, int64_t n_entries, const int64_t* ctg_links_dev,
+                              int64_t n_records, int64_t n_used, int64_t stream_end) {
+    HH_REQUIRE(lk && ctg_links_dev && (entries_dev || n_entries == 0), HH_ERR_ARG, "hh_links_adopt: NULL argument");
+    HH_REQUIRE(n_entries >= 0 && stream_end >= 0 && stream_end <= 0xFFFFFFFELL, HH_ERR_ARG, "hh_links_adopt: bad sizes");
+    hh_scope _scope(lk->ctx);
+    hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    // the hash table is not needed any more: every consumer works on the entry list
+    hh_dfree(lk->d_keys);
+    hh_dfree(lk->d_vals);
+    lk->d_keys = nullptr;
+    lk->d_vals = nullptr;
+    lk->cap = 0;
+    hh_dfree(lk->d_compact);
+    lk->d_compact = nullptr;
+    HH_CHECK(hh_dmalloc(&lk->d_compact, (size_t)(n_entries > 0 ? n_entries : 1) * 9));
+    HH_CUDA(cudaMemsetAsync(lk->d_counters + 2, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (n_entries) {
+        HH_CUDA(cudaMemcpyAsync(lk->d_compact, entries_dev, (size_t)n_entries * 9 * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+        int64_t blocks = (n_entries + 255) / 256;
+        int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
+        HH_LAUNCH(ctx, hh_k_list_count_flank, grid, 256, 0, lk->d_compact, n_entries, lk->d_counters);
+    }
+    HH_CUDA(cudaMemcpyAsync(lk->d_ctg, ctg_links_dev, (size_t)lk->n_ctg * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    unsigned long long c[8];
+    HH_CHECK(links_read_counters(lk, c));
+    lk->nnz = n_entries;
+    lk->nnz_flank = (int64_t)c[3];
+    lk->n_records = n_records;
+    lk->n_used = n_used;
+    lk->peer_used = 0;
+    lk->stream_end = stream_end;
+    lk->finished = true;
+    lk->ordered = false;
+    return HH_OK;
+}
+
+// put an adopted / partition list into dict insertion order (first_full ascending; the values are unique stream indices)
+static int links_order_list(hh_links* lk) {
+    if (lk->ordered || lk->nnz == 0) {
+        lk->ordered = true;
+        return HH_OK;
+    }
+    hh_ctx* ctx = lk->ctx;
+    const int64_t S = lk->stream_end;
+    const int64_t nb = (S + HH_CMP_TILE - 1) / HH_CMP_TILE;
+    uint32_t *d_order = nullptr, *d_sorted = nullptr;
+    int* d_bcnt = nullptr;
+    int64_t* d_boff = nullptr;
+    int rc = HH_OK;
+    do {
+        if ((rc = hh_dmalloc(&d_order, (size_t)S)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&d_sorted, (size_t)lk->nnz * 9)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&d_bcnt, (size_t)nb)) != HH_OK) break;
+        if ((rc = hh_dmalloc(&d_boff, (size_t)nb + 1)) != HH_OK) break;
+    } while (0);
+    unsigned long long c[8] = {0};
+    if (rc == HH_OK) {
+        rc = [&]() -> int {
+            HH_CUDA(cudaMemsetAsync(d_order, 0xFF, (size_t)S * sizeof(uint32_t), ctx->stream));
+            HH_CUDA(cudaMemsetAsync(lk->d_counters + 2, 0, sizeof(unsigned long long), ctx->stream));
+            int64_t blocks = (lk->nnz + 255) / 256;
+            int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
+            HH_LAUNCH(ctx, hh_k_list_scatter_order, grid, 256, 0, lk->d_compact, lk->nnz, d_order, S, lk->d_counters);
+            HH_LAUNCH(ctx, hh_k_compact_count, (unsigned)nb, 256, 0, d_order, S, d_bcnt);
+            HH_CHECK(hh_exclusive_scan_i32(ctx, d_bcnt, d_boff, (int)nb));
+            HH_LAUNCH(ctx, hh_k_compact_gather, (unsigned)nb, 256, 0, d_order, S, d_boff, (const uint64_t*)nullptr,
+                      reinterpret_cast<const hh_slot*>(lk->d_compact), d_sorted, lk->d_counters);
+            HH_CHECK(links_read_counters(lk, c));
+            return HH_OK;
+        }();
+    }
+    hh_dfree(d_order);
+    hh_dfree(d_bcnt);
+    hh_dfree(d_boff);
+    if (rc == HH_OK && c[2] != 0) {
+        hh_dfree(d_sorted);
+        HH_REQUIRE(false, HH_ERR_STATE, "hh_links: first-seen index beyond the stream end (stream_end misuse in hh_links_adopt)");
+    }
+    if (rc != HH_OK) {
+        hh_dfree(d_sorted);
+        return rc;
+    }
+    hh_dfree(lk->d_compact);
+    lk->d_compact = d_sorted;
+    lk->ordered = true;
+    return HH_OK;
+}
+
 extern "C" int hh_links_fetch(hh_links* lk, int32_t* key_i, int32_t* key_j, uint32_t* full, uint32_t* flank,
                               uint32_t* first_full, uint32_t* first_flank, uint32_t* ht) {
     HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_fetch: NULL handle");
@@ -714,6 +1043,8 @@ extern "C" int hh_links_fetch(hh_links* lk, int32_t* key_i, int32_t* key_j, uint
     HH_REQUIRE(lk->finished, HH_ERR_STATE, "hh_links_fetch: call hh_links_finish first");
     if (lk->nnz == 0) return HH_OK;
     hh_ctx* ctx = lk->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    HH_CHECK(links_order_list(lk));
     const int64_t nnz = lk->nnz;
     uint32_t* d_soa = nullptr;
     HH_CHECK(hh_dmalloc(&d_soa, (size_t)nnz * 10 + 4));
@@ -761,6 +1092,7 @@ extern "C" int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t
                               int64_t n_records, int64_t n_used) {
     HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_merge: NULL handle");
     hh_scope _scope(lk->ctx);
+    HH_REQUIRE(lk->d_keys != nullptr, HH_ERR_STATE, "hh_links_merge: the table was replaced by hh_links_adopt");
     lk->finished = false;   // a finished table is re-opened: the next hh_links_finish rebuilds the ordered view
     HH_REQUIRE(n_entries >= 0 && (entries_dev || n_entries == 0), HH_ERR_ARG, "hh_links_merge: bad entries");
     hh_ctx* ctx = lk->ctx;

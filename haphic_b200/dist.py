@@ -86,6 +86,51 @@ def merge_link_tables(table, group=None):
         table.merge(ents[r], tots[r], int(metas[r][0].item()), int(metas[r][1].item()))
 
 
+def routed_link_build(table, rec, stream_lo: int, group=None):
+    """Sharded link counting without a reduction: every rank holds a contiguous shard `rec` of the
+    read stream (global index of rec[0] = stream_lo).  Records are routed to the rank that owns their contig pair
+    (one all-to-all of records + stream indices), counted there into disjoint partition tables, and the compact
+    partitions are all-gathered so that every rank ends with the whole table (unordered until somebody fetches it).
+    Returns the LinksInfo of the whole table."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    rec_out, pos_out, counts = table.route(rec, stream_lo, world)
+    dev = rec_out.device
+    send = torch.tensor(counts, dtype=torch.int64, device=dev)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_counts = [int(x) for x in recv.tolist()]
+    rec_in = torch.empty((sum(recv_counts), 4), dtype=rec_out.dtype, device=dev)
+    pos_in = torch.empty(sum(recv_counts), dtype=pos_out.dtype, device=dev)
+    dist.all_to_all_single(rec_in, rec_out, recv_counts, counts, group=group)
+    dist.all_to_all_single(pos_in, pos_out, recv_counts, counts, group=group)
+    _wait_collectives(rec_in)
+    table.add_routed(rec_in, pos_in)
+    del rec_out, pos_out
+    part = table.finish_partition()
+    ent, tot, _, _ = table.export()
+    # sizes, then the partitions straight into one buffer (uneven all-gather)
+    meta = torch.tensor([int(ent.shape[0]), int(rec.shape[0]), int(part.n_used), int(stream_lo) + int(rec.shape[0])],
+                        dtype=torch.int64, device=dev)
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [m.tolist() for m in metas]
+    sizes = [int(m[0]) for m in metas]
+    whole = torch.empty((sum(sizes), 9), dtype=ent.dtype, device=dev)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    views = [whole[int(offs[r]):int(offs[r + 1])] for r in range(world)]
+    if len(set(sizes)) == 1:
+        dist.all_gather_into_tensor(whole, ent, group=group)
+    else:
+        for r in range(world):              # uneven partitions: one broadcast per owner
+            if r == rank:
+                views[r].copy_(ent)
+            dist.broadcast(views[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    _wait_collectives(whole)
+    return table.adopt(whole, tot, sum(int(m[1]) for m in metas), sum(int(m[2]) for m in metas), max(int(m[3]) for m in metas))
+
+
 def sharded_mcl_run(engine, inflation: float, max_iter: int, pruning: float, blocks, group=None):
     """One mcl() call (HapHiC_cluster.py:2026-2062) over column shards.
 
@@ -157,7 +202,7 @@ def bench_multi(a, world: int, rank_id: int, local: int):
     keep = np.ones(n, np.uint8)
     ctx = Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    hint = int(min(a.pairs, n * (n - 1) // 2) * (0.45 if a.pairs > 4_000_000 else 1.0))
+    hint = int(min(a.pairs, n * (n - 1) // 2) * (0.45 if a.pairs > 4_000_000 else 1.0) / world * 1.1)   # one partition
 
     def barrier():
         dist.barrier()
@@ -168,9 +213,7 @@ def bench_multi(a, world: int, rank_id: int, local: int):
         barrier()
         ev[0].record(stream)
         tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
-        tab.add(rec, stream_offset=stream_lo, asynchronous=True)
-        merge_link_tables(tab)
-        info = tab.finish()
+        info = routed_link_build(tab, rec, stream_lo)
         index, n_linked = tab.linked_index(keep)
         mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))
         ev[1].record(stream)
@@ -215,9 +258,9 @@ def bench_multi(a, world: int, rank_id: int, local: int):
         barrier()
         t0 = time.perf_counter()
         tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
-        tab.add(rec_host, stream_offset=stream_lo)
-        merge_link_tables(tab)
-        tab.finish()
+        rec_dev = rec_host.to(dev, non_blocking=True)       # H2D of this rank's shard, inside the timed region
+        routed_link_build(tab, rec_dev, stream_lo)
+        del rec_dev
         if rank_id == 0:
             table = tab.fetch(pinned=True)
             tot = tab.fetch_ctg()
@@ -261,10 +304,12 @@ def bench_multi(a, world: int, rank_id: int, local: int):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32 counts / fp32 matrix",
             "data": "synthetic",
             "config": {"workload": B.workload_name(a), "inflations": inflations, "max_iter": a.max_iter,
-                       "pruning": a.pruning, "parallelism": "pair stream sharded x{0}; MCL column blocks x{0}, one "
-                       "all-gather of pruned columns per iteration".format(world),
+                       "pruning": a.pruning, "parallelism": "pair stream sharded x{0}, records routed to the owner of their contig pair "
+                       "(all-to-all), disjoint partition tables all-gathered; MCL column blocks x{0}, one all-gather of "
+                       "pruned columns per iteration".format(world),
                        "cache": "inputs and the dense pre-expanded matrix exceed the 126 MB L2",
-                       "step": "link build + table all-gather/merge + index + CSC + normalise + pre-expansion + MCL sweep"},
+                       "step": "route + all-to-all + link build + partition all-gather + index + CSC + normalise + pre-expansion + "
+                               "MCL sweep"},
             "stage_ms": {"link_build_and_matrix": build_ms, "mcl_sweep": mcl_ms},
             "mcl": {"metric": "mcl_iterations_per_sec", "value": steps[-1]["iters"] / (mcl_ms / 1000.0), "unit": "iter/s",
                     "iterations": steps[-1]["iters"], "e2e": mcl_e2e},

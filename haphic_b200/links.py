@@ -168,6 +168,41 @@ class LinkTable:
         check(load().hh_links_merge(self._h, ptr(entries) if n else None, n, ptr(ctg_totals), int(n_records), int(n_used)))
         self.info = None        # re-opened: finish() again
 
+    # routed counting: route -> (all-to-all) -> add_routed -> finish_partition -> export -> (all-gather) -> adopt
+    def route(self, rec, stream_offset: int, world: int):
+        """Split a CUDA shard of the stream by owner rank.  Returns (records [m, 4] int32, stream indices [m] int32
+        holding uint32 values, counts list of `world` ints); group d is rows sum(counts[:d]) .. sum(counts[:d+1])."""
+        import torch
+        if not rec.is_cuda or rec.dtype != torch.int32 or rec.dim() != 2 or rec.shape[1] != 4 or not rec.is_contiguous():
+            raise ValueError("records must be a contiguous int32 [P, 4] CUDA tensor")
+        n_rec = int(rec.shape[0])
+        rec_out = torch.empty((max(n_rec, 1), 4), dtype=torch.int32, device=rec.device)
+        pos_out = torch.empty(max(n_rec, 1), dtype=torch.int32, device=rec.device)
+        counts = np.zeros(world, np.int64)
+        check(load().hh_links_route(self._h, ptr(rec) if n_rec else None, n_rec, int(stream_offset), int(world),
+                                    ptr(rec_out), ptr(pos_out), ptr(counts)))
+        m = int(counts.sum())
+        self._stream_pos = max(self._stream_pos, int(stream_offset) + n_rec)
+        return rec_out[:m], pos_out[:m], [int(c) for c in counts]
+
+    def add_routed(self, rec, pos):
+        n_rec = int(rec.shape[0])
+        if n_rec:
+            check(load().hh_links_add_routed(self._h, ptr(rec), ptr(pos), n_rec))
+
+    def finish_partition(self) -> LinksInfo:
+        info = LinksInfo()
+        check(load().hh_links_finish_partition(self._h, C.byref(info)))
+        self.info = info
+        return info
+
+    def adopt(self, entries, ctg_totals, n_records: int, n_used: int, stream_end: int):
+        n = int(entries.shape[0])
+        check(load().hh_links_adopt(self._h, ptr(entries) if n else None, n, ptr(ctg_totals), int(n_records), int(n_used),
+                                    int(stream_end)))
+        self.info = None
+        return self.finish()
+
     def close(self):
         if self._h:
             load().hh_links_destroy(self._h)

@@ -124,6 +124,23 @@ int hh_links_fetch_ctg(hh_links* lk, int64_t* ctg_links);
 int hh_links_export(hh_links* lk, uint32_t* entries_dev, int64_t* ctg_links_dev);
 int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t n_entries, const int64_t* ctg_links_dev,
                    int64_t n_records, int64_t n_used);
+/* Routed multi-GPU counting (SURVEY.md 8e "route each pair to its owner"): every contig pair is owned by one rank
+ * (hash of the unordered contig pair), so the partition tables are disjoint and nothing is reduced afterwards.
+ *   hh_links_route:  split this rank's shard of the stream (device records, global index of rec[0] = stream_offset)
+ *     into `world` destination groups: rec_out_dev [n_rec][4] / pos_out_dev [n_rec] receive records and their stream
+ *     indices grouped by owner, counts[world] (host) the group sizes.  Records that can never be used (same contig,
+ *     ids outside the FASTA) are dropped here.  The caller exchanges the groups (all-to-all).
+ *   hh_links_add_routed: count records with explicit stream indices (any order).
+ *   hh_links_finish_partition: compact list of this rank's partition (unordered); hh_links_export hands it out.
+ *   hh_links_adopt: the table becomes the union of all partitions (entries = concatenated exports [n][9],
+ *     ctg_links / n_records / n_used summed over ranks, stream_end = length of the whole stream).  The index,
+ *     the matrix and hh_links_fetch (which restores dict insertion order on first use) work as after hh_links_finish. */
+int hh_links_route(hh_links* lk, const int32_t* rec_dev, int64_t n_rec, int64_t stream_offset, int world,
+                   int32_t* rec_out_dev, uint32_t* pos_out_dev, int64_t* counts);
+int hh_links_add_routed(hh_links* lk, const int32_t* rec_dev, const uint32_t* pos_dev, int64_t n_rec);
+int hh_links_finish_partition(hh_links* lk, hh_links_info* info);
+int hh_links_adopt(hh_links* lk, const uint32_t* entries_dev, int64_t n_entries, const int64_t* ctg_links_dev,
+                   int64_t n_records, int64_t n_used, int64_t stream_end);
 int hh_links_destroy(hh_links* lk);
 
 /* ---- dict_to_matrix, HapHiC_cluster.py:310-373 ------------------------------------------------

@@ -95,6 +95,65 @@ class FakeTable:
         self.n_used += n_used
 
 
+class FakeRoutedTable:
+    """route / add_routed / finish_partition / export / adopt with the library's semantics, on the CPU oracle."""
+
+    def __init__(self, lengths, rk, nx, flank):
+        self.args = (lengths, rk, nx, flank)
+        self.rec = []
+        self.pos = []
+        self.whole = None
+
+    @staticmethod
+    def owner(a, b, world):
+        lo, hi = min(a, b), max(a, b)
+        return (lo * 1000003 + hi) % world
+
+    def route(self, rec, stream_lo, world):
+        r = rec.numpy()
+        n = len(self.args[0])
+        ok = (r[:, 0] != r[:, 2]) & (r[:, 0] >= 0) & (r[:, 0] < n) & (r[:, 2] >= 0) & (r[:, 2] < n)
+        dest = np.array([self.owner(int(a), int(b), world) if o else -1 for a, b, o in zip(r[:, 0], r[:, 2], ok)])
+        pos = np.arange(len(r)) + stream_lo
+        order = np.concatenate([np.nonzero(dest == d)[0] for d in range(world)]).astype(np.int64)
+        counts = [int((dest == d).sum()) for d in range(world)]
+        return torch.from_numpy(r[order]), torch.from_numpy(pos[order].astype(np.int32)), counts
+
+    def add_routed(self, rec, pos):
+        self.rec.append(rec.numpy())
+        self.pos.append(pos.numpy())
+
+    def finish_partition(self):
+        from oracle import haphic_oracle as orc
+        rec = np.concatenate(self.rec) if self.rec else np.zeros((0, 4), np.int32)
+        pos = np.concatenate(self.pos) if self.pos else np.zeros(0, np.int32)
+        o = np.argsort(pos, kind="stable")         # the oracle counts in stream order
+        rec, pos = rec[o], pos[o]
+        r = orc.count_links_numpy(rec, *self.args)
+        ent = np.zeros((len(r["full_vals"]), 9), np.int64)
+        ent[:, 0:2] = r["full_keys"]
+        ent[:, 2] = r["full_vals"]
+        ent[:, 4] = pos[r["full_first"]]
+        ent[:, 5] = 0xFFFFFFFF
+        fl = {tuple(k): (v, f) for k, v, f in zip(r["flank_keys"].tolist(), r["flank_vals"].tolist(), r["flank_first"].tolist())}
+        for e, k in enumerate(r["full_keys"].tolist()):
+            if tuple(k) in fl:
+                ent[e, 3] = fl[tuple(k)][0]
+                ent[e, 5] = pos[fl[tuple(k)][1]]
+        self.part = (ent, r["ctg_link_total"].astype(np.int64), r["n_used"])
+
+        class Info:
+            n_used = r["n_used"]
+        return Info()
+
+    def export(self):
+        return torch.from_numpy(self.part[0]), torch.from_numpy(self.part[1].copy()), 0, self.part[2]
+
+    def adopt(self, entries, tot, n_rec, n_used, stream_end):
+        self.whole = (entries.numpy().copy(), tot.numpy().copy(), n_rec, n_used, stream_end)
+        return self.whole
+
+
 def _worker(rank, world, port, q):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -139,6 +198,15 @@ def _worker(rank, world, port, q):
         for k in whole.e:
             assert np.array_equal(mine.e[k][:4], whole.e[k][:4]), k
         assert np.array_equal(mine.tot, whole.tot) and mine.n_rec == 4000 and mine.n_used == whole.n_used
+        # 2b) routed counting: all-to-all of records, disjoint partitions, adopted union == single-stream table
+        rt = FakeRoutedTable(lengths, rk, nx, 100)
+        shard = pairs[:half] if rank == 0 else pairs[half:]
+        ent, tot, n_rec, n_used, s_end = hdist.routed_link_build(rt, torch.from_numpy(shard.astype(np.int32)), 0 if rank == 0 else half)
+        assert (n_rec, n_used, s_end) == (4000, whole.n_used, 4000) and np.array_equal(tot, whole.tot)
+        got = {(int(r[0]), int(r[1])): r[2:] for r in ent}
+        assert set(got) == set(whole.e) and len(ent) == len(whole.e)
+        for k in whole.e:
+            assert np.array_equal(got[k][:4], whole.e[k][:4]), k
         # 3) sharded MCL == single MCL (rounds, convergence, final matrix), uneven blocks included
         link, _ = planted_blocks(6, 30, seed=3, noise=0.5)
         n = link.shape[0]

@@ -169,6 +169,65 @@ def test_links_sharded_merge_equals_single(ctx):
         t.close()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_links_routed_equals_single(ctx, world):
+    """The routed protocol of dist.routed_link_build emulated on one GPU: shards of the stream are routed to the
+    owner of their contig pair, counted into disjoint partitions, and the adopted union equals the single table
+    (dict order restored by the fetch), index and matrix included."""
+    import torch
+    from haphic_b200.links import LinkTable
+    asm, pairs = synth_case(4, 400, 30000, 300_000, seed=23)
+    pairs[::991, 0] = asm.n + 3                   # ids outside the FASTA are dropped by the router
+    rank = rank_of(asm.names)
+    nx = (np.random.default_rng(1).random(asm.n) < 0.8).astype(np.uint8)
+    keep = np.ones(asm.n, np.uint8)
+    one = LinkTable(ctx, asm.lengths, rank, nx, 20000)
+    one.add(pairs)
+    info1 = one.finish()
+    want, want_tot = one.fetch(), one.fetch_ctg()
+    want_index, want_nl = one.linked_index(keep)
+    m1 = one.to_matrix(keep, np.nonzero(want_index < 0)[0].astype(np.int32)).to_scipy()
+    cuts = np.linspace(0, len(pairs), world + 1).astype(int)
+    cuts[1] += 7                                   # uneven shards
+    tabs = [LinkTable(ctx, asm.lengths, rank, nx, 20000) for _ in range(world)]
+    routed = []
+    for r in range(world):
+        shard = torch.from_numpy(np.ascontiguousarray(pairs[cuts[r]:cuts[r + 1]])).cuda()
+        rec_out, pos_out, counts = tabs[r].route(shard, int(cuts[r]), world)
+        assert sum(counts) <= len(shard)
+        routed.append((rec_out, pos_out, np.concatenate([[0], np.cumsum(counts)])))
+    parts, tots, n_used = [], [], 0
+    for d in range(world):                          # "all-to-all": destination d takes its group from every source
+        for r in range(world):
+            rec_out, pos_out, off = routed[r]
+            tabs[d].add_routed(rec_out[off[d]:off[d + 1]].contiguous(), pos_out[off[d]:off[d + 1]].contiguous())
+        part = tabs[d].finish_partition()
+        n_used += int(part.n_used)
+        ent, tot, _, _ = tabs[d].export()
+        parts.append(ent)
+        tots.append(tot)
+    keys = [set(map(tuple, p[:, :2].cpu().numpy().tolist())) for p in parts]
+    for a in range(world):
+        for b in range(a + 1, world):
+            assert not (keys[a] & keys[b])          # disjoint partitions
+    whole = torch.cat(parts)
+    tot = torch.stack(tots).sum(0)
+    for d in (0, world - 1):
+        info = tabs[d].adopt(whole, tot, len(pairs), n_used, len(pairs))
+        assert (info.n_records, info.n_used, info.nnz_full, info.nnz_flank) == \
+               (info1.n_records, info1.n_used, info1.nnz_full, info1.nnz_flank)
+        index, nl = tabs[d].linked_index(keep)     # works on the unordered list
+        assert nl == want_nl and np.array_equal(index, want_index)
+        m = tabs[d].to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32)).to_scipy()
+        assert (m != m1).nnz == 0
+        got = tabs[d].fetch()                       # restores dict insertion order
+        for k in want:
+            assert np.array_equal(want[k], got[k]), k
+        assert np.array_equal(want_tot, tabs[d].fetch_ctg())
+    for t in tabs + [one]:
+        t.close()
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_matrix_from_links_matches_reference_golden(ctx, tag):
     """dict_to_matrix: first-seen indices and the symmetric CSC with self loops (and, for case b,
