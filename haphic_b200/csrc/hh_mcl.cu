@@ -686,6 +686,33 @@ __global__ void hh_k_cc_hook_csc(const int64_t* __restrict__ colptr, const int32
     }
 }
 
+// keep the entries of `src` that fall into [lo, hi), order preserved (one block; n is small)
+__global__ void __launch_bounds__(1024) hh_k_filter_range(const int* __restrict__ src, int n, int lo, int hi, int* __restrict__ dst) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int b = 0; b < n; b += 1024) {
+        const int k = b + threadIdx.x;
+        const int v = (k < n) ? src[k] : -1;
+        const bool keep = v >= lo && v < hi;
+        const unsigned m = __ballot_sync(HH_FULL_MASK, keep);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (keep) dst[off + __popc(m & ((1u << lane) - 1u))] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += s_warp[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void hh_k_cc_jump(int* __restrict__ label, int n) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
@@ -1838,9 +1865,9 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         a.dense_out = mc->d_m1;
         a.flat = choose_flat(mc, (double)mc->nnz_m0);
         const float pre_thr = (float)env_int("HH_MCL_PREORDER", 10);     // 0 = off; else link count that makes an edge "strong"
-        if (pre_thr > 0.f && col_lo == 0 && col_hi == m->n) {
+        if (pre_thr > 0.f) {
             const int n = m->n;
-            int* d_lab = mc->d_root;
+            int* d_lab = mc->d_comp_lo;        // n-sized scratch, rewritten by mcl_build_perm later
             int* d_flag = mc->d_bigcount + 2;
             HH_LAUNCH(ctx, hh_k_cc_init, (n + 255) / 256, 256, 0, d_lab, n);
             int gridc = (n + 7) / 8;
@@ -1857,6 +1884,11 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
             HH_CUDA(cudaMemsetAsync(mc->d_cnt, 0, (size_t)n * sizeof(int), ctx->stream));
             HH_LAUNCH(ctx, hh_k_cc_rank, (n + 255) / 256, 256, 0, d_lab, n, mc->d_perm, mc->d_inv, mc->d_cnt);
             a.order = mc->d_inv;              // columns sorted by (component, index)
+            if (col_lo != 0 || col_hi != n) {
+                // column shard: the owned columns in the same order
+                HH_LAUNCH(ctx, hh_k_filter_range, 1, 1024, 0, mc->d_inv, n, (int)col_lo, (int)col_hi, mc->d_order);
+                a.order = mc->d_order;
+            }
         }
         a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
         HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));

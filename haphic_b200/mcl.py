@@ -102,6 +102,17 @@ class Mcl:
         check(load().hh_mcl_pack(self._h, ptr(ln), ptr(idx), ptr(val)))
         return ln, idx[:nnz_owned], val[:nnz_owned]
 
+    def pack_flat(self, nnz_owned: int, capacity: int):
+        """The same three arrays laid out back to back in ONE int32 CUDA tensor of `capacity` words
+        ([ncols] lengths, [nnz] row indices, [nnz] fp32 bit patterns): one collective moves a whole block."""
+        import torch
+        dev = torch.device("cuda", self.ctx.device)
+        ncols = self.col_hi - self.col_lo
+        buf = torch.empty(max(int(capacity), ncols + 2 * nnz_owned, 1), dtype=torch.int32, device=dev)
+        base = buf.data_ptr()
+        check(load().hh_mcl_pack(self._h, C.c_void_p(base), C.c_void_p(base + 4 * ncols), C.c_void_p(base + 4 * (ncols + nnz_owned))))
+        return buf
+
     def unpack(self, col_lo: int, col_hi: int, ln, idx, val):
         check(load().hh_mcl_unpack(self._h, int(col_lo), int(col_hi), ptr(ln), ptr(idx), ptr(val), int(idx.shape[0])))
 
