@@ -78,6 +78,7 @@ _SIGNATURES = {
     "hh_mcl_pack": (C.c_int, [_P, _P, _P, _P]),
     "hh_mcl_unpack": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64]),
     "hh_mcl_commit": (C.c_int, [_P]),
+    "hh_mcl_set_block": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "hh_mcl_destroy": (C.c_int, [_P]),
     "hh_pairs_open": (C.c_int, [C.c_char_p, _P, C.c_int32, C.c_char_p, C.c_int, C.POINTER(_P)]),
     "hh_pairs_next": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),

@@ -1388,6 +1388,7 @@ struct hh_mcl {
     unsigned long long* d_stats;   // [0] nnz [1] products [2] delta bits [3] err
     int64_t nnz_m0, preexp_products;
     int flat, l2pf;                // expansion inner-loop variant / L2 prefetch (HH_MCL_FLAT, HH_MCL_L2PF)
+    int32_t own_lo, own_hi;        // the column block given to hh_mcl_create (dense M1 block); col_lo/col_hi = active block
     int use_order;                 // cluster-sorted column processing (HH_MCL_ORDER)
     int* d_attr;                   // [n] strongest row per column of the current iterate
     int* d_order;                  // [ncols] processing order for the next expansion
@@ -1805,6 +1806,8 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
     mc->n = m->n;
     mc->col_lo = col_lo;
     mc->col_hi = col_hi;
+    mc->own_lo = col_lo;
+    mc->own_hi = col_hi;
     mc->expansion = expansion;
     mc->cur = -1;
     mc->use_small = env_int("HH_MCL_SMALL", 1);
@@ -1828,8 +1831,8 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         HH_CHECK(hh_dmalloc(&mc->d_counter, 1));
         HH_CHECK(hh_dmalloc(&mc->d_stats, 4));
         HH_CHECK(hh_dmalloc(&mc->d_attr, (size_t)m->n));
-        HH_CHECK(hh_dmalloc(&mc->d_order, (size_t)(col_hi - col_lo)));
-        HH_CHECK(hh_dmalloc(&mc->d_root, (size_t)(col_hi - col_lo)));
+        HH_CHECK(hh_dmalloc(&mc->d_order, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_root, (size_t)m->n));
         HH_CHECK(hh_dmalloc(&mc->d_cnt, (size_t)m->n * 2));
         HH_CHECK(hh_dmalloc(&mc->d_start, (size_t)m->n + 1));
         HH_CHECK(hh_dmalloc(&mc->d_bigcount, 4));
@@ -1837,10 +1840,10 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         HH_CHECK(hh_dmalloc(&mc->d_inv, (size_t)m->n));
         HH_CHECK(hh_dmalloc(&mc->d_comp_lo, (size_t)m->n));
         HH_CHECK(hh_dmalloc(&mc->d_comp_hi, (size_t)m->n));
-        HH_CHECK(hh_dmalloc(&mc->d_owned, (size_t)(col_hi - col_lo)));
-        HH_CHECK(hh_dmalloc(&mc->d_win_list, (size_t)(col_hi - col_lo)));
-        HH_CHECK(hh_dmalloc(&mc->d_big_list, (size_t)(col_hi - col_lo)));
-        HH_CHECK(hh_dmalloc(&mc->d_overflow, (size_t)(col_hi - col_lo)));
+        HH_CHECK(hh_dmalloc(&mc->d_owned, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_win_list, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_big_list, (size_t)m->n));
+        HH_CHECK(hh_dmalloc(&mc->d_overflow, (size_t)m->n));
         HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
         // 1) M0 = normalize(link_matrix, 'l1', axis=0)   (2144)
         int cap0 = 0;
@@ -1928,7 +1931,7 @@ extern "C" int hh_mcl_fetch_m0(hh_mcl* mc, int64_t* indptr, int32_t* indices, fl
 extern "C" int hh_mcl_fetch_m1(hh_mcl* mc, float* dense) {
     HH_REQUIRE(mc && dense, HH_ERR_ARG, "hh_mcl_fetch_m1: NULL argument");
     HH_CUDA(cudaSetDevice(mc->ctx->device));
-    const int ncols = mc->col_hi - mc->col_lo;
+    const int ncols = mc->own_hi - mc->own_lo;
     HH_CUDA(cudaMemcpy2DAsync(dense, (size_t)mc->n * sizeof(float), mc->d_m1, (size_t)mc->ld * sizeof(float),
                               (size_t)mc->n * sizeof(float), (size_t)ncols, cudaMemcpyDeviceToHost, mc->ctx->stream));
     HH_CUDA(cudaStreamSynchronize(mc->ctx->stream));
@@ -2035,6 +2038,8 @@ extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
     // iterate of the same mcl() call, which is what makes the row windows safe
     mc->perm_valid = false;
     mc->perm_space = false;
+    mc->col_lo = mc->own_lo;      // hh_mcl_set_block is per mcl() call
+    mc->col_hi = mc->own_hi;
     mc->begun = true;
     return HH_OK;
 }
@@ -2215,6 +2220,35 @@ extern "C" int hh_mcl_unpack(hh_mcl* mc, int32_t col_lo, int32_t col_hi, const i
     return rc;
 }
 
+// change the block of columns the following steps compute (sparse iterations only: iteration 0 streams the dense M1
+// block given to hh_mcl_create).  Column shards use it to stop exchanging once the iterate is tiny: every rank then
+// computes all columns itself -- same kernels, same order of additions, so all ranks keep identical iterates.
+extern "C" int hh_mcl_set_block(hh_mcl* mc, int32_t col_lo, int32_t col_hi) {
+    HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_set_block: NULL handle");
+    hh_scope _scope(mc->ctx);
+    HH_REQUIRE(mc->begun && mc->cur >= 0 && !mc->have_pending, HH_ERR_STATE,
+               "hh_mcl_set_block: only between hh_mcl_commit and the next hh_mcl_step, after iteration 0");
+    HH_REQUIRE(0 <= col_lo && col_lo < col_hi && col_hi <= mc->n, HH_ERR_ARG, "hh_mcl_set_block: bad column block");
+    hh_ctx* ctx = mc->ctx;
+    HH_CUDA(cudaSetDevice(ctx->device));
+    mc->col_lo = col_lo;
+    mc->col_hi = col_hi;
+    mc->order_valid = false;
+    if (mc->perm_space) {
+        const int ncols = col_hi - col_lo;
+        const int wlimit = env_int("HH_MCL_WMAX", 4096);
+        HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, 2 * sizeof(int), ctx->stream));
+        HH_LAUNCH(ctx, hh_k_cc_lists, (ncols + 255) / 256, 256, 0, mc->d_perm, mc->col_lo, ncols, mc->d_comp_lo, mc->d_comp_hi, wlimit,
+                  mc->d_owned, mc->d_win_list, mc->d_big_list, mc->d_bigcount);
+        int counts[2] = {0, 0};
+        HH_CUDA(cudaMemcpyAsync(counts, mc->d_bigcount, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        mc->n_win = counts[0];
+        mc->n_big = counts[1];
+    }
+    return HH_OK;
+}
+
 extern "C" int hh_mcl_commit(hh_mcl* mc) {
     HH_REQUIRE(mc != nullptr, HH_ERR_ARG, "hh_mcl_commit: NULL handle");
     HH_REQUIRE(mc->have_pending, HH_ERR_STATE, "hh_mcl_commit: nothing to commit");
@@ -2231,7 +2265,7 @@ extern "C" int hh_mcl_commit(hh_mcl* mc) {
 extern "C" int hh_mcl_run(hh_mcl* mc, double inflation, int max_iter, double pruning, hh_mcl_result* res, int64_t* iter_nnz,
                           int64_t* iter_products, float* iter_delta, float* iter_ms) {
     HH_REQUIRE(mc && res, HH_ERR_ARG, "hh_mcl_run: NULL argument");
-    HH_REQUIRE(mc->col_lo == 0 && mc->col_hi == mc->n, HH_ERR_STATE,
+    HH_REQUIRE(mc->own_lo == 0 && mc->own_hi == mc->n, HH_ERR_STATE,
                "hh_mcl_run needs a context that owns every column; use the step interface for column shards");
     HH_REQUIRE(max_iter >= 1, HH_ERR_ARG, "hh_mcl_run: max_iter must be >= 1");
     HH_CHECK(hh_mcl_begin(mc, inflation, pruning));

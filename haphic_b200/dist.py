@@ -91,6 +91,9 @@ def merge_link_tables(table, group=None):
         table.merge(ents[r], tots[r], int(metas[r][0].item()), int(metas[r][1].item()))
 
 
+REPLICATE_BELOW = 8      # entries per column under which column shards stop exchanging (see sharded_mcl_run)
+
+
 def routed_link_build(table, rec, stream_lo: int, group=None):
     """Sharded link counting without a reduction: every rank holds a contiguous shard `rec` of the
     read stream (global index of rec[0] = stream_lo).  Records are routed to the rank that owns their contig pair
@@ -148,8 +151,21 @@ def sharded_mcl_run(engine, inflation: float, max_iter: int, pruning: float, blo
     rounds, converged = 0, False
     it_nnz, it_prod, it_ms = [], [], []
     ncols = [hi - lo for lo, hi in blocks]
+    n_total = blocks[-1][1]
+    replicated = False
     for it in range(max_iter):
         nnz, prod, delta = engine.step(it)
+        if replicated:
+            # every rank computes the whole (tiny) iterate itself: identical on all ranks, nothing to exchange
+            engine.commit()
+            it_nnz.append(nnz)
+            it_prod.append(prod)
+            it_ms.append(getattr(engine, "last_step_ms", 0.0))
+            rounds = it + 1
+            if it > 1 and delta <= 1e-8:
+                converged = True
+                break
+            continue
         # exchange 1 (tiny): every rank's nnz / products / convergence term -> sizes of the blocks and the statistics
         dev = engine_device(engine)
         meta = torch.tensor([float(nnz), float(prod), float(delta)], dtype=torch.float64, device=dev)
@@ -176,6 +192,9 @@ def sharded_mcl_run(engine, inflation: float, max_iter: int, pruning: float, blo
                 c, z = ncols[r], nnzs[r]
                 engine.unpack(blocks[r][0], blocks[r][1], out[r, :c], out[r, c: c + z], out[r, c + z: c + 2 * z].view(torch.float32))
         engine.commit()
+        if world > 1 and it >= 1 and sum(nnzs) <= REPLICATE_BELOW * n_total and hasattr(engine, "set_block"):
+            engine.set_block(0, n_total)     # nearly converged: a full step costs less than one exchange
+            replicated = True
         it_nnz.append(sum(nnzs))
         it_prod.append(sum(int(m[1]) for m in metas))
         it_ms.append(getattr(engine, "last_step_ms", 0.0))

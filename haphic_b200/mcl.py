@@ -24,6 +24,7 @@ class Mcl:
         self.n = matrix.n
         self.col_lo = int(col_lo)
         self.col_hi = self.n if col_hi is None else int(col_hi)
+        self._own = (self.col_lo, self.col_hi)
         self._h = C.c_void_p()
         check(load().hh_mcl_create(matrix._h, int(expansion), self.col_lo, self.col_hi, C.byref(self._h)))
         n = C.c_int32()
@@ -81,6 +82,7 @@ class Mcl:
     # -- step interface (column shards) -------------------------------------------------------
     def begin(self, inflation: float, pruning: float = 1e-4):
         check(load().hh_mcl_begin(self._h, float(inflation), float(pruning)))
+        self.col_lo, self.col_hi = self._own
 
     def step(self, it: int):
         nnz = C.c_int64()
@@ -118,6 +120,11 @@ class Mcl:
 
     def commit(self):
         check(load().hh_mcl_commit(self._h))
+
+    def set_block(self, col_lo: int, col_hi: int):
+        """Columns the following sparse steps compute (reset by begin())."""
+        check(load().hh_mcl_set_block(self._h, int(col_lo), int(col_hi)))
+        self.col_lo, self.col_hi = int(col_lo), int(col_hi)
 
     def close(self):
         if self._h:

@@ -211,6 +211,10 @@ int hh_mcl_pack(hh_mcl* mc, int32_t* len_dev, int32_t* idx_dev, float* val_dev);
 int hh_mcl_unpack(hh_mcl* mc, int32_t col_lo, int32_t col_hi, const int32_t* len_dev,
                   const int32_t* idx_dev, const float* val_dev, int64_t nnz_block);
 int hh_mcl_commit(hh_mcl* mc);
+/* change the block of columns the following steps compute (between hh_mcl_commit and hh_mcl_step, after iteration 0;
+ * reset by hh_mcl_begin).  Column shards switch to (0, n) once the iterate is tiny: no exchange is needed any more
+ * because every rank then computes the identical full iterate. */
+int hh_mcl_set_block(hh_mcl* mc, int32_t col_lo, int32_t col_hi);
 int hh_mcl_destroy(hh_mcl* mc);
 
 /* ---- host-side I/O around the path (native, no CUDA) ------------------------------------------------

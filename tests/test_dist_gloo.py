@@ -33,6 +33,8 @@ class OracleShard:
         self.orc = orc
         self.n = link.shape[0]
         self.lo, self.hi = lo, hi
+        self.own = (lo, hi)
+        self.set_block_calls = 0
         m0 = orc.col_normalize_l1(link)
         self.m1_block = sp.csc_matrix(orc.expand(m0, 2)[:, lo:hi])
         self.cur = None
@@ -41,6 +43,12 @@ class OracleShard:
         self.r, self.p = inflation, pruning
         self.cur = None
         self.blocks = {}
+        self.lo, self.hi = self.own
+
+    def set_block(self, lo, hi):
+        assert self.cur is not None
+        self.lo, self.hi = lo, hi
+        self.set_block_calls += 1
 
     def step(self, it):
         orc = self.orc
@@ -218,6 +226,7 @@ def _worker(rank, world, port, q):
             assert (st["rounds"], st["converged"]) == (rounds, conv)
             assert abs(eng.cur - fin).max() < 1e-7
             assert st["iter_nnz"][-1] == fin.nnz
+            assert eng.set_block_calls == 1 and (eng.lo, eng.hi) == (0, n)      # the tail ran replicated, without exchange
         dist.destroy_process_group()
         q.put((rank, "ok"))
     except Exception:

@@ -7,6 +7,7 @@ has an unspecified accumulation order, so bit-equality of products is not define
 counts, convergence flags and final cluster assignments must be identical."""
 
 import numpy as np
+import torch
 import pytest
 import scipy.sparse as sp
 
@@ -162,22 +163,35 @@ def test_mcl_step_interface_two_column_shards_equal_single(ctx):
     s0.begin(1.8, 1e-4)
     s1.begin(1.8, 1e-4)
     rounds = 0
+    replicated = False
     for it in range(200):
         n0, p0, d0 = s0.step(it)
         n1, p1, d1 = s1.step(it)
-        b0, b1 = s0.pack(n0), s1.pack(n1)
-        s0.unpack(cut, n, *b1)
-        s1.unpack(0, cut, *b0)
+        if replicated:
+            assert (n0, d0) == (n1, d1) == (int(st["iter_nnz"][it]), float(st["iter_delta"][it]))
+        else:
+            b0, b1 = s0.pack_flat(n0, 0), s1.pack(n1)          # both packings
+            f = b0
+            s1.unpack(0, cut, f[:cut], f[cut:cut + n0], f[cut + n0:cut + 2 * n0].view(torch.float32))
+            s0.unpack(cut, n, *b1)
         s0.commit()
         s1.commit()
+        if not replicated and it >= 3:       # what dist.sharded_mcl_run does for a tiny iterate: stop exchanging
+            s0.set_block(0, n)
+            s1.set_block(0, n)
+            replicated = True
         rounds = it + 1
         if it > 1 and max(d0, d1) <= 1e-8:
             break
-    assert rounds == st["rounds"]
+    assert replicated and rounds == st["rounds"]
+
     for s in (s0, s1):
         got = canon(s.result())
         assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
         assert np.array_equal(got.data, want.data)
+    # the next mcl() call starts from the owned blocks again
+    s0.begin(2.5, 1e-4)
+    assert (s0.col_lo, s0.col_hi) == (0, cut)
     for o in (whole, s0, s1):
         o.close()
     mat.close()
