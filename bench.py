@@ -46,7 +46,7 @@ def parse_args():
     p.add_argument("--max-iter", type=int, default=200)
     p.add_argument("--pruning", type=float, default=1e-4)
     p.add_argument("--seed", type=int, default=12345)
-    p.add_argument("--e2e-steps", type=int, default=1)
+    p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--cpu-sample-pairs", type=int, default=4_000_000)
     p.add_argument("--cpu-sample-cols", type=int, default=24)
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -358,7 +358,7 @@ def run_b200(a):
         mc.close()
         mat.close()
         tab.close()
-    e2e_pairs = P / (sum(e2e_build) / len(e2e_build)) if e2e_build else None
+    e2e_pairs = P / float(np.median(e2e_build)) if e2e_build else None          # median over the passes
     e2e_iters = sum(x[1] for x in e2e_mcl) / sum(x[0] for x in e2e_mcl) if e2e_mcl else None
 
     # ---- CPU baseline on this box's host cores (bounded samples) ------------------------------------

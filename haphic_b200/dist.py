@@ -102,7 +102,17 @@ def routed_link_build(table, rec, stream_lo: int, group=None):
     Returns the LinksInfo of the whole table."""
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
+    dbg = os.environ.get("HH_BENCH_DEBUG") == "2"
+    marks = []
+
+    def mark(tag):
+        if dbg:
+            import time
+            torch.cuda.synchronize()
+            marks.append((tag, time.perf_counter()))
+    mark("start")
     rec_out, pos_out, counts = table.route(rec, stream_lo, world)
+    mark("route")
     dev = rec_out.device
     send = torch.tensor(counts, dtype=torch.int64, device=dev)
     recv = torch.empty_like(send)
@@ -113,10 +123,12 @@ def routed_link_build(table, rec, stream_lo: int, group=None):
     dist.all_to_all_single(rec_in, rec_out, recv_counts, counts, group=group)
     dist.all_to_all_single(pos_in, pos_out, recv_counts, counts, group=group)
     _wait_collectives(rec_in)
+    mark("all-to-all")
     table.add_routed(rec_in, pos_in)
     del rec_out, pos_out
     part = table.finish_partition()
     ent, tot, _, _ = table.export()
+    mark("insert+partition+export")
     # sizes, then the partitions straight into one buffer (uneven all-gather)
     meta = torch.tensor([int(ent.shape[0]), int(rec.shape[0]), int(part.n_used), int(stream_lo) + int(rec.shape[0])],
                         dtype=torch.int64, device=dev)
@@ -136,7 +148,13 @@ def routed_link_build(table, rec, stream_lo: int, group=None):
             dist.broadcast(views[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
     _wait_collectives(whole)
-    return table.adopt(whole, tot, sum(int(m[1]) for m in metas), sum(int(m[2]) for m in metas), max(int(m[3]) for m in metas))
+    mark("all-gather")
+    info = table.adopt(whole, tot, sum(int(m[1]) for m in metas), sum(int(m[2]) for m in metas), max(int(m[3]) for m in metas))
+    mark("adopt")
+    if dbg:
+        print("rank", rank, "routed build ms:", [(b[0], round(1000 * (b[1] - a[1]), 1)) for a, b in zip(marks, marks[1:])],
+              file=sys.stderr, flush=True)
+    return info
 
 
 def sharded_mcl_run(engine, inflation: float, max_iter: int, pruning: float, blocks, group=None):
@@ -351,7 +369,7 @@ def bench_multi(a, world: int, rank_id: int, local: int):
         e2e = None
         mcl_e2e = None
         if e2e_t:
-            e2e = {"value": a.pairs / (sum(x[0] for x in e2e_t) / len(e2e_t)), "unit": "pairs/s",
+            e2e = {"value": a.pairs / float(np.median([x[0] for x in e2e_t])), "unit": "pairs/s", "passes": len(e2e_t),
                    "h2d_bytes_per_step": 16 * a.pairs + 13 * n * world, "d2h_bytes_per_step": int(d2h / len(e2e_t))}
             mcl_e2e = {"value": sum(x[2] for x in e2e_t) / sum(x[1] for x in e2e_t), "unit": "iter/s"}
         line = {
