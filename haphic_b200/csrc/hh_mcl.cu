@@ -958,6 +958,61 @@ __global__ void __launch_bounds__(32) hh_k_col_win(const hh_colargs a, int W, co
     }
 }
 
+// relabelling copy inside the component window: new column j <- old column inv[j], rows through perm (they land in
+// [comp_lo[j], comp_hi[j])), re-sorted by a scatter into the window and an ordered compaction.  One warp per column.
+__global__ void __launch_bounds__(32) hh_k_relabel_win(const hh_slotmat src, const hh_slotmat out, int W, int T,
+                                                       const int* __restrict__ list, int nlist, const int* __restrict__ perm,
+                                                       const int* __restrict__ inv, const int* __restrict__ comp_lo,
+                                                       const int* __restrict__ comp_hi, int wmax, int* __restrict__ err) {
+    extern __shared__ __align__(16) float acc[];      // wmax floats, zero between columns
+    const int lane = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int k = lane; k < wmax; k += 32) acc[k] = 0.f;
+    __syncwarp();
+    for (int jj = blockIdx.x; jj < nlist; jj += gridDim.x) {
+        const int j = list[jj];
+        const int lo = comp_lo[j], width = comp_hi[j] - lo;
+        const int jsrc = inv[j];
+        const int L = src.len[jsrc];
+        const uint2* __restrict__ se = src.ent + (size_t)jsrc * (size_t)src.cap;
+        for (int p = lane; p < L; p += 32) {
+            const uint2 e = se[p];
+            const unsigned r = (unsigned)perm[e.x] - (unsigned)lo;
+            if (r < (unsigned)width) acc[r] = __uint_as_float(e.y);
+            else atomicExch(err, 2);
+        }
+        __syncwarp();
+        uint2* __restrict__ oent = out.ent + (size_t)j * (size_t)out.cap;
+        int* __restrict__ oblk = out.blk + (size_t)j * (W + 1);
+        int bnext = 0, off = 0;
+        for (int r0 = 0; r0 < width; r0 += 32) {
+            const int r = r0 + lane;
+            const float x = (r < width) ? acc[r] : 0.f;
+            const bool f = x != 0.f;
+            const unsigned bal = __ballot_sync(HH_FULL_MASK, f);
+            while (bnext <= W && (long long)bnext * T <= (long long)(lo + r0 + 31)) {
+                const long long brow = (long long)bnext * T;
+                const int nlt = (brow <= lo + r0) ? 0 : (int)(brow - (lo + r0));
+                const unsigned below = (nlt >= 32) ? 0xFFFFFFFFu : ((1u << nlt) - 1u);
+                if (lane == 0) oblk[bnext] = min(off + __popc(bal & below), out.cap);
+                bnext++;
+            }
+            if (f) {
+                const int pos = off + __popc(bal & lt_mask);
+                if (pos < out.cap) oent[pos] = make_uint2((unsigned)(lo + r), __float_as_uint(x));
+                acc[r] = 0.f;
+            }
+            off += __popc(bal);
+        }
+        if (lane == 0) {
+            for (; bnext <= W; ++bnext) oblk[bnext] = min(off, out.cap);
+            out.len[j] = min(off, out.cap);
+            if (off > out.cap || off != L) atomicExch(err, 1);
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // nearly converged iterates: a column has a handful of entries, and the CTA-per-column kernel is bound
 // by its per-column latency chain (one column in flight per SM).  Here ONE WARP expands a column by a
@@ -1970,38 +2025,61 @@ static int mcl_build_perm(hh_mcl* mc) {
         HH_LAUNCH(ctx, hh_k_cc_ranges, (n + 255) / 256, 256, 0, d_lab, mc->d_perm, d_csize, n, mc->d_comp_lo, mc->d_comp_hi);
         // window size: the largest component that still fits (4 private accumulators of wmax floats, several CTAs per SM)
         const int wlimit = env_int("HH_MCL_WMAX", 4096);
-        HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, 2 * sizeof(int), ctx->stream));
-        HH_LAUNCH(ctx, hh_k_cc_lists, (ncols + 255) / 256, 256, 0, mc->d_perm, mc->col_lo, ncols, mc->d_comp_lo, mc->d_comp_hi, wlimit,
-                  mc->d_owned, mc->d_win_list, mc->d_big_list, mc->d_bigcount);
-        int counts[2] = {0, 0};
-        HH_CUDA(cudaMemcpyAsync(counts, mc->d_bigcount, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         if (!mc->h_inv) mc->h_inv = new std::vector<int>((size_t)n);
         HH_CUDA(cudaMemcpyAsync(mc->h_inv->data(), mc->d_inv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         std::vector<int> csz((size_t)n);
         HH_CUDA(cudaMemcpyAsync(csz.data(), d_csize, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
-        mc->n_win = counts[0];
-        mc->n_big = counts[1];
         int wmax = 32;
         for (int v = 0; v < n; ++v)
             if (csz[(size_t)v] <= wlimit && csz[(size_t)v] > wmax) wmax = csz[(size_t)v];
         mc->wmax = (wmax + 31) & ~31;
-        // rewrite the iterate in new indices: column j' <- column inv[j'], rows through perm, rows re-sorted
+        // rewrite the iterate in new indices: column j' <- column inv[j'], rows through perm, rows re-sorted.
+        // Columns of small components do it inside their window (one warp each); the others on the n-row accumulator.
+        int all_counts[2] = {0, 0};
+        HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, 2 * sizeof(int), ctx->stream));
+        HH_LAUNCH(ctx, hh_k_cc_lists, (n + 255) / 256, 256, 0, mc->d_perm, 0, n, mc->d_comp_lo, mc->d_comp_hi, wlimit, mc->d_owned,
+                  mc->d_win_list, mc->d_big_list, mc->d_bigcount);
+        HH_CUDA(cudaMemcpyAsync(all_counts, mc->d_bigcount, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
         hh_colargs a;
         mcl_base_args(mc, a);
-        a.col_lo = 0;
-        a.ncols = n;
-        a.B = M;
-        a.slot_src = 1;
-        a.perm = mc->d_perm;
-        a.orig = mc->d_inv;
-        a.out = mc->it[mc->cur ^ 1];
-        a.raw = 1;
-        HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-        HH_CHECK((launch_col<SRC_CSC, EPI_NORM>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+        if (all_counts[0] > 0) {
+            const size_t smem = (size_t)mc->wmax * sizeof(float);
+            auto kern = hh_k_relabel_win;
+            HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+            int grid = per_sm * ctx->sm_count;
+            if (grid > all_counts[0]) grid = all_counts[0];
+            HH_LAUNCH(ctx, kern, grid, 32, smem, M, mc->it[mc->cur ^ 1], g.W, g.T, mc->d_win_list, all_counts[0], mc->d_perm, mc->d_inv,
+                      mc->d_comp_lo, mc->d_comp_hi, mc->wmax, a.err);
+        }
+        if (all_counts[1] > 0) {
+            a.col_lo = 0;
+            a.ncols = all_counts[1];
+            a.order = mc->d_big_list;
+            a.B = M;
+            a.slot_src = 1;
+            a.perm = mc->d_perm;
+            a.orig = mc->d_inv;
+            a.out = mc->it[mc->cur ^ 1];
+            a.raw = 1;
+            HH_CHECK((launch_col<SRC_CSC, EPI_NORM>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+        }
         unsigned long long st[4];
         HH_CHECK(read_stats(ctx, mc->d_stats, st));
         HH_REQUIRE((int)(st[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY, "hh_mcl: slot overflow while relabelling");
+        // the lists of the columns this context steps
+        HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, 2 * sizeof(int), ctx->stream));
+        HH_LAUNCH(ctx, hh_k_cc_lists, (ncols + 255) / 256, 256, 0, mc->d_perm, mc->col_lo, ncols, mc->d_comp_lo, mc->d_comp_hi, wlimit,
+                  mc->d_owned, mc->d_win_list, mc->d_big_list, mc->d_bigcount);
+        int counts[2] = {0, 0};
+        HH_CUDA(cudaMemcpyAsync(counts, mc->d_bigcount, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        mc->n_win = counts[0];
+        mc->n_big = counts[1];
         mc->cur ^= 1;
         mc->perm_valid = true;
         mc->perm_space = true;

@@ -32,7 +32,7 @@ def main():
     mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))
     tab.close()
     del rec
-    configs = [dict(PREORDER=0), dict(PREORDER=10), dict(PREORDER=40)]
+    configs = [dict(WINDOW=1)]
     sel = os.environ.get("TUNE_CONFIGS")
     if sel:
         configs = [configs[int(k)] for k in sel.split(",")]
@@ -43,7 +43,7 @@ def main():
         t0 = time.perf_counter()
         mc = Mcl(mat)
         out = {"cfg": cfg, "preexp_ms": round(mc.preexp_ms, 1), "norm_ms": round(mc.normalize_ms, 2)}
-        for r, iters in ((2.0, 200),):
+        for r, iters in ((1.5, 200), (2.0, 200)):
             st = mc.run(r, iters, 1e-4)
             out["r{}".format(r)] = [round(float(x), 2) for x in st["iter_ms"]][:12]
             out["tot{}".format(r)] = round(float(st["iter_ms"].sum()), 1)
