@@ -104,8 +104,12 @@ def parse_gfa(gfa_list, fa_dict, logger=logger):
     raise NotImplementedError("haphic_b200: --gfa (hifiasm read depth / phasing, HapHiC_cluster.py:150-185) is not supported")
 
 
-def remove_allelic_HiC_links(*_a, **_k):
-    raise NotImplementedError("haphic_b200: --remove_allelic_links (HapHiC_cluster.py:474-692) is not supported yet")
+def remove_allelic_HiC_links(fa_dict, ctg_coord_dict, full_link_dict, args, flank_link_dict=None, filtered_frags=None,
+                             ctg_pair_to_frag=None, logger=logger):
+    """474-692, see haphic_b200/allelic.py (HapHiC_reassign.py:23 imports this name)."""
+    from . import allelic
+    return allelic.remove_allelic_HiC_links(fa_dict, ctg_coord_dict, full_link_dict, args, flank_link_dict, filtered_frags,
+                                            ctg_pair_to_frag, logger=logger, dict_to_matrix=dict_to_matrix)
 
 
 def stat_fragments(fa_dict, RE, read_depth_dict, whitelist, nchrs=0, flank=0, Nx=100, bin_size=0, logger=logger):
@@ -242,8 +246,6 @@ def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag
     bins (1658-1752): flank links and per-fragment totals are keyed by FRAGMENTS (second device table in
     fragment mode), full / HT / clm stay contig-level."""
     logger.info("Parsing input alignments...")
-    if args.remove_allelic_links or args.remove_concentrated_links:
-        raise NotImplementedError("haphic_b200: --remove_allelic_links / --remove_concentrated_links are not supported yet")
     from .links import LinkTable, link_dicts, name_rank
     names = list(fa_dict.keys())
     ctg_len = np.array([fa_dict[n][1] for n in names], dtype=np.int64)
@@ -261,7 +263,14 @@ def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag
     parse_alignments.last_clm = (clm_rec, names, ctg_len, name_rank(names))
     parse_alignments.last_table = ftab
     parse_alignments.frag_names = frag_names
-    return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, defaultdict(list), defaultdict(set)
+    ctg_coord_dict, ctg_pair_to_frag = defaultdict(list), defaultdict(set)
+    if args.remove_allelic_links or args.remove_concentrated_links:
+        from . import allelic
+        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, name_rank(names), args, pos_int_type)
+        if args.remove_allelic_links:
+            ctg_pair_to_frag = allelic.ctg_pair_to_frag_dict(clm_rec, names, name_rank(names), frag_names, frag_base, frag_rank,
+                                                             int(bin_size))
+    return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict, ctg_pair_to_frag
 
 
 def clm_arrays(clm_rec, n_names, ctg_len, rank, sort_within=True):
@@ -335,8 +344,6 @@ def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_se
     (ref, mref, pos, mpos) tuples as the reference's generators yield.  ``build_clm=False`` (used by run())
     leaves clm_dict empty and keeps the usable records in ``.last_clm`` for the native CLM writer."""
     logger.info("Parsing input alignments...")
-    if args.remove_allelic_links or args.remove_concentrated_links:
-        raise NotImplementedError("haphic_b200: --remove_allelic_links / --remove_concentrated_links are not supported yet")
     names = list(fa_dict.keys())
     ctg_len = np.array([ctg_len_dict[n] for n in names], dtype=np.int64)
     from .links import link_dicts, name_rank
@@ -346,7 +353,11 @@ def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_se
     clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type) if build_clm else defaultdict(list)
     parse_alignments_for_ctgs.last_table = table          # run() keeps using the device table
     parse_alignments_for_ctgs.last_clm = (clm_rec, names, ctg_len, name_rank(names))
-    return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, ctg_link_dict, defaultdict(list)
+    ctg_coord_dict = defaultdict(list)
+    if args.remove_allelic_links or args.remove_concentrated_links:
+        from . import allelic
+        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, name_rank(names), args, pos_int_type)
+    return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, ctg_link_dict, ctg_coord_dict
 
 
 def _as_batches(alignments, names, batch=1 << 20):
@@ -974,14 +985,15 @@ def run(args, log_file=None):
         alignments = hicio.pairs_batches(args.alignments, args.aln_format, name_index, inter_only=inter_only)
 
     if split_ctg_set:
-        full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, _coords, _c2f = parse_alignments(
+        full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict, ctg_pair_to_frag = parse_alignments(
             alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type,
             build_clm=False)
         table = parse_alignments.last_table
         clm_src = parse_alignments.last_clm
         names = parse_alignments.frag_names         # the matrix lives in fragment space from here on
     else:
-        full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, _coords = parse_alignments_for_ctgs(
+        ctg_pair_to_frag = None
+        full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict = parse_alignments_for_ctgs(
             alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_int_type, dist_int_type, build_clm=False)
         table = parse_alignments_for_ctgs.last_table
         clm_src = parse_alignments_for_ctgs.last_clm
@@ -996,16 +1008,31 @@ def run(args, log_file=None):
 
     if args.normalize_by_nlinks:
         normalize_by_nlinks(flank_link_dict, frag_link_dict)
+    if args.remove_concentrated_links:                      # 2899-2902
+        for ctg_name_pair, data in ctg_coord_dict.items():
+            if isinstance(data, list):
+                full_link_dict[ctg_name_pair] *= data[1]
     filtered_frags = filter_fragments(
         Nx_frag_set, RE_site_dict, args.RE_site_cutoff, frag_link_dict, args.density_lower, args.density_upper,
         args.topN, args.rank_sum_upper, args.rank_sum_hard_cutoff, flank_link_dict, read_depth_dict,
         args.read_depth_upper, whitelist, device_table=table, device_names=names, normalized=args.normalize_by_nlinks)
+    if args.remove_allelic_links:                           # 2910-2919
+        filtered_frags = remove_allelic_HiC_links(fa_dict, ctg_coord_dict, full_link_dict, args, flank_link_dict, filtered_frags,
+                                                  ctg_pair_to_frag if split_ctg_set else None)
+    del ctg_coord_dict
     output_pickle(full_link_dict, "full_link_dict", "full_links.pkl")
 
-    # dict_to_matrix on the device: first-seen indices from the table, unlinked fragments appended in
-    # the reference's set-iteration order (355-359)
-    link_matrix, frag_index_dict = device_matrix(table, names, filtered_frags, normalize_by_nlinks=args.normalize_by_nlinks,
-                                                 add_self_loops=True)
+    if args.remove_allelic_links:
+        # the host edited flank_link_dict: the matrix comes from the edited dict (hh_matrix_from_csc), same
+        # first-seen indexing as the reference's dict_to_matrix
+        from .links import LinkMatrix
+        host_matrix, frag_index_dict = dict_to_matrix(flank_link_dict, filtered_frags, dense_matrix=False, add_self_loops=True)
+        link_matrix = LinkMatrix.from_csc(_context(), host_matrix)
+    else:
+        # dict_to_matrix on the device: first-seen indices from the table, unlinked fragments appended in
+        # the reference's set-iteration order (355-359)
+        link_matrix, frag_index_dict = device_matrix(table, names, filtered_frags, normalize_by_nlinks=args.normalize_by_nlinks,
+                                                     add_self_loops=True)
     table.close()
     matrix_time = time.time()
     logger.info("Hi-C linking matrix was constructed in {}s".format(matrix_time - start_time))

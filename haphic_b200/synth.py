@@ -97,8 +97,13 @@ def make_pairs_range(asm: Assembly, lo: int, hi: int, seed: int = 12345, cis_fra
 
 
 def make_pairs(asm: Assembly, n_pairs: int, seed: int = 12345, cis_frac: float = 0.85,
-               device: str | torch.device = "cpu", chunk: int = 1 << 24) -> torch.Tensor:
-    """Return an int32 tensor [n_pairs, 4] of (ctg_a, pos_a, ctg_b, pos_b)."""
+               device: str | torch.device = "cpu", chunk: int = 1 << 24, homolog=None) -> torch.Tensor:
+    """Return an int32 tensor [n_pairs, 4] of (ctg_a, pos_a, ctg_b, pos_b).
+
+    ``homolog=(ploidy, frac)`` treats every ``ploidy`` consecutive chromosomes as the haplotypes of one
+    chromosome (as simulation/sim_haplotypes.py lays them out) and re-maps the second end of a fraction ``frac`` of
+    the cis pairs to the SAME locus (+- 500 bp) of another haplotype -- the collinear "allelic" Hi-C links that
+    remove_allelic_HiC_links (HapHiC_cluster.py:474-692) detects by their concordance ratio."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -121,7 +126,7 @@ def make_pairs(asm: Assembly, n_pairs: int, seed: int = 12345, cis_frac: float =
     done = 0
     while done < n_pairs:
         m = min(chunk, n_pairs - done)
-        u = torch.rand((m, 5), generator=g, device=dev, dtype=torch.float64)
+        u = torch.rand((m, 5 if homolog is None else 8), generator=g, device=dev, dtype=torch.float64)
         is_cis = u[:, 0] < cis_frac
         chrom_a = torch.clamp((u[:, 1] * nchr).long(), max=nchr - 1)
         pos_a = torch.clamp((u[:, 2] * L).long(), max=L - 1)
@@ -137,6 +142,13 @@ def make_pairs(asm: Assembly, n_pairs: int, seed: int = 12345, cis_frac: float =
         pos_t = torch.clamp((u[:, 4] * L).long(), max=L - 1)
         g_a = chrom_a * L + pos_a
         g_b = torch.where(is_cis, chrom_a * L + pos_c, chrom_t * L + pos_t)
+        if homolog is not None:
+            ploidy, frac = int(homolog[0]), float(homolog[1])
+            switch = is_cis & (u[:, 5] < frac)
+            hap = chrom_a % ploidy
+            other = (hap + 1 + torch.clamp((u[:, 6] * (ploidy - 1)).long(), max=ploidy - 2)) % ploidy
+            pos_h = torch.clamp(pos_a + ((u[:, 7] - 0.5) * 1000.0).long(), 0, L - 1)
+            g_b = torch.where(switch, (chrom_a - hap + other) * L + pos_h, g_b)
         ia, pa = locate(g_a)
         ib, pb = locate(g_b)
         out[done:done + m, 0] = ia

@@ -309,11 +309,75 @@ def block_matrix(n_blocks, block, seed, noise=0.02):
     return sp.csc_matrix(a, dtype=np.float32)
 
 
-def run_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, seed, **argkw):
+def allelic_case(ref, tag, nchr, ploidy, n_contigs, mean_len, n_pairs, frac, seed, concentrated=False, bin_kb=0, **argkw):
+    """Golden for record_coord_pairs / the two ratios / remove_allelic_HiC_links (a9): nchr chromosomes x ploidy
+    haplotypes, a fraction of the cis pairs re-mapped to the same locus of another haplotype."""
+    from haphic_b200 import synth
+    asm = synth.make_assembly(nchr * ploidy, n_contigs, mean_len, seed=seed)
+    pairs = synth.make_pairs(asm, n_pairs, seed=seed + 1, homolog=(ploidy, frac)).numpy()
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            fasta = os.path.join(tmp, "asm.fa")
+            pfile = os.path.join(tmp, "aln.pairs")
+            synth.write_fasta(asm, fasta, seed=seed + 3)
+            synth.write_pairs(asm, pairs, pfile)
+            args = make_args(fasta=fasta, alignments=pfile, nchrs=nchr * ploidy, bin_size=bin_kb, aln_format="pairs",
+                             remove_allelic_links=ploidy, remove_concentrated_links=concentrated, **argkw)
+            fa_dict = ref.parse_fasta(fasta, RE=args.RE)
+            pos_t, dist_t = ref.determine_int_type(fa_dict)
+            _, bin_set, bin_size, frag_len_dict, Nx_frag_set, RE_site_dict, split_ctg_set = ref.stat_fragments(
+                fa_dict, args.RE, dict(), set(), nchrs=args.nchrs, flank=args.flank, Nx=args.Nx, bin_size=bin_kb)
+            c2f = None
+            if split_ctg_set:
+                alignments = ref.pairs_generator(pfile, "pairs")
+                full, flank_d, HT, clm, frag_links, coord, c2f = ref.parse_alignments(
+                    alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_t, dist_t)
+            else:
+                alignments = ref.pairs_generator_inter_ctgs(pfile, "pairs")
+                full, flank_d, HT, clm, frag_links, coord = ref.parse_alignments_for_ctgs(
+                    alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_t, dist_t)
+            coord_json = [[a, b, (list(v) if isinstance(v, list) else None), (None if isinstance(v, list) else v.tolist())]
+                          for (a, b), v in coord.items()]
+            out["coord_json"] = np.array(json.dumps(coord_json))
+            if c2f is not None:
+                out["c2f_json"] = np.array(json.dumps(sorted([[a, b, sorted(map(list, v))] for (a, b), v in c2f.items() if a != b])))
+            if concentrated:
+                for pair, data in coord.items():
+                    if isinstance(data, list):
+                        full[pair] *= data[1]
+            filtered = ref.filter_fragments(
+                Nx_frag_set, RE_site_dict, args.RE_site_cutoff, frag_links, args.density_lower, args.density_upper,
+                args.topN, args.rank_sum_upper, args.rank_sum_hard_cutoff, flank_d, dict(), args.read_depth_upper, set())
+            out["full_before_json"] = np.array(json.dumps([[a, b, v] for (a, b), v in full.items()]))
+            out["flank_before_json"] = np.array(json.dumps([[a, b, v] for (a, b), v in flank_d.items()]))
+            out["filtered_json"] = np.array(json.dumps(sorted(filtered)))
+            remaining = ref.remove_allelic_HiC_links(fa_dict, coord, full, args, flank_d, filtered, c2f if split_ctg_set else None)
+            out["full_after_json"] = np.array(json.dumps([[a, b, v] for (a, b), v in full.items()]))
+            out["flank_after_json"] = np.array(json.dumps([[a, b, v] for (a, b), v in flank_d.items()]))
+            out["remaining_json"] = np.array(json.dumps(sorted(remaining)))
+            out["names"] = np.array(asm.names)
+            out["lengths"] = asm.lengths
+            out["pairs"] = pairs.astype(np.int32)
+            out["ploidy"] = np.int64(ploidy)
+            out["bin_size"] = np.int64(bin_size if split_ctg_set else 0)
+            out["argkw"] = np.array(json.dumps(dict(argkw, bin_size=bin_kb, remove_allelic_links=ploidy,
+                                                    remove_concentrated_links=concentrated, nchrs=nchr * ploidy)))
+            n_before, n_after = len(json.loads(str(out["full_before_json"]))), len(full)
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "allelic_{}.npz".format(tag)), **out)
+    print("allelic_{}: contig pairs {} -> {} after removal, fragments {} -> {}, pairs with >= max_read_pairs: {}".format(
+        tag, n_before, n_after, len(filtered), len(remaining), sum(1 for c in coord_json if c[2] is not None)))
+
+
+def run_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, seed, homolog=None, **argkw):
     """Golden for the whole `haphic cluster` run (boundary b): output files as text."""
     from haphic_b200 import synth
     asm = synth.make_assembly(nchr, n_contigs, mean_len, seed=seed)
-    pairs = synth.make_pairs(asm, n_pairs, seed=seed + 1).numpy()
+    pairs = synth.make_pairs(asm, n_pairs, seed=seed + 1, homolog=homolog).numpy()
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
         cwd = os.getcwd()
@@ -358,6 +422,7 @@ def run_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, seed, **argkw):
             out["argkw"] = np.array(json.dumps(argkw, sort_keys=True))
             out["seed"] = np.int64(seed)
             out["shape"] = np.array([nchr, n_contigs, mean_len, n_pairs], dtype=np.int64)
+            out["homolog"] = np.array(json.dumps(list(homolog) if homolog else None))
         finally:
             os.chdir(cwd)
     np.savez_compressed(os.path.join(HERE, "run_{}.npz".format(tag)), **out)
@@ -365,19 +430,38 @@ def run_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, seed, **argkw):
 
 
 def main():
+    """`make_golden.py` regenerates everything; `make_golden.py allelic run_allelic4` only the named groups."""
     ref = import_reference()
-    m_a = link_case(ref, "a", nchr=3, n_contigs=60, mean_len=40000, n_pairs=30000, flank=500, Nx=100, seed=101)
-    link_case(ref, "b", nchr=4, n_contigs=120, mean_len=60000, n_pairs=60000, flank=10, Nx=80, seed=202,
-              normalize=True)
-    mcl_case(ref, "links_a", m_a, inflations=[1.2, 2.0, 3.0])
-    mcl_case(ref, "block200", block_matrix(4, 50, seed=7), inflations=[1.1, 1.5, 2.0, 2.7])
-    mcl_case(ref, "block600", block_matrix(6, 100, seed=9, noise=0.05), inflations=[1.4, 2.0], keep_iters=3)
-    run_case(ref, "c1", nchr=4, n_contigs=200, mean_len=40000, n_pairs=150000, seed=303, Nx=100, bin_size=0)
-    run_case(ref, "c1_nx80", nchr=4, n_contigs=200, mean_len=40000, n_pairs=150000, seed=303, Nx=80, bin_size=0,
-             min_inflation=1.2, max_inflation=2.0, inflation_step=0.2)
-    link_case_bins(ref, "bins", nchr=3, n_contigs=45, mean_len=300000, n_pairs=60000, flank=40, Nx=90, bin_kb=100, seed=404)
-    run_case(ref, "bins", nchr=3, n_contigs=60, mean_len=350000, n_pairs=120000, seed=505, Nx=100, bin_size=120, flank=60,
-             min_inflation=1.4, max_inflation=2.2, inflation_step=0.4)
+    only = set(sys.argv[1:])
+
+    def want(group):
+        return not only or group in only
+
+    if want("links") or want("mcl"):
+        m_a = link_case(ref, "a", nchr=3, n_contigs=60, mean_len=40000, n_pairs=30000, flank=500, Nx=100, seed=101)
+        link_case(ref, "b", nchr=4, n_contigs=120, mean_len=60000, n_pairs=60000, flank=10, Nx=80, seed=202,
+                  normalize=True)
+    if want("mcl"):
+        mcl_case(ref, "links_a", m_a, inflations=[1.2, 2.0, 3.0])
+        mcl_case(ref, "block200", block_matrix(4, 50, seed=7), inflations=[1.1, 1.5, 2.0, 2.7])
+        mcl_case(ref, "block600", block_matrix(6, 100, seed=9, noise=0.05), inflations=[1.4, 2.0], keep_iters=3)
+    if want("run"):
+        run_case(ref, "c1", nchr=4, n_contigs=200, mean_len=40000, n_pairs=150000, seed=303, Nx=100, bin_size=0)
+        run_case(ref, "c1_nx80", nchr=4, n_contigs=200, mean_len=40000, n_pairs=150000, seed=303, Nx=80, bin_size=0,
+                 min_inflation=1.2, max_inflation=2.0, inflation_step=0.2)
+    if want("bins"):
+        link_case_bins(ref, "bins", nchr=3, n_contigs=45, mean_len=300000, n_pairs=60000, flank=40, Nx=90, bin_kb=100, seed=404)
+        run_case(ref, "bins", nchr=3, n_contigs=60, mean_len=350000, n_pairs=120000, seed=505, Nx=100, bin_size=120, flank=60,
+                 min_inflation=1.4, max_inflation=2.2, inflation_step=0.4)
+    if want("allelic"):
+        allelic_case(ref, "p2", nchr=3, ploidy=2, n_contigs=120, mean_len=60000, n_pairs=120000, frac=0.2, seed=606, Nx=100)
+        allelic_case(ref, "p4", nchr=2, ploidy=4, n_contigs=160, mean_len=50000, n_pairs=200000, frac=0.3, seed=707, Nx=100,
+                     concentrated=True, max_read_pairs=60)
+        allelic_case(ref, "p4bins", nchr=2, ploidy=4, n_contigs=64, mean_len=300000, n_pairs=150000, frac=0.3, seed=808,
+                     Nx=100, bin_kb=100, flank=40)
+    if want("run_allelic4"):
+        run_case(ref, "allelic4", nchr=8, n_contigs=160, mean_len=50000, n_pairs=200000, seed=909, homolog=(4, 0.3), Nx=100,
+                 bin_size=0, remove_allelic_links=4, min_inflation=1.4, max_inflation=2.2, inflation_step=0.4)
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "sklearn": sklearn.__version__,
             "python": sys.version.split()[0], "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED"),
             "reference": "zengxiaofei/HapHiC scripts/HapHiC_cluster.py (v1.0.7, commit 1f29080), imported unmodified",

@@ -180,3 +180,53 @@ def test_native_pairs_reader_gz_and_comments(tmp_path):
                    "nope\t6\t6\tr3/1\t255\t.", "c\t0\t0\tr3/2\t255\t.", "c\t2\t2\tr4/1\t255\t.", "ctgA\t3\t3\tr4/2\t255\t."]
     all_pairs = np.concatenate(list(hicio.pairs_batches(str(p), "bgzipped_pairs", idx, bed_path=None, inter_only=False)))
     assert all_pairs.tolist() == [[0, 9, 1, 19], [1, 4, 1, 8], [-1, 6, 2, 0], [2, 2, 0, 3]]
+
+
+@pytest.mark.parametrize("tag", ["p2", "p4", "p4bins"])
+def test_allelic_link_removal_matches_reference_golden(tag):
+    """record_coord_pairs / concordance + concentration ratios / remove_allelic_HiC_links (HapHiC_cluster.py:419-692)
+    against dicts frozen from the unmodified reference (tests/golden/make_golden.py allelic_case)."""
+    import logging
+    from math import ceil
+    from haphic_b200 import allelic, cluster
+    from haphic_b200.links import name_rank
+    g = load_golden("allelic_{}.npz".format(tag))
+    names = g["names"].tolist()
+    lengths = g["lengths"].astype(np.int64)
+    kw = json.loads(str(g["argkw"]))
+    args = argparse.Namespace(remove_allelic_links=kw["remove_allelic_links"], remove_concentrated_links=kw["remove_concentrated_links"],
+                              max_read_pairs=kw.get("max_read_pairs", 200), min_read_pairs=20, nwindows=50,
+                              concordance_ratio_cutoff=0.2)
+    rank = name_rank(names)
+    pairs = g["pairs"]
+    rec = pairs[pairs[:, 0] != pairs[:, 2]]
+    coord = allelic.coord_pair_dict(rec, names, lengths, rank, args)
+    want = json.loads(str(g["coord_json"]))
+    assert [list(k) for k in coord.keys()] == [w[:2] for w in want]            # first-seen order of the contig pairs
+    n_ratio = 0
+    for (key, data), w in zip(coord.items(), want):
+        if w[2] is not None:
+            assert isinstance(data, list) and data == w[2], key               # [concordance, adj] bit-identical floats
+            n_ratio += 1
+        else:
+            assert not isinstance(data, list) and data.tolist() == w[3], key
+    assert n_ratio > 50
+    fa_dict = {n: [None, int(l), 0] for n, l in zip(names, lengths)}
+    c2f = None
+    if "c2f_json" in g:
+        bin_size = int(g["bin_size"])
+        frag_names, frag_base = [], [0]
+        for n, l in zip(names, lengths.tolist()):
+            frag_names += ["{}_bin{}".format(n, k + 1) for k in range(ceil(l / bin_size))] if l > bin_size else [n]
+            frag_base.append(len(frag_names))
+        c2f = allelic.ctg_pair_to_frag_dict(rec, names, rank, frag_names, frag_base, name_rank(frag_names), bin_size)
+        got = sorted([[a, b, sorted(map(list, v))] for (a, b), v in c2f.items()])
+        assert got == json.loads(str(g["c2f_json"]))
+    full = {(a, b): v for a, b, v in json.loads(str(g["full_before_json"]))}
+    flank = {(a, b): v for a, b, v in json.loads(str(g["flank_before_json"]))}
+    filtered = set(json.loads(str(g["filtered_json"])))
+    remaining = cluster.remove_allelic_HiC_links(fa_dict, coord, full, args, flank, filtered, c2f, logger=logging.getLogger("t"))
+    assert [[a, b, v] for (a, b), v in full.items()] == json.loads(str(g["full_after_json"]))
+    assert [[a, b, v] for (a, b), v in flank.items()] == json.loads(str(g["flank_after_json"]))
+    assert sorted(remaining) == json.loads(str(g["remaining_json"]))
+    assert len(full) < len(json.loads(str(g["full_before_json"]))) // 2            # the case really removes links
