@@ -980,7 +980,7 @@ def run(args, log_file=None):
     name_index = hicio.NameIndex(names)
     inter_only = not split_ctg_set          # bins need the intra-contig pairs too (2849-2856)
     if args.aln_format == "bam":
-        alignments = hicio.bam_batches(args.alignments, name_index, inter_only=inter_only, logger=logger)
+        alignments = hicio.bam_batches(args.alignments, name_index, inter_only=inter_only, logger=logger, threads=args.threads)
     else:
         alignments = hicio.pairs_batches(args.alignments, args.aln_format, name_index, inter_only=inter_only)
 

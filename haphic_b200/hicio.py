@@ -3,8 +3,8 @@ batches [m, 4] = (ctg_a, pos_a, ctg_b, pos_b) with 0-based positions -- the tupl
 generators yield (scripts/HapHiC_cluster.py:1539-1593) after name -> id translation
 (-1 = name not in the FASTA, skipped downstream like HapHiC_cluster.py:1625).
 
-pysam/htslib are not required: BAM is decoded here (BGZF = concatenated gzip members, so the
-standard gzip module inflates it; records are walked with numpy).  A minimal BAM writer is
+pysam/htslib are not required: both formats are decoded natively (hh_pairs_* / hh_bam_* in
+libhaphic_b200.so; BGZF blocks are inflated on several host threads).  A minimal BAM writer is
 included for fixtures and tests.
 """
 
@@ -121,15 +121,25 @@ def read_bam_header(f):
     return BamHeader(text, names, lens)
 
 
-def bam_batches(path, name_to_id, inter_only=True, batch_bytes=64 << 20, logger=None):
+def bam_batches(path, name_to_id, inter_only=True, batch_records=4_000_000, logger=None, threads=0):
     """Yield int32 [m, 4] record batches from a BAM file: one record per read1 alignment
     (``flag.read1``; plus ``refid != mrefid`` with ``inter_only`` -- the htslib filter strings at
     HapHiC_cluster.py:2855/2862), fields (reference_name, reference_start, next_reference_name,
     next_reference_start) as in bam_generator (1586-1593).  Sorting order is checked like
-    check_sorting_order (1347-1359)."""
-    with gzip.open(path, "rb") as f:
-        hdr = read_bam_header(f)
-        so = hdr.sort_order
+    check_sorting_order (1347-1359).  BGZF inflation and the record walk are native (hh_bam_* in
+    libhaphic_b200.so, `threads` inflate threads; 0 = the host's cores, at most 16)."""
+    import ctypes as C
+    from ._lib import check, load
+    lib = load()
+    names = name_to_id.names
+    if threads <= 0:
+        threads = max(1, min(16, os.cpu_count() or 1))
+    h = C.c_void_p()
+    check(lib.hh_bam_open(os.fsencode(path), names_blob(names), len(names), int(bool(inter_only)), int(threads), C.byref(h)))
+    try:
+        text, ln = C.c_char_p(), C.c_int64()
+        check(lib.hh_bam_header_text(h, C.byref(text), C.byref(ln)))
+        so = BamHeader(C.string_at(text, ln.value).decode(), None, None).sort_order
         if so in ("unsorted", "queryname"):
             if logger:
                 logger.info("The sorting order of the BAM file is {}".format(so))
@@ -140,46 +150,16 @@ def bam_batches(path, name_to_id, inter_only=True, batch_bytes=64 << 20, logger=
             raise RuntimeError(msg)
         elif logger:
             logger.warning("The sorting order of the BAM file is unknown, but the program will continue")
-        ref_to_id = np.array([name_to_id[n] for n in hdr.ref_names] + [-1], dtype=np.int32)   # refID -1 -> last slot
-        carry = b""
+        n_out = C.c_int64()
         while True:
-            chunk = f.read(batch_bytes)
-            buf = carry + chunk
-            if not buf:
+            rec = np.empty((batch_records, 4), np.int32)
+            check(lib.hh_bam_next(h, rec.ctypes.data_as(C.c_void_p), batch_records, C.byref(n_out)))
+            m = int(n_out.value)
+            if m == 0:
                 break
-            offs = []
-            p, n = 0, len(buf)
-            unpack = struct.unpack_from
-            while p + 4 <= n:
-                (bs,) = unpack("<i", buf, p)
-                if p + 4 + bs > n:
-                    break
-                offs.append(p + 4)
-                p += 4 + bs
-            carry = buf[p:]
-            if not chunk and carry:
-                raise EOFError("truncated BAM record")
-            if offs:
-                a = np.frombuffer(buf, dtype=np.uint8)
-                o = np.asarray(offs, dtype=np.int64)
-
-                def i32(at):
-                    idx = (o + at)[:, None] + np.arange(4)
-                    return a[idx].copy().view("<i4").ravel()
-
-                def u16(at):
-                    idx = (o + at)[:, None] + np.arange(2)
-                    return a[idx].copy().view("<u2").ravel()
-
-                refid, pos, flag, mrefid, mpos = i32(0), i32(4), u16(14), i32(20), i32(24)
-                sel = (flag & 0x40) != 0
-                if inter_only:
-                    sel &= refid != mrefid
-                if sel.any():
-                    rec = np.stack([ref_to_id[refid[sel]], pos[sel], ref_to_id[mrefid[sel]], mpos[sel]], axis=1)
-                    yield np.ascontiguousarray(rec, dtype=np.int32)
-            if not chunk:
-                break
+            yield rec[:m]
+    finally:
+        lib.hh_bam_close(h)
 
 
 def _bgzf_block(data: bytes) -> bytes:

@@ -227,6 +227,17 @@ int hh_pairs_open(const char* path, const char* names_blob, int32_t n_names, con
                   hh_pairs_reader** out);
 int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_records, int64_t* n_out);   /* *n_out == 0: end of file */
 int hh_pairs_close(hh_pairs_reader* r);
+/* BAM input (bam_generator, HapHiC_cluster.py:1586-1593, with the htslib filters `flag.read1 [&& refid != mrefid]` of
+ * 2855 / 2862): BGZF blocks are inflated on `threads` host threads; one record per read1 alignment,
+ * (id(reference_name), reference_start, id(next_reference_name), next_reference_start), ids through the BAM header's
+ * reference names (-1 = not in the FASTA / unmapped).  hh_bam_header_text gives the SAM header (sorting order check,
+ * check_sorting_order 1347-1359); the pointer stays valid until hh_bam_close. */
+typedef struct hh_bam_reader hh_bam_reader;
+int hh_bam_open(const char* path, const char* names_blob, int32_t n_names, int inter_only, int threads, hh_bam_reader** out);
+int hh_bam_header_text(hh_bam_reader* r, const char** text, int64_t* len);
+int hh_bam_next(hh_bam_reader* r, int32_t* rec, int64_t max_records, int64_t* n_out);
+int hh_bam_close(hh_bam_reader* r);
+
 /* paired_links.clm writer: output_clm, HapHiC_cluster.py:376-392.  Pair e links contigs key_i[e], key_j[e]; its
  * links occupy [offsets[e], offsets[e+1]) of each of the four orientation rows of dist[4][total_links], already
  * sorted ascending; pairs with fewer than 2 links are skipped, every distance is printed twice. */

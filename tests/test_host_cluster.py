@@ -114,7 +114,7 @@ def test_pairs_and_bam_readers_agree(tmp_path):
     want[:, 0][want[:, 0] == asm.n] = -1
     want[:, 2][want[:, 2] == asm.n] = -1
     got_p = np.concatenate(list(hicio.pairs_batches(ppath, "pairs", idx, bed_path=str(tmp_path / "a.bed"), batch_lines=700)))
-    got_b = np.concatenate(list(hicio.bam_batches(bpath, idx, batch_bytes=20000)))
+    got_b = np.concatenate(list(hicio.bam_batches(bpath, idx, batch_records=333)))
     assert np.array_equal(got_p, want) and np.array_equal(got_b, want)
     with open(tmp_path / "a.bed") as f:
         bed = f.read().splitlines()
@@ -126,6 +126,41 @@ def test_pairs_and_bam_readers_agree(tmp_path):
     hicio.write_bam(bpath, names, asm.lengths.tolist() + [1000], pairs[:10], sort_order="coordinate")
     with pytest.raises(RuntimeError):
         list(hicio.bam_batches(bpath, idx))
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_native_bam_reader_matches_python_decoder(tmp_path, threads):
+    """hh_bam_* (threaded BGZF inflate + record walk) against an independent gzip/numpy decoder: many BGZF blocks,
+    records straddling block and batch boundaries, intra-contig pairs kept when inter_only is off, unmapped mates,
+    truncated files."""
+    from haphic_b200 import hicio, synth
+    from haphic_b200._lib import HHError
+    from tests.util import bam_batches_py
+    asm = synth.make_assembly(3, 40, 30000, seed=19)
+    pairs = synth.make_pairs(asm, 60000, seed=20).numpy()        # ~8 MB of records -> > 100 BGZF blocks
+    pairs[::97, 2] = -1                                          # mate unmapped: next_refID = -1
+    pairs[5::101, 0] = asm.n                                     # reference missing from the FASTA
+    names = asm.names + ["ghost"]
+    bpath = str(tmp_path / "big.bam")
+    hicio.write_bam(bpath, names, asm.lengths.tolist() + [500], pairs, sort_order="queryname")
+    idx = hicio.NameIndex(asm.names)
+    for inter_only in (True, False):
+        want = np.concatenate(list(bam_batches_py(bpath, idx, inter_only=inter_only, batch_bytes=1 << 20)))
+        got = np.concatenate(list(hicio.bam_batches(bpath, idx, inter_only=inter_only, batch_records=7777, threads=threads)))
+        assert np.array_equal(got, want)
+        sel = np.ones(len(pairs), bool) if not inter_only else pairs[:, 0] != pairs[:, 2]
+        assert len(got) == int(sel.sum())
+    # a file cut in the middle of a block / of a record is an error, never a silent short read
+    raw = open(bpath, "rb").read()
+    cut = str(tmp_path / "cut.bam")
+    with open(cut, "wb") as f:
+        f.write(raw[: len(raw) // 2])
+    with pytest.raises(HHError):
+        list(hicio.bam_batches(cut, idx, threads=threads))
+    with open(cut, "wb") as f:
+        f.write(b"not a bam at all" * 10)
+    with pytest.raises(HHError):
+        list(hicio.bam_batches(cut, idx, threads=threads))
 
 
 def test_clm_writer_matches_reference(tmp_path, monkeypatch):

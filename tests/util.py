@@ -55,3 +55,49 @@ def planted_blocks(n_blocks, block, seed, noise=0.0, strength=30.0):
     truth = np.empty(n, dtype=np.int64)
     truth[perm] = np.repeat(np.arange(n_blocks), block)
     return m, truth
+
+
+def bam_batches_py(path, name_to_id, inter_only=True, batch_bytes=64 << 20):
+    """Pure-Python BAM decoder (gzip module + numpy), the independent check of the native reader hh_bam_*."""
+    import gzip
+    import struct
+    from haphic_b200.hicio import read_bam_header
+    with gzip.open(path, "rb") as f:
+        hdr = read_bam_header(f)
+        ref_to_id = np.array([name_to_id[n] for n in hdr.ref_names] + [-1], dtype=np.int32)   # refID -1 -> last slot
+        carry = b""
+        while True:
+            chunk = f.read(batch_bytes)
+            buf = carry + chunk
+            if not buf:
+                break
+            offs = []
+            p, n = 0, len(buf)
+            while p + 4 <= n:
+                (bs,) = struct.unpack_from("<i", buf, p)
+                if p + 4 + bs > n:
+                    break
+                offs.append(p + 4)
+                p += 4 + bs
+            carry = buf[p:]
+            if not chunk and carry:
+                raise EOFError("truncated BAM record")
+            if offs:
+                a = np.frombuffer(buf, dtype=np.uint8)
+                o = np.asarray(offs, dtype=np.int64)
+
+                def i32(at):
+                    return a[(o + at)[:, None] + np.arange(4)].copy().view("<i4").ravel()
+
+                def u16(at):
+                    return a[(o + at)[:, None] + np.arange(2)].copy().view("<u2").ravel()
+
+                refid, pos, flag, mrefid, mpos = i32(0), i32(4), u16(14), i32(20), i32(24)
+                sel = (flag & 0x40) != 0
+                if inter_only:
+                    sel &= refid != mrefid
+                if sel.any():
+                    yield np.ascontiguousarray(np.stack([ref_to_id[refid[sel]], pos[sel], ref_to_id[mrefid[sel]], mpos[sel]], axis=1),
+                                               dtype=np.int32)
+            if not chunk:
+                break
