@@ -80,7 +80,7 @@ _SIGNATURES = {
     "hh_mcl_commit": (C.c_int, [_P]),
     "hh_mcl_set_block": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "hh_mcl_destroy": (C.c_int, [_P]),
-    "hh_pairs_open": (C.c_int, [C.c_char_p, _P, C.c_int32, C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "hh_pairs_open": (C.c_int, [C.c_char_p, _P, C.c_int32, C.c_char_p, C.c_int, C.c_int, C.POINTER(_P)]),
     "hh_pairs_next": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "hh_pairs_close": (C.c_int, [_P]),
     "hh_bam_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int, C.c_int, C.POINTER(_P)]),

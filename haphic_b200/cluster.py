@@ -982,7 +982,7 @@ def run(args, log_file=None):
     if args.aln_format == "bam":
         alignments = hicio.bam_batches(args.alignments, name_index, inter_only=inter_only, logger=logger, threads=args.threads)
     else:
-        alignments = hicio.pairs_batches(args.alignments, args.aln_format, name_index, inter_only=inter_only)
+        alignments = hicio.pairs_batches(args.alignments, args.aln_format, name_index, inter_only=inter_only, threads=args.threads)
 
     if split_ctg_set:
         full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict, ctg_pair_to_frag = parse_alignments(

@@ -1,6 +1,9 @@
 // Host-side I/O of the cluster step, native so that the GPU path is not starved by Python:
 //   * .pairs / .pairs.gz tokenizer with name -> id translation and the alignments.bed side product
-//     (pairs_generator / pairs_generator_inter_ctgs, scripts/HapHiC_cluster.py:1539-1583),
+//     (pairs_generator / pairs_generator_inter_ctgs, scripts/HapHiC_cluster.py:1539-1583), multi-threaded:
+//     the text is cut at line boundaries and parsed by a pool of threads, BGZF-compressed input is inflated
+//     block-parallel,
+//   * BAM reader (bam_generator, 1586-1593),
 //   * paired_links.clm text writer (output_clm, 376-392).
 // Pure C++ (no CUDA); part of libhaphic_b200.so, declared in include/haphic_b200.h.
 #include <stdint.h>
@@ -9,7 +12,13 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -17,53 +26,354 @@
 
 void hh_set_error(const char* fmt, ...);
 
+static inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline uint16_t le16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+static int hh_io_threads(int requested) {
+    if (requested > 0) return requested;
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(16u, hc ? hc : 1u));
+}
+
+// ---------------------------------------------------------------------------------------------
+// BGZF (blocked gzip: BAM, bgzipped .pairs): every block is an independent deflate stream with its
+// compressed size in the gzip extra field and its uncompressed size in the trailer, so a batch of
+// blocks inflates in parallel straight into its final place.
+// ---------------------------------------------------------------------------------------------
+struct hh_bgzf {
+    FILE* f = nullptr;
+    std::vector<uint8_t> comp;        // compressed bytes not yet consumed
+    size_t comp_pos = 0, comp_len = 0;
+    bool file_eof = false;
+    std::vector<uint8_t> raw;         // decompressed bytes not yet consumed: [raw_pos, raw_len)
+    size_t raw_pos = 0, raw_len = 0;
+    int threads = 1;
+};
+
+struct hh_bgzf_block {
+    size_t in_off, in_len;            // deflate payload inside comp
+    size_t out_off;                   // destination offset inside raw
+    uint32_t isize, crc;
+};
+
+// inflate the next batch of whole blocks (about target_bytes of compressed input); appends to raw.
+// Returns 0 = appended something, 1 = end of file, <0 = error (message set).
+static int bgzf_fill(hh_bgzf* r, size_t target_bytes) {
+    if (r->comp_pos > 0) {
+        memmove(r->comp.data(), r->comp.data() + r->comp_pos, r->comp_len - r->comp_pos);
+        r->comp_len -= r->comp_pos;
+        r->comp_pos = 0;
+    }
+    if (!r->file_eof && r->comp_len < target_bytes) {
+        if (r->comp.size() < target_bytes + (1u << 16)) r->comp.resize(target_bytes + (1u << 16));
+        const size_t got = fread(r->comp.data() + r->comp_len, 1, r->comp.size() - r->comp_len, r->f);
+        if (got == 0) r->file_eof = true;
+        r->comp_len += got;
+    }
+    if (r->comp_len == 0) return 1;
+    std::vector<hh_bgzf_block> blocks;
+    size_t p = 0, out_total = 0;
+    while (p + 18 <= r->comp_len) {
+        const uint8_t* h = r->comp.data() + p;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) {
+            hh_set_error("BGZF: bad block header (the file is corrupt or not blocked gzip)");
+            return -1;
+        }
+        const size_t xlen = le16(h + 10);
+        if (p + 12 + xlen > r->comp_len) break;
+        size_t bsize = 0;
+        for (size_t q = 0; q + 4 <= xlen;) {
+            const uint8_t* sf = h + 12 + q;
+            const size_t slen = le16(sf + 2);
+            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2) bsize = (size_t)le16(sf + 4) + 1;
+            q += 4 + slen;
+        }
+        if (bsize == 0 || bsize < 12 + xlen + 8) {
+            hh_set_error("BGZF: block without a valid BC subfield");
+            return -1;
+        }
+        if (p + bsize > r->comp_len) break;          // incomplete block: wait for more input
+        hh_bgzf_block b;
+        b.in_off = p + 12 + xlen;
+        b.in_len = bsize - 12 - xlen - 8;
+        b.crc = le32(h + bsize - 8);
+        b.isize = le32(h + bsize - 4);
+        b.out_off = out_total;
+        out_total += b.isize;
+        blocks.push_back(b);
+        p += bsize;
+    }
+    if (blocks.empty()) {
+        if (r->file_eof) {
+            hh_set_error("BGZF: truncated block at the end of the file");
+            return -1;
+        }
+        return bgzf_fill(r, target_bytes * 2);       // blocks are <= 64 KiB: cannot recurse more than once
+    }
+    if (r->raw_pos > 0) {
+        memmove(r->raw.data(), r->raw.data() + r->raw_pos, r->raw_len - r->raw_pos);
+        r->raw_len -= r->raw_pos;
+        r->raw_pos = 0;
+    }
+    if (r->raw.size() < r->raw_len + out_total) r->raw.resize(r->raw_len + out_total);
+    uint8_t* out_base = r->raw.data() + r->raw_len;
+    const uint8_t* in_base = r->comp.data();
+    std::atomic<size_t> next(0);
+    std::atomic<int> failed(0);
+    auto work = [&]() {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) {
+            failed = 1;
+            return;
+        }
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= blocks.size()) break;
+            const hh_bgzf_block& b = blocks[k];
+            inflateReset(&zs);
+            zs.next_in = const_cast<Bytef*>(in_base + b.in_off);
+            zs.avail_in = (uInt)b.in_len;
+            zs.next_out = out_base + b.out_off;
+            zs.avail_out = b.isize;
+            const int rc = b.isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+            if ((b.isize && rc != Z_STREAM_END) || zs.avail_out != 0 ||
+                (uint32_t)crc32(crc32(0L, Z_NULL, 0), out_base + b.out_off, b.isize) != b.crc) {
+                failed = 1;
+                break;
+            }
+        }
+        inflateEnd(&zs);
+    };
+    const int nt = (int)std::min<size_t>((size_t)std::max(1, r->threads), blocks.size());
+    if (nt <= 1) {
+        work();
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    if (failed) {
+        hh_set_error("BGZF: a block failed to inflate (corrupt file)");
+        return -1;
+    }
+    r->raw_len += out_total;
+    r->comp_pos = p;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// contig name -> id: open addressing over the caller's NUL-separated name blob
+// ---------------------------------------------------------------------------------------------
+struct hh_name_table {
+    struct slot {
+        uint64_t hash;
+        const char* s;
+        uint32_t len;
+        int32_t id;
+    };
+    std::vector<slot> slots;
+    uint64_t mask = 0;
+    std::string blob;                 // private copy: the caller's buffer need not outlive hh_*_open
+
+    static inline uint64_t hash_of(const char* s, size_t n) {
+        uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)n;
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            uint64_t w;
+            memcpy(&w, s + i, 8);
+            h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 29;
+        }
+        uint64_t w = 0;
+        memcpy(&w, s + i, n - i);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 32;
+        return h | 1ull;              // 0 marks an empty slot
+    }
+    void build(const char* names_blob, int32_t n_names) {
+        size_t total = 0;
+        const char* p = names_blob;
+        for (int32_t i = 0; i < n_names; ++i) {
+            const size_t l = strlen(p);
+            total += l + 1;
+            p += l + 1;
+        }
+        blob.assign(names_blob, total);
+        size_t cap = 16;
+        while (cap < (size_t)n_names * 2 + 2) cap <<= 1;
+        slots.assign(cap, slot{0, nullptr, 0, -1});
+        mask = cap - 1;
+        p = blob.data();
+        for (int32_t i = 0; i < n_names; ++i) {
+            const size_t l = strlen(p);
+            const uint64_t h = hash_of(p, l);
+            uint64_t k = h & mask;
+            bool dup = false;
+            while (slots[k].hash) {
+                if (slots[k].hash == h && slots[k].len == l && memcmp(slots[k].s, p, l) == 0) {
+                    dup = true;       // duplicate names: the first one wins, like a dict comprehension would not -- FASTA names are unique
+                    break;
+                }
+                k = (k + 1) & mask;
+            }
+            if (!dup) slots[k] = slot{h, p, (uint32_t)l, i};
+            p += l + 1;
+        }
+    }
+    inline int32_t find(const char* s, size_t n) const {
+        const uint64_t h = hash_of(s, n);
+        uint64_t k = h & mask;
+        while (slots[k].hash) {
+            if (slots[k].hash == h && slots[k].len == n && memcmp(slots[k].s, s, n) == 0) return slots[k].id;
+            k = (k + 1) & mask;
+        }
+        return -1;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// .pairs reader
+// ---------------------------------------------------------------------------------------------
+struct hh_bytes {                     // grow-only byte buffer without the zero fill of std::vector::resize
+    char* data = nullptr;
+    size_t len = 0, cap = 0;
+    hh_bytes() = default;
+    hh_bytes(const hh_bytes&) = delete;
+    hh_bytes& operator=(const hh_bytes&) = delete;
+    hh_bytes(hh_bytes&& o) noexcept : data(o.data), len(o.len), cap(o.cap) { o.data = nullptr; o.len = o.cap = 0; }
+    hh_bytes& operator=(hh_bytes&& o) noexcept {
+        if (this != &o) {
+            free(data);
+            data = o.data;
+            len = o.len;
+            cap = o.cap;
+            o.data = nullptr;
+            o.len = o.cap = 0;
+        }
+        return *this;
+    }
+    ~hh_bytes() { free(data); }
+    inline char* room(size_t need) {
+        if (len + need > cap) {
+            size_t ncap = cap ? cap * 2 : (1u << 20);
+            while (ncap < len + need) ncap *= 2;
+            data = (char*)realloc(data, ncap);
+            cap = ncap;
+        }
+        return data + len;
+    }
+    void release() {
+        free(data);
+        data = nullptr;
+        len = cap = 0;
+    }
+};
+
+struct hh_pairs_part {                // what one thread produced from its slice of a text window
+    std::vector<int32_t> rec;
+    hh_bytes bed;
+    int64_t lines = 0;
+    int64_t err_line = -1;            // first bad line (index inside the part), -1 = none
+    int err_kind = 0;                 // 1 = fewer than 5 columns, 2 = position is not an integer
+};
+
 struct hh_pairs_reader {
-    gzFile gz = nullptr;              // zlib reads plain files transparently as well
+    int mode = 0;                     // 0 plain text, 1 gzip stream (zlib), 2 BGZF
+    FILE* f = nullptr;
+    gzFile gz = nullptr;
+    hh_bgzf bg;
     FILE* bed = nullptr;
-    std::unordered_map<std::string, int32_t> ids;
-    std::vector<char> buf;            // unconsumed bytes
+    hh_name_table names;
+    std::vector<uint8_t> text;        // undigested bytes of modes 0 / 1: [pos, len)
     size_t pos = 0, len = 0;
     bool eof = false;
     int inter_only = 1;
-    int64_t lines = 0;
-    std::vector<char> bedbuf;
-    size_t bedlen = 0;
+    int threads = 1;
+    int64_t lines = 0;                // lines consumed by finished windows
+    std::vector<hh_pairs_part> parts; // parsed, not yet handed out
+    size_t part_k = 0, part_off = 0;
+    // alignments.bed is written behind the parser by its own thread, slices in input order
+    std::thread bed_writer;
+    std::mutex bed_mu;
+    std::condition_variable bed_cv;
+    std::deque<hh_bytes> bed_queue;
+    size_t bed_queued_bytes = 0;
+    bool bed_done = false, bed_failed = false;
 };
 
+static void pairs_bed_writer(hh_pairs_reader* r) {
+    for (;;) {
+        hh_bytes buf;
+        {
+            std::unique_lock<std::mutex> lk(r->bed_mu);
+            r->bed_cv.wait(lk, [&] { return r->bed_done || !r->bed_queue.empty(); });
+            if (r->bed_queue.empty()) return;
+            buf = std::move(r->bed_queue.front());
+            r->bed_queue.pop_front();
+        }
+        if (fwrite(buf.data, 1, buf.len, r->bed) != buf.len) r->bed_failed = true;
+        {
+            std::lock_guard<std::mutex> lk(r->bed_mu);
+            r->bed_queued_bytes -= buf.len;
+        }
+        r->bed_cv.notify_all();
+    }
+}
+
 extern "C" int hh_pairs_open(const char* path, const char* names_blob, int32_t n_names, const char* bed_path, int inter_only,
-                             hh_pairs_reader** out) {
+                             int threads, hh_pairs_reader** out) {
     if (!path || !names_blob || !out || n_names < 0) {
         hh_set_error("hh_pairs_open: bad argument");
         return HH_ERR_ARG;
     }
     *out = nullptr;
     hh_pairs_reader* r = new hh_pairs_reader();
-    r->gz = gzopen(path, "rb");
-    if (!r->gz) {
+    r->threads = hh_io_threads(threads);
+    r->f = fopen(path, "rb");
+    if (!r->f) {
         hh_set_error("hh_pairs_open: cannot open %s", path);
         delete r;
         return HH_ERR_ARG;
     }
-    gzbuffer(r->gz, 1 << 20);
+    // plain text, a gzip stream, or blocked gzip (bgzip): look at the first member's header
+    uint8_t h[18];
+    const size_t got = fread(h, 1, sizeof(h), r->f);
+    if (got >= 4 && h[0] == 0x1f && h[1] == 0x8b) {
+        r->mode = 1;
+        if (got == 18 && h[2] == 8 && (h[3] & 4) && le16(h + 10) >= 6 && h[12] == 'B' && h[13] == 'C') r->mode = 2;
+    }
+    if (r->mode == 1) {
+        fclose(r->f);
+        r->f = nullptr;
+        r->gz = gzopen(path, "rb");
+        if (!r->gz) {
+            hh_set_error("hh_pairs_open: cannot open %s", path);
+            delete r;
+            return HH_ERR_ARG;
+        }
+        gzbuffer(r->gz, 1 << 20);
+    } else {
+        fseek(r->f, 0, SEEK_SET);
+        if (r->mode == 2) {
+            r->bg.f = r->f;
+            r->bg.threads = r->threads;
+        }
+    }
     if (bed_path && *bed_path) {
         r->bed = fopen(bed_path, "w");
         if (!r->bed) {
             hh_set_error("hh_pairs_open: cannot create %s", bed_path);
-            gzclose(r->gz);
+            if (r->gz) gzclose(r->gz);
+            if (r->f) fclose(r->f);
             delete r;
             return HH_ERR_ARG;
         }
-        setvbuf(r->bed, nullptr, _IOFBF, 1 << 22);
+        setvbuf(r->bed, nullptr, _IONBF, 0);          // whole slices are written with one fwrite each
+        r->bed_writer = std::thread(pairs_bed_writer, r);
     }
-    const char* p = names_blob;
-    r->ids.reserve((size_t)n_names * 2);
-    for (int32_t i = 0; i < n_names; ++i) {
-        const size_t l = strlen(p);
-        r->ids.emplace(std::string(p, l), i);
-        p += l + 1;
-    }
+    r->names.build(names_blob, n_names);
     r->inter_only = inter_only;
-    r->buf.resize(1 << 24);
     *out = r;
     return HH_OK;
 }
@@ -102,50 +412,29 @@ static inline bool parse_int(const char* s, const char* e, int64_t* out) {
     return true;
 }
 
-extern "C" int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_records, int64_t* n_out) {
-    if (!r || !rec || !n_out || max_records <= 0) {
-        hh_set_error("hh_pairs_next: bad argument");
-        return HH_ERR_ARG;
-    }
-    int64_t n = 0;
-    *n_out = 0;
-    while (n < max_records) {
-        // make sure a whole line is buffered
-        char* base = r->buf.data();
-        char* nl = (char*)memchr(base + r->pos, '\n', r->len - r->pos);
-        if (!nl && !r->eof) {
-            if (r->pos > 0) {
-                memmove(base, base + r->pos, r->len - r->pos);
-                r->len -= r->pos;
-                r->pos = 0;
-            }
-            if (r->len == r->buf.size()) {
-                r->buf.resize(r->buf.size() * 2);
-                base = r->buf.data();
-            }
-            const int got = gzread(r->gz, base + r->len, (unsigned)(r->buf.size() - r->len));
-            if (got < 0) {
-                hh_set_error("hh_pairs_next: read error");
-                return HH_ERR_ARG;
-            }
-            if (got == 0) r->eof = true;
-            r->len += (size_t)got;
-            continue;
-        }
-        if (!nl && r->pos >= r->len) break;       // EOF, nothing left
-        char* ls = base + r->pos;
-        char* le = nl ? nl : base + r->len;        // last line without newline
-        r->pos = nl ? (size_t)(nl - base) + 1 : r->len;
-        r->lines++;
+// one thread's share: whole lines in [s, e)
+static void pairs_parse_slice(const hh_pairs_reader* r, const char* s, const char* e, hh_pairs_part* out) {
+    const bool want_bed = r->bed != nullptr;
+    const char* last_name[2] = {nullptr, nullptr};       // the previous line's contig names: Hi-C text is full of runs
+    size_t last_len[2] = {0, 0};
+    int32_t last_id[2] = {-1, -1};
+    out->rec.reserve((size_t)(e - s) / 12);
+    if (want_bed) out->bed.room((size_t)(e - s) * 2 + 256);
+    while (s < e) {
+        const char* nl = (const char*)memchr(s, '\n', (size_t)(e - s));
+        const char* le = nl ? nl : e;
+        const char* ls = s;
+        s = nl ? nl + 1 : e;
+        out->lines++;
         // `if not line.strip() or line.startswith('#'): continue`
-        char* t = ls;
+        const char* t = ls;
         while (t < le && is_ws(*t)) ++t;
         if (t == le || *ls == '#') continue;
         // cols = line.split(): first five whitespace-separated tokens
         const char* tok[5];
         const char* tend[5];
         int k = 0;
-        char* c = t;
+        const char* c = t;
         while (k < 5 && c < le) {
             while (c < le && is_ws(*c)) ++c;
             if (c == le) break;
@@ -155,24 +444,27 @@ extern "C" int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_recor
             ++k;
         }
         if (k < 5) {
-            hh_set_error("hh_pairs_next: line %lld has fewer than 5 columns", (long long)r->lines);
-            return HH_ERR_ARG;
+            out->err_line = out->lines - 1;
+            out->err_kind = 1;
+            return;
         }
         int64_t p1, p2;
         if (!parse_int(tok[2], tend[2], &p1) || !parse_int(tok[4], tend[4], &p2)) {
-            hh_set_error("hh_pairs_next: line %lld: position is not an integer", (long long)r->lines);
-            return HH_ERR_ARG;
+            out->err_line = out->lines - 1;
+            out->err_kind = 2;
+            return;
         }
         p1 -= 1;                                    // pysam / BED are 0-based
         p2 -= 1;
-        if (r->bed) {
+        const size_t l1 = (size_t)(tend[1] - tok[1]), l3 = (size_t)(tend[3] - tok[3]);
+        if (want_bed) {
             // '{ref}\t{pos}\t{pos}\t{readID}/1\t255\t.\n{mref}\t{mpos}\t{mpos}\t{readID}/2\t255\t.\n'  (1557, 1580)
-            const size_t need = 2 * (size_t)(tend[0] - tok[0]) + (size_t)(tend[1] - tok[1]) + (size_t)(tend[3] - tok[3]) + 128;
-            if (r->bedbuf.size() < r->bedlen + need) r->bedbuf.resize((r->bedlen + need) * 2);
-            char* q = r->bedbuf.data() + r->bedlen;
+            const size_t l0 = (size_t)(tend[0] - tok[0]);
+            const size_t need = 2 * l0 + l1 + l3 + 128;
+            char* q = out->bed.room(need);
             for (int side = 0; side < 2; ++side) {
                 const char* cs = side ? tok[3] : tok[1];
-                const size_t cl = side ? (size_t)(tend[3] - tok[3]) : (size_t)(tend[1] - tok[1]);
+                const size_t cl = side ? l3 : l1;
                 const int64_t pv = side ? p2 : p1;
                 memcpy(q, cs, cl);
                 q += cl;
@@ -181,27 +473,165 @@ extern "C" int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_recor
                 *q++ = '\t';
                 q = put_i64(q, pv);
                 *q++ = '\t';
-                memcpy(q, tok[0], (size_t)(tend[0] - tok[0]));
-                q += tend[0] - tok[0];
+                memcpy(q, tok[0], l0);
+                q += l0;
                 memcpy(q, side ? "/2\t255\t.\n" : "/1\t255\t.\n", 9);
                 q += 9;
             }
-            r->bedlen = (size_t)(q - r->bedbuf.data());
-            if (r->bedlen > (1u << 22)) {
-                fwrite(r->bedbuf.data(), 1, r->bedlen, r->bed);
-                r->bedlen = 0;
+            out->bed.len = (size_t)(q - out->bed.data);
+        }
+        if (r->inter_only && l1 == l3 && memcmp(tok[1], tok[3], l1) == 0) continue;    // ref != mref (1582)
+        int32_t id[2];
+        for (int side = 0; side < 2; ++side) {
+            const char* cs = side ? tok[3] : tok[1];
+            const size_t cl = side ? l3 : l1;
+            if (last_name[side] && last_len[side] == cl && memcmp(last_name[side], cs, cl) == 0) {
+                id[side] = last_id[side];
+            } else {
+                id[side] = r->names.find(cs, cl);
+                last_name[side] = cs;
+                last_len[side] = cl;
+                last_id[side] = id[side];
             }
         }
-        const size_t l1 = (size_t)(tend[1] - tok[1]), l3 = (size_t)(tend[3] - tok[3]);
-        if (r->inter_only && l1 == l3 && memcmp(tok[1], tok[3], l1) == 0) continue;    // ref != mref (1582)
-        auto a = r->ids.find(std::string(tok[1], l1));
-        auto b = r->ids.find(std::string(tok[3], l3));
-        int32_t* o = rec + n * 4;
-        o[0] = a == r->ids.end() ? -1 : a->second;
-        o[1] = (int32_t)p1;
-        o[2] = b == r->ids.end() ? -1 : b->second;
-        o[3] = (int32_t)p2;
-        ++n;
+        const int32_t four[4] = {id[0], (int32_t)p1, id[1], (int32_t)p2};
+        out->rec.insert(out->rec.end(), four, four + 4);
+    }
+}
+
+// read + parse the next window of text; 0 = parts ready, 1 = end of input, <0 error
+static int pairs_next_window(hh_pairs_reader* r) {
+    const size_t WINDOW = 64u << 20;
+    const uint8_t* base = nullptr;
+    size_t avail = 0;
+    bool at_eof = false;
+    if (r->mode == 2) {
+        hh_bgzf* b = &r->bg;
+        while (b->raw_len - b->raw_pos < WINDOW) {
+            const int rc = bgzf_fill(b, 32u << 20);
+            if (rc < 0) return -1;
+            if (rc == 1) {
+                at_eof = true;
+                break;
+            }
+        }
+        base = b->raw.data() + b->raw_pos;
+        avail = b->raw_len - b->raw_pos;
+    } else {
+        if (r->pos > 0) {
+            memmove(r->text.data(), r->text.data() + r->pos, r->len - r->pos);
+            r->len -= r->pos;
+            r->pos = 0;
+        }
+        while (!r->eof && r->len < WINDOW) {
+            if (r->text.size() < r->len + (8u << 20)) r->text.resize(std::max(r->text.size() * 2, r->len + (16u << 20)));
+            const size_t room = std::min(r->text.size() - r->len, (size_t)1 << 30);
+            long got;
+            if (r->mode == 1) {
+                got = gzread(r->gz, r->text.data() + r->len, (unsigned)room);
+                if (got < 0) {
+                    hh_set_error("hh_pairs_next: read error (corrupt gzip stream)");
+                    return -1;
+                }
+            } else {
+                got = (long)fread(r->text.data() + r->len, 1, room, r->f);
+            }
+            if (got == 0) r->eof = true;
+            r->len += (size_t)got;
+        }
+        at_eof = r->eof;
+        base = r->text.data();
+        avail = r->len;
+    }
+    if (avail == 0) return 1;
+    // whole lines only (at the end of the input the last line may lack its newline)
+    size_t use = avail;
+    if (!at_eof) {
+        const uint8_t* last = (const uint8_t*)memrchr(base, '\n', avail);
+        if (!last) {
+            hh_set_error("hh_pairs_next: a line longer than %zu MiB", WINDOW >> 20);
+            return -1;
+        }
+        use = (size_t)(last - base) + 1;
+    }
+    // slices at line boundaries
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)r->threads, use / (1u << 20) + 1));
+    std::vector<size_t> cut((size_t)nt + 1, use);
+    cut[0] = 0;
+    for (int t = 1; t < nt; ++t) {
+        size_t c = use / (size_t)nt * (size_t)t;
+        if (c < cut[(size_t)t - 1]) c = cut[(size_t)t - 1];
+        const uint8_t* nl = (const uint8_t*)memchr(base + c, '\n', use - c);
+        cut[(size_t)t] = nl ? (size_t)(nl - base) + 1 : use;
+    }
+    r->parts.clear();
+    r->parts.resize((size_t)nt);
+    r->part_k = 0;
+    r->part_off = 0;
+    if (nt == 1) {
+        pairs_parse_slice(r, (const char*)base, (const char*)base + use, &r->parts[0]);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t)
+            pool.emplace_back(pairs_parse_slice, r, (const char*)base + cut[(size_t)t], (const char*)base + cut[(size_t)t + 1],
+                              &r->parts[(size_t)t]);
+        for (auto& th : pool) th.join();
+    }
+    // errors in input order; BED in input order
+    for (int t = 0; t < nt; ++t) {
+        hh_pairs_part& p = r->parts[(size_t)t];
+        if (r->bed && p.bed.len) {
+            std::unique_lock<std::mutex> lk(r->bed_mu);
+            r->bed_cv.wait(lk, [&] { return r->bed_queued_bytes < ((size_t)1 << 30); });     // bounded backlog
+            r->bed_queued_bytes += p.bed.len;
+            r->bed_queue.push_back(std::move(p.bed));
+            lk.unlock();
+            r->bed_cv.notify_all();
+        }
+        p.bed.release();
+        if (p.err_line >= 0) {
+            const long long line = (long long)(r->lines + p.err_line + 1);
+            if (p.err_kind == 1) hh_set_error("hh_pairs_next: line %lld has fewer than 5 columns", line);
+            else hh_set_error("hh_pairs_next: line %lld: position is not an integer", line);
+            return -1;
+        }
+        r->lines += p.lines;
+    }
+    if (r->mode == 2) r->bg.raw_pos += use;
+    else r->pos += use;
+    if (r->bed_failed) {
+        hh_set_error("hh_pairs_next: writing alignments.bed failed (disk full?)");
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_records, int64_t* n_out) {
+    if (!r || !rec || !n_out || max_records <= 0) {
+        hh_set_error("hh_pairs_next: bad argument");
+        return HH_ERR_ARG;
+    }
+    int64_t n = 0;
+    *n_out = 0;
+    while (n < max_records) {
+        if (r->part_k >= r->parts.size()) {
+            const int rc = pairs_next_window(r);
+            if (rc < 0) return HH_ERR_ARG;
+            if (rc == 1) break;
+            continue;
+        }
+        const std::vector<int32_t>& src = r->parts[r->part_k].rec;
+        const size_t have = src.size() / 4 - r->part_off;
+        if (have == 0) {
+            std::vector<int32_t>().swap(r->parts[r->part_k].rec);
+            r->part_k++;
+            r->part_off = 0;
+            continue;
+        }
+        const size_t take = std::min<size_t>(have, (size_t)(max_records - n));
+        memcpy(rec + n * 4, src.data() + r->part_off * 4, take * 16);
+        r->part_off += take;
+        n += (int64_t)take;
     }
     *n_out = n;
     return HH_OK;
@@ -209,13 +639,23 @@ extern "C" int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_recor
 
 extern "C" int hh_pairs_close(hh_pairs_reader* r) {
     if (!r) return HH_OK;
+    int rc = HH_OK;
+    if (r->bed_writer.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(r->bed_mu);
+            r->bed_done = true;
+        }
+        r->bed_cv.notify_all();
+        r->bed_writer.join();
+    }
     if (r->gz) gzclose(r->gz);
-    if (r->bed) {
-        if (r->bedlen) fwrite(r->bedbuf.data(), 1, r->bedlen, r->bed);
-        fclose(r->bed);
+    if (r->f) fclose(r->f);
+    if (r->bed && (fclose(r->bed) != 0 || r->bed_failed)) {
+        hh_set_error("hh_pairs_close: writing alignments.bed failed (disk full?)");
+        rc = HH_ERR_ARG;
     }
     delete r;
-    return HH_OK;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -293,146 +733,19 @@ extern "C" int hh_clm_write(const char* path, const char* names_blob, int32_t n_
 // records are walked in the decompressed stream and one int32 record per read1 alignment is produced:
 // (id(reference_name), reference_start, id(next_reference_name), next_reference_start).
 // ---------------------------------------------------------------------------------------------
-#include <atomic>
-#include <thread>
-
 struct hh_bam_reader {
-    FILE* f = nullptr;
-    std::vector<uint8_t> comp;        // compressed bytes not yet consumed
-    size_t comp_pos = 0, comp_len = 0;
-    bool file_eof = false;
-    std::vector<uint8_t> raw;         // decompressed bytes not yet consumed
-    size_t raw_pos = 0, raw_len = 0;
+    hh_bgzf z;
     std::string header_text;
     std::vector<int32_t> ref_to_id;   // BAM refID -> contig id (-1 = not in the FASTA)
     int inter_only = 1;
-    int threads = 1;
     int64_t n_records = 0;
 };
 
-static inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
-static inline uint16_t le16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
-
-struct hh_bgzf_block {
-    size_t in_off, in_len;            // deflate payload inside comp
-    size_t out_off;                   // destination offset inside raw
-    uint32_t isize, crc;
-};
-
-// decompress the next batch of whole BGZF blocks (up to ~target_bytes of compressed input); appends to raw.
-// Returns 0 = appended something, 1 = end of file, <0 = error (message set).
-static int bam_fill(hh_bam_reader* r, size_t target_bytes) {
-    // compact the compressed buffer and read more of the file
-    if (r->comp_pos > 0) {
-        memmove(r->comp.data(), r->comp.data() + r->comp_pos, r->comp_len - r->comp_pos);
-        r->comp_len -= r->comp_pos;
-        r->comp_pos = 0;
-    }
-    if (!r->file_eof && r->comp_len < target_bytes) {
-        if (r->comp.size() < target_bytes + (1u << 16)) r->comp.resize(target_bytes + (1u << 16));
-        const size_t got = fread(r->comp.data() + r->comp_len, 1, r->comp.size() - r->comp_len, r->f);
-        if (got == 0) r->file_eof = true;
-        r->comp_len += got;
-    }
-    if (r->comp_len == 0) return 1;
-    // block boundaries
-    std::vector<hh_bgzf_block> blocks;
-    size_t p = 0, out_total = 0;
-    while (p + 18 <= r->comp_len) {
-        const uint8_t* h = r->comp.data() + p;
-        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) {
-            hh_set_error("hh_bam: not a BGZF block at compressed offset (file is not a BAM / is corrupt)");
-            return -1;
-        }
-        const size_t xlen = le16(h + 10);
-        if (p + 12 + xlen > r->comp_len) break;
-        size_t bsize = 0;
-        for (size_t q = 0; q + 4 <= xlen;) {
-            const uint8_t* sf = h + 12 + q;
-            const size_t slen = le16(sf + 2);
-            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2) bsize = (size_t)le16(sf + 4) + 1;
-            q += 4 + slen;
-        }
-        if (bsize == 0 || bsize < 12 + xlen + 8) {
-            hh_set_error("hh_bam: BGZF block without a valid BC subfield");
-            return -1;
-        }
-        if (p + bsize > r->comp_len) break;          // incomplete block: wait for more input
-        hh_bgzf_block b;
-        b.in_off = p + 12 + xlen;
-        b.in_len = bsize - 12 - xlen - 8;
-        b.crc = le32(h + bsize - 8);
-        b.isize = le32(h + bsize - 4);
-        b.out_off = out_total;
-        out_total += b.isize;
-        blocks.push_back(b);
-        p += bsize;
-    }
-    if (blocks.empty()) {
-        if (r->file_eof) {
-            hh_set_error("hh_bam: truncated BGZF block at the end of the file");
-            return -1;
-        }
-        // a single block larger than what is buffered cannot happen (blocks are <= 64 KiB): read more
-        return bam_fill(r, target_bytes * 2);
-    }
-    // make room in raw (keep the unconsumed tail)
-    if (r->raw_pos > 0) {
-        memmove(r->raw.data(), r->raw.data() + r->raw_pos, r->raw_len - r->raw_pos);
-        r->raw_len -= r->raw_pos;
-        r->raw_pos = 0;
-    }
-    if (r->raw.size() < r->raw_len + out_total) r->raw.resize(r->raw_len + out_total);
-    uint8_t* out_base = r->raw.data() + r->raw_len;
-    const uint8_t* in_base = r->comp.data();
-    std::atomic<size_t> next(0);
-    std::atomic<int> failed(0);
-    auto work = [&]() {
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) {
-            failed = 1;
-            return;
-        }
-        for (;;) {
-            const size_t k = next.fetch_add(1);
-            if (k >= blocks.size()) break;
-            const hh_bgzf_block& b = blocks[k];
-            inflateReset(&zs);
-            zs.next_in = const_cast<Bytef*>(in_base + b.in_off);
-            zs.avail_in = (uInt)b.in_len;
-            zs.next_out = out_base + b.out_off;
-            zs.avail_out = b.isize;
-            const int rc = b.isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
-            if ((b.isize && rc != Z_STREAM_END) || zs.avail_out != 0 ||
-                (uint32_t)crc32(crc32(0L, Z_NULL, 0), out_base + b.out_off, b.isize) != b.crc) {
-                failed = 1;
-                break;
-            }
-        }
-        inflateEnd(&zs);
-    };
-    const int nt = (int)std::min<size_t>((size_t)std::max(1, r->threads), blocks.size());
-    if (nt <= 1) {
-        work();
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nt; ++t) pool.emplace_back(work);
-        for (auto& t : pool) t.join();
-    }
-    if (failed) {
-        hh_set_error("hh_bam: BGZF block failed to inflate (corrupt file)");
-        return -1;
-    }
-    r->raw_len += out_total;
-    r->comp_pos = p;
-    return 0;
-}
-
 // make sure `need` decompressed bytes are available at raw_pos; returns 0 ok, 1 clean EOF (nothing left), -1 error
-static int bam_need(hh_bam_reader* r, size_t need) {
+static int bam_need(hh_bam_reader* rd, size_t need) {
+    hh_bgzf* r = &rd->z;
     while (r->raw_len - r->raw_pos < need) {
-        const int rc = bam_fill(r, 32u << 20);
+        const int rc = bgzf_fill(r, 32u << 20);
         if (rc < 0) return -1;
         if (rc == 1) {
             if (r->raw_len == r->raw_pos) return 1;
@@ -451,47 +764,40 @@ extern "C" int hh_bam_open(const char* path, const char* names_blob, int32_t n_n
     }
     *out = nullptr;
     hh_bam_reader* r = new hh_bam_reader();
-    r->f = fopen(path, "rb");
-    if (!r->f) {
+    r->z.f = fopen(path, "rb");
+    if (!r->z.f) {
         hh_set_error("hh_bam_open: cannot open %s", path);
         delete r;
         return HH_ERR_ARG;
     }
     r->inter_only = inter_only;
-    r->threads = threads > 0 ? threads : 1;
+    r->z.threads = hh_io_threads(threads);
     auto fail = [&](const char* msg) {
         if (msg) hh_set_error("%s", msg);
-        fclose(r->f);
+        fclose(r->z.f);
         delete r;
         return HH_ERR_ARG;
     };
     if (bam_need(r, 12) != 0) return fail(nullptr);
-    const uint8_t* p = r->raw.data() + r->raw_pos;
+    const uint8_t* p = r->z.raw.data() + r->z.raw_pos;
     if (memcmp(p, "BAM\1", 4) != 0) return fail("hh_bam_open: not a BAM file");
     const size_t l_text = le32(p + 4);
     if (bam_need(r, 12 + l_text) != 0) return fail(nullptr);
-    p = r->raw.data() + r->raw_pos;
+    p = r->z.raw.data() + r->z.raw_pos;
     r->header_text.assign(reinterpret_cast<const char*>(p + 8), l_text);
     while (!r->header_text.empty() && r->header_text.back() == '\0') r->header_text.pop_back();
     const int32_t n_ref = (int32_t)le32(p + 8 + l_text);
-    r->raw_pos += 12 + l_text;
-    std::unordered_map<std::string, int32_t> ids;
-    ids.reserve((size_t)n_names * 2);
-    const char* q = names_blob;
-    for (int32_t i = 0; i < n_names; ++i) {
-        const size_t l = strlen(q);
-        ids.emplace(std::string(q, l), i);
-        q += l + 1;
-    }
+    r->z.raw_pos += 12 + l_text;
+    hh_name_table ids;
+    ids.build(names_blob, n_names);
     r->ref_to_id.assign((size_t)(n_ref > 0 ? n_ref : 0), -1);
     for (int32_t k = 0; k < n_ref; ++k) {
         if (bam_need(r, 4) != 0) return fail("hh_bam_open: truncated BAM header");
-        const size_t l_name = le32(r->raw.data() + r->raw_pos);
+        const size_t l_name = le32(r->z.raw.data() + r->z.raw_pos);
         if (bam_need(r, 8 + l_name) != 0) return fail("hh_bam_open: truncated BAM header");
-        const char* nm = reinterpret_cast<const char*>(r->raw.data() + r->raw_pos + 4);
-        auto it = ids.find(std::string(nm, l_name ? l_name - 1 : 0));
-        if (it != ids.end()) r->ref_to_id[(size_t)k] = it->second;
-        r->raw_pos += 8 + l_name;
+        const char* nm = reinterpret_cast<const char*>(r->z.raw.data() + r->z.raw_pos + 4);
+        r->ref_to_id[(size_t)k] = ids.find(nm, l_name ? l_name - 1 : 0);
+        r->z.raw_pos += 8 + l_name;
     }
     *out = r;
     return HH_OK;
@@ -519,7 +825,7 @@ extern "C" int hh_bam_next(hh_bam_reader* r, int32_t* rec, int64_t max_records, 
         int rc = bam_need(r, 4);
         if (rc == 1) break;
         if (rc < 0) return HH_ERR_ARG;
-        const size_t bs = le32(r->raw.data() + r->raw_pos);
+        const size_t bs = le32(r->z.raw.data() + r->z.raw_pos);
         if (bs < 32) {
             hh_set_error("hh_bam_next: corrupt BAM record (block_size %zu)", bs);
             return HH_ERR_ARG;
@@ -529,8 +835,8 @@ extern "C" int hh_bam_next(hh_bam_reader* r, int32_t* rec, int64_t max_records, 
             if (rc == 1) hh_set_error("hh_bam_next: truncated BAM record");
             return HH_ERR_ARG;
         }
-        const uint8_t* p = r->raw.data() + r->raw_pos + 4;
-        r->raw_pos += 4 + bs;
+        const uint8_t* p = r->z.raw.data() + r->z.raw_pos + 4;
+        r->z.raw_pos += 4 + bs;
         r->n_records++;
         const int32_t refid = (int32_t)le32(p), pos = (int32_t)le32(p + 4);
         const uint16_t flag = le16(p + 14);
@@ -550,7 +856,7 @@ extern "C" int hh_bam_next(hh_bam_reader* r, int32_t* rec, int64_t max_records, 
 
 extern "C" int hh_bam_close(hh_bam_reader* r) {
     if (!r) return HH_OK;
-    if (r->f) fclose(r->f);
+    if (r->z.f) fclose(r->z.f);
     delete r;
     return HH_OK;
 }

@@ -36,15 +36,16 @@ def names_blob(names):
     return b"".join(n.encode() + b"\x00" for n in names)
 
 
-def pairs_batches(path, aln_format, name_to_id, bed_path="alignments.bed", batch_lines=4_000_000, inter_only=True):
+def pairs_batches(path, aln_format, name_to_id, bed_path="alignments.bed", batch_lines=4_000_000, inter_only=True, threads=0):
     """Yield int32 [m, 4] record batches from a 4DN .pairs / .pairs.gz file.
 
     Mirrors pairs_generator / pairs_generator_inter_ctgs (1539-1583): blank lines and lines starting
     with '#' are skipped; columns are whitespace separated; ``ref, pos, mref, mpos = cols[1],
     int(cols[2])-1, cols[3], int(cols[4])-1``; two BED lines per pair go to ``alignments.bed``
     (needed later by `haphic build` for .pairs input); with ``inter_only`` pairs on one contig are
-    dropped (1582).  Tokenising, name lookup and the BED writer are native (hh_pairs_* in
-    libhaphic_b200.so)."""
+    dropped (1582).  Tokenising, name lookup and the BED writer are native and multi-threaded (hh_pairs_* in
+    libhaphic_b200.so; ``threads`` = 0 uses the host's cores, at most 16); plain gzip streams are inflated by zlib,
+    bgzipped files block-parallel."""
     import ctypes as C
     from ._lib import check, load
     assert aln_format in ("pairs", "bgzipped_pairs"), aln_format
@@ -53,7 +54,7 @@ def pairs_batches(path, aln_format, name_to_id, bed_path="alignments.bed", batch
     h = C.c_void_p()
     lib = load()
     check(lib.hh_pairs_open(os.fsencode(path), blob, len(names), os.fsencode(bed_path) if bed_path else None,
-                            int(bool(inter_only)), C.byref(h)))
+                            int(bool(inter_only)), int(threads), C.byref(h)))
     try:
         n_out = C.c_int64()
         while True:
@@ -63,8 +64,11 @@ def pairs_batches(path, aln_format, name_to_id, bed_path="alignments.bed", batch
             if m == 0:
                 break
             yield rec[:m]
+        check(lib.hh_pairs_close(h))          # reports a failed alignments.bed write
+        h = None
     finally:
-        lib.hh_pairs_close(h)
+        if h is not None:
+            lib.hh_pairs_close(h)
 
 
 class NameIndex:

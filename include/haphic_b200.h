@@ -221,10 +221,12 @@ int hh_mcl_destroy(hh_mcl* mc);
  * .pairs / .pairs.gz reader: pairs_generator / pairs_generator_inter_ctgs, HapHiC_cluster.py:1539-1583.  Skips blank
  * and '#' lines, takes `cols[1], int(cols[2])-1, cols[3], int(cols[4])-1`, writes the two BED lines per pair
  * to `bed_path` (may be NULL) and returns int32 records {id_a, pos_a, id_b, pos_b} (id -1 = name not in the table);
- * with inter_only pairs whose two names are equal are dropped (1582).  names_blob = n_names NUL-terminated names. */
+ * with inter_only pairs whose two names are equal are dropped (1582).  names_blob = n_names NUL-terminated names.
+ * The text is cut at line boundaries and parsed on `threads` host threads (0 = all cores, at most 16); bgzipped
+ * input is inflated block-parallel, other gzip streams by zlib. */
 typedef struct hh_pairs_reader hh_pairs_reader;
 int hh_pairs_open(const char* path, const char* names_blob, int32_t n_names, const char* bed_path, int inter_only,
-                  hh_pairs_reader** out);
+                  int threads, hh_pairs_reader** out);
 int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_records, int64_t* n_out);   /* *n_out == 0: end of file */
 int hh_pairs_close(hh_pairs_reader* r);
 /* BAM input (bam_generator, HapHiC_cluster.py:1586-1593, with the htslib filters `flag.read1 [&& refid != mrefid]` of

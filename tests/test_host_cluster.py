@@ -217,6 +217,48 @@ def test_native_pairs_reader_gz_and_comments(tmp_path):
     assert all_pairs.tolist() == [[0, 9, 1, 19], [1, 4, 1, 8], [-1, 6, 2, 0], [2, 2, 0, 3]]
 
 
+@pytest.mark.parametrize("compress", ["plain", "gzip", "bgzf"])
+@pytest.mark.parametrize("threads", [1, 5])
+def test_native_pairs_reader_threads_and_compressions(tmp_path, compress, threads):
+    """The threaded tokenizer gives the same records and the same alignments.bed whatever the thread count, the
+    compression (plain text, one gzip stream, blocked gzip inflated in parallel) and the batch size; malformed lines
+    are reported with their line number."""
+    import gzip
+    from haphic_b200 import hicio, synth
+    from haphic_b200._lib import HHError
+    asm = synth.make_assembly(3, 300, 30000, seed=31)
+    pairs = synth.make_pairs(asm, 120000, seed=32).numpy()        # ~6 MB of text: several slices per window
+    names = asm.names
+    lines = ["## pairs format v1.0", "#columns: readID chr1 pos1 chr2 pos2 strand1 strand2"]
+    lines += ["r{}\t{}\t{}\t{}\t{}\t+\t-".format(k, names[a], pa + 1, names[b], pb + 1) for k, (a, pa, b, pb) in enumerate(pairs.tolist())]
+    text = ("\n".join(lines) + "\n").encode()
+    path = str(tmp_path / ("a.pairs" if compress == "plain" else "a.pairs.gz"))
+    with open(path, "wb") as f:
+        if compress == "plain":
+            f.write(text)
+        elif compress == "gzip":
+            f.write(gzip.compress(text, 1))
+        else:
+            for i in range(0, len(text), 0xFF00):
+                f.write(hicio._bgzf_block(text[i:i + 0xFF00]))
+            f.write(hicio._bgzf_block(b""))
+    fmt = "pairs" if compress == "plain" else "bgzipped_pairs"
+    idx = hicio.NameIndex(names)
+    bed = str(tmp_path / "a.bed")
+    got = np.concatenate(list(hicio.pairs_batches(path, fmt, idx, bed_path=bed, batch_lines=9999, threads=threads)))
+    assert np.array_equal(got, pairs[pairs[:, 0] != pairs[:, 2]])
+    want_bed = "".join("{}\t{}\t{}\tr{}/1\t255\t.\n{}\t{}\t{}\tr{}/2\t255\t.\n".format(names[a], pa, pa, k, names[b], pb, pb, k)
+                       for k, (a, pa, b, pb) in enumerate(pairs.tolist()))
+    with open(bed) as f:
+        assert f.read() == want_bed
+    if compress == "plain":
+        bad = lines[:50002] + ["r\tx\tnotanumber\ty\t5"] + lines[50002:]
+        with open(path, "w") as f:
+            f.write("\n".join(bad) + "\n")
+        with pytest.raises(HHError, match="line 50003"):
+            list(hicio.pairs_batches(path, fmt, idx, bed_path=None, threads=threads))
+
+
 @pytest.mark.parametrize("tag", ["p2", "p4", "p4bins"])
 def test_allelic_link_removal_matches_reference_golden(tag):
     """record_coord_pairs / concordance + concentration ratios / remove_allelic_HiC_links (HapHiC_cluster.py:419-692)
