@@ -49,6 +49,8 @@ def parse_args():
     p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--cpu-sample-pairs", type=int, default=4_000_000)
     p.add_argument("--cpu-sample-cols", type=int, default=24)
+    p.add_argument("--ingest-lines", type=int, default=1_000_000,
+                   help="lines of .pairs text for the host ingest measurement (0 = skip)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--verbose", action="store_true")
     return p.parse_args()
@@ -147,6 +149,31 @@ def cpu_mcl_iter_per_sec(m_csc, n_cols, inflation, pruning, seed=0):
     dt = time.perf_counter() - t0
     full = dt * n / len(cols)
     return 1.0 / full, dt, len(cols)
+
+
+def ingest_rate(asm, sample, threads=0):
+    """Host side of the file -> records path (SURVEY.md 8d reports it beside the device numbers): the native
+    threaded tokenizer (hh_pairs_*) on a .pairs text of the sample, with the alignments.bed side product."""
+    import tempfile
+    from haphic_b200 import hicio
+    names = asm.names
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "sample.pairs")
+        with open(path, "w") as f:
+            f.write("## pairs format v1.0\n#columns: readID chr1 pos1 chr2 pos2 strand1 strand2\n")
+            f.write("".join("r{}\t{}\t{}\t{}\t{}\t+\t-\n".format(k, names[a], pa + 1, names[b], pb + 1)
+                            for k, (a, pa, b, pb) in enumerate(sample.tolist())))
+        size = os.path.getsize(path)
+        idx = hicio.NameIndex(names)
+        out = {}
+        for tag, bed in (("with_bed", os.path.join(tmp, "alignments.bed")), ("without_bed", None)):
+            t0 = time.perf_counter()
+            n = sum(len(b) for b in hicio.pairs_batches(path, "pairs", idx, bed_path=bed, threads=threads))
+            dt = time.perf_counter() - t0
+            out[tag] = len(sample) / dt
+        return {"unit": "lines/s", "pairs_text": out, "lines": len(sample), "text_bytes": size,
+                "threads": max(1, min(16, os.cpu_count() or 1)) if threads <= 0 else threads,
+                "note": "native tokenizer + name lookup (+ alignments.bed writer), page-cache resident file"}
 
 
 def make_inputs(a, device, rank_id=0, world=1):
@@ -386,6 +413,9 @@ def run_b200(a):
         mc.close()
         mat.close()
         tab.close()
+    ingest = None
+    if not a.no_cpu_baseline and a.ingest_lines > 0:
+        ingest = ingest_rate(asm, rec[: a.ingest_lines].cpu().numpy())
 
     line = {
         "metric": "hic_pairs_per_sec_matrix_build", "value": pairs_per_s, "unit": "pairs/s", "n_gpus": 1,
@@ -418,6 +448,7 @@ def run_b200(a):
         "roofline_build": {"kernel": "hh_k_links_insert + finish", "bound": "hbm", "achieved": build_achieved, "peak": peak,
                            "unit": "GB/s", "frac": build_achieved / peak, "traffic": traffic.get("hh_k_links_insert")},
         "cpu_baseline": cpu,
+        "ingest": ingest,
     }
     print(json.dumps(line))
     ctx.close()
