@@ -324,17 +324,16 @@ def build_clm_dict(clm_rec, names, ctg_len, rank, dist_int_type="int32"):
     return clm
 
 
-def write_clm(clm_rec, names, ctg_len, rank, path="paired_links.clm"):
-    """paired_links.clm straight from the records with the native writer (hh_clm_write)."""
-    import ctypes as C
+def write_clm(clm_rec, names, ctg_len, rank, path="paired_links.clm", threads=0):
+    """paired_links.clm straight from the records: grouping by contig pair, the per-pair distance sorts and the text
+    are native and threaded (hh_clm_from_records)."""
     from . import hicio
     from ._lib import check, load, ptr
     logger.info("Writing clm_dict to paired_links.clm...")
-    ki, kj, off, dist = clm_arrays(clm_rec, len(names), ctg_len, rank)
-    dist = np.ascontiguousarray(dist)
-    check(load().hh_clm_write(os.fsencode(path), hicio.names_blob(names), len(names), ptr(np.ascontiguousarray(ki)),
-                              ptr(np.ascontiguousarray(kj)), len(ki), ptr(np.ascontiguousarray(off)), ptr(dist),
-                              dist.shape[1]))
+    rec = np.ascontiguousarray(clm_rec, dtype=np.int32)
+    check(load().hh_clm_from_records(os.fsencode(path), hicio.names_blob(names), len(names), ptr(rec) if len(rec) else None,
+                                     len(rec), ptr(np.ascontiguousarray(ctg_len, dtype=np.int64)),
+                                     ptr(np.ascontiguousarray(rank, dtype=np.int32)), int(threads)))
 
 
 def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_set, pos_int_type, dist_int_type,
@@ -1003,7 +1002,7 @@ def run(args, log_file=None):
     if args.quick_view:
         logger.info("Program finished in {}s".format(time.time() - start_time))
         return None
-    write_clm(*clm_src)          # same file as output_clm(clm_dict), from the records, native formatter
+    write_clm(*clm_src, threads=args.threads)          # same file as output_clm(clm_dict), from the records, native
     del clm_dict, clm_src
 
     if args.normalize_by_nlinks:

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -858,5 +859,241 @@ extern "C" int hh_bam_close(hh_bam_reader* r) {
     if (!r) return HH_OK;
     if (r->z.f) fclose(r->z.f);
     delete r;
+    return HH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// paired_links.clm straight from the record stream (update_clm_dict 395-401 + output_clm 376-392), threaded:
+// records are partitioned by contig pair (stable, so stream order survives inside a pair), every partition is
+// grouped by a stable sort, the pairs with >= 2 links are ordered by their first record (= dict insertion order),
+// and slices of that list are turned into text by a pool of threads while one thread writes the slices in order.
+// ---------------------------------------------------------------------------------------------
+struct hh_clm_seg {
+    uint32_t first;                   // stream index of the pair's first record
+    uint32_t len;                     // links
+    uint64_t start;                   // position of its (key, idx) run in the grouped array
+};
+
+extern "C" int hh_clm_from_records(const char* path, const char* names_blob, int32_t n_names, const int32_t* rec, int64_t n_rec,
+                                   const int64_t* ctg_len, const int32_t* name_rank, int threads) {
+    if (!path || !names_blob || !ctg_len || !name_rank || n_names <= 0 || n_rec < 0 || (n_rec > 0 && !rec)) {
+        hh_set_error("hh_clm_from_records: bad argument");
+        return HH_ERR_ARG;
+    }
+    if (n_rec > 0xFFFFFFFELL) {
+        hh_set_error("hh_clm_from_records: more than 2^32 records");
+        return HH_ERR_UNSUPPORTED;
+    }
+    const int T = hh_io_threads(threads);
+    std::vector<const char*> name((size_t)n_names);
+    std::vector<size_t> nlen((size_t)n_names);
+    {
+        const char* p = names_blob;
+        for (int32_t i = 0; i < n_names; ++i) {
+            name[(size_t)i] = p;
+            nlen[(size_t)i] = strlen(p);
+            p += nlen[(size_t)i] + 1;
+        }
+    }
+    FILE* f = fopen(path, "w");
+    if (!f) {
+        hh_set_error("hh_clm_from_records: cannot create %s", path);
+        return HH_ERR_ARG;
+    }
+    setvbuf(f, nullptr, _IONBF, 0);
+    const uint64_t N = (uint64_t)n_names;
+    // key of a record: (i, j) ordered by name rank; 0 = unusable (same contig / id outside the FASTA)
+    auto key_of = [&](int64_t r, bool* swapped) -> uint64_t {
+        const int32_t a = rec[4 * r], b = rec[4 * r + 2];
+        if (a == b || (uint32_t)a >= (uint32_t)n_names || (uint32_t)b >= (uint32_t)n_names) return 0;
+        const bool sw = name_rank[a] > name_rank[b];
+        *swapped = sw;
+        const uint64_t i = (uint64_t)(sw ? b : a), j = (uint64_t)(sw ? a : b);
+        return i * N + j + 1;
+    };
+    auto mix = [](uint64_t k) {
+        k ^= k >> 33;
+        k *= 0xff51afd7ed558ccdull;
+        k ^= k >> 33;
+        return k;
+    };
+    auto run_pool = [&](int n_workers, const std::function<void(int)>& fn) {
+        if (n_workers <= 1) {
+            fn(0);
+            return;
+        }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_workers; ++t) pool.emplace_back(fn, t);
+        for (auto& th : pool) th.join();
+    };
+    // ---- A/B/C: stable partition of (key, idx) into buckets
+    const int NB = 1024;
+    const int64_t chunk = (n_rec + T - 1) / T;
+    std::vector<std::vector<uint64_t>> cnt((size_t)T, std::vector<uint64_t>((size_t)NB, 0));
+    run_pool(T, [&](int t) {
+        const int64_t lo = std::min<int64_t>(n_rec, chunk * t), hi = std::min<int64_t>(n_rec, lo + chunk);
+        bool sw;
+        for (int64_t r = lo; r < hi; ++r) {
+            const uint64_t k = key_of(r, &sw);
+            if (k) cnt[(size_t)t][mix(k) & (NB - 1)]++;
+        }
+    });
+    std::vector<uint64_t> bucket_start((size_t)NB + 1, 0);
+    std::vector<std::vector<uint64_t>> cursor((size_t)T, std::vector<uint64_t>((size_t)NB, 0));
+    {
+        uint64_t acc = 0;
+        for (int b = 0; b < NB; ++b) {
+            bucket_start[(size_t)b] = acc;
+            for (int t = 0; t < T; ++t) {
+                cursor[(size_t)t][(size_t)b] = acc;        // thread t's share of bucket b starts here: idx ascending inside a bucket
+                acc += cnt[(size_t)t][(size_t)b];
+            }
+        }
+        bucket_start[(size_t)NB] = acc;
+    }
+    const uint64_t n_used = bucket_start[(size_t)NB];
+    struct kv {
+        uint64_t key;
+        uint32_t idx;
+    };
+    std::vector<kv> items((size_t)n_used);
+    run_pool(T, [&](int t) {
+        const int64_t lo = std::min<int64_t>(n_rec, chunk * t), hi = std::min<int64_t>(n_rec, lo + chunk);
+        bool sw;
+        std::vector<uint64_t>& cur = cursor[(size_t)t];
+        for (int64_t r = lo; r < hi; ++r) {
+            const uint64_t k = key_of(r, &sw);
+            if (k) items[(size_t)cur[mix(k) & (NB - 1)]++] = kv{k, (uint32_t)r};
+        }
+    });
+    // ---- D: group every bucket; E: pairs with >= 2 links in first-seen order
+    std::vector<std::vector<hh_clm_seg>> per_bucket((size_t)NB);
+    std::atomic<int> next_bucket(0);
+    run_pool(T, [&](int) {
+        for (;;) {
+            const int b = next_bucket.fetch_add(1);
+            if (b >= NB) break;
+            kv* s = items.data() + bucket_start[(size_t)b];
+            kv* e = items.data() + bucket_start[(size_t)b + 1];
+            std::stable_sort(s, e, [](const kv& x, const kv& y) { return x.key < y.key; });
+            for (kv* p = s; p < e;) {
+                kv* q = p + 1;
+                while (q < e && q->key == p->key) ++q;
+                if (q - p >= 2) per_bucket[(size_t)b].push_back(hh_clm_seg{p->idx, (uint32_t)(q - p), (uint64_t)(p - items.data())});
+                p = q;
+            }
+        }
+    });
+    std::vector<hh_clm_seg> segs;
+    {
+        size_t total = 0;
+        for (auto& v : per_bucket) total += v.size();
+        segs.reserve(total);
+        for (auto& v : per_bucket) {
+            segs.insert(segs.end(), v.begin(), v.end());
+            std::vector<hh_clm_seg>().swap(v);
+        }
+        std::sort(segs.begin(), segs.end(), [](const hh_clm_seg& x, const hh_clm_seg& y) { return x.first < y.first; });
+    }
+    // ---- F: text.  Slices of ~256k links; formatted by the pool, written in order by this thread.
+    std::vector<size_t> slice_start{0};
+    {
+        uint64_t acc = 0;
+        for (size_t k = 0; k < segs.size(); ++k) {
+            acc += segs[k].len;
+            if (acc >= (1u << 18)) {
+                slice_start.push_back(k + 1);
+                acc = 0;
+            }
+        }
+        if (slice_start.back() != segs.size()) slice_start.push_back(segs.size());
+    }
+    const size_t n_slices = slice_start.size() - 1;
+    std::vector<hh_bytes> text(n_slices);
+    std::vector<char> ready(n_slices, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<size_t> next_slice(0);
+    size_t written = 0;                // slices already on disk (guarded by mu)
+    const size_t max_ahead = (size_t)T * 4;
+    bool failed = false;
+    static const char sg[4][2] = {{'+', '+'}, {'+', '-'}, {'-', '+'}, {'-', '-'}};
+    auto format_slices = [&](int) {
+        std::vector<int64_t> d[4];
+        for (;;) {
+            const size_t sidx = next_slice.fetch_add(1);
+            if (sidx >= n_slices) break;
+            {
+                std::unique_lock<std::mutex> lk(mu);          // do not run too far ahead of the writer
+                cv.wait(lk, [&] { return sidx < written + max_ahead; });
+            }
+            hh_bytes& out = text[sidx];
+            for (size_t k = slice_start[sidx]; k < slice_start[sidx + 1]; ++k) {
+                const hh_clm_seg& sgm = segs[k];
+                const kv* it = items.data() + sgm.start;
+                const uint64_t key = it->key - 1;
+                const int32_t ci = (int32_t)(key / N), cj = (int32_t)(key % N);
+                const int64_t li = ctg_len[ci], lj = ctg_len[cj];
+                for (int o = 0; o < 4; ++o) d[o].resize(sgm.len);
+                for (uint32_t t = 0; t < sgm.len; ++t) {
+                    const int32_t* r = rec + 4 * (int64_t)it[t].idx;
+                    const bool sw = r[0] != ci;                 // the record names the pair as (j, i)
+                    const int64_t a0 = sw ? r[3] : r[1], b0 = sw ? r[1] : r[3];
+                    d[0][t] = li - a0 + b0;                     // ++  (395-401)
+                    d[1][t] = li - a0 + lj - b0;                // +-
+                    d[2][t] = a0 + b0;                          // -+
+                    d[3][t] = a0 + lj - b0;                     // --
+                }
+                const size_t per_line = nlen[(size_t)ci] + nlen[(size_t)cj] + 64 + (size_t)sgm.len * 2 * 21;
+                for (int o = 0; o < 4; ++o) {
+                    std::sort(d[o].begin(), d[o].end());
+                    char* q = out.room(per_line);
+                    memcpy(q, name[(size_t)ci], nlen[(size_t)ci]);
+                    q += nlen[(size_t)ci];
+                    *q++ = sg[o][0];
+                    *q++ = ' ';
+                    memcpy(q, name[(size_t)cj], nlen[(size_t)cj]);
+                    q += nlen[(size_t)cj];
+                    *q++ = sg[o][1];
+                    *q++ = '\t';
+                    q = put_i64(q, (int64_t)sgm.len * 2);
+                    *q++ = '\t';
+                    for (uint32_t t = 0; t < sgm.len; ++t) {
+                        if (t) *q++ = ' ';
+                        q = put_i64(q, d[o][t]);
+                        *q++ = ' ';
+                        q = put_i64(q, d[o][t]);
+                    }
+                    *q++ = '\n';
+                    out.len = (size_t)(q - out.data);
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready[sidx] = 1;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t) pool.emplace_back(format_slices, t);
+    for (size_t sidx = 0; sidx < n_slices; ++sidx) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return ready[sidx] != 0; });
+        }
+        if (text[sidx].len && fwrite(text[sidx].data, 1, text[sidx].len, f) != text[sidx].len) failed = true;
+        text[sidx].release();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            written = sidx + 1;
+        }
+        cv.notify_all();
+    }
+    for (auto& th : pool) th.join();
+    if (fclose(f) != 0 || failed) {
+        hh_set_error("hh_clm_from_records: write to %s failed", path);
+        return HH_ERR_ARG;
+    }
     return HH_OK;
 }

@@ -245,6 +245,12 @@ int hh_bam_close(hh_bam_reader* r);
  * sorted ascending; pairs with fewer than 2 links are skipped, every distance is printed twice. */
 int hh_clm_write(const char* path, const char* names_blob, int32_t n_names, const int32_t* key_i, const int32_t* key_j,
                  int64_t n_pairs, const int64_t* offsets, const int64_t* dist, int64_t total_links);
+/* the same file straight from the record stream (update_clm_dict 395-401 + output_clm 376-392): rec = n_rec int32 records
+ * {id_a, pos_a, id_b, pos_b} in stream order (same-contig records and ids outside [0, n_names) are skipped),
+ * ctg_len / name_rank per contig id.  Grouping, the per-pair sorts and the text formatting run on `threads` host
+ * threads (0 = all cores, at most 16). */
+int hh_clm_from_records(const char* path, const char* names_blob, int32_t n_names, const int32_t* rec, int64_t n_rec,
+                        const int64_t* ctg_len, const int32_t* name_rank, int threads);
 
 #ifdef __cplusplus
 }
