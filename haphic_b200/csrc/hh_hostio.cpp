@@ -4,7 +4,7 @@
 //     the text is cut at line boundaries and parsed by a pool of threads, BGZF-compressed input is inflated
 //     block-parallel,
 //   * BAM reader (bam_generator, 1586-1593),
-//   * paired_links.clm text writer (output_clm, 376-392).
+//   * paired_links.clm from the record stream (update_clm_dict 395-401 + output_clm 376-392), threaded.
 // Pure C++ (no CUDA); part of libhaphic_b200.so, declared in include/haphic_b200.h.
 #include <stdint.h>
 #include <stdio.h>
@@ -657,75 +657,6 @@ extern "C" int hh_pairs_close(hh_pairs_reader* r) {
     }
     delete r;
     return rc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// paired_links.clm: for every contig pair with >= 2 links, four lines (orientations ++ +- -+ --),
-// each `{ci}{s} {cj}{s}\t{2*links}\t{d d d d ...}` with every ascending distance printed twice.
-//   names_blob: NUL-separated contig names; key_i / key_j: contig ids per pair;
-//   offsets[n_pairs+1]: start of each pair's block in dist (in links); dist: [4][total_links] int64,
-//   each orientation's block of a pair already sorted ascending.
-// ---------------------------------------------------------------------------------------------
-extern "C" int hh_clm_write(const char* path, const char* names_blob, int32_t n_names, const int32_t* key_i, const int32_t* key_j,
-                            int64_t n_pairs, const int64_t* offsets, const int64_t* dist, int64_t total_links) {
-    if (!path || !names_blob || !offsets || (n_pairs > 0 && (!key_i || !key_j || !dist))) {
-        hh_set_error("hh_clm_write: bad argument");
-        return HH_ERR_ARG;
-    }
-    std::vector<const char*> name(n_names);
-    std::vector<size_t> nlen(n_names);
-    const char* p = names_blob;
-    for (int32_t i = 0; i < n_names; ++i) {
-        name[i] = p;
-        nlen[i] = strlen(p);
-        p += nlen[i] + 1;
-    }
-    FILE* f = fopen(path, "w");
-    if (!f) {
-        hh_set_error("hh_clm_write: cannot create %s", path);
-        return HH_ERR_ARG;
-    }
-    setvbuf(f, nullptr, _IOFBF, 1 << 22);
-    static const char sg[4][2] = {{'+', '+'}, {'+', '-'}, {'-', '+'}, {'-', '-'}};
-    std::vector<char> line;
-    for (int64_t e = 0; e < n_pairs; ++e) {
-        const int64_t s = offsets[e], links = offsets[e + 1] - s;
-        if (links < 2) continue;                                   // `if len(list_) < 8: continue`
-        const int32_t a = key_i[e], b = key_j[e];
-        if (a < 0 || a >= n_names || b < 0 || b >= n_names || s < 0 || s + links > total_links) {
-            fclose(f);
-            hh_set_error("hh_clm_write: pair %lld is out of range", (long long)e);
-            return HH_ERR_ARG;
-        }
-        line.resize(nlen[a] + nlen[b] + 64 + (size_t)links * 2 * 21);
-        for (int k = 0; k < 4; ++k) {
-            char* q = line.data();
-            memcpy(q, name[a], nlen[a]);
-            q += nlen[a];
-            *q++ = sg[k][0];
-            *q++ = ' ';
-            memcpy(q, name[b], nlen[b]);
-            q += nlen[b];
-            *q++ = sg[k][1];
-            *q++ = '\t';
-            q = put_i64(q, links * 2);
-            *q++ = '\t';
-            const int64_t* d = dist + (size_t)k * (size_t)total_links + s;
-            for (int64_t t = 0; t < links; ++t) {
-                if (t) *q++ = ' ';
-                q = put_i64(q, d[t]);
-                *q++ = ' ';
-                q = put_i64(q, d[t]);
-            }
-            *q++ = '\n';
-            fwrite(line.data(), 1, (size_t)(q - line.data()), f);
-        }
-    }
-    if (fclose(f) != 0) {
-        hh_set_error("hh_clm_write: write to %s failed", path);
-        return HH_ERR_ARG;
-    }
-    return HH_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -240,12 +240,9 @@ int hh_bam_header_text(hh_bam_reader* r, const char** text, int64_t* len);
 int hh_bam_next(hh_bam_reader* r, int32_t* rec, int64_t max_records, int64_t* n_out);
 int hh_bam_close(hh_bam_reader* r);
 
-/* paired_links.clm writer: output_clm, HapHiC_cluster.py:376-392.  Pair e links contigs key_i[e], key_j[e]; its
- * links occupy [offsets[e], offsets[e+1]) of each of the four orientation rows of dist[4][total_links], already
- * sorted ascending; pairs with fewer than 2 links are skipped, every distance is printed twice. */
-int hh_clm_write(const char* path, const char* names_blob, int32_t n_names, const int32_t* key_i, const int32_t* key_j,
-                 int64_t n_pairs, const int64_t* offsets, const int64_t* dist, int64_t total_links);
-/* the same file straight from the record stream (update_clm_dict 395-401 + output_clm 376-392): rec = n_rec int32 records
+/* paired_links.clm straight from the record stream (update_clm_dict 395-401 + output_clm 376-392): for every contig
+ * pair with >= 2 links, in dict insertion order, four lines (orientations ++ +- -+ --)
+ * `{ci}{s} {cj}{s}\t{2*links}\t{every ascending distance printed twice}`.  rec = n_rec int32 records
  * {id_a, pos_a, id_b, pos_b} in stream order (same-contig records and ids outside [0, n_names) are skipped),
  * ctg_len / name_rank per contig id.  Grouping, the per-pair sorts and the text formatting run on `threads` host
  * threads (0 = all cores, at most 16). */
