@@ -63,7 +63,6 @@ struct hh_colargs {
     int slot_src;                // SRC_CSC: read the column from slotted matrix B (column orig[j] when orig != NULL) instead of a CSC
     const int* ncols_ptr;        // optional: number of columns to process is read from device memory (overflow list)
     const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
-    int* attr_out;               // EPI_PRUNE: strongest row of every produced column
     int flat;                    // expansion inner loop: 1 = flat 32-entry walk, 0 = one segment at a time
     int l2pf;                    // expansion: prefetch the next batch's segments into L2
     float* scratch;
@@ -555,7 +554,6 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 a.out.len[j] = min(total, a.out.cap);
                 if (total > a.out.cap) atomicExch(a.err, 1);
                 nnz_acc += (unsigned long long)total;
-                if (a.attr_out) a.attr_out[j] = (vmax > 0.f) ? kmax : j;   // strongest row: groups columns of one cluster
             }
             if (SRC == SRC_PRODUCT && conv) {
                 // E4: entries of the previous iterate L = B[:, j]  ->  |M - L| - 1e-5|L|  (fp32, 2045)
@@ -594,29 +592,6 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
         if (prod_acc) atomicAdd(a.stats + 1, prod_acc);
     }
     if (threadIdx.x == 0 && nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
-}
-
-// ---------------------------------------------------------------------------------------------
-// cluster-sorted processing order: columns whose strongest rows chain to the same root are handed to
-// the CTAs back to back, so the operand columns they gather are still in L2
-// ---------------------------------------------------------------------------------------------
-__global__ void hh_k_order_roots(const int* __restrict__ attr, int n, int col_lo, int ncols, int jumps, int* __restrict__ root,
-                                 int* __restrict__ count) {
-    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
-    if (jj >= ncols) return;
-    int r = attr[col_lo + jj];
-    for (int t = 0; t < jumps; ++t) r = attr[r];
-    if (r < 0 || r >= n) r = 0;
-    root[jj] = r;
-    atomicAdd(count + r, 1);
-}
-
-__global__ void hh_k_order_scatter(const int* __restrict__ root, int col_lo, int ncols, const int64_t* __restrict__ start,
-                                   int* __restrict__ cursor, int* __restrict__ order) {
-    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
-    if (jj >= ncols) return;
-    const int r = root[jj];
-    order[start[r] + atomicAdd(cursor + r, 1)] = col_lo + jj;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -925,7 +900,6 @@ __global__ void __launch_bounds__(32) hh_k_col_win(const hh_colargs a, int W, co
             a.out.len[j] = min(total, a.out.cap);
             if (total > a.out.cap) atomicExch(a.err, 1);
             nnz_acc += (unsigned long long)total;
-            if (a.attr_out) a.attr_out[j] = (vmax > 0.f) ? kmax : j;
         }
         __syncwarp();
         if (conv) {
@@ -1192,7 +1166,6 @@ __global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W,
             a.out.len[j] = min(total, a.out.cap);
             if (total > a.out.cap) atomicExch(a.err, 1);
             nnz_acc += (unsigned long long)total;
-            if (a.attr_out) a.attr_out[j] = (vmax > 0.f) ? kmax : j;
         }
         // ---- convergence term against the previous iterate L = B[:, j] (its entries sit in the lanes)
         if (a.do_conv) {
@@ -1444,13 +1417,8 @@ struct hh_mcl {
     int64_t nnz_m0, preexp_products;
     int flat, l2pf;                // expansion inner-loop variant / L2 prefetch (HH_MCL_FLAT, HH_MCL_L2PF)
     int32_t own_lo, own_hi;        // the column block given to hh_mcl_create (dense M1 block); col_lo/col_hi = active block
-    int use_order;                 // cluster-sorted column processing (HH_MCL_ORDER)
-    int* d_attr;                   // [n] strongest row per column of the current iterate
     int* d_order;                  // [ncols] processing order for the next expansion
-    int* d_root;                   // [ncols]
     int* d_cnt;                    // [2n] histogram + cursors
-    int64_t* d_start;              // [n+1]
-    bool order_valid;
     int use_small;                 // warp-per-column kernel for nearly converged iterates (HH_MCL_SMALL)
     int* d_bigcount;
     // cluster-contiguous relabelling + windowed expansion (HH_MCL_WINDOW)
@@ -1790,11 +1758,8 @@ extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     hh_dfree(mc->d_scratch);
     hh_dfree(mc->d_counter);
     hh_dfree(mc->d_stats);
-    hh_dfree(mc->d_attr);
     hh_dfree(mc->d_order);
-    hh_dfree(mc->d_root);
     hh_dfree(mc->d_cnt);
-    hh_dfree(mc->d_start);
     hh_dfree(mc->d_bigcount);
     hh_dfree(mc->d_perm);
     hh_dfree(mc->d_inv);
@@ -1867,7 +1832,6 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
     mc->cur = -1;
     mc->use_small = env_int("HH_MCL_SMALL", 1);
     mc->use_window = env_int("HH_MCL_WINDOW", 1);
-    mc->use_order = env_int("HH_MCL_ORDER", 0);   // measured on B200 (50k contigs): no gain, the gathers are latency- not L2-bound
     mc->flat = env_int("HH_MCL_FLAT", -1);      // -1 = choose per launch from the mean segment length
     mc->l2pf = env_int("HH_MCL_L2PF", -1);       // -1 = prefetch in segment-wise mode only (long segments)
     const hh_geom g = geom_for(ctx, m->n);
@@ -1885,11 +1849,8 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         if (!g.smem_acc) HH_CHECK(hh_dmalloc(&mc->d_scratch, (size_t)mc->grid_cap * (size_t)g.n_pad));
         HH_CHECK(hh_dmalloc(&mc->d_counter, 1));
         HH_CHECK(hh_dmalloc(&mc->d_stats, 4));
-        HH_CHECK(hh_dmalloc(&mc->d_attr, (size_t)m->n));
         HH_CHECK(hh_dmalloc(&mc->d_order, (size_t)m->n));
-        HH_CHECK(hh_dmalloc(&mc->d_root, (size_t)m->n));
         HH_CHECK(hh_dmalloc(&mc->d_cnt, (size_t)m->n * 2));
-        HH_CHECK(hh_dmalloc(&mc->d_start, (size_t)m->n + 1));
         HH_CHECK(hh_dmalloc(&mc->d_bigcount, 4));
         HH_CHECK(hh_dmalloc(&mc->d_perm, (size_t)m->n));
         HH_CHECK(hh_dmalloc(&mc->d_inv, (size_t)m->n));
@@ -2000,13 +1961,11 @@ static int mcl_build_perm(hh_mcl* mc) {
     const int n = mc->n;
     const hh_geom g = mcl_geom(mc);
     const hh_slotmat& M = mc->it[mc->cur];
-    int* d_label = mc->d_root;            // scratch
     int* d_csize = mc->d_cnt;             // [n] component sizes (+ [n..2n) unused)
     int* d_flag = mc->d_bigcount + 2;
     const int ncols = mc->col_hi - mc->col_lo;
     int* d_lab = nullptr;
     HH_CHECK(hh_dmalloc(&d_lab, (size_t)n));
-    (void)d_label;
     int rc = [&]() -> int {
         HH_LAUNCH(ctx, hh_k_cc_init, (n + 255) / 256, 256, 0, d_lab, n);
         int grid = (n + 7) / 8;
@@ -2111,7 +2070,6 @@ extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
     mc->prune = (float)pruning;   // `matrix >= pruning` compares in fp32
     mc->cur = -1;
     mc->have_pending = false;
-    mc->order_valid = false;
     // the relabelling is rebuilt from this inflation's own first pruned iterate: its components bound every later
     // iterate of the same mcl() call, which is what makes the row windows safe
     mc->perm_valid = false;
@@ -2139,7 +2097,6 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
     a.prune = mc->prune;
     const int dst = (mc->cur < 0) ? 0 : (mc->cur ^ 1);
     a.out = mc->it[dst];
-    a.attr_out = mc->d_attr;
     HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
     const int ncols_owned = mc->col_hi - mc->col_lo;
     if (it == 0) {
@@ -2193,24 +2150,12 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
         a.A = mc->it[mc->cur];
         a.B = mc->it[mc->cur];
         a.do_conv = 1;
-        // cluster-sorted processing order while the iterate is big enough for operand reuse to matter
-        if (mc->use_order && mc->order_valid && mc->cur_nnz > 8ll * mc->n) {
-            const int ncols = mc->col_hi - mc->col_lo;
-            const bool whole = (ncols == mc->n);     // attr of foreign columns is not exchanged between shards
-            HH_CUDA(cudaMemsetAsync(mc->d_cnt, 0, (size_t)mc->n * 2 * sizeof(int), ctx->stream));
-            HH_LAUNCH(ctx, hh_k_order_roots, (ncols + 255) / 256, 256, 0, mc->d_attr, mc->n, mc->col_lo, ncols, whole ? 3 : 0,
-                      mc->d_root, mc->d_cnt);
-            HH_CHECK(hh_exclusive_scan_i32(ctx, mc->d_cnt, mc->d_start, mc->n));
-            HH_LAUNCH(ctx, hh_k_order_scatter, (ncols + 255) / 256, 256, 0, mc->d_root, mc->col_lo, ncols, mc->d_start,
-                      mc->d_cnt + mc->n, mc->d_order);
-            a.order = mc->d_order;
-        }
         // expected products per column ~ (nnz/n)^2; track dirty chunks when that is well below n
         const double dcol = (double)mc->cur_nnz / (double)mc->n;
         a.track = (dcol * dcol * 4.0 < (double)mc->n) ? 1 : 0;
         a.flat = choose_flat(mc, (double)mc->cur_nnz);
         a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
-        if (mc->use_small && !a.order && mc->cur_nnz <= 8ll * mc->n) {
+        if (mc->use_small && mc->cur_nnz <= 8ll * mc->n) {
             // nearly converged: one warp per column; what does not fit goes to the accumulator kernel
             const int ncols = mc->col_hi - mc->col_lo;
             HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, sizeof(int), ctx->stream));
@@ -2241,7 +2186,6 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
     mc->pending = dst;
     mc->have_pending = true;
     mc->last_step_it = it;
-    mc->order_valid = true;       // d_attr now describes the pending iterate (owned columns)
     return HH_OK;
 }
 
@@ -2311,7 +2255,6 @@ extern "C" int hh_mcl_set_block(hh_mcl* mc, int32_t col_lo, int32_t col_hi) {
     HH_CUDA(cudaSetDevice(ctx->device));
     mc->col_lo = col_lo;
     mc->col_hi = col_hi;
-    mc->order_valid = false;
     if (mc->perm_space) {
         const int ncols = col_hi - col_lo;
         const int wlimit = env_int("HH_MCL_WMAX", 4096);
