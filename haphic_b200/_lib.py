@@ -87,6 +87,7 @@ _SIGNATURES = {
     "hh_bam_header_text": (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
     "hh_bam_next": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "hh_bam_close": (C.c_int, [_P]),
+    "hh_pickle_links": (C.c_int, [C.c_char_p, _P, C.c_int32, _P, _P, C.c_int64, _P, _P, _P]),
     "hh_clm_from_records": (C.c_int, [C.c_char_p, _P, C.c_int32, _P, C.c_int64, _P, _P, C.c_int]),
 }
 

@@ -240,13 +240,10 @@ def fragment_layout(fa_dict, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set
     return frag_names, np.asarray(frag_base, np.int32), frag_len, name_rank(frag_names), in_nx
 
 
-def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type,
-                     build_clm=True):
-    """Signature and return value of the reference function for the case that some contigs are split into
-    bins (1658-1752): flank links and per-fragment totals are keyed by FRAGMENTS (second device table in
-    fragment mode), full / HT / clm stay contig-level."""
-    logger.info("Parsing input alignments...")
-    from .links import LinkTable, link_dicts, name_rank
+def _stream_bins(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set):
+    """Count one pass of the alignments into the contig-level table (full / HT links) and the fragment-level table
+    (flank links, per-fragment totals).  Returns a dict with both tables, the usable records and the fragment layout."""
+    from .links import LinkTable, name_rank
     names = list(fa_dict.keys())
     ctg_len = np.array([fa_dict[n][1] for n in names], dtype=np.int64)
     frag_names, frag_base, frag_len, frag_rank, frag_nx = fragment_layout(fa_dict, bin_size, frag_len_dict, Nx_frag_set,
@@ -256,19 +253,33 @@ def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag
     batches = _as_batches(alignments, names)
     # contig-level table: Nx membership is irrelevant there (flank links are counted per fragment)
     table, clm_rec = count_links(batches, names, ctg_len, set(), args.flank, frag_table=ftab)
+    return dict(table=table, ftab=ftab, clm_rec=clm_rec, names=names, ctg_len=ctg_len, rank=name_rank(names),
+                frag_names=frag_names, frag_base=frag_base, frag_rank=frag_rank)
+
+
+def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type,
+                     build_clm=True):
+    """Signature and return value of the reference function for the case that some contigs are split into
+    bins (1658-1752): flank links and per-fragment totals are keyed by FRAGMENTS (second device table in
+    fragment mode), full / HT / clm stay contig-level."""
+    logger.info("Parsing input alignments...")
+    from .links import link_dicts
+    st = _stream_bins(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set)
+    table, ftab, clm_rec, names, ctg_len, rank = st["table"], st["ftab"], st["clm_rec"], st["names"], st["ctg_len"], st["rank"]
+    frag_names = st["frag_names"]
     full_link_dict, _unused_flank, HT_link_dict, _unused_tot = link_dicts(table, names)
     table.close()
     _unused_full, flank_link_dict, _unused_ht, frag_link_dict = link_dicts(ftab, frag_names)
-    clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type) if build_clm else defaultdict(list)
-    parse_alignments.last_clm = (clm_rec, names, ctg_len, name_rank(names))
+    clm_dict = build_clm_dict(clm_rec, names, ctg_len, rank, dist_int_type) if build_clm else defaultdict(list)
+    parse_alignments.last_clm = (clm_rec, names, ctg_len, rank)
     parse_alignments.last_table = ftab
     parse_alignments.frag_names = frag_names
     ctg_coord_dict, ctg_pair_to_frag = defaultdict(list), defaultdict(set)
     if args.remove_allelic_links or args.remove_concentrated_links:
         from . import allelic
-        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, name_rank(names), args, pos_int_type)
+        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, rank, args, pos_int_type)
         if args.remove_allelic_links:
-            ctg_pair_to_frag = allelic.ctg_pair_to_frag_dict(clm_rec, names, name_rank(names), frag_names, frag_base, frag_rank,
+            ctg_pair_to_frag = allelic.ctg_pair_to_frag_dict(clm_rec, names, rank, frag_names, st["frag_base"], st["frag_rank"],
                                                              int(bin_size))
     return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict, ctg_pair_to_frag
 
@@ -336,6 +347,16 @@ def write_clm(clm_rec, names, ctg_len, rank, path="paired_links.clm", threads=0)
                                      ptr(np.ascontiguousarray(rank, dtype=np.int32)), int(threads)))
 
 
+def _stream_contigs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_set):
+    """Count one pass of the alignments into the device table; returns table, usable records and the id space."""
+    from .links import name_rank
+    names = list(fa_dict.keys())
+    ctg_len = np.array([ctg_len_dict[n] for n in names], dtype=np.int64)
+    batches = _as_batches(alignments, names)
+    table, clm_rec = count_links(batches, names, ctg_len, Nx_ctg_set, args.flank)
+    return dict(table=table, ftab=None, clm_rec=clm_rec, names=names, ctg_len=ctg_len, rank=name_rank(names))
+
+
 def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_set, pos_int_type, dist_int_type,
                               build_clm=True):
     """Signature and return value of the reference function (1596-1655).  ``alignments`` is an
@@ -343,19 +364,17 @@ def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_se
     (ref, mref, pos, mpos) tuples as the reference's generators yield.  ``build_clm=False`` (used by run())
     leaves clm_dict empty and keeps the usable records in ``.last_clm`` for the native CLM writer."""
     logger.info("Parsing input alignments...")
-    names = list(fa_dict.keys())
-    ctg_len = np.array([ctg_len_dict[n] for n in names], dtype=np.int64)
-    from .links import link_dicts, name_rank
-    batches = _as_batches(alignments, names)
-    table, clm_rec = count_links(batches, names, ctg_len, Nx_ctg_set, args.flank)
+    from .links import link_dicts
+    st = _stream_contigs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_set)
+    table, clm_rec, names, ctg_len, rank = st["table"], st["clm_rec"], st["names"], st["ctg_len"], st["rank"]
     full_link_dict, flank_link_dict, HT_link_dict, ctg_link_dict = link_dicts(table, names)
-    clm_dict = build_clm_dict(clm_rec, names, ctg_len, name_rank(names), dist_int_type) if build_clm else defaultdict(list)
+    clm_dict = build_clm_dict(clm_rec, names, ctg_len, rank, dist_int_type) if build_clm else defaultdict(list)
     parse_alignments_for_ctgs.last_table = table          # run() keeps using the device table
-    parse_alignments_for_ctgs.last_clm = (clm_rec, names, ctg_len, name_rank(names))
+    parse_alignments_for_ctgs.last_clm = (clm_rec, names, ctg_len, rank)
     ctg_coord_dict = defaultdict(list)
     if args.remove_allelic_links or args.remove_concentrated_links:
         from . import allelic
-        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, name_rank(names), args, pos_int_type)
+        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, rank, args, pos_int_type)
     return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, ctg_link_dict, ctg_coord_dict
 
 
@@ -746,6 +765,73 @@ def parse_link_dict(link_dict, ctg_group_dict):
     return out
 
 
+class LinkArrays:
+    """full_link_dict as the arrays the device table hands out (entry order = dict insertion order): run() keeps the
+    links in this form so that no 10^7-entry Python dict is ever built; `to_dict()` gives the reference's object."""
+
+    def __init__(self, names, key_i, key_j, values):
+        self.names = names
+        self.key_i = np.ascontiguousarray(key_i, dtype=np.int32)
+        self.key_j = np.ascontiguousarray(key_j, dtype=np.int32)
+        self.values = np.ascontiguousarray(values, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.key_i)
+
+    def to_dict(self):
+        d = defaultdict(int)
+        names = self.names
+        for a, b, v in zip(self.key_i.tolist(), self.key_j.tolist(), self.values.tolist()):
+            d[(names[a], names[b])] = v
+        return d
+
+    def write_pickle(self, path, ht=None):
+        """full_links.pkl (or HT_links.pkl when the [n, 4] HT counters are given) with the native writer."""
+        from . import hicio
+        from ._lib import check, load, ptr
+        n = len(self.key_i)
+        check(load().hh_pickle_links(os.fsencode(path), hicio.names_blob(self.names), len(self.names), ptr(self.key_i) if n else None,
+                                     ptr(self.key_j) if n else None, n, ptr(self.values) if ht is None else None, None,
+                                     ptr(np.ascontiguousarray(ht, dtype=np.uint32)) if ht is not None else None))
+
+
+def ranked_group_links(link_dict, ctg_group_dict):
+    """For every contig with links to grouped contigs: [(group, links), ...] ranked by links descending, ties in the
+    order parse_link_dict (2245-2258) first meets the group -- what output_statistics sorts out of it (2373)."""
+    if not isinstance(link_dict, LinkArrays):
+        return {ctg: sorted(groups.items(), key=lambda x: x[1], reverse=True)
+                for ctg, groups in parse_link_dict(link_dict, ctg_group_dict).items()}
+    names = link_dict.names
+    gid = np.array([-1 if ctg_group_dict[nm] == "ungrouped" else ctg_group_dict[nm] for nm in names], dtype=np.int64)
+    ki, kj = link_dict.key_i.astype(np.int64), link_dict.key_j.astype(np.int64)
+    e = np.arange(len(ki), dtype=np.int64)
+    ctg = np.concatenate([ki, kj])
+    grp = np.concatenate([gid[kj], gid[ki]])                 # ci collects gj's group first, then cj collects gi's
+    pos = np.concatenate([2 * e, 2 * e + 1])
+    val = np.concatenate([link_dict.values, link_dict.values])
+    ok = grp >= 0
+    ctg, grp, pos, val = ctg[ok], grp[ok], pos[ok], val[ok]
+    if len(ctg) == 0:
+        return {}
+    ng = int(gid.max()) + 1
+    key = ctg * ng + grp
+    order = np.lexsort((pos, key))
+    ks = key[order]
+    starts = np.concatenate([[0], np.nonzero(np.diff(ks))[0] + 1])
+    sums = np.add.reduceat(val[order], starts)
+    first = pos[order][starts]
+    c_of, g_of = ks[starts] // ng, ks[starts] % ng
+    rank = np.lexsort((first, -sums, c_of))
+    c_of, g_of, sums = c_of[rank], g_of[rank], sums[rank]
+    cuts = np.concatenate([[0], np.nonzero(np.diff(c_of))[0] + 1, [len(c_of)]])
+    out = {}
+    g_list, s_list = g_of.tolist(), sums.tolist()
+    for k in range(len(cuts) - 1):
+        lo, hi = int(cuts[k]), int(cuts[k + 1])
+        out[names[int(c_of[lo])]] = list(zip(g_list[lo:hi], s_list[lo:hi]))
+    return out
+
+
 def cal_link_density(max_group, current_group, max_links, group_RE_sites, ctg_RE_sites):
     if max_group == current_group:
         return max_links / group_RE_sites
@@ -796,7 +882,7 @@ def output_statistics(fa_dict, link_dict, result_clusters_list):
                 ctg_group[ctg] = gid
                 group_RE[gid] += fa_dict[ctg][2] - 1
         add_ungrouped_ctgs(fa_dict, ctg_group)
-        group_links = parse_link_dict(link_dict, ctg_group)
+        group_links = ranked_group_links(link_dict, ctg_group)
         best_links, best_density, best_ratio = [], [], []
         for ctg in fa_dict:
             if ctg not in group_links:
@@ -804,7 +890,7 @@ def output_statistics(fa_dict, link_dict, result_clusters_list):
                 best_density.append((ctg, 0))
                 best_ratio.append((ctg, 0))
                 continue
-            ranked = sorted(group_links[ctg].items(), key=lambda x: x[1], reverse=True)
+            ranked = group_links[ctg]
             top_group, top_links = ranked[0]
             cur = ctg_group[ctg]
             ctg_RE = fa_dict[ctg][2]
@@ -983,30 +1069,54 @@ def run(args, log_file=None):
     else:
         alignments = hicio.pairs_batches(args.alignments, args.aln_format, name_index, inter_only=inter_only, threads=args.threads)
 
-    if split_ctg_set:
-        full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict, ctg_pair_to_frag = parse_alignments(
-            alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type,
-            build_clm=False)
-        table = parse_alignments.last_table
-        clm_src = parse_alignments.last_clm
-        names = parse_alignments.frag_names         # the matrix lives in fragment space from here on
+    # Two ways through the host side.  With --remove_allelic_links / --remove_concentrated_links the link dicts are
+    # edited on the host, so they are built as the reference's Python objects.  Otherwise nothing on the host needs
+    # them: the links stay arrays (LinkArrays), the pickles are written natively and no 10^7-entry dict is built.
+    edits_dicts = bool(args.remove_allelic_links or args.remove_concentrated_links)
+    ctg_coord_dict, ctg_pair_to_frag, flank_link_dict = None, None, None
+    if edits_dicts:
+        if split_ctg_set:
+            full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict, ctg_pair_to_frag = parse_alignments(
+                alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set, pos_int_type, dist_int_type,
+                build_clm=False)
+            table = parse_alignments.last_table
+            clm_src = parse_alignments.last_clm
+            names = parse_alignments.frag_names         # the matrix lives in fragment space from here on
+        else:
+            full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict = parse_alignments_for_ctgs(
+                alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_int_type, dist_int_type, build_clm=False)
+            table = parse_alignments_for_ctgs.last_table
+            clm_src = parse_alignments_for_ctgs.last_clm
+        output_pickle(HT_link_dict, "HT_link_dict", "HT_links.pkl")
+        del HT_link_dict, clm_dict
     else:
-        ctg_pair_to_frag = None
-        full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict = parse_alignments_for_ctgs(
-            alignments, fa_dict, args, frag_len_dict, Nx_frag_set, pos_int_type, dist_int_type, build_clm=False)
-        table = parse_alignments_for_ctgs.last_table
-        clm_src = parse_alignments_for_ctgs.last_clm
-
-    output_pickle(HT_link_dict, "HT_link_dict", "HT_links.pkl")
-    del HT_link_dict
+        logger.info("Parsing input alignments...")
+        if split_ctg_set:
+            st = _stream_bins(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set)
+        else:
+            st = _stream_contigs(alignments, fa_dict, args, frag_len_dict, Nx_frag_set)
+        fetched = st["table"].fetch()
+        full_link_dict = LinkArrays(st["names"], fetched["key_i"], fetched["key_j"], fetched["full"])
+        logger.info("Writing {} to {}...".format("HT_link_dict", "HT_links.pkl"))
+        full_link_dict.write_pickle("HT_links.pkl", ht=fetched["ht"])
+        del fetched
+        clm_src = (st["clm_rec"], st["names"], st["ctg_len"], st["rank"])
+        if split_ctg_set:
+            st["table"].close()                         # full / HT links were contig-level; the rest is fragment-level
+            table, names = st["ftab"], st["frag_names"]
+        else:
+            table = st["table"]
+        totals = table.fetch_ctg()
+        frag_link_dict = {names[c]: int(totals[c]) for c in np.nonzero(totals)[0].tolist()}
+        del st
     if args.quick_view:
         logger.info("Program finished in {}s".format(time.time() - start_time))
         return None
     write_clm(*clm_src, threads=args.threads)          # same file as output_clm(clm_dict), from the records, native
-    del clm_dict, clm_src
+    del clm_src
 
-    if args.normalize_by_nlinks:
-        normalize_by_nlinks(flank_link_dict, frag_link_dict)
+    if args.normalize_by_nlinks and edits_dicts:
+        normalize_by_nlinks(flank_link_dict, frag_link_dict)          # (the device normalises its own copy)
     if args.remove_concentrated_links:                      # 2899-2902
         for ctg_name_pair, data in ctg_coord_dict.items():
             if isinstance(data, list):
@@ -1019,7 +1129,11 @@ def run(args, log_file=None):
         filtered_frags = remove_allelic_HiC_links(fa_dict, ctg_coord_dict, full_link_dict, args, flank_link_dict, filtered_frags,
                                                   ctg_pair_to_frag if split_ctg_set else None)
     del ctg_coord_dict
-    output_pickle(full_link_dict, "full_link_dict", "full_links.pkl")
+    if isinstance(full_link_dict, LinkArrays):
+        logger.info("Writing {} to {}...".format("full_link_dict", "full_links.pkl"))
+        full_link_dict.write_pickle("full_links.pkl")
+    else:
+        output_pickle(full_link_dict, "full_link_dict", "full_links.pkl")
 
     if args.remove_allelic_links:
         # the host edited flank_link_dict: the matrix comes from the edited dict (hh_matrix_from_csc), same

@@ -1028,3 +1028,178 @@ extern "C" int hh_clm_from_records(const char* path, const char* names_blob, int
     }
     return HH_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// full_links.pkl / HT_links.pkl (output_pickle, 710-715) without building the Python dicts: a pickle stream
+// (protocol 3 opcodes) that loads as `defaultdict(int, {(name_i, name_j): value, ...})` in entry order.
+// Strings are memoised like pickle does, so the loaded keys share one str object per contig.
+//   mode 0: one entry per pair, value = values_i64[e] (or values_f64[e] when given);
+//   mode 1: HT_link_dict -- ht[e][4] = {HH, HT, TH, TT}; non-zero counters become the keys
+//           (name_i + '_H'|'_T', name_j + '_H'|'_T') (update_HT_link_dict, 404-416).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct pickle_out {
+    FILE* f;
+    std::vector<char> buf;
+    bool failed = false;
+    explicit pickle_out(FILE* fp) : f(fp) { buf.reserve(1u << 22); }
+    inline void flush_if(size_t need) {
+        if (buf.size() + need > (1u << 22)) flush();
+    }
+    void flush() {
+        if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) failed = true;
+        buf.clear();
+    }
+    inline void byte(uint8_t b) { buf.push_back((char)b); }
+    inline void raw(const void* p, size_t n) { buf.insert(buf.end(), (const char*)p, (const char*)p + n); }
+    inline void u32(uint32_t v) {
+        const uint8_t b[4] = {(uint8_t)v, (uint8_t)(v >> 8), (uint8_t)(v >> 16), (uint8_t)(v >> 24)};
+        raw(b, 4);
+    }
+    inline void put(uint32_t memo) {          // BINPUT / LONG_BINPUT
+        if (memo < 256) {
+            byte('q');
+            byte((uint8_t)memo);
+        } else {
+            byte('r');
+            u32(memo);
+        }
+    }
+    inline void get(uint32_t memo) {          // BINGET / LONG_BINGET
+        if (memo < 256) {
+            byte('h');
+            byte((uint8_t)memo);
+        } else {
+            byte('j');
+            u32(memo);
+        }
+    }
+    inline void integer(int64_t v) {
+        if (v >= 0 && v < 256) {
+            byte('K');
+            byte((uint8_t)v);
+        } else if (v >= 0 && v < 65536) {
+            byte('M');
+            byte((uint8_t)v);
+            byte((uint8_t)(v >> 8));
+        } else if (v >= -2147483648LL && v <= 2147483647LL) {
+            byte('J');
+            u32((uint32_t)(int32_t)v);
+        } else {                              // LONG1, 8 bytes little-endian two's complement
+            byte(0x8a);
+            byte(8);
+            for (int k = 0; k < 8; ++k) byte((uint8_t)((uint64_t)v >> (8 * k)));
+        }
+    }
+    inline void real(double d) {              // BINFLOAT: big-endian IEEE double
+        uint64_t u;
+        memcpy(&u, &d, 8);
+        byte('G');
+        for (int k = 7; k >= 0; --k) byte((uint8_t)(u >> (8 * k)));
+    }
+};
+}   // namespace
+
+extern "C" int hh_pickle_links(const char* path, const char* names_blob, int32_t n_names, const int32_t* key_i, const int32_t* key_j,
+                               int64_t n_entries, const int64_t* values_i64, const double* values_f64, const uint32_t* ht) {
+    if (!path || !names_blob || n_names <= 0 || n_entries < 0 || (n_entries > 0 && (!key_i || !key_j)) ||
+        (n_entries > 0 && !values_i64 && !values_f64 && !ht)) {
+        hh_set_error("hh_pickle_links: bad argument");
+        return HH_ERR_ARG;
+    }
+    std::vector<const char*> name((size_t)n_names);
+    std::vector<uint32_t> nlen((size_t)n_names);
+    {
+        const char* p = names_blob;
+        for (int32_t i = 0; i < n_names; ++i) {
+            name[(size_t)i] = p;
+            nlen[(size_t)i] = (uint32_t)strlen(p);
+            p += nlen[(size_t)i] + 1;
+        }
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        hh_set_error("hh_pickle_links: cannot create %s", path);
+        return HH_ERR_ARG;
+    }
+    pickle_out o(f);
+    // defaultdict.__reduce__ -> (defaultdict, (int,), None, None, items): GLOBAL GLOBAL TUPLE1 REDUCE, then SETITEMS batches
+    o.byte(0x80);
+    o.byte(3);
+    static const char g1[] = "ccollections\ndefaultdict\n";
+    static const char g2[] = "cbuiltins\nint\n";
+    o.raw(g1, sizeof(g1) - 1);
+    o.put(0);
+    o.raw(g2, sizeof(g2) - 1);
+    o.put(1);
+    o.byte(0x85);
+    o.put(2);
+    o.byte('R');
+    o.put(3);
+    uint32_t next_memo = 4;
+    const int variants = ht ? 2 : 1;            // HT mode: name_H and name_T are different strings
+    std::vector<uint32_t> memo((size_t)n_names * (size_t)variants, 0);
+    auto key_string = [&](int32_t c, int suffix) {   // suffix: -1 none, 0 '_H', 1 '_T'
+        uint32_t& m = memo[(size_t)c * (size_t)variants + (size_t)(suffix < 0 ? 0 : suffix)];
+        if (m) {
+            o.get(m);
+            return;
+        }
+        const uint32_t l = nlen[(size_t)c] + (suffix < 0 ? 0u : 2u);
+        o.byte('X');
+        o.u32(l);
+        o.raw(name[(size_t)c], nlen[(size_t)c]);
+        if (suffix >= 0) o.raw(suffix ? "_T" : "_H", 2);
+        m = next_memo++;
+        o.put(m);
+    };
+    int in_batch = 0;
+    auto open_batch = [&]() {
+        if (in_batch == 0) o.byte('(');
+    };
+    auto close_batch = [&](bool force) {
+        if (in_batch > 0 && (force || in_batch >= 1000)) {
+            o.byte('u');
+            in_batch = 0;
+        }
+    };
+    for (int64_t e = 0; e < n_entries; ++e) {
+        const int32_t a = key_i[e], b = key_j[e];
+        if ((uint32_t)a >= (uint32_t)n_names || (uint32_t)b >= (uint32_t)n_names) {
+            fclose(f);
+            hh_set_error("hh_pickle_links: entry %lld names a contig outside [0, %d)", (long long)e, n_names);
+            return HH_ERR_ARG;
+        }
+        o.flush_if((size_t)nlen[(size_t)a] + nlen[(size_t)b] + 256);
+        if (!ht) {
+            open_batch();
+            key_string(a, -1);
+            key_string(b, -1);
+            o.byte(0x86);
+            if (values_f64) o.real(values_f64[e]);
+            else o.integer(values_i64[e]);
+            ++in_batch;
+            close_batch(false);
+        } else {
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t v = ht[e * 4 + c];
+                if (!v) continue;
+                open_batch();
+                key_string(a, c >> 1);
+                key_string(b, c & 1);
+                o.byte(0x86);
+                o.integer((int64_t)v);
+                ++in_batch;
+                close_batch(false);
+            }
+        }
+    }
+    close_batch(true);
+    o.byte('.');
+    o.flush();
+    if (fclose(f) != 0 || o.failed) {
+        hh_set_error("hh_pickle_links: write to %s failed", path);
+        return HH_ERR_ARG;
+    }
+    return HH_OK;
+}

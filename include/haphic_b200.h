@@ -248,6 +248,12 @@ int hh_bam_close(hh_bam_reader* r);
  * threads (0 = all cores, at most 16). */
 int hh_clm_from_records(const char* path, const char* names_blob, int32_t n_names, const int32_t* rec, int64_t n_rec,
                         const int64_t* ctg_len, const int32_t* name_rank, int threads);
+/* full_links.pkl / HT_links.pkl (output_pickle, 710-715) written from the fetched arrays, without materialising the
+ * Python dicts: the file loads (pickle.load) as `defaultdict(int, {(name_i, name_j): value})` in entry order.
+ * Give values_i64 or values_f64 for one entry per pair, or ht[n_entries][4] = {HH, HT, TH, TT} for HT_link_dict, whose
+ * keys are (name_i + '_H'|'_T', name_j + '_H'|'_T') for the non-zero counters (update_HT_link_dict, 404-416). */
+int hh_pickle_links(const char* path, const char* names_blob, int32_t n_names, const int32_t* key_i, const int32_t* key_j,
+                    int64_t n_entries, const int64_t* values_i64, const double* values_f64, const uint32_t* ht);
 
 #ifdef __cplusplus
 }

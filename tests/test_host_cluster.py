@@ -307,3 +307,46 @@ def test_allelic_link_removal_matches_reference_golden(tag):
     assert [[a, b, v] for (a, b), v in flank.items()] == json.loads(str(g["flank_after_json"]))
     assert sorted(remaining) == json.loads(str(g["remaining_json"]))
     assert len(full) < len(json.loads(str(g["full_before_json"]))) // 2            # the case really removes links
+
+
+def test_array_backed_links_give_the_same_pickles_and_statistics(tmp_path, monkeypatch):
+    """run() keeps full_link_dict as arrays (LinkArrays): the native pickle loads as the reference's defaultdict and
+    output_statistics writes the same files as from the dict (ties between groups included)."""
+    import pickle
+    from haphic_b200 import cluster
+    g = load_golden("links_b.npz")
+    names = g["names"].tolist()
+    rng = np.random.default_rng(4)
+    ki, kj = g["full_keys"][:, 0], g["full_keys"][:, 1]
+    vals = g["full_vals"].copy()
+    vals[rng.random(len(vals)) < 0.5] = 1                       # plenty of ties between groups
+    la = cluster.LinkArrays(names, ki, kj, vals)
+    full = la.to_dict()
+    monkeypatch.chdir(tmp_path)
+    la.write_pickle("full_links.pkl")
+    with open("full_links.pkl", "rb") as f:
+        got = pickle.load(f)
+    assert type(got).__name__ == "defaultdict" and got.default_factory is int
+    assert got == full and list(got) == list(full)
+    ht = rng.integers(0, 3, size=(len(ki), 4)).astype(np.uint32)
+    la.write_pickle("HT_links.pkl", ht=ht)
+    with open("HT_links.pkl", "rb") as f:
+        got = pickle.load(f)
+    want = {}
+    for e, (a, b) in enumerate(zip(ki.tolist(), kj.tolist())):
+        for c in range(4):
+            if ht[e, c]:
+                want[(names[a] + "_" + "HT"[c >> 1], names[b] + "_" + "HT"[c & 1])] = int(ht[e, c])
+    assert got == want
+    # statistics: random groups of different sizes, some contigs ungrouped
+    fa_dict = {n: [None, int(l), int(r)] for n, l, r in zip(names, g["lengths"].tolist(), g["RE_sites"].tolist())}
+    lab = rng.integers(-1, 5, size=len(names))
+    clusters = [[[n for n, l in zip(names, lab.tolist()) if l == k], 0] for k in range(5)]
+    for tag, links in (("dict", full), ("arrays", la)):
+        os.makedirs(tmp_path / tag / "inflation_1.5")
+        monkeypatch.chdir(tmp_path / tag)
+        cluster.output_statistics(fa_dict, links, [("1.5", clusters)])
+    for fn in sorted(os.listdir(tmp_path / "dict" / "inflation_1.5")):
+        if fn.endswith(".txt"):
+            assert (tmp_path / "dict" / "inflation_1.5" / fn).read_text() == (tmp_path / "arrays" / "inflation_1.5" / fn).read_text(), fn
+    assert len(os.listdir(tmp_path / "arrays" / "inflation_1.5")) >= 4
