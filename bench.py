@@ -203,7 +203,10 @@ def run_reference(a):
     asm = synth.make_assembly(a.nchr, a.contigs, a.mean_len, seed=a.seed)
     rank = name_rank(asm.names)
     in_nx = np.ones(asm.n, np.uint8)
-    sample = synth.make_pairs_range(asm, 0, a.cpu_sample_pairs, seed=a.seed + 1, device="cpu").numpy()
+    # every step is a bounded sample of the workload; the whole --steps/--warmup run is sized for about two minutes of
+    # the single-threaded loop (~5 us per record)
+    per_step = max(200_000, min(a.cpu_sample_pairs, int(120.0 / max(1, a.steps + a.warmup) / 5e-6)))
+    sample = synth.make_pairs_range(asm, 0, per_step, seed=a.seed + 1, device="cpu").numpy()
     times = []
     for s in range(a.warmup + a.steps):
         v, dt = cpu_pairs_per_sec(asm, rank, in_nx, sample)
