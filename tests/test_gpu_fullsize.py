@@ -1,0 +1,153 @@
+"""GPU checks at BASELINE.json's full size (configs[2]: 50k contigs / 200M pairs, the bench workload): the oracle
+cannot follow there, so the path is held to size-independent properties -- conservation of counts, key order and
+uniqueness, an independent count of the same stream with torch.unique, equality of the routed (sharded) and the
+single-table builds, stochastic columns, a valid and chromosome-pure clustering, idempotence, and equality of the
+column-sharded and the single MCL run."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N_CONTIGS, N_CHR, MEAN_LEN, N_PAIRS, SEED = 50000, 24, 20000, 200_000_000, 12345
+
+
+@pytest.fixture(scope="module")
+def c3():
+    from haphic_b200 import synth
+    from haphic_b200._lib import Context
+    from haphic_b200.links import LinkTable, name_rank
+    ctx = Context(0)
+    asm = synth.make_assembly(N_CHR, N_CONTIGS, MEAN_LEN, seed=SEED)
+    rank = name_rank(asm.names)
+    in_nx = np.ones(asm.n, np.uint8)
+    rec = synth.make_pairs_range(asm, 0, N_PAIRS, seed=SEED + 1, device="cuda")
+    tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=int(0.45 * N_PAIRS))
+    tab.add(rec, asynchronous=True)
+    info = tab.finish()
+    yield dict(ctx=ctx, asm=asm, rank=rank, in_nx=in_nx, rec=rec, tab=tab, info=info)
+    tab.close()
+    ctx.close()
+
+
+def test_c3_link_table_properties(c3):
+    asm, rank, rec, tab, info = c3["asm"], c3["rank"], c3["rec"], c3["tab"], c3["info"]
+    n = asm.n
+    inter = rec[:, 0] != rec[:, 2]
+    n_used = int(inter.sum().item())
+    assert info.n_records == N_PAIRS and info.n_used == n_used
+    f = tab.fetch()
+    ki, kj = f["key_i"].astype(np.int64), f["key_j"].astype(np.int64)
+    full = f["full"].astype(np.int64)
+    assert len(ki) == info.nnz_full
+    assert int(full.sum()) == n_used                                  # every usable record is counted exactly once
+    assert (rank[ki] < rank[kj]).all()                                # keys are name-ordered (1629)
+    assert (np.diff(f["first_full"].astype(np.int64)) > 0).all()      # dict insertion order = first appearance
+    assert (f["flank"] <= f["full"]).all()
+    assert np.array_equal(f["ht"].astype(np.int64).sum(1), full)      # HH + HT + TH + TT = links of the pair
+    assert int(tab.fetch_ctg().sum()) == 2 * int(f["flank"].astype(np.int64).sum())
+    # the same stream counted independently (torch.unique over name-ordered pair keys)
+    rk = torch.from_numpy(rank.astype(np.int64)).cuda()
+    a, b = rec[inter, 0].long(), rec[inter, 2].long()
+    swap = rk[a] > rk[b]
+    key = torch.where(swap, b, a) * n + torch.where(swap, a, b)
+    del a, b, swap
+    uniq, counts = torch.unique(key, return_counts=True)
+    del key
+    tkey = ki * n + kj
+    order = np.argsort(tkey, kind="stable")
+    assert np.array_equal(tkey[order], uniq.cpu().numpy())
+    assert np.array_equal(full[order], counts.cpu().numpy())
+
+
+def test_c3_routed_build_equals_single(c3):
+    """Three shards routed to their owners, counted into disjoint partitions and adopted: the same table."""
+    from haphic_b200.links import LinkTable
+    ctx, asm, rank, in_nx, rec, tab = c3["ctx"], c3["asm"], c3["rank"], c3["in_nx"], c3["rec"], c3["tab"]
+    world = 3
+    want = tab.fetch()
+    cuts = np.linspace(0, N_PAIRS, world + 1).astype(np.int64)
+    tabs = [LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=int(0.2 * N_PAIRS)) for _ in range(world)]
+    routed = []
+    for r in range(world):
+        rec_out, pos_out, counts = tabs[r].route(rec[int(cuts[r]):int(cuts[r + 1])], int(cuts[r]), world)
+        routed.append((rec_out, pos_out, np.concatenate([[0], np.cumsum(counts)])))
+    parts, tots, n_used = [], [], 0
+    for d in range(world):
+        for r in range(world):
+            rec_out, pos_out, off = routed[r]
+            tabs[d].add_routed(rec_out[int(off[d]):int(off[d + 1])], pos_out[int(off[d]):int(off[d + 1])])
+        n_used += int(tabs[d].finish_partition().n_used)
+        ent, tot, _, _ = tabs[d].export()
+        parts.append(ent)
+        tots.append(tot)
+    del routed
+    info = tabs[0].adopt(torch.cat(parts), torch.stack(tots).sum(0), N_PAIRS, n_used, N_PAIRS)
+    del parts
+    assert (info.n_used, info.nnz_full, info.nnz_flank) == (c3["info"].n_used, c3["info"].nnz_full, c3["info"].nnz_flank)
+    got = tabs[0].fetch()
+    for k in want:
+        assert np.array_equal(want[k], got[k]), k
+    for t in tabs:
+        t.close()
+
+
+def test_c3_mcl_properties(c3):
+    from haphic_b200.mcl import Mcl, interpret_result
+    asm, tab = c3["asm"], c3["tab"]
+    keep = np.ones(asm.n, np.uint8)
+    index, n_linked = tab.linked_index(keep)
+    tail = np.nonzero(index < 0)[0].astype(np.int32)
+    mat = tab.to_matrix(keep, tail)
+    n = mat.n
+    assert n == asm.n
+    ctg_of = np.empty(n, np.int64)                   # matrix index -> contig id
+    ctg_of[index[index >= 0]] = np.nonzero(index >= 0)[0]
+    ctg_of[n_linked + np.arange(len(tail))] = tail
+    whole = Mcl(mat)
+    st = whole.run(2.0, 200, 1e-4)
+    assert st["converged"] and st["rounds"] < 200
+    fin = whole.result()
+    assert abs(np.asarray(fin.sum(axis=0)).ravel() - 1.0).max() < 1e-6          # column stochastic
+    clusters = interpret_result(fin)
+    assert clusters is not None                                                   # a partition of all contigs
+    assert sum(len(c) for c in clusters) == n and len(clusters) >= N_CHR
+    chrom = asm.chrom[ctg_of]
+    pure = sum(int(np.bincount(chrom[list(c)]).max()) for c in clusters)
+    assert pure >= 0.99 * n                                                       # clusters do not mix chromosomes
+    # idempotence: the same call again gives the same bytes
+    st2 = whole.run(2.0, 200, 1e-4)
+    fin2 = whole.result()
+    assert st2["rounds"] == st["rounds"]
+    assert np.array_equal(fin.indptr, fin2.indptr) and np.array_equal(fin.indices, fin2.indices) and np.array_equal(fin.data, fin2.data)
+    whole.close()
+    # two column shards stepped side by side (what two ranks do) end in the same matrix
+    cut = n // 2
+    s0, s1 = Mcl(mat, col_lo=0, col_hi=cut), Mcl(mat, col_lo=cut, col_hi=n)
+    s0.begin(2.0, 1e-4)
+    s1.begin(2.0, 1e-4)
+    rounds, replicated = 0, False
+    for it in range(200):
+        n0, _, d0 = s0.step(it)
+        n1, _, d1 = s1.step(it)
+        if not replicated:
+            b0, b1 = s0.pack(n0), s1.pack(n1)
+            s0.unpack(cut, n, *b1)
+            s1.unpack(0, cut, *b0)
+            del b0, b1
+        s0.commit()
+        s1.commit()
+        if not replicated and it >= 1 and n0 + n1 <= 8 * n:
+            s0.set_block(0, n)
+            s1.set_block(0, n)
+            replicated = True
+        rounds = it + 1
+        if it > 1 and max(d0, d1) <= 1e-8:
+            break
+    assert rounds == st["rounds"] and replicated
+    for s in (s0, s1):
+        got = s.result()
+        assert np.array_equal(got.indptr, fin.indptr) and np.array_equal(got.indices, fin.indices) and np.array_equal(got.data, fin.data)
+        s.close()
+    mat.close()
