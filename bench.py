@@ -130,6 +130,19 @@ def cpu_pairs_per_sec(asm, rank, in_nx, sample):
     return len(sample) / dt, dt
 
 
+def cpu_c_pairs_per_sec(asm, rank, in_nx, sample):
+    """The same loop as a single-core C port (oracle/haphic_oracle.c: hash table, entries in first-seen order,
+    software-prefetched): what an optimised CPU implementation of the counting step does.  Second of two calls (the
+    first one pays the page faults of the fresh buffers)."""
+    from oracle import haphic_oracle as orc
+    dt = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        orc.count_links_c(sample, asm.lengths, rank, in_nx, 500000)
+        dt = time.perf_counter() - t0
+    return len(sample) / dt, dt
+
+
 def cpu_mcl_iter_per_sec(m_csc, n_cols, inflation, pruning, seed=0):
     """One MCL iteration (expand -> inflate -> normalise -> prune, HapHiC_cluster.py:2029-2042) of the CPU
     port (scipy SpGEMM standing in for MKL) on a random sample of columns of the given iterate;
@@ -400,6 +413,14 @@ def run_b200(a):
         cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
                "sample": "first {} records through oracle.count_links_loop ({:.1f} s; the reference's loop is "
                          "single-threaded Python)".format(len(sample), dt)}
+        try:
+            big = rec[: 2 * a.cpu_sample_pairs].cpu().numpy()
+            vc, dtc = cpu_c_pairs_per_sec(asm, rank, in_nx, big)
+            cpu["c_port"] = {"value": vc, "unit": "pairs/s", "cores": 1,
+                             "sample": "first {} records through oracle/haphic_oracle.c, warm call {:.1f} s (single-core C "
+                                       "port of the same loop, not the reference's speed)".format(len(big), dtc)}
+        except Exception as exc:                       # no gcc on the box: the Python port above stands
+            cpu["c_port"] = {"unavailable": str(exc)[:200]}
         # MCL: iterate M_1 (after iteration 0) of the last inflation, a sample of columns
         tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
         tab.add(rec, asynchronous=True)

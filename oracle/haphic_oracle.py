@@ -84,6 +84,53 @@ def count_links_loop(pairs, lengths, name_rank, in_nx, flank_bp):
     return full, flank_d, HT, clm, ctg_links
 
 
+def build_c(force=False):
+    """gcc-compile oracle/haphic_oracle.c into oracle/_build/ (git-ignored) and return the ctypes library."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "haphic_oracle.c")
+    out_dir = os.path.join(here, "_build")
+    lib = os.path.join(out_dir, "libhaphic_oracle.so")
+    if force or not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", lib, src], check=True)
+    cdll = ctypes.CDLL(lib)
+    cdll.hho_count_links.restype = ctypes.c_int64
+    return cdll
+
+
+def count_links_c(pairs, lengths, name_rank, in_nx, flank_bp, cap=None):
+    """The same loop in plain C (oracle/haphic_oracle.c): single core, hash table, entries in first-seen order.
+    Returns the arrays of count_links_numpy that do not involve the clm distances."""
+    import ctypes as C
+    lib = build_c()
+    rec = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4)
+    n = len(lengths)
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    name_rank = np.ascontiguousarray(name_rank, dtype=np.int32)
+    in_nx = np.ascontiguousarray(in_nx, dtype=np.uint8)
+    cap = int(cap if cap is not None else max(16, min(len(rec), n * (n - 1) // 2)))
+    ki, kj = np.empty(cap, np.int32), np.empty(cap, np.int32)
+    full, flank = np.empty(cap, np.int64), np.empty(cap, np.int64)
+    ff, fl = np.empty(cap, np.int64), np.empty(cap, np.int64)
+    ht = np.empty((cap, 4), np.int64)
+    tot = np.empty(n, np.int64)
+    used = C.c_int64()
+    p = lambda x: x.ctypes.data_as(C.c_void_p)       # noqa: E731
+    nnz = lib.hho_count_links(p(rec), C.c_int64(len(rec)), C.c_int32(n), p(lengths), p(name_rank), p(in_nx), C.c_int64(flank_bp),
+                              C.c_int64(cap), p(ki), p(kj), p(full), p(flank), p(ff), p(fl), p(ht), p(tot), C.byref(used))
+    if nnz < 0:
+        raise MemoryError("count_links_c: more than {} contig pairs".format(cap))
+    ki, kj, full, flank, ff, fl, ht = ki[:nnz], kj[:nnz], full[:nnz], flank[:nnz], ff[:nnz], fl[:nnz], ht[:nnz]
+    sel = np.nonzero(flank > 0)[0]
+    sel = sel[np.argsort(fl[sel], kind="stable")]
+    return {"n_used": int(used.value), "full_keys": np.stack([ki, kj], 1), "full_vals": full, "full_first": ff,
+            "flank_keys": np.stack([ki[sel], kj[sel]], 1), "flank_vals": flank[sel], "flank_first": fl[sel],
+            "ht": ht, "ctg_link_total": tot}
+
+
 def count_links_numpy(pairs, lengths, name_rank, in_nx, flank_bp):
     """Vectorised restatement of the same loop; identical outputs as arrays.
 

@@ -53,6 +53,30 @@ def test_link_counts_match_reference(tag):
     assert sum((v for v in clm.values()), []) == r2["clm_vals"].tolist()
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_c_oracle_link_counts_match_reference(tag):
+    """oracle/haphic_oracle.c (the single-core C port timed as a CPU baseline) against the reference's dicts."""
+    g = load("links_{}.npz".format(tag))
+    names = g["names"].tolist()
+    rank = name_rank_of(names)
+    res = orc.count_links_c(g["pairs"], g["lengths"], rank, g["in_nx"], int(g["flank_kb"]) * 1000)
+    for k in ("full_keys", "full_vals", "flank_keys", "flank_vals"):
+        assert np.array_equal(res[k], g[k]), k
+    want = {tuple(k): int(v) for k, v in zip(g["HT_keys"].tolist(), g["HT_vals"].tolist())}
+    got = {}
+    for (i, j), row in zip(res["full_keys"].tolist(), res["ht"].tolist()):
+        for c, v in enumerate(row):
+            if v:
+                got[(i, c >> 1, j, c & 1)] = v
+    assert got == want
+    tot = np.zeros(len(names), np.int64)
+    tot[g["ctg_link_ids"]] = g["ctg_link_vals"]
+    assert np.array_equal(res["ctg_link_total"], tot)
+    ref = orc.count_links_numpy(g["pairs"], g["lengths"], rank, g["in_nx"], int(g["flank_kb"]) * 1000)
+    assert res["n_used"] == ref["n_used"] and np.array_equal(res["full_first"], ref["full_first"])
+    assert np.array_equal(res["flank_first"], ref["flank_first"])
+
+
 def test_normalize_by_nlinks_matches_reference():
     g = load("links_b.npz")
     rank = name_rank_of(g["names"].tolist())
