@@ -54,12 +54,14 @@ def cal_concentration_adj_ratio(coord_list, bin_width=10000):
 # record_coord_pairs (454-471) over the whole record array
 # ------------------------------------------------------------------------------------------------
 
-def coord_pair_dict(rec, names, ctg_len, rank, args, pos_int_type="int32"):
+def coord_pair_dict(rec, names, ctg_len, rank, args, pos_int_type="int32", skip_below=0):
     """ctg_coord_dict as parse_alignments(_for_ctgs) returns it (1609-1611, 1652-1653): for every contig pair in
     first-seen order either the ``array`` of its (coord_i, coord_j) values in stream order (fewer than
     ``args.max_read_pairs`` links) or ``[concordance_ratio, adj_ratio]`` computed from the first max_read_pairs links.
 
-    ``rec`` holds the usable inter-contig records (int32 [m, 4], stream order, ids into ``names``)."""
+    ``rec`` holds the usable inter-contig records (int32 [m, 4], stream order, ids into ``names``).
+    ``skip_below`` > 0 leaves out the pairs with fewer links than that: remove_allelic_HiC_links only writes a debug
+    line for pairs under ``min_read_pairs``, so run() skips them unless --verbose (10^7 tiny Python arrays otherwise)."""
     code = "i" if pos_int_type == "int32" else "l"
     out = defaultdict(lambda: array(code))
     if len(rec) == 0:
@@ -77,6 +79,8 @@ def coord_pair_dict(rec, names, ctg_len, rank, args, pos_int_type="int32"):
     starts = np.concatenate([[0], np.nonzero(np.diff(ks))[0] + 1])
     ends = np.concatenate([starts[1:], [len(ks)]])
     first_seen = np.argsort(order[starts], kind="stable")
+    if skip_below > 0:
+        first_seen = first_seen[(ends - starts)[first_seen] >= skip_below]
     limit = int(args.max_read_pairs)
     xy = np.empty((len(ks), 2), dtype=np.int64)
     xy[:, 0] = ci[order]

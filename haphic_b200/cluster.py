@@ -240,6 +240,11 @@ def fragment_layout(fa_dict, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set
     return frag_names, np.asarray(frag_base, np.int32), frag_len, name_rank(frag_names), in_nx
 
 
+# run() sets this to --min_read_pairs (unless --verbose): contig pairs with fewer links only get a debug line in
+# remove_allelic_HiC_links, so their coordinate arrays are not materialised.  0 = the reference's complete dict.
+_COORD_SKIP = [0]
+
+
 def _stream_bins(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag_set, split_ctg_set):
     """Count one pass of the alignments into the contig-level table (full / HT links) and the fragment-level table
     (flank links, per-fragment totals).  Returns a dict with both tables, the usable records and the fragment layout."""
@@ -277,7 +282,7 @@ def parse_alignments(alignments, fa_dict, args, bin_size, frag_len_dict, Nx_frag
     ctg_coord_dict, ctg_pair_to_frag = defaultdict(list), defaultdict(set)
     if args.remove_allelic_links or args.remove_concentrated_links:
         from . import allelic
-        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, rank, args, pos_int_type)
+        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, rank, args, pos_int_type, skip_below=_COORD_SKIP[0])
         if args.remove_allelic_links:
             ctg_pair_to_frag = allelic.ctg_pair_to_frag_dict(clm_rec, names, rank, frag_names, st["frag_base"], st["frag_rank"],
                                                              int(bin_size))
@@ -374,7 +379,7 @@ def parse_alignments_for_ctgs(alignments, fa_dict, args, ctg_len_dict, Nx_ctg_se
     ctg_coord_dict = defaultdict(list)
     if args.remove_allelic_links or args.remove_concentrated_links:
         from . import allelic
-        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, rank, args, pos_int_type)
+        ctg_coord_dict = allelic.coord_pair_dict(clm_rec, names, ctg_len, rank, args, pos_int_type, skip_below=_COORD_SKIP[0])
     return full_link_dict, flank_link_dict, HT_link_dict, clm_dict, ctg_link_dict, ctg_coord_dict
 
 
@@ -1074,6 +1079,7 @@ def run(args, log_file=None):
     # them: the links stay arrays (LinkArrays), the pickles are written natively and no 10^7-entry dict is built.
     edits_dicts = bool(args.remove_allelic_links or args.remove_concentrated_links)
     ctg_coord_dict, ctg_pair_to_frag, flank_link_dict = None, None, None
+    _COORD_SKIP[0] = 0 if (args.verbose or args.remove_concentrated_links) else int(args.min_read_pairs)
     if edits_dicts:
         if split_ctg_set:
             full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict, ctg_pair_to_frag = parse_alignments(

@@ -307,6 +307,14 @@ def test_allelic_link_removal_matches_reference_golden(tag):
     assert [[a, b, v] for (a, b), v in flank.items()] == json.loads(str(g["flank_after_json"]))
     assert sorted(remaining) == json.loads(str(g["remaining_json"]))
     assert len(full) < len(json.loads(str(g["full_before_json"]))) // 2            # the case really removes links
+    # run() leaves out the pairs below --min_read_pairs (they only get a debug line): same removals
+    sparse = allelic.coord_pair_dict(rec, names, lengths, rank, args, skip_below=args.min_read_pairs)
+    assert len(sparse) < len(coord) and all(k in coord for k in sparse)
+    full2 = {(a, b): v for a, b, v in json.loads(str(g["full_before_json"]))}
+    flank2 = {(a, b): v for a, b, v in json.loads(str(g["flank_before_json"]))}
+    remaining2 = cluster.remove_allelic_HiC_links(fa_dict, sparse, full2, args, flank2, set(json.loads(str(g["filtered_json"]))), c2f,
+                                                  logger=logging.getLogger("t"))
+    assert list(full2.items()) == list(full.items()) and list(flank2.items()) == list(flank.items()) and remaining2 == remaining
 
 
 def test_array_backed_links_give_the_same_pickles_and_statistics(tmp_path, monkeypatch):
