@@ -358,3 +358,63 @@ def test_array_backed_links_give_the_same_pickles_and_statistics(tmp_path, monke
         if fn.endswith(".txt"):
             assert (tmp_path / "dict" / "inflation_1.5" / fn).read_text() == (tmp_path / "arrays" / "inflation_1.5" / fn).read_text(), fn
     assert len(os.listdir(tmp_path / "arrays" / "inflation_1.5")) >= 4
+
+
+def _python_pairs_reference(text, names, inter_only):
+    """pairs_generator / pairs_generator_inter_ctgs (HapHiC_cluster.py:1539-1583) restated literally in Python:
+    str.split(), int(), skip blank and '#' lines, BED lines for every data line, `ref != mref` filter."""
+    ids = {n: i for i, n in enumerate(names)}
+    rec, bed = [], []
+    for line in text.split("\n"):
+        if not line.strip() or line.startswith("#"):
+            continue
+        cols = line.split()
+        ref, pos, mref, mpos = cols[1], int(cols[2]) - 1, cols[3], int(cols[4]) - 1
+        bed.append("{0}\t{1}\t{1}\t{2}/1\t255\t.\n{3}\t{4}\t{4}\t{2}/2\t255\t.\n".format(ref, pos, cols[0], mref, mpos))
+        if inter_only and ref == mref:
+            continue
+        rec.append((ids.get(ref, -1), pos, ids.get(mref, -1), mpos))
+    return np.array(rec, dtype=np.int64).reshape(-1, 4), "".join(bed)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_native_pairs_tokenizer_fuzz_against_python_semantics(tmp_path, seed):
+    """Randomly formatted .pairs text (mixed blanks, CRLF, comment and blank lines in the middle, signs / underscores /
+    leading zeros in the integers, extra columns, unknown and repeated contig names, missing final newline) must give
+    the records and the BED text that Python's str.split() / int() give."""
+    import random
+    from haphic_b200 import hicio
+    rnd = random.Random(seed)
+    names = ["ctg{}".format(k) for k in range(40)] + ["scaffold_1|arrow", "x", "chr1_bin2", "A" * 60]
+    pool = names + ["unknown_ctg", "ctg1x", "ctg"]
+
+    def blank():
+        return rnd.choice([" ", "\t", "  ", "\t\t", " \t", "\x0b", "\x0c"])
+
+    def integer():
+        v = rnd.randrange(1, 2_000_000)
+        return rnd.choice(["{}", "+{}", "0{}", "{:_}", "00{}"]).format(v)
+
+    lines = ["## pairs format v1.0", "#columns: readID chr1 pos1 chr2 pos2 strand1 strand2"]
+    for k in range(30000):
+        roll = rnd.random()
+        if roll < 0.02:
+            lines.append(rnd.choice(["", "   ", "\t", "# a comment", "#"]))
+            continue
+        a = rnd.choice(pool)
+        b = a if rnd.random() < 0.2 else rnd.choice(pool)
+        cols = ["read{}".format(k), a, integer(), b, integer()] + ["+", "-", "extra"][: rnd.randrange(0, 4)]
+        line = (blank() if rnd.random() < 0.1 else "") + "".join(c + blank() for c in cols[:-1]) + cols[-1]
+        lines.append(line + ("\r" if rnd.random() < 0.1 else "") + (blank() if rnd.random() < 0.1 else ""))
+    text = "\n".join(lines) + ("" if seed == 2 else "\n")
+    path = tmp_path / "fuzz.pairs"
+    path.write_bytes(text.encode())
+    idx = hicio.NameIndex(names)
+    for inter_only in (True, False):
+        want_rec, want_bed = _python_pairs_reference(text, names, inter_only)
+        bed = str(tmp_path / "fuzz.bed")
+        got = list(hicio.pairs_batches(str(path), "pairs", idx, bed_path=bed, batch_lines=4096, inter_only=inter_only, threads=3))
+        got = np.concatenate(got) if got else np.zeros((0, 4), np.int32)
+        assert np.array_equal(got.astype(np.int64), want_rec)
+        with open(bed) as f:
+            assert f.read() == want_bed
