@@ -72,12 +72,10 @@ def pairs_batches(path, aln_format, name_to_id, bed_path="alignments.bed", batch
 
 
 class NameIndex:
-    """name -> dense id with vectorised lookup (pandas Categorical codes; -1 = unknown)."""
+    """The contig names in id order (= FASTA order) with a name -> id lookup (-1 = unknown)."""
 
     def __init__(self, names):
-        import pandas as pd
         self.names = list(names)
-        self.categories = pd.Index(self.names)
         self._d = {n: i for i, n in enumerate(self.names)}
 
     def __getitem__(self, name):
