@@ -268,7 +268,6 @@ def ncu_traffic(workload):
 
 def run_b200(a):
     import torch
-    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank_id = int(os.environ.get("RANK", "0"))

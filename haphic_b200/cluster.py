@@ -26,7 +26,6 @@ import random
 import sys
 import time
 from collections import OrderedDict, defaultdict
-from decimal import Decimal
 from itertools import combinations
 from math import ceil, inf
 

@@ -13,7 +13,7 @@ from collections import defaultdict
 import numpy as np
 
 from . import _lib
-from ._lib import Context, HHError, LinksInfo, check, load, ptr
+from ._lib import Context, LinksInfo, check, load, ptr
 
 NONE32 = 0xFFFFFFFF
 

@@ -11,7 +11,7 @@ from decimal import Decimal
 
 import numpy as np
 
-from ._lib import HHError, MclResult, check, load, ptr
+from ._lib import MclResult, check, load, ptr
 from .links import LinkMatrix
 
 
