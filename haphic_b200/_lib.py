@@ -31,6 +31,14 @@ class MclResult(C.Structure):
                 ("bytes", C.c_int64)]
 
 
+class PreexpInfo(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("a_planes", C.c_int32), ("passes", C.c_int32), ("cta_group", C.c_int32),
+                ("stages", C.c_int32), ("chunk_kb", C.c_int32), ("total_ms", C.c_float), ("densify_ms", C.c_float),
+                ("gemm_ms", C.c_float), ("flops", C.c_double), ("products", C.c_int64)]
+
+
+HH_PREEXP_AUTO, HH_PREEXP_SPARSE, HH_PREEXP_DENSE = 0, 1, 2
+
 # name -> (restype, argtypes): every symbol include/haphic_b200.h declares
 _P = C.c_void_p
 _SIGNATURES = {
@@ -66,6 +74,8 @@ _SIGNATURES = {
     "hh_matrix_fetch_csc": (C.c_int, [_P, _P, _P, _P]),
     "hh_matrix_destroy": (C.c_int, [_P]),
     "hh_mcl_create": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "hh_mcl_create_ex": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, C.c_int, C.POINTER(_P)]),
+    "hh_mcl_preexp_info": (C.c_int, [_P, C.POINTER(PreexpInfo)]),
     "hh_mcl_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                               C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "hh_mcl_fetch_m0": (C.c_int, [_P, _P, _P, _P]),

@@ -1,0 +1,630 @@
+// Dense-block pre-expansion on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// What it computes (scripts/HapHiC_cluster.py:2144-2149, dense mode 2035 / 2149): the one-off pre-expansion
+//     M1 = M0 . M0,   M0 = normalize(link_matrix, 'l1', axis=0)
+// for the part of the product that is a true GEMM.  With C the symmetric link matrix and s its column sums,
+//     M1[r, c] = ( sum_k C[r, k] * M0[c, k] ) / s[c]          (C[k, c] = C[c, k],  M0[c, k] = C[c, k] / s[k])
+// so S[r, c] = sum_k C[r, k] * M0[c, k] is a "TN" GEMM of two row-major (K-major) n x n operands and S is symmetric:
+// only tiles on or above the diagonal are computed; the epilogue writes M1[r, c] = S / s[c] and the mirror image
+// M1[c, r] = S / s[r].
+//
+// Precision.  The reference multiplies fp32 by fp32.  Tensor cores take bf16, so each operand is split into bf16
+// "planes" whose sum is the fp32 value EXACTLY:
+//   A = C      link counts are integers: <= 256 -> one plane, < 65536 -> two, anything else (weights) three;
+//   B = M0     three planes (8 + 8 + 8 significant bits).
+// A bf16 x bf16 product is exact in fp32, so the passes (plane_a, plane_b) below reproduce the fp32 product up to
+// dropped terms of relative size 2^-24.  The accumulation inside the tensor core is not IEEE round-to-nearest, so a
+// tile's K range is cut into chunks: each chunk accumulates in TMEM, is drained by the epilogue warps and added to fp32
+// REGISTER accumulators with round-to-nearest (HH_GEMM_CHUNK k-blocks per chunk).
+//
+// Kernel shape (one persistent CTA pair per two SMs, cta_group::2):
+//   tile 256 x 256 (128 rows of A and 128 rows of B per CTA), BLOCK_K = 64 bf16 = one 128-byte swizzle atom;
+//   warp 0   TMA producer: per k-block one 128x64 box per operand plane (cp.async.bulk.tensor, SWIZZLE_128B)
+//            into a ring of shared-memory stages, completion on the LEADER CTA's mbarrier;
+//   warp 1   allocates TMEM; in the leader CTA one thread issues tcgen05.mma (M=256, N=256, K=16) for every pass and
+//            commits to the stage's "empty" barrier (multicast to both CTAs) and to the chunk's "full" barrier;
+//   warps 2-9  epilogue: tcgen05.ld the chunk (32 lanes x 128 columns per warp), add into registers, release the TMEM
+//            buffer; after the last chunk scale and store the tile and its mirror image.
+// HH_GEMM_CG=1 selects a single-CTA variant (tile 128 x 128, cta_group::1) with the same shared-memory layout.
+#include "hh_common.cuh"
+#include "hh_internal.cuh"
+#include "hh_gemm.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+#include <algorithm>
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t hg_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void hg_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t hg_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void hg_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hg_fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void hg_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void hg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hg_mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void hg_mbar_arrive_cluster(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+
+template <int CG>
+__device__ __forceinline__ void hg_tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t mbar, int c0, int c1, int c2) {
+    if (CG == 2) {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+            "l"(tm), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+    } else {
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                     "l"(tm), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void hg_prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+template <int CG>
+__device__ __forceinline__ void hg_tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    if (CG == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void hg_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void hg_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void hg_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 operands, fp32 accumulator
+template <int CG>
+__device__ __forceinline__ void hg_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// all MMAs issued so far by this thread -> arrive on an mbarrier when they have completed (both CTAs of the pair)
+template <int CG>
+__device__ __forceinline__ void hg_umma_commit(uint32_t bar) {
+    if (CG == 2) {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                     "h"((uint16_t)3)
+                     : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+}
+// 32 lanes x 32 consecutive columns of TMEM -> 32 registers per thread (lane = TMEM lane, register = column)
+__device__ __forceinline__ void hg_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void hg_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor of a K-major tile stored as [rows][64 bf16] with the 128-byte swizzle TMA applies:
+// 8-row groups 1024 bytes apart (SBO), version 1 (Blackwell), layout SWIZZLE_128B.  The start address moves by 32 bytes
+// per K = 16 step inside the swizzle atom.
+__device__ __forceinline__ uint64_t hg_make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;               // leading byte offset: unused for swizzled K-major layouts
+    d |= (uint64_t)(1024 >> 4) << 32;     // stride byte offset
+    d |= (uint64_t)1 << 46;               // descriptor version
+    d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ---------------------------------------------------------------------------------------------------------------------
+#define HG_THREADS 320
+#define HG_PLANE_BYTES 16384        // 128 rows x 64 bf16
+#define HG_MAX_STAGES 4
+
+struct hh_gemm_args {
+    const hh_gemm_item* items;
+    int n_items;
+    int n;                 // matrix dimension
+    int na;                // planes of A per k-block (1..3); B always has 3
+    int npass;
+    int pa[8], pb[8];      // pass list: plane of A, plane of B
+    int chunk_kb;          // k-blocks accumulated in TMEM before they are drained into registers
+    int stages;
+    float* m1;             // dense column-major [ld x (col_hi - col_lo)]
+    long long ld;
+    int col_lo, col_hi;
+    const float* inv_s;    // 1 / column sum
+};
+
+template <int CG>
+__global__ void __launch_bounds__(HG_THREADS, 1)
+hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const hh_gemm_args a) {
+    constexpr int BN = 128 * CG;              // tile columns (= TMEM columns per accumulator buffer)
+    constexpr int CW = BN / 2;                // columns per epilogue warp
+    constexpr uint32_t TMEM_COLS = 2 * BN;    // two accumulator buffers
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+
+    extern __shared__ uint8_t hg_smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[HG_MAX_STAGES];
+    __shared__ __align__(8) uint64_t s_empty[HG_MAX_STAGES];
+    __shared__ __align__(8) uint64_t s_tfull[2];
+    __shared__ __align__(8) uint64_t s_tempty[2];
+    __shared__ uint32_t s_tmem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? hg_cluster_ctarank() : 0u;
+    const int pair = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+    const int npairs = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
+    const uint32_t smem_base = (hg_smem_u32(hg_smem_raw) + 1023u) & ~1023u;
+    const uint32_t stage_bytes = (uint32_t)(a.na + 3) * HG_PLANE_BYTES;
+    const int S = a.stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            hg_mbar_init(hg_smem_u32(&s_full[s]), 1);
+            hg_mbar_init(hg_smem_u32(&s_empty[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            hg_mbar_init(hg_smem_u32(&s_tfull[b]), 1);
+            hg_mbar_init(hg_smem_u32(&s_tempty[b]), 8 * CG);     // every epilogue warp of the pair
+        }
+        hg_fence_barrier_init();
+        hg_prefetch_tmap(&tmA);
+        hg_prefetch_tmap(&tmB);
+    }
+    __syncwarp();
+    if (warp == 1) hg_tmem_alloc<CG>(hg_smem_u32(&s_tmem), TMEM_COLS);
+    hg_tc_fence_before();
+    if (CG == 2) hg_cluster_sync();
+    else __syncthreads();
+    hg_tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t full0 = (CG == 2) ? hg_mapa(hg_smem_u32(&s_full[0]), 0) : hg_smem_u32(&s_full[0]);
+            for (int it = pair; it < a.n_items; it += npairs) {
+                const hh_gemm_item w = a.items[it];
+                const int rowA = w.m_tile * (128 * CG) + (int)rank * 128;
+                const int rowB = w.n_tile * (128 * CG) + (int)rank * 128;
+                for (int seg = 0; seg < 2; ++seg) {
+                    for (int kb = w.kb_lo[seg]; kb < w.kb_hi[seg]; ++kb) {
+                        hg_mbar_wait(hg_smem_u32(&s_empty[s]), ph ^ 1u);
+                        if (rank == 0) hg_mbar_expect_tx(hg_smem_u32(&s_full[s]), stage_bytes * CG);
+                        const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
+                        const uint32_t bar = full0 + (uint32_t)s * 8u;
+                        for (int p = 0; p < a.na; ++p) hg_tma_load_3d<CG>(dst + (uint32_t)p * HG_PLANE_BYTES, &tmA, bar, kb * 64, rowA, p);
+                        for (int p = 0; p < 3; ++p)
+                            hg_tma_load_3d<CG>(dst + (uint32_t)(a.na + p) * HG_PLANE_BYTES, &tmB, bar, kb * 64, rowB, p);
+                        if (++s == S) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();     // the other lanes wait here: the teardown barrier is .aligned
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------- MMA issuer
+        if (rank == 0 && lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            uint32_t g = 0;     // running chunk counter: TMEM buffer g & 1, phase (g >> 1) & 1
+            for (int it = pair; it < a.n_items; it += npairs) {
+                const hh_gemm_item w = a.items[it];
+                int in_chunk = 0;
+                const int total = (w.kb_hi[0] - w.kb_lo[0]) + (w.kb_hi[1] - w.kb_lo[1]);
+                for (int t = 0; t < total; ++t) {
+                    const uint32_t buf = g & 1u;
+                    if (in_chunk == 0) {
+                        hg_mbar_wait(hg_smem_u32(&s_tempty[buf]), ((g >> 1) & 1u) ^ 1u);
+                        hg_tc_fence_after();
+                    }
+                    hg_mbar_wait(hg_smem_u32(&s_full[s]), ph);
+                    hg_tc_fence_after();
+                    const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+                    const uint32_t d = tmem_base + buf * (uint32_t)BN;
+                    for (int p = 0; p < a.npass; ++p) {
+                        const uint64_t ad = hg_make_desc(st + (uint32_t)a.pa[p] * HG_PLANE_BYTES);
+                        const uint64_t bd = hg_make_desc(st + (uint32_t)(a.na + a.pb[p]) * HG_PLANE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) hg_umma<CG>(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (in_chunk | p | k) ? 1u : 0u);
+                    }
+                    hg_umma_commit<CG>(hg_smem_u32(&s_empty[s]));      // the stage is free once these MMAs have read it
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                    if (++in_chunk == a.chunk_kb || t + 1 == total) {
+                        hg_umma_commit<CG>(hg_smem_u32(&s_tfull[buf]));    // chunk complete -> epilogue
+                        in_chunk = 0;
+                        ++g;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------------------------------- epilogue
+        const int e = warp - 2;
+        const int quarter = warp & 3;          // TMEM lanes this warp may touch: 32 * (warp id % 4)
+        const int half = e >> 2;               // column half of the tile
+        const uint32_t lane_addr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * CW);
+        const uint32_t tempty0 = (CG == 2) ? hg_mapa(hg_smem_u32(&s_tempty[0]), 0) : hg_smem_u32(&s_tempty[0]);
+        uint32_t g = 0;
+        float acc[CW];
+        for (int it = pair; it < a.n_items; it += npairs) {
+            const hh_gemm_item w = a.items[it];
+            const int total = (w.kb_hi[0] - w.kb_lo[0]) + (w.kb_hi[1] - w.kb_lo[1]);
+            const int nchunks = (total + a.chunk_kb - 1) / a.chunk_kb;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+            for (int ch = 0; ch < nchunks; ++ch, ++g) {
+                const uint32_t buf = g & 1u;
+                hg_mbar_wait(hg_smem_u32(&s_tfull[buf]), (g >> 1) & 1u);
+                hg_tc_fence_after();
+#pragma unroll
+                for (int q = 0; q < CW / 32; ++q) {
+                    uint32_t v[32];
+                    hg_tmem_ld32(tmem_base + buf * (uint32_t)BN + lane_addr + (uint32_t)(q * 32), v);
+                    hg_tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[q * 32 + j] = __fadd_rn(acc[q * 32 + j], __uint_as_float(v[j]));
+                }
+                hg_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) hg_mbar_arrive_cluster(tempty0 + buf * 8u);
+                    else hg_mbar_arrive_local(tempty0 + buf * 8u);
+                }
+            }
+            // ---- scale and store: M1[r, c] = S / s[c]; mirror image M1[c, r] = S / s[r]
+            const int r = w.m_tile * (128 * CG) + (int)rank * 128 + quarter * 32 + lane;
+            const int c0 = w.n_tile * BN + half * CW;
+            if (r < a.n) {
+                if (w.flags & HH_GEMM_DIRECT) {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        const int c = c0 + j;
+                        if (c < a.n && c >= a.col_lo && c < a.col_hi) a.m1[(size_t)(c - a.col_lo) * (size_t)a.ld + (size_t)r] = acc[j] * __ldg(a.inv_s + c);
+                    }
+                }
+                if ((w.flags & HH_GEMM_MIRROR) && r >= a.col_lo && r < a.col_hi) {
+                    const float sr = __ldg(a.inv_s + r);
+                    float* __restrict__ dst = a.m1 + (size_t)(r - a.col_lo) * (size_t)a.ld;
+#pragma unroll
+                    for (int j = 0; j < CW; j += 4) {
+                        const int c = c0 + j;
+                        if (c + 3 < a.n) {
+                            *reinterpret_cast<float4*>(dst + c) = make_float4(acc[j] * sr, acc[j + 1] * sr, acc[j + 2] * sr, acc[j + 3] * sr);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (c + q < a.n) dst[c + q] = acc[j + q] * sr;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- teardown: every MMA has completed (the epilogues consumed the last chunk), free TMEM
+    hg_tc_fence_before();
+    if (CG == 2) hg_cluster_sync();
+    else __syncthreads();
+    hg_tc_fence_after();
+    if (warp == 1) hg_tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// operand preparation: CSC of the symmetric link matrix -> dense row-major bf16 planes
+// ---------------------------------------------------------------------------------------------------------------------
+// column sums in fp64 (sklearn normalize accumulates in double, 2144) and their fp32 reciprocals
+__global__ void hh_k_gemm_colsum(const int64_t* __restrict__ colptr, const float* __restrict__ val, int n, double* __restrict__ s,
+                                 float* __restrict__ inv_s) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const int lane = threadIdx.x & 31;
+    double t = 0.0;
+    for (int64_t p = colptr[c] + lane; p < colptr[c + 1]; p += 32) t += fabs((double)val[p]);
+    t = hh_warp_sum(t);
+    if (lane == 0) {
+        s[c] = t;
+        inv_s[c] = (t != 0.0) ? (float)(1.0 / t) : 1.f;
+    }
+}
+
+// flags[0] |= 1 if some value is not an integer in [0, 65536); flags[0] |= 2 if some value exceeds 256
+__global__ void hh_k_gemm_valstats(const float* __restrict__ val, int64_t nnz, int* __restrict__ flags) {
+    int f = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        const float v = val[p];
+        if (!(v >= 0.f && v < 65536.f && v == floorf(v))) f |= 1;
+        if (v > 256.f) f |= 2;
+    }
+    f = __reduce_or_sync(HH_FULL_MASK, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
+__device__ __forceinline__ void hg_split3(float x, unsigned short& h1, unsigned short& h2, unsigned short& h3) {
+    const uint32_t b1 = __float_as_uint(x) & 0xFFFF0000u;          // bf16 by truncation: the remainder stays exact
+    const float r1 = x - __uint_as_float(b1);
+    const uint32_t b2 = __float_as_uint(r1) & 0xFFFF0000u;
+    const float r2 = r1 - __uint_as_float(b2);
+    h1 = (unsigned short)(b1 >> 16);
+    h2 = (unsigned short)(b2 >> 16);
+    h3 = (unsigned short)(__float_as_uint(r2) >> 16);              // at most 8 significant bits are left
+}
+
+// one warp per column c of the CSC = row c of both operands:  A[c, k] = C[c, k],  B[c, k] = fp32(C[c, k] / s[k])
+__global__ void hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row, const float* __restrict__ val, int n,
+                                  const double* __restrict__ s, unsigned short* __restrict__ A, int na, unsigned short* __restrict__ B,
+                                  long long ldk, long long plane) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const int lane = threadIdx.x & 31;
+    unsigned short* __restrict__ a0 = A + (size_t)c * (size_t)ldk;
+    unsigned short* __restrict__ b0 = B + (size_t)c * (size_t)ldk;
+    for (int64_t p = colptr[c] + lane; p < colptr[c + 1]; p += 32) {
+        const int k = row[p];
+        const float v = val[p];
+        unsigned short h1, h2, h3;
+        hg_split3(v, h1, h2, h3);
+        a0[k] = h1;
+        if (na > 1) a0[(size_t)plane + k] = h2;
+        if (na > 2) a0[2 * (size_t)plane + k] = h3;
+        const double sk = s[k];
+        const float y = (sk != 0.0) ? (float)((double)v / sk) : v;
+        hg_split3(y, h1, h2, h3);
+        b0[k] = h1;
+        b0[(size_t)plane + k] = h2;
+        b0[2 * (size_t)plane + k] = h3;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*hg_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int hg_encode(CUtensorMap* tm, void* base, int n, long long ldk, long long plane_elems, int planes) {
+    static hg_encode_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        HH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        HH_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, HH_ERR_CUDA, "hh_gemm: the driver does not export cuTensorMapEncodeTiled");
+        fn = reinterpret_cast<hg_encode_fn>(p);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldk * 2ull, (cuuint64_t)plane_elems * 2ull};
+    const cuuint32_t box[3] = {64u, 128u, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HH_REQUIRE(r == CUDA_SUCCESS, HH_ERR_CUDA, "hh_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HH_OK;
+}
+
+static int hg_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int CG>
+static int hg_launch(hh_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const hh_gemm_args& a, size_t smem) {
+    auto kern = hh_k_syrk<CG>;
+    HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    int pairs = ctx->sm_count / CG;
+    if (pairs > a.n_items) pairs = a.n_items;
+    if (pairs < 1) pairs = 1;
+    cfg.gridDim = dim3((unsigned)(pairs * CG));
+    cfg.blockDim = dim3(HG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HH_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));
+    ctx->launches++;
+    return HH_OK;
+}
+
+int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, float* d_m1, long long ld, const hh_gemm_item* h_items,
+                      int n_items, hh_gemm_stats* st) {
+    const int n = m->n;
+    HH_REQUIRE(n >= 1 && n_items >= 1, HH_ERR_ARG, "hh_gemm_preexpand: empty problem");
+    const int cg = hg_env_int("HH_GEMM_CG", 2) == 1 ? 1 : 2;
+    const long long ldk = ((long long)n + 63) & ~63ll;       // row pitch in elements (128-byte multiple)
+    const long long plane = ldk * (long long)n;
+    double* d_s = nullptr;
+    float* d_inv = nullptr;
+    int* d_flags = nullptr;
+    unsigned short *d_A = nullptr, *d_B = nullptr;
+    hh_gemm_item* d_items = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    int rc = [&]() -> int {
+        for (int k = 0; k < 3; ++k) HH_CUDA(cudaEventCreate(&ev[k]));
+        HH_CHECK(hh_dmalloc(&d_s, (size_t)n));
+        HH_CHECK(hh_dmalloc(&d_inv, (size_t)n));
+        HH_CHECK(hh_dmalloc(&d_flags, 1));
+        HH_CUDA(cudaEventRecord(ev[0], ctx->stream));
+        HH_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->stream));
+        HH_LAUNCH(ctx, hh_k_gemm_colsum, (n + 7) / 8, 256, 0, m->d_colptr, m->d_val, n, d_s, d_inv);
+        HH_LAUNCH(ctx, hh_k_gemm_valstats, ctx->sm_count * 8, 256, 0, m->d_val, m->nnz, d_flags);
+        int flags = 0;
+        HH_CUDA(cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        int na = (flags & 1) ? 3 : ((flags & 2) ? 2 : 1);
+        const int na_env = hg_env_int("HH_GEMM_NA", 0);
+        if (na_env > na && na_env <= 3) na = na_env;
+        HH_CHECK(hh_dmalloc(&d_A, (size_t)plane * (size_t)na));
+        HH_CHECK(hh_dmalloc(&d_B, (size_t)plane * 3));
+        HH_CUDA(cudaMemsetAsync(d_A, 0, (size_t)plane * (size_t)na * 2, ctx->stream));
+        HH_CUDA(cudaMemsetAsync(d_B, 0, (size_t)plane * 3 * 2, ctx->stream));
+        HH_LAUNCH(ctx, hh_k_gemm_densify, (n + 7) / 8, 256, 0, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, ldk, plane);
+        // rows [n, ld) of every M1 column stay zero; entries that no tile writes (none on one GPU) as well
+        HH_CUDA(cudaMemsetAsync(d_m1, 0, (size_t)ld * (size_t)(col_hi - col_lo) * sizeof(float), ctx->stream));
+        HH_CHECK(hh_dmalloc(&d_items, (size_t)n_items));
+        HH_CUDA(cudaMemcpyAsync(d_items, h_items, (size_t)n_items * sizeof(hh_gemm_item), cudaMemcpyHostToDevice, ctx->stream));
+        CUtensorMap tmA, tmB;
+        HH_CHECK(hg_encode(&tmA, d_A, n, ldk, plane, na));
+        HH_CHECK(hg_encode(&tmB, d_B, n, ldk, plane, 3));
+        hh_gemm_args a;
+        memset(&a, 0, sizeof(a));
+        a.items = d_items;
+        a.n_items = n_items;
+        a.n = n;
+        a.na = na;
+        static const int P1[3][2] = {{0, 0}, {0, 1}, {0, 2}};
+        static const int P2[5][2] = {{0, 0}, {0, 1}, {1, 0}, {0, 2}, {1, 1}};
+        static const int P3[6][2] = {{0, 0}, {0, 1}, {1, 0}, {0, 2}, {1, 1}, {2, 0}};
+        const int(*pl)[2] = na == 1 ? P1 : (na == 2 ? P2 : P3);
+        a.npass = na == 1 ? 3 : (na == 2 ? 5 : 6);
+        const int np_env = hg_env_int("HH_GEMM_NPASS", 0);      // experiments only: fewer passes = lower precision
+        if (np_env >= 1 && np_env < a.npass) a.npass = np_env;
+        for (int p = 0; p < a.npass; ++p) {
+            a.pa[p] = pl[p][0];
+            a.pb[p] = pl[p][1];
+        }
+        a.chunk_kb = hg_env_int("HH_GEMM_CHUNK", 2);
+        if (a.chunk_kb < 1) a.chunk_kb = 1 << 30;               // 0 = accumulate the whole K range in TMEM
+        const size_t stage_bytes = (size_t)(na + 3) * HG_PLANE_BYTES;
+        int stages = (int)((ctx->smem_optin - 2048) / stage_bytes);
+        if (stages > HG_MAX_STAGES) stages = HG_MAX_STAGES;
+        HH_REQUIRE(stages >= 2, HH_ERR_UNSUPPORTED, "hh_gemm: shared memory too small for two pipeline stages");
+        a.stages = stages;
+        a.m1 = d_m1;
+        a.ld = ld;
+        a.col_lo = col_lo;
+        a.col_hi = col_hi;
+        a.inv_s = d_inv;
+        const size_t smem = (size_t)stages * stage_bytes + 1024;
+        HH_CUDA(cudaEventRecord(ev[1], ctx->stream));
+        if (cg == 2) HH_CHECK(hg_launch<2>(ctx, tmA, tmB, a, smem));
+        else HH_CHECK(hg_launch<1>(ctx, tmA, tmB, a, smem));
+        HH_CUDA(cudaEventRecord(ev[2], ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (st) {
+            memset(st, 0, sizeof(*st));
+            st->a_planes = na;
+            st->passes = a.npass;
+            st->cta_group = cg;
+            st->stages = stages;
+            st->chunk_kb = a.chunk_kb;
+            HH_CUDA(cudaEventElapsedTime(&st->densify_ms, ev[0], ev[1]));
+            HH_CUDA(cudaEventElapsedTime(&st->gemm_ms, ev[1], ev[2]));
+            double kb = 0.0;
+            for (int i = 0; i < n_items; ++i) kb += (double)((h_items[i].kb_hi[0] - h_items[i].kb_lo[0]) + (h_items[i].kb_hi[1] - h_items[i].kb_lo[1]));
+            const double tile = 128.0 * cg;
+            st->flops = 2.0 * tile * tile * 64.0 * kb * (double)a.npass;
+        }
+        return HH_OK;
+    }();
+    hh_dfree(d_s);
+    hh_dfree(d_inv);
+    hh_dfree(d_flags);
+    hh_dfree(d_A);
+    hh_dfree(d_B);
+    hh_dfree(d_items);
+    for (int k = 0; k < 3; ++k)
+        if (ev[k]) cudaEventDestroy(ev[k]);
+    return rc;
+}
+
+int hh_gemm_tile_size() { return 128 * (hg_env_int("HH_GEMM_CG", 2) == 1 ? 1 : 2); }
+
+// work list of the whole-matrix product: every tile pair on or above the diagonal whose result (or mirror image)
+// falls into the owned column block [col_lo, col_hi)
+int hh_gemm_items_full(int n, int col_lo, int col_hi, std::vector<hh_gemm_item>& out) {
+    const int T = hh_gemm_tile_size();
+    const int nt = (n + T - 1) / T;
+    const int nkb = (n + 63) / 64;
+    out.clear();
+    const bool all = (col_lo == 0 && col_hi == n);
+    for (int mt = 0; mt < nt; ++mt) {
+        for (int t = all ? mt : 0; t < nt; ++t) {
+            hh_gemm_item w;
+            memset(&w, 0, sizeof(w));
+            w.m_tile = mt;
+            w.n_tile = t;
+            w.kb_lo[0] = 0;
+            w.kb_hi[0] = nkb;
+            if (all) {
+                w.flags = HH_GEMM_DIRECT | (t > mt ? HH_GEMM_MIRROR : 0);
+            } else {
+                // column shard: plain tiles of the owned columns, no mirror images
+                const int c0 = t * T, c1 = std::min(n, c0 + T);
+                if (c1 <= col_lo || c0 >= col_hi) continue;
+                w.flags = HH_GEMM_DIRECT;
+            }
+            out.push_back(w);
+        }
+    }
+    return HH_OK;
+}

@@ -24,6 +24,7 @@
 //               optional convergence term max(|M-L| - 1e-5|L|) (2045)
 #include "hh_common.cuh"
 #include "hh_internal.cuh"
+#include "hh_gemm.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <algorithm>
@@ -1438,6 +1439,8 @@ struct hh_mcl {
     std::vector<int>* h_inv;       // host copy of d_inv (result export)
     cudaEvent_t ev0, ev1;
     float create_ms[2];            // device time of the normalisation / pre-expansion kernels
+    int preexp_mode;               // HH_PREEXP_SPARSE or HH_PREEXP_DENSE: the engine that built M1
+    hh_gemm_stats gemm;            // tensor-core path: planes, passes, flops, times
 };
 
 static void slot_free(hh_slotmat& s) {
@@ -1809,7 +1812,27 @@ static int choose_flat(const hh_mcl* mc, double nnz_operand) {
     return seg < 16.0 ? 1 : 0;
 }
 
+// Which engine builds M1.  The Gustavson kernel does n*d^2 multiply-adds on a scattered accumulator
+// (measured ~0.5e12 products/s on B200); the tensor-core GEMM does passes*n^3/2 at ~1e15 flop/s.  AUTO picks the
+// cheaper estimate; HH_MCL_PREEXP=sparse|dense overrides.
+static int choose_preexp(const hh_matrix* m, int requested) {
+    const char* e = getenv("HH_MCL_PREEXP");
+    if (e && *e) {
+        if (!strcmp(e, "sparse")) return HH_PREEXP_SPARSE;
+        if (!strcmp(e, "dense")) return HH_PREEXP_DENSE;
+    }
+    if (requested == HH_PREEXP_SPARSE || requested == HH_PREEXP_DENSE) return requested;
+    const double n = (double)m->n, d = (double)m->nnz / (n > 0 ? n : 1.0);
+    const double t_sparse = n * d * d / 0.5e12;
+    const double t_dense = 2.0 * 5.0 * n * n * n / 2.0 / 1.0e15 + 2e-4;      // 5 passes (counts above 256), symmetric half
+    return (t_dense < t_sparse) ? HH_PREEXP_DENSE : HH_PREEXP_SPARSE;
+}
+
 extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, hh_mcl** out) {
+    return hh_mcl_create_ex(m, expansion, col_lo, col_hi, HH_PREEXP_AUTO, out);
+}
+
+extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, int preexp_mode, hh_mcl** out) {
     HH_REQUIRE(m && out, HH_ERR_ARG, "hh_mcl_create: NULL argument");
     hh_scope _scope(m->ctx);
     *out = nullptr;
@@ -1877,6 +1900,16 @@ extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_
         const int ncols = col_hi - col_lo;
         HH_CHECK(hh_dmalloc(&mc->d_m1, (size_t)mc->ld * (size_t)ncols));
         HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        mc->preexp_mode = choose_preexp(m, preexp_mode);
+        if (mc->preexp_mode == HH_PREEXP_DENSE) {
+            // dense-block path: the whole product as a symmetric GEMM on the tensor cores (hh_gemm.cu)
+            std::vector<hh_gemm_item> items;
+            HH_CHECK(hh_gemm_items_full(m->n, col_lo, col_hi, items));
+            HH_CHECK(hh_gemm_preexpand(ctx, m, col_lo, col_hi, mc->d_m1, mc->ld, items.data(), (int)items.size(), &mc->gemm));
+            mc->create_ms[1] = mc->gemm.densify_ms + mc->gemm.gemm_ms;
+            mc->preexp_products = 0;
+            return HH_OK;
+        }
         hh_colargs a;
         mcl_base_args(mc, a);
         a.A = mc->m0;
@@ -1934,6 +1967,26 @@ extern "C" int hh_mcl_info(hh_mcl* mc, int32_t* n, int64_t* nnz_m0, int64_t* pre
     if (preexp_products) *preexp_products = mc->preexp_products;
     if (normalize_ms) *normalize_ms = mc->create_ms[0];
     if (preexp_ms) *preexp_ms = mc->create_ms[1];
+    return HH_OK;
+}
+
+extern "C" int hh_mcl_preexp_info(hh_mcl* mc, hh_preexp_info* info) {
+    HH_REQUIRE(mc && info, HH_ERR_ARG, "hh_mcl_preexp_info: NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->mode = mc->preexp_mode;
+    info->total_ms = mc->create_ms[1];
+    if (mc->preexp_mode == HH_PREEXP_DENSE) {
+        info->a_planes = mc->gemm.a_planes;
+        info->passes = mc->gemm.passes;
+        info->cta_group = mc->gemm.cta_group;
+        info->stages = mc->gemm.stages;
+        info->chunk_kb = mc->gemm.chunk_kb;
+        info->densify_ms = mc->gemm.densify_ms;
+        info->gemm_ms = mc->gemm.gemm_ms;
+        info->flops = mc->gemm.flops;
+    } else {
+        info->products = mc->preexp_products;
+    }
     return HH_OK;
 }
 

@@ -11,7 +11,7 @@ from decimal import Decimal
 
 import numpy as np
 
-from ._lib import MclResult, check, load, ptr
+from ._lib import HH_PREEXP_AUTO, HH_PREEXP_DENSE, HH_PREEXP_SPARSE, MclResult, PreexpInfo, check, load, ptr
 from .links import LinkMatrix
 
 
@@ -19,14 +19,18 @@ class Mcl:
     """M0 = column-normalised link matrix and M1 = M0^expansion resident on the device, shared
     by every inflation of the sweep (HapHiC_cluster.py:2144-2158)."""
 
-    def __init__(self, matrix: LinkMatrix, expansion: int = 2, col_lo: int = 0, col_hi: int | None = None):
+    PREEXP = {"auto": HH_PREEXP_AUTO, "sparse": HH_PREEXP_SPARSE, "dense": HH_PREEXP_DENSE}
+
+    def __init__(self, matrix: LinkMatrix, expansion: int = 2, col_lo: int = 0, col_hi: int | None = None,
+                 preexp: str = "auto"):
         self.ctx = matrix.ctx
         self.n = matrix.n
         self.col_lo = int(col_lo)
         self.col_hi = self.n if col_hi is None else int(col_hi)
         self._own = (self.col_lo, self.col_hi)
         self._h = C.c_void_p()
-        check(load().hh_mcl_create(matrix._h, int(expansion), self.col_lo, self.col_hi, C.byref(self._h)))
+        check(load().hh_mcl_create_ex(matrix._h, int(expansion), self.col_lo, self.col_hi, self.PREEXP[preexp],
+                                      C.byref(self._h)))
         n = C.c_int32()
         nnz0 = C.c_int64()
         pre = C.c_int64()
@@ -35,6 +39,10 @@ class Mcl:
         self.nnz_m0 = int(nnz0.value)
         self.preexp_products = int(pre.value)
         self.normalize_ms, self.preexp_ms = float(t0.value), float(t1.value)
+        pi = PreexpInfo()
+        check(load().hh_mcl_preexp_info(self._h, C.byref(pi)))
+        self.preexp = {k: getattr(pi, k) for k, _t in PreexpInfo._fields_}
+        self.preexp["mode"] = {HH_PREEXP_SPARSE: "sparse", HH_PREEXP_DENSE: "dense"}.get(pi.mode, "?")
         self.last = None
 
     # -- inspection (parity tests) ------------------------------------------------------------

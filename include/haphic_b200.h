@@ -175,6 +175,30 @@ int hh_matrix_destroy(hh_matrix* m);
  * this context owns (0, n for one GPU): M1 and every iterate are computed for owned columns only.
  */
 int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, hh_mcl** out);
+/* The same with the engine of the pre-expansion (2146-2149) chosen by the caller:
+ *   HH_PREEXP_SPARSE  Gustavson SpGEMM on a shared-memory column accumulator (the reference's sparse mode,
+ *                     mkl_matrix_power 2017-2023);
+ *   HH_PREEXP_DENSE   the product as a symmetric dense GEMM on the tensor cores (tcgen05 / TMEM / TMA; bf16 operand
+ *                     planes that reproduce the fp32 product, fp32 accumulation) -- the reference's dense mode
+ *                     (`--dense_matrix`, numpy.linalg.matrix_power 2035 / 2149);
+ *   HH_PREEXP_AUTO    whichever is estimated cheaper for this matrix (hh_mcl_create; env HH_MCL_PREEXP overrides).
+ * Both engines give M1 within fp32 rounding of the exact product; every later step is shared. */
+enum { HH_PREEXP_AUTO = 0, HH_PREEXP_SPARSE = 1, HH_PREEXP_DENSE = 2 };
+int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, int preexp_mode, hh_mcl** out);
+typedef struct {
+    int32_t mode;          /* HH_PREEXP_SPARSE or HH_PREEXP_DENSE: what ran                              */
+    int32_t a_planes;      /* dense: bf16 planes of the count operand (1: counts <= 256, 2: < 65536, 3)   */
+    int32_t passes;        /* dense: tensor-core passes per k-block                                        */
+    int32_t cta_group;     /* dense: 2 = CTA pairs (256 x 256 tiles), 1 = single CTAs (128 x 128)          */
+    int32_t stages;        /* dense: shared-memory pipeline stages                                         */
+    int32_t chunk_kb;      /* dense: 64-wide k-blocks accumulated in TMEM between two register drains      */
+    float total_ms;        /* device time of the pre-expansion                                             */
+    float densify_ms;      /* dense: operand planes from the CSC                                           */
+    float gemm_ms;         /* dense: the GEMM kernel                                                       */
+    double flops;          /* dense: tensor-core flops issued                                              */
+    int64_t products;      /* sparse: Gustavson products                                                   */
+} hh_preexp_info;
+int hh_mcl_preexp_info(hh_mcl* mc, hh_preexp_info* info);
 /* normalize_ms / preexp_ms: device time of the two kernels hh_mcl_create ran */
 int hh_mcl_info(hh_mcl* mc, int32_t* n, int64_t* nnz_m0, int64_t* preexp_products, float* normalize_ms,
                 float* preexp_ms);
