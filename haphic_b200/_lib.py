@@ -34,7 +34,7 @@ class MclResult(C.Structure):
 class PreexpInfo(C.Structure):
     _fields_ = [("mode", C.c_int32), ("a_planes", C.c_int32), ("passes", C.c_int32), ("cta_group", C.c_int32),
                 ("stages", C.c_int32), ("chunk_kb", C.c_int32), ("total_ms", C.c_float), ("densify_ms", C.c_float),
-                ("gemm_ms", C.c_float), ("flops", C.c_double), ("products", C.c_int64)]
+                ("gemm_ms", C.c_float), ("clip_ms", C.c_float), ("flops", C.c_double), ("products", C.c_int64)]
 
 
 HH_PREEXP_AUTO, HH_PREEXP_SPARSE, HH_PREEXP_DENSE = 0, 1, 2

@@ -696,7 +696,11 @@ def run_mcl_clustering(link_matrix, bin_set, frag_len_dict, frag_index_dict, exp
     if not isinstance(link_matrix, LinkMatrix):
         link_matrix = LinkMatrix.from_csc(_context(), link_matrix)
     index_frag = {i: f for f, i in frag_index_dict.items()}
-    engine = Mcl(link_matrix, expansion)          # normalise + pre-expand once for the whole sweep
+    # normalise + pre-expand once for the whole sweep.  --dense_matrix selects the reference's dense mode (2035 / 2149,
+    # numpy.linalg.matrix_power): here the pre-expansion as a dense GEMM on the tensor cores; without the flag the
+    # engine is chosen from the matrix (HH_MCL_PREEXP overrides).  Results agree within fp32 rounding either way.
+    engine = Mcl(link_matrix, expansion, preexp="dense" if dense_matrix else "auto")
+    logger.debug("Pre-expansion engine: {} ({:.1f} ms)".format(engine.preexp["mode"], engine.preexp["total_ms"]))
     result_clusters_list = []
     mcl_nrounds = 0
     for inflation in inflation_values(min_inflation, max_inflation, inflation_step):
@@ -1043,8 +1047,8 @@ def run(args, log_file=None):
     for flag in ("density_lower", "density_upper", "read_depth_upper", "rank_sum_upper"):
         check_param("--" + flag, getattr(args, flag), {"X", "x"})
     if args.dense_matrix:
-        logger.warning("--dense_matrix is set: the GPU path stores the pre-expanded matrix densely and every iterate "
-                       "sparsely in either mode, results are identical")
+        logger.info("--dense_matrix is set: the pre-expansion runs as a dense GEMM on the tensor cores (tcgen05); "
+                    "the iterates are stored sparsely in either mode")
     if args.aln_format == "auto":
         detect_format(args)
     unsupported = [("--correct_nrounds", args.correct_nrounds), ("--ul", args.ul), ("--gfa", args.gfa)]

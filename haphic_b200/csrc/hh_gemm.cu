@@ -417,7 +417,7 @@ __device__ __forceinline__ void hg_split3(float x, unsigned short& h1, unsigned 
 // one warp per column c of the CSC = row c of both operands:  A[c, k] = C[c, k],  B[c, k] = fp32(C[c, k] / s[k])
 __global__ void hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row, const float* __restrict__ val, int n,
                                   const double* __restrict__ s, unsigned short* __restrict__ A, int na, unsigned short* __restrict__ B,
-                                  long long ldk, long long plane) {
+                                  long long ldk, long long plane, float clip) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
     const int lane = threadIdx.x & 31;
@@ -425,7 +425,7 @@ __global__ void hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int3
     unsigned short* __restrict__ b0 = B + (size_t)c * (size_t)ldk;
     for (int64_t p = colptr[c] + lane; p < colptr[c + 1]; p += 32) {
         const int k = row[p];
-        const float v = val[p];
+        const float v = fminf(val[p], clip);      // counts above `clip` are finished by the caller's sparse correction
         unsigned short h1, h2, h3;
         hg_split3(v, h1, h2, h3);
         a0[k] = h1;
@@ -520,14 +520,19 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
         int flags = 0;
         HH_CUDA(cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
-        int na = (flags & 1) ? 3 : ((flags & 2) ? 2 : 1);
-        const int na_env = hg_env_int("HH_GEMM_NA", 0);
-        if (na_env > na && na_env <= 3) na = na_env;
+        // integer link counts: one exact bf16 plane of min(count, 256), the excess is the caller's sparse correction;
+        // anything else (weights of --normalize_by_nlinks, allele-aware scaling): three planes, no clipping
+        int na = (flags & 1) ? 3 : 1;
+        float clip = (flags & 1) ? 3.0e38f : 256.f;
+        if (hg_env_int("HH_GEMM_NA", 0) == 2 && !(flags & 1)) {      // experiment: two planes instead of clipping
+            na = 2;
+            clip = 3.0e38f;
+        }
         HH_CHECK(hh_dmalloc(&d_A, (size_t)plane * (size_t)na));
         HH_CHECK(hh_dmalloc(&d_B, (size_t)plane * 3));
         HH_CUDA(cudaMemsetAsync(d_A, 0, (size_t)plane * (size_t)na * 2, ctx->stream));
         HH_CUDA(cudaMemsetAsync(d_B, 0, (size_t)plane * 3 * 2, ctx->stream));
-        HH_LAUNCH(ctx, hh_k_gemm_densify, (n + 7) / 8, 256, 0, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, ldk, plane);
+        HH_LAUNCH(ctx, hh_k_gemm_densify, (n + 7) / 8, 256, 0, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, ldk, plane, clip);
         // rows [n, ld) of every M1 column stay zero; entries that no tile writes (none on one GPU) as well
         HH_CUDA(cudaMemsetAsync(d_m1, 0, (size_t)ld * (size_t)(col_hi - col_lo) * sizeof(float), ctx->stream));
         HH_CHECK(hh_dmalloc(&d_items, (size_t)n_items));
@@ -573,6 +578,7 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
         if (st) {
             memset(st, 0, sizeof(*st));
             st->a_planes = na;
+            st->clipped = (clip < 1.0e38f && (flags & 2)) ? 1 : 0;
             st->passes = a.npass;
             st->cta_group = cg;
             st->stages = stages;
@@ -599,30 +605,32 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
 
 int hh_gemm_tile_size() { return 128 * (hg_env_int("HH_GEMM_CG", 2) == 1 ? 1 : 2); }
 
-// work list of the whole-matrix product: every tile pair on or above the diagonal whose result (or mirror image)
-// falls into the owned column block [col_lo, col_hi)
+// work list of the whole-matrix product: every tile pair (a <= b) on or above the diagonal whose result (columns of
+// tile b) or mirror image (columns of tile a) falls into the owned column block [col_lo, col_hi).  A column shard
+// computes every element exactly as the single-GPU run does (same tile, same orientation), so M1 is bit-identical
+// for any number of shards.
 int hh_gemm_items_full(int n, int col_lo, int col_hi, std::vector<hh_gemm_item>& out) {
     const int T = hh_gemm_tile_size();
     const int nt = (n + T - 1) / T;
     const int nkb = (n + 63) / 64;
     out.clear();
-    const bool all = (col_lo == 0 && col_hi == n);
-    for (int mt = 0; mt < nt; ++mt) {
-        for (int t = all ? mt : 0; t < nt; ++t) {
+    auto owned = [&](int t) {
+        const int c0 = t * T, c1 = std::min(n, c0 + T);
+        return c1 > col_lo && c0 < col_hi;
+    };
+    for (int ta = 0; ta < nt; ++ta) {
+        for (int tb = ta; tb < nt; ++tb) {
+            int flags = 0;
+            if (owned(tb)) flags |= HH_GEMM_DIRECT;
+            if (tb > ta && owned(ta)) flags |= HH_GEMM_MIRROR;
+            if (!flags) continue;
             hh_gemm_item w;
             memset(&w, 0, sizeof(w));
-            w.m_tile = mt;
-            w.n_tile = t;
+            w.m_tile = ta;
+            w.n_tile = tb;
             w.kb_lo[0] = 0;
             w.kb_hi[0] = nkb;
-            if (all) {
-                w.flags = HH_GEMM_DIRECT | (t > mt ? HH_GEMM_MIRROR : 0);
-            } else {
-                // column shard: plain tiles of the owned columns, no mirror images
-                const int c0 = t * T, c1 = std::min(n, c0 + T);
-                if (c1 <= col_lo || c0 >= col_hi) continue;
-                w.flags = HH_GEMM_DIRECT;
-            }
+            w.flags = flags;
             out.push_back(w);
         }
     }

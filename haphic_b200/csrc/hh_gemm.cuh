@@ -17,6 +17,7 @@ struct hh_gemm_item {
 
 struct hh_gemm_stats {
     int a_planes, passes, cta_group, stages, chunk_kb;
+    int clipped;           // 1: counts above 256 were clipped and the caller owes the sparse correction
     float densify_ms, gemm_ms;
     double flops;          // tensor-core flops issued (2 * M * N * K * passes over all tiles)
 };

@@ -41,6 +41,9 @@ struct hh_slotmat {
 
 enum { SRC_CSC = 0, SRC_PRODUCT = 1, SRC_DENSE = 2 };
 enum { EPI_NORM = 0, EPI_DUMP = 1, EPI_PRUNE = 2 };
+// Link counts above HH_CLIP are split: min(x, HH_CLIP) goes through the tensor-core GEMM as ONE exact bf16 plane
+// (integers up to 256 are bf16 numbers), the rest through two small Gustavson corrections (hh_mcl_create_ex).
+#define HH_CLIP 256.0f
 
 struct hh_colargs {
     int n, T, ch_shift, n_pad;
@@ -66,6 +69,9 @@ struct hh_colargs {
     const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
     int flat;                    // expansion inner loop: 1 = flat 32-entry walk, 0 = one segment at a time
     int l2pf;                    // expansion: prefetch the next batch's segments into L2
+    int clip_mode;               // SRC_CSC + EPI_NORM: 0 = x / S;  2 = only the part of a count above HH_CLIP, (x - HH_CLIP) / S
+    const float* bclip;          // SRC_PRODUCT: B values of column j are clipped to bclip[j] (= fp32(HH_CLIP / S_j))
+    int accumulate;              // EPI_DUMP: add the non-zero accumulator rows to the dense column instead of overwriting it
     float* scratch;
     unsigned long long* stats;   // [0] nnz written  [1] products
     int* delta_bits;
@@ -180,18 +186,19 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             const int* __restrict__ Ablk = a.A.blk;
             const size_t capA = (size_t)a.A.cap;
             unsigned long long warp_prod = 0ull;
+            const float bcl = a.bclip ? a.bclip[j] : 3.0e38f;
             // software pipeline over batches: B entries two batches ahead, block pointers one batch ahead
             int i1 = 0, i2 = 0, s1 = 0, e1 = 0;
             float v1 = 0.f, v2 = 0.f;
             if (lane < lenB) {
                 const uint2 be = Bent[lane];
                 i1 = (int)be.x;
-                v1 = __uint_as_float(be.y);
+                v1 = fminf(__uint_as_float(be.y), bcl);
             }
             if (32 + lane < lenB) {
                 const uint2 be = Bent[32 + lane];
                 i2 = (int)be.x;
-                v2 = __uint_as_float(be.y);
+                v2 = fminf(__uint_as_float(be.y), bcl);
             }
             if (lane < lenB) {
                 const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 if (t0 + 64 + lane < lenB) {
                     const uint2 be = Bent[t0 + 64 + lane];
                     i2 = (int)be.x;
-                    v2 = __uint_as_float(be.y);
+                    v2 = fminf(__uint_as_float(be.y), bcl);
                 }
                 const unsigned ne = __ballot_sync(HH_FULL_MASK, seg_len > 0);
                 if (!FLAT) {
@@ -373,20 +380,33 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
 
         if (EPI == EPI_DUMP) {
             float* __restrict__ col = a.dense_out + (size_t)jloc * (size_t)a.ld;
+            if (a.accumulate) {
+                for (int r = tile0 + lane; r < tile0 + T; r += 32) {
+                    if (r < a.ld) {
+                        const float x = acc[r];
+                        if (x != 0.f) {
+                            col[r] += x;
+                            acc[r] = 0.f;
+                        }
+                    }
+                }
+            } else {
             for (int r = tile0 + lane; r < tile0 + T; r += 32) {
                 if (r < a.ld) {          // rows in [n, ld) are zero padding (never accumulated)
                     col[r] = acc[r];
                     acc[r] = 0.f;
                 }
             }
+            }
         } else if (EPI == EPI_NORM) {
             double s = 0.0;
             int cnt = 0;
+            const bool upper = a.clip_mode == 2;     // keep only the part of every count above HH_CLIP
             HH_FOR_DIRTY_ROWS({
                 const float x = acc[k];
                 if (x != 0.f) {
                     s += fabs((double)x);
-                    cnt++;
+                    if (!upper || x > HH_CLIP) cnt++;
                 }
             })
             s = hh_warp_sum(s);
@@ -410,7 +430,8 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             int off = base;
             uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
             HH_FOR_DIRTY_ROWS({
-                const float x = acc[k];
+                const float x0 = acc[k];
+                const float x = upper ? (x0 > HH_CLIP ? x0 - HH_CLIP : 0.f) : x0;
                 const bool f = (x != 0.f);
                 const unsigned bal = __ballot_sync(HH_FULL_MASK, f);
                 if (f) {
@@ -418,8 +439,8 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     if (pos < a.out.cap) {
                         oent[pos] = make_uint2((unsigned)k, __float_as_uint((a.raw || S == 0.0) ? x : (float)((double)x / S)));
                     }
-                    acc[k] = 0.f;
                 }
+                if (x0 != 0.f) acc[k] = 0.f;
                 off += __popc(bal);
             })
             if (lane == 0) a.out.blk[(size_t)j * (W + 1) + w] = base;
@@ -1392,6 +1413,27 @@ __global__ void hh_k_gather_len(const int* __restrict__ len, const int* __restri
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// per column: number of counts above HH_CLIP (atomicMax into *max_out) and bclip[c] = fp32(HH_CLIP / column sum)
+__global__ void hh_k_clip_stats(const int64_t* __restrict__ colptr, const float* __restrict__ val, int n, float* __restrict__ bclip,
+                                int* __restrict__ max_out) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const int lane = threadIdx.x & 31;
+    double t = 0.0;
+    int big = 0;
+    for (int64_t p = colptr[c] + lane; p < colptr[c + 1]; p += 32) {
+        const float v = val[p];
+        t += fabs((double)v);
+        big += v > HH_CLIP;
+    }
+    t = hh_warp_sum(t);
+    big = hh_warp_sum(big);
+    if (lane == 0) {
+        bclip[c] = (t != 0.0) ? (float)((double)HH_CLIP / t) : HH_CLIP;
+        if (big) atomicMax(max_out, big);
+    }
+}
+
 struct hh_mcl {
     hh_ctx* ctx;
     int n, W, T, ch_shift, n_pad;
@@ -1440,6 +1482,7 @@ struct hh_mcl {
     cudaEvent_t ev0, ev1;
     float create_ms[2];            // device time of the normalisation / pre-expansion kernels
     int preexp_mode;               // HH_PREEXP_SPARSE or HH_PREEXP_DENSE: the engine that built M1
+    float clip_ms;                 // dense engine: the sparse correction for counts above HH_CLIP
     hh_gemm_stats gemm;            // tensor-core path: planes, passes, flops, times
 };
 
@@ -1585,9 +1628,10 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
 
 // unsorted CSC -> slotted (raw or column-normalised); cap must be >= the longest column
 static int slot_from_csc(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, int* d_counter, unsigned long long* d_stats,
-                         const hh_matrix* m, int raw, hh_slotmat& out) {
+                         const hh_matrix* m, int raw, hh_slotmat& out, int clip_mode = 0) {
     hh_colargs a;
     memset(&a, 0, sizeof(a));
+    a.clip_mode = clip_mode;
     a.n = m->n;
     a.col_lo = 0;
     a.ncols = m->n;
@@ -1812,9 +1856,8 @@ static int choose_flat(const hh_mcl* mc, double nnz_operand) {
     return seg < 16.0 ? 1 : 0;
 }
 
-// Which engine builds M1.  The Gustavson kernel does n*d^2 multiply-adds on a scattered accumulator
-// (measured ~0.5e12 products/s on B200); the tensor-core GEMM does passes*n^3/2 at ~1e15 flop/s.  AUTO picks the
-// cheaper estimate; HH_MCL_PREEXP=sparse|dense overrides.
+// Which engine builds M1.  The Gustavson kernel does n*d^2 multiply-adds on a scattered accumulator, the tensor-core
+// GEMM 3 passes of n^3/2.  AUTO picks the cheaper estimate; HH_MCL_PREEXP=sparse|dense overrides.
 static int choose_preexp(const hh_matrix* m, int requested) {
     const char* e = getenv("HH_MCL_PREEXP");
     if (e && *e) {
@@ -1822,10 +1865,12 @@ static int choose_preexp(const hh_matrix* m, int requested) {
         if (!strcmp(e, "dense")) return HH_PREEXP_DENSE;
     }
     if (requested == HH_PREEXP_SPARSE || requested == HH_PREEXP_DENSE) return requested;
+    // measured on B200: Gustavson ~0.5e12 products/s; tensor-core GEMM ~1.5e15 flop/s issued over three bf16 passes of the
+    // symmetric half, plus operand planes (memset + scatter) and allocation
     const double n = (double)m->n, d = (double)m->nnz / (n > 0 ? n : 1.0);
     const double t_sparse = n * d * d / 0.5e12;
-    const double t_dense = 2.0 * 5.0 * n * n * n / 2.0 / 1.0e15 + 2e-4;      // 5 passes (counts above 256), symmetric half
-    return (t_dense < t_sparse) ? HH_PREEXP_DENSE : HH_PREEXP_SPARSE;
+    const double t_dense = 2.0e-15 * n * n * n + 3.0e-12 * n * n + 5.0e-4;
+    return (1.2 * t_dense < t_sparse) ? HH_PREEXP_DENSE : HH_PREEXP_SPARSE;
 }
 
 extern "C" int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, hh_mcl** out) {
@@ -1908,6 +1953,54 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
             HH_CHECK(hh_gemm_preexpand(ctx, m, col_lo, col_hi, mc->d_m1, mc->ld, items.data(), (int)items.size(), &mc->gemm));
             mc->create_ms[1] = mc->gemm.densify_ms + mc->gemm.gemm_ms;
             mc->preexp_products = 0;
+            if (mc->gemm.clipped) {
+                // C = Cs + Cl, Cs = min(C, 256): the GEMM did (Cs D Cs) D.  What is left,
+                //     M1 += M0 . M0l  +  M0l . M0s,     M0l = Cl D (a few entries per column),  M0s = Cs D = min(M0, bclip),
+                // are two Gustavson passes of the column kernel that add into the dense columns.
+                float* d_bclip = nullptr;
+                hh_slotmat m0l;
+                memset(&m0l, 0, sizeof(m0l));
+                int rc2 = [&]() -> int {
+                    HH_CHECK(hh_dmalloc(&d_bclip, (size_t)m->n));
+                    int* d_max = mc->d_bigcount + 3;
+                    HH_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
+                    HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
+                    HH_LAUNCH(ctx, hh_k_clip_stats, (m->n + 7) / 8, 256, 0, m->d_colptr, m->d_val, m->n, d_bclip, d_max);
+                    int capl = 0;
+                    HH_CUDA(cudaMemcpyAsync(&capl, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                    HH_CUDA(cudaStreamSynchronize(ctx->stream));
+                    HH_CHECK(slot_alloc(m0l, m->n, capl > 0 ? capl : 1, g.W));
+                    HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+                    HH_CHECK(slot_from_csc(ctx, g, mc->d_scratch, mc->grid_cap, mc->d_counter, mc->d_stats, m, 0, m0l, 2));
+                    hh_colargs a;
+                    mcl_base_args(mc, a);
+                    a.dense_out = mc->d_m1;
+                    a.accumulate = 1;
+                    a.A = mc->m0;            // M0 . M0l: few B entries per column, long operand segments
+                    a.B = m0l;
+                    a.flat = 0;
+                    a.l2pf = 0;
+                    HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+                    a.A = m0l;               // M0l . M0s: every B entry meets a (mostly empty) operand column
+                    a.B = mc->m0;
+                    a.bclip = d_bclip;
+                    a.flat = 1;
+                    HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+                    HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
+                    unsigned long long st2[4];
+                    HH_CHECK(read_stats(ctx, mc->d_stats, st2));
+                    HH_REQUIRE((int)(st2[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY, "hh_mcl_create: slot overflow in the clip correction");
+                    float ms = 0.f;
+                    HH_CUDA(cudaEventElapsedTime(&ms, mc->ev0, mc->ev1));
+                    mc->clip_ms = ms;
+                    mc->create_ms[1] += ms;
+                    mc->preexp_products = (int64_t)st2[1];
+                    return HH_OK;
+                }();
+                hh_dfree(d_bclip);
+                slot_free(m0l);
+                HH_CHECK(rc2);
+            }
             return HH_OK;
         }
         hh_colargs a;
@@ -1984,6 +2077,8 @@ extern "C" int hh_mcl_preexp_info(hh_mcl* mc, hh_preexp_info* info) {
         info->densify_ms = mc->gemm.densify_ms;
         info->gemm_ms = mc->gemm.gemm_ms;
         info->flops = mc->gemm.flops;
+        info->clip_ms = mc->clip_ms;
+        info->products = mc->preexp_products;
     } else {
         info->products = mc->preexp_products;
     }

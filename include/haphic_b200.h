@@ -195,8 +195,9 @@ typedef struct {
     float total_ms;        /* device time of the pre-expansion                                             */
     float densify_ms;      /* dense: operand planes from the CSC                                           */
     float gemm_ms;         /* dense: the GEMM kernel                                                       */
+    float clip_ms;         /* dense: sparse correction for link counts above 256 (0 when there are none)   */
     double flops;          /* dense: tensor-core flops issued                                              */
-    int64_t products;      /* sparse: Gustavson products                                                   */
+    int64_t products;      /* sparse: Gustavson products (dense: products of the clip correction)          */
 } hh_preexp_info;
 int hh_mcl_preexp_info(hh_mcl* mc, hh_preexp_info* info);
 /* normalize_ms / preexp_ms: device time of the two kernels hh_mcl_create ran */
