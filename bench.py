@@ -3,7 +3,7 @@
 and MCL iterations/sec, on the synthetic 50k-contig / 200M-pair workload (BASELINE.json configs[2]).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [...]                          # the CPU port of the reference path
+    python bench.py --impl reference [...]                          # the UNMODIFIED reference (baseline/_ref) on the host cores
 
 One "step" = one pass of the hot path over the whole synthetic input:
     link counting (200M records) -> first-seen index -> symmetric CSC -> column normalise ->
@@ -47,11 +47,12 @@ def parse_args():
     p.add_argument("--pruning", type=float, default=1e-4)
     p.add_argument("--seed", type=int, default=12345)
     p.add_argument("--e2e-steps", type=int, default=3)
-    p.add_argument("--cpu-sample-pairs", type=int, default=4_000_000)
+    p.add_argument("--cpu-sample-pairs", type=int, default=1_500_000)
     p.add_argument("--cpu-sample-cols", type=int, default=24)
     p.add_argument("--ingest-lines", type=int, default=1_000_000,
                    help="lines of .pairs text for the host ingest measurement (0 = skip)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-default-sweep", action="store_true", help="skip the 20-inflation default sweep figure")
     p.add_argument("--verbose", action="store_true")
     return p.parse_args()
 
@@ -69,6 +70,66 @@ def measured_peaks():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s: the sustained figure (the GEMM is timed inside a long step, under the power cap)."""
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json: sustained / burst)"
+    except Exception:
+        return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def preexp_roofline(pre, n, nnz_m0, ncols, traffic):
+    """Roofline of the pre-expansion launch, the dominant kernel of the step.
+    dense engine (hh_k_syrk, tcgen05): tensor bound.  achieved = bf16 tensor flops the launch issues (2 * 256 * 256 * 64 per
+    tile k-block and pass) / its CUDA-event time; the algorithmic figure of SURVEY.md 8(d) (2 b^3 for the block product, fp32
+    accuracy needing `passes` bf16 passes) is reported beside it -- the symmetric half is skipped, so issued = passes * b^3.
+    sparse engine (hh_k_col<SRC_PRODUCT,EPI_DUMP>): HBM bound, operand once + dense result once."""
+    peak_hbm, src_hbm = measured_peaks()
+    if pre["mode"] == "dense":
+        sus, burst, src = measured_tensor_peak()
+        ach = pre["flops"] / (pre["gemm_ms"] / 1000.0) / 1e12
+        alg = 2.0 * float(n) * float(n) * float(ncols)
+        return {"kernel": "hh_k_syrk<cta_group::{}> (tcgen05.mma + TMA + TMEM; pre-expansion M0*M0 -> dense M1, one launch per step)"
+                .format(pre["cta_group"]), "bound": "tensor", "achieved": ach, "peak": sus, "unit": "TFLOP/s", "frac": ach / sus,
+                "peak_burst": burst, "traffic": traffic.get("hh_k_syrk"), "issued_flops": pre["flops"], "passes": pre["passes"],
+                "algorithmic_flops": alg, "algorithmic_frac_8d": alg / (pre["gemm_ms"] / 1000.0) / (sus * 1e12 / pre["passes"]),
+                "launch_ms": pre["gemm_ms"], "densify_ms": pre["densify_ms"], "clip_correction_ms": pre["clip_ms"],
+                "peak_source": src, "note": "algorithmic_frac_8d = 2 n^2 ncols / t / (peak / passes); above 1 because S = C D C is "
+                "symmetric and only tiles on or above the diagonal are computed"}
+    alg = 8 * nnz_m0 + 4 * n * ncols
+    ach = alg / (pre["total_ms"] / 1000.0) / 1e9
+    return {"kernel": "hh_k_col<SRC_PRODUCT,EPI_DUMP> (pre-expansion M0*M0 -> dense M1, one launch per step)", "bound": "hbm",
+            "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm, "traffic": traffic.get("hh_k_col_preexpansion"),
+            "algorithmic_bytes": alg, "launch_ms": pre["total_ms"], "peak_source": src_hbm,
+            "gather_GBps": 8.0 * pre["products"] / (pre["total_ms"] / 1000.0) / 1e9}
+
+
+def cpu_baseline_block(a, asm, rank, in_nx, rec):
+    """CPU legs on this box's host cores, bounded samples of the same stream: the unmodified reference's pair loop
+    (kind "reference"), and beside it the single-core C port of the same loop (oracle/haphic_oracle.c)."""
+    import tempfile
+    n_ref = min(int(rec.shape[0]), a.cpu_sample_pairs)
+    sample = rec[:n_ref].cpu().numpy()
+    with tempfile.TemporaryDirectory() as tmp:
+        v, dt, nnz = ref_pairs_per_sec(asm, sample, tmp)
+    cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "reference",
+           "sample": "first {} records as .pairs text through the unmodified HapHiC_cluster.parse_alignments_for_ctgs("
+                     "pairs_generator_inter_ctgs(...)) from baseline/_ref, {:.1f} s (single-threaded Python by construction; "
+                     "host has {} cores)".format(len(sample), dt, os.cpu_count())}
+    try:
+        big = rec[: 8_000_000].cpu().numpy()
+        vc, dtc = cpu_c_pairs_per_sec(asm, rank, in_nx, big)
+        cpu["c_port"] = {"value": vc, "unit": "pairs/s", "cores": 1, "kind": "port",
+                         "sample": "first {} records through oracle/haphic_oracle.c, warm call {:.1f} s (single-core C port of the "
+                                   "same loop, not the reference's speed)".format(len(big), dtc)}
+    except Exception as exc:                       # no gcc on the box: the reference number above stands
+        cpu["c_port"] = {"unavailable": str(exc)[:200]}
+    return cpu
 
 
 class ClockSampler:
@@ -128,6 +189,42 @@ def cpu_pairs_per_sec(asm, rank, in_nx, sample):
     orc.count_links_loop(sample, asm.lengths, rank, in_nx, 500000)
     dt = time.perf_counter() - t0
     return len(sample) / dt, dt
+
+
+def ref_pairs_per_sec(asm, sample, tmp):
+    """The reference's OWN per-read-pair loop, unmodified (baseline/_ref/HapHiC_cluster.py imported by oracle/refimpl.py):
+    parse_alignments_for_ctgs over pairs_generator_inter_ctgs on a .pairs text of the sample (1562-1583, 1596-1655),
+    single-threaded by construction.  Returns (pairs/s, seconds, distinct pairs)."""
+    from oracle import refimpl
+    path = os.path.join(tmp, "sample_{}.pairs".format(len(sample)))
+    if not os.path.exists(path):
+        refimpl.write_pairs(path, asm.names, sample)
+    dt, nnz, _ = refimpl.time_pair_loop(asm.names, asm.lengths, path, tmp)
+    return len(sample) / dt, dt, nnz
+
+
+def ref_mcl_small(a, inflations):
+    """The reference's own normalize + pre-expansion + mcl() (2144-2149, 2026-2062) on a 2,000-contig instance of the same
+    generator (the 50k-contig problem is hours of CPU and a 10 GB dense intermediate): iterations/s in the reference's sparse
+    mode (SciPy '@' standing in for the absent Intel MKL) and in its dense mode (what it falls back to without MKL, 2764-2766)."""
+    from haphic_b200 import synth
+    from haphic_b200.links import name_rank
+    from oracle import haphic_oracle as orc
+    from oracle import refimpl
+    small = synth.make_assembly(max(2, a.nchr // 8), 2000, a.mean_len, seed=a.seed)
+    sp_pairs = synth.make_pairs(small, min(a.pairs // max(1, a.contigs // 2000), 2_000_000), seed=a.seed + 1).numpy()
+    r = orc.count_links_numpy(sp_pairs, small.lengths, name_rank(small.names), np.ones(small.n, np.uint8), 500000)
+    m, _ = orc.dict_to_matrix(r["flank_keys"], r["flank_vals"], np.ones(small.n, np.uint8))
+    out = {}
+    for tag, dense in (("sparse", False), ("dense", True)):
+        dt, iters, rounds, _ = refimpl.time_mcl_sweep(m, inflations, a.max_iter, a.pruning, dense=dense)
+        out[tag] = {"value": iters / dt, "unit": "iter/s", "iterations": iters, "rounds": rounds, "seconds": round(dt, 2)}
+    out["sample"] = ("unmodified reference normalize + matrix power + mcl() over inflations {} on a 2,000-contig / {}-pair instance "
+                     "of the same generator; sparse = SciPy '@' standing in for MKL's SpGEMM, dense = numpy matrix_power".format(
+                         inflations, len(sp_pairs)))
+    out["kind"] = "reference"
+    out["host_cores"] = os.cpu_count()
+    return out
 
 
 def cpu_c_pairs_per_sec(asm, rank, in_nx, sample):
@@ -205,51 +302,44 @@ def make_inputs(a, device, rank_id=0, world=1):
 
 
 def run_reference(a):
-    """`--impl reference`: the CPU port of the reference path on the host cores, bounded samples."""
-    import torch
+    """`--impl reference`: the unmodified reference's hot loops on the host cores, bounded samples of the same workload."""
     rank_id = int(os.environ.get("RANK", "0"))
     if rank_id != 0:
         return
+    import tempfile
     from haphic_b200 import synth
-    from haphic_b200.links import name_rank
-    from oracle import haphic_oracle as orc
+    from oracle import refimpl
+    if not refimpl.available():
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/HapHiC_cluster.py missing (run __graft_entry__.build() "
+                                                                "in the build container)"}))
+        return
     asm = synth.make_assembly(a.nchr, a.contigs, a.mean_len, seed=a.seed)
-    rank = name_rank(asm.names)
-    in_nx = np.ones(asm.n, np.uint8)
-    # every step is a bounded sample of the workload; the whole --steps/--warmup run is sized for about two minutes of
-    # the single-threaded loop (~5 us per record)
-    per_step = max(200_000, min(a.cpu_sample_pairs, int(120.0 / max(1, a.steps + a.warmup) / 5e-6)))
+    inflations = [float(x) for x in a.inflations.split(",")]
+    # every step is a bounded sample of the stream; the whole --steps/--warmup run is sized for about two minutes of the
+    # reference's single-threaded loop (~10 us per record on this class of host, text parsing and BED writing included)
+    per_step = max(100_000, min(a.cpu_sample_pairs, int(110.0 / max(1, a.steps + a.warmup) / 10e-6)))
     sample = synth.make_pairs_range(asm, 0, per_step, seed=a.seed + 1, device="cpu").numpy()
     times = []
-    for s in range(a.warmup + a.steps):
-        v, dt = cpu_pairs_per_sec(asm, rank, in_nx, sample)
-        if s >= a.warmup:
-            times.append(dt)
+    with tempfile.TemporaryDirectory() as tmp:
+        for s in range(a.warmup + a.steps):
+            _v, dt, nnz = ref_pairs_per_sec(asm, sample, tmp)
+            if s >= a.warmup:
+                times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
     value = len(sample) / (ms / 1000.0)
-    # MCL on a reduced instance of the same generator (the port cannot hold the 50k-contig dense
-    # pre-expansion): 2,000 contigs, same pairs-per-contig ratio
-    small = synth.make_assembly(max(2, a.nchr // 8), 2000, a.mean_len, seed=a.seed)
-    sp_pairs = synth.make_pairs(small, min(a.pairs // max(1, a.contigs // 2000), 2_000_000), seed=a.seed + 1).numpy()
-    r = orc.count_links_numpy(sp_pairs, small.lengths, name_rank(small.names), np.ones(small.n, np.uint8), 500000)
-    m, _ = orc.dict_to_matrix(r["flank_keys"], r["flank_vals"], np.ones(small.n, np.uint8))
-    t0 = time.perf_counter()
-    sweep = orc.run_mcl_sweep(m, 2, [float(x) for x in a.inflations.split(",")], a.max_iter, a.pruning)
-    t_mcl = time.perf_counter() - t0
-    iters = sum(s[2] for s in sweep)
+    mcl = ref_mcl_small(a, inflations)
     line = {
         "impl": "reference", "metric": "hic_pairs_per_sec_matrix_build", "value": value, "unit": "pairs/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int32 counts / fp32 matrix", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": "first {} records of the stream per step".format(len(sample))},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": 1, "kind": "port",
-                         "sample": "{} records through oracle.count_links_loop (single-threaded like the reference's loop)"
-                         .format(len(sample))},
+        "config": {"workload": workload_name(a), "inflations": inflations, "max_iter": a.max_iter, "pruning": a.pruning,
+                   "sample": "first {} records of the stream per step, as .pairs text".format(len(sample))},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": 1, "kind": "reference",
+                         "sample": "{} records per step through the unmodified HapHiC_cluster.parse_alignments_for_ctgs("
+                                   "pairs_generator_inter_ctgs(...)) (single-threaded Python by construction; host has {} cores)"
+                                   .format(len(sample), os.cpu_count())},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "mcl": {"metric": "mcl_iterations_per_sec", "value": iters / t_mcl, "unit": "iter/s", "iterations": iters,
-                "sample": "full sweep on a 2,000-contig instance of the same generator (scipy SpGEMM standing in for MKL); "
-                          "the 50k-contig pre-expansion (10 GB dense) does not fit the port's budget",
-                "host_cores": os.cpu_count()},
+        "mcl": {"metric": "mcl_iterations_per_sec", "value": mcl["sparse"]["value"], "unit": "iter/s", "reference": mcl},
     }
     print(json.dumps(line))
 
@@ -326,7 +416,7 @@ def run_b200(a):
             "iters": iters, "kernel_ms": kernel_ms, "alg_bytes": alg_bytes, "products": products,
             "nnz_full": int(info.nnz_full), "nnz_flank": int(info.nnz_flank), "n_used": int(info.n_used),
             "nnz_m0": mc.nnz_m0, "preexp_ms": mc.preexp_ms, "preexp_products": mc.preexp_products,
-            "normalize_ms": mc.normalize_ms, "per_inflation": per_infl, "n_matrix": mat.n,
+            "normalize_ms": mc.normalize_ms, "per_inflation": per_infl, "n_matrix": mat.n, "preexp": dict(mc.preexp),
         }
         mc.close()
         mat.close()
@@ -353,15 +443,11 @@ def run_b200(a):
     pairs_per_s = P / ((build_ms + matrix_ms) / 1000.0)
     iters_per_s = s0["iters"] / (mcl_ms / 1000.0)
     peak, peak_src = measured_peaks()
-    # dominant kernel launch: the pre-expansion pass of the MCL column kernel (hh_k_col<SRC_PRODUCT,EPI_DUMP>), one
-    # launch per step; algorithmic bytes per SURVEY.md 8(d): read the sparse operand once, write dense M1 once
+    # dominant kernel launch: the pre-expansion (one launch per step), see preexp_roofline()
     pre_bytes = 8 * s0["nnz_m0"] + 4 * s0["n_matrix"] ** 2
-    pre_achieved = pre_bytes / (s0["preexp_ms"] / 1000.0) / 1e9
     # all launches of the column kernels of the sweep (pre-expansion + every iteration), same definition
     mcl_bytes = s0["alg_bytes"] + pre_bytes
     mcl_achieved = mcl_bytes / (s0["kernel_ms"] / 1000.0) / 1e9
-    # what a column-at-a-time Gustavson expansion has to gather: one 8-byte operand entry per product
-    gather_achieved = 8.0 * s0["preexp_products"] / (s0["preexp_ms"] / 1000.0) / 1e9
     traffic = ncu_traffic(workload_name(a))
     build_bytes = 16 * P + 12 * s0["nnz_full"] + 12 * s0["nnz_flank"] + 4 * n
     build_achieved = build_bytes / (build_ms / 1000.0) / 1e9
@@ -403,24 +489,40 @@ def run_b200(a):
     e2e_pairs = P / float(np.median(e2e_build)) if e2e_build else None          # median over the passes
     e2e_iters = sum(x[1] for x in e2e_mcl) / sum(x[0] for x in e2e_mcl) if e2e_mcl else None
 
+    # ---- the default sweep of `haphic cluster` (20 inflations 1.1 .. 3.0, HapHiC_cluster.py:2139-2155, 2699-2705) ----------
+    default_sweep = None
+    if not a.no_default_sweep:
+        from haphic_b200.mcl import inflation_values
+        tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
+        tab.add(rec, asynchronous=True)
+        tab.finish()
+        index, _ = tab.linked_index(keep)
+        mat = tab.to_matrix(keep, np.nonzero(index < 0)[0].astype(np.int32))
+        e0, e1 = ev(), ev()
+        e0.record(stream)
+        mc = Mcl(mat)
+        rounds = []
+        for r in inflation_values(1.1, 3.0, 0.1):
+            st = mc.run(float(r), a.max_iter, a.pruning)
+            rounds.append(st["rounds"])
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        default_sweep = {"inflations": 20, "iterations": int(sum(rounds)), "rounds": rounds, "ms": ms,
+                         "value": sum(rounds) / (ms / 1000.0), "unit": "iter/s",
+                         "note": "normalise + pre-expansion + 20 mcl() calls, device time (the reference's MCL total, 2951-2953)"}
+        mc.close()
+        mat.close()
+        tab.close()
+
     # ---- CPU baseline on this box's host cores (bounded samples) ------------------------------------
     cpu = None
     mcl_cpu = None
     if not a.no_cpu_baseline:
-        sample = rec[: a.cpu_sample_pairs].cpu().numpy()
-        v, dt = cpu_pairs_per_sec(asm, rank, in_nx, sample)
-        cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
-               "sample": "first {} records through oracle.count_links_loop ({:.1f} s; the reference's loop is "
-                         "single-threaded Python)".format(len(sample), dt)}
-        try:
-            big = rec[: 2 * a.cpu_sample_pairs].cpu().numpy()
-            vc, dtc = cpu_c_pairs_per_sec(asm, rank, in_nx, big)
-            cpu["c_port"] = {"value": vc, "unit": "pairs/s", "cores": 1,
-                             "sample": "first {} records through oracle/haphic_oracle.c, warm call {:.1f} s (single-core C "
-                                       "port of the same loop, not the reference's speed)".format(len(big), dtc)}
-        except Exception as exc:                       # no gcc on the box: the Python port above stands
-            cpu["c_port"] = {"unavailable": str(exc)[:200]}
-        # MCL: iterate M_1 (after iteration 0) of the last inflation, a sample of columns
+        cpu = cpu_baseline_block(a, asm, rank, in_nx, rec)
+        mcl_cpu = ref_mcl_small(a, inflations)
+        # the C3 matrix itself is beyond the reference's reach (10 GB dense intermediate, hours of SpGEMM): one iteration
+        # of the CPU port on a sample of columns of iterate M_1, extrapolated
         tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
         tab.add(rec, asynchronous=True)
         tab.finish()
@@ -430,9 +532,10 @@ def run_b200(a):
         mc.run(inflations[len(inflations) // 2], 1, a.pruning)
         m_iter1 = mc.result()
         ips, dt, ncols = cpu_mcl_iter_per_sec(m_iter1, a.cpu_sample_cols, inflations[len(inflations) // 2], a.pruning)
-        mcl_cpu = {"value": ips, "unit": "iter/s", "cores": 1, "kind": "port",
-                   "sample": "iteration 1 (expand+inflate+prune) of inflation {} on {} of {} columns, {:.1f} s, scaled by n/cols; "
-                             "scipy SpGEMM stands in for MKL".format(inflations[len(inflations) // 2], ncols, n, dt)}
+        mcl_cpu["port_extrapolated"] = {
+            "value": ips, "unit": "iter/s", "cores": 1, "kind": "port",
+            "sample": "iteration 1 (expand+inflate+prune) of inflation {} on {} of {} columns of the benchmark's own matrix, {:.1f} s, "
+                      "scaled by n/cols; scipy SpGEMM stands in for MKL".format(inflations[len(inflations) // 2], ncols, n, dt)}
         mc.close()
         mat.close()
         tab.close()
@@ -451,23 +554,17 @@ def run_b200(a):
         "stage_ms": {"link_build": build_ms, "matrix": matrix_ms, "mcl_sweep": mcl_ms},
         "mcl": {"metric": "mcl_iterations_per_sec", "value": iters_per_s, "unit": "iter/s", "iterations": s0["iters"],
                 "products": s0["products"], "preexp_ms": s0["preexp_ms"], "normalize_ms": s0["normalize_ms"],
-                "per_inflation": s0["per_inflation"], "e2e": {"value": e2e_iters, "unit": "iter/s"},
-                "cpu_baseline": mcl_cpu},
+                "preexp": s0["preexp"], "per_inflation": s0["per_inflation"], "e2e": {"value": e2e_iters, "unit": "iter/s"},
+                "default_sweep": default_sweep, "cpu_baseline": mcl_cpu},
         "links": {"pairs": P, "used": s0["n_used"], "nnz_full": s0["nnz_full"], "nnz_flank": s0["nnz_flank"],
                   "n_matrix": s0["n_matrix"], "nnz_m0": s0["nnz_m0"]},
         "e2e": {"value": e2e_pairs, "unit": "pairs/s", "h2d_bytes_per_step": 16 * P + 13 * n, "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "hh_k_col<SRC_PRODUCT,EPI_DUMP> (pre-expansion M0*M0 -> dense M1, one launch per step)",
-                     "bound": "hbm", "achieved": pre_achieved, "peak": peak, "unit": "GB/s", "frac": pre_achieved / peak,
-                     "traffic": traffic.get("hh_k_col_preexpansion"), "algorithmic_bytes": pre_bytes,
-                     "launch_ms": s0["preexp_ms"], "peak_source": peak_src},
+        "roofline": preexp_roofline(s0["preexp"], s0["n_matrix"], s0["nnz_m0"], s0["n_matrix"], traffic),
         "roofline_mcl": {"kernel": "all hh_k_col / hh_k_col_win / hh_k_col_small launches of the sweep", "bound": "hbm",
                          "achieved": mcl_achieved, "peak": peak, "unit": "GB/s", "frac": mcl_achieved / peak,
                          "algorithmic_bytes": mcl_bytes, "kernel_ms": s0["kernel_ms"]},
-        "roofline_gather": {"kernel": "pre-expansion, against the operand bytes a column-wise SpGEMM gathers (8 B/product)",
-                            "achieved": gather_achieved, "peak": peak, "unit": "GB/s", "frac": gather_achieved / peak,
-                            "products": s0["preexp_products"]},
         "roofline_build": {"kernel": "hh_k_links_insert + finish", "bound": "hbm", "achieved": build_achieved, "peak": peak,
                            "unit": "GB/s", "frac": build_achieved / peak, "traffic": traffic.get("hh_k_links_insert")},
         "cpu_baseline": cpu,

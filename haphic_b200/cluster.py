@@ -10,8 +10,8 @@ unchanged.  The per-read-pair link counting, dict_to_matrix and the Markov-clust
 libhaphic_b200.so on the GPU; file parsing, fragment statistics, filters on per-fragment scalars,
 result interpretation and the writers are host Python, as in the reference.
 
-Not supported yet (raise, never silently degrade): ``--correct_nrounds``, ``--ul``, ``--gfa``,
-``--remove_allelic_links``, ``--remove_concentrated_links``.
+Not supported (raise, never silently degrade): ``--correct_nrounds``, ``--ul``, ``--gfa`` (out of the hot-path scope,
+SURVEY.md section 2).
 
 Reference line numbers below refer to scripts/HapHiC_cluster.py (v1.0.7).
 """
@@ -553,7 +553,10 @@ def filter_fragments(Nx_frag_set, RE_site_dict, RE_site_cutoff, frag_link_dict, 
     if device_table is not None:
         dmat, frag_index = device_matrix(device_table, device_names, filtered, normalize_by_nlinks=normalized,
                                          add_self_loops=False)
-        device_rs = dmat.rank_sums(topN)
+        # `[:topN]` of the reference just truncates (874-878): fewer fragments than topN use them all, and fewer than two
+        # neighbours have no pair to rank (rank sum 0)
+        eff_top = min(int(topN), len(filtered))
+        device_rs = dmat.rank_sums(eff_top) if eff_top >= 2 else np.zeros(dmat.n, np.int64)
         dmat.close()
     else:
         matrix, frag_index = dict_to_matrix(flank_link_dict, filtered)
@@ -1082,7 +1085,8 @@ def run(args, log_file=None):
     # them: the links stay arrays (LinkArrays), the pickles are written natively and no 10^7-entry dict is built.
     edits_dicts = bool(args.remove_allelic_links or args.remove_concentrated_links)
     ctg_coord_dict, ctg_pair_to_frag, flank_link_dict = None, None, None
-    _COORD_SKIP[0] = 0 if (args.verbose or args.remove_concentrated_links) else int(args.min_read_pairs)
+    # pairs that reach max_read_pairs are always evaluated by the reference, whatever min_read_pairs says
+    _COORD_SKIP[0] = 0 if (args.verbose or args.remove_concentrated_links) else min(int(args.min_read_pairs), int(args.max_read_pairs))
     if edits_dicts:
         if split_ctg_set:
             full_link_dict, flank_link_dict, HT_link_dict, clm_dict, frag_link_dict, ctg_coord_dict, ctg_pair_to_frag = parse_alignments(

@@ -407,6 +407,7 @@ static inline bool parse_int(const char* s, const char* e, int64_t* out) {
     for (; s < e; ++s) {
         if (*s == '_') continue;                 // int('1_000') is valid Python
         if (*s < '0' || *s > '9') return false;
+        if (v > (INT64_MAX - 9) / 10) return false;     // does not fit: refuse instead of wrapping
         v = v * 10 + (*s - '0');
     }
     *out = neg ? -v : v;
@@ -457,6 +458,11 @@ static void pairs_parse_slice(const hh_pairs_reader* r, const char* s, const cha
         }
         p1 -= 1;                                    // pysam / BED are 0-based
         p2 -= 1;
+        if (p1 < INT32_MIN || p1 > INT32_MAX || p2 < INT32_MIN || p2 > INT32_MAX) {     // records carry int32 positions
+            out->err_line = out->lines - 1;
+            out->err_kind = 2;
+            return;
+        }
         const size_t l1 = (size_t)(tend[1] - tok[1]), l3 = (size_t)(tend[3] - tok[3]);
         if (want_bed) {
             // '{ref}\t{pos}\t{pos}\t{readID}/1\t255\t.\n{mref}\t{mpos}\t{mpos}\t{readID}/2\t255\t.\n'  (1557, 1580)

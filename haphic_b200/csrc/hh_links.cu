@@ -151,17 +151,27 @@ hh_k_links_insert(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_o
                 // convert_frags (1662-1670)
                 int fa = fbase[a], fb = fbase[b];
                 const bool sa = fbase[a + 1] - fa > 1, sb = fbase[b + 1] - fb > 1;
+                // a position outside the contig (.pairs position 0, or beyond the last bin) names a bin that does not
+                // exist: the reference dies with a KeyError on frag_len_dict['ctg_binK']; here the record is refused and
+                // hh_links_finish reports it
+                bool bad = false;
                 if (sa) {
                     const int64_t nb = ((int64_t)pa + 1 + bin_size - 1) / bin_size;
+                    bad = bad || pa < 0 || nb < 1 || nb > (int64_t)(fbase[a + 1] - fa);
                     fa += (int)(nb - 1);
                     pa = (int)((int64_t)pa - (nb - 1) * bin_size);
                 }
                 if (sb) {
                     const int64_t nb = ((int64_t)pb + 1 + bin_size - 1) / bin_size;
+                    bad = bad || pb < 0 || nb < 1 || nb > (int64_t)(fbase[b + 1] - fb);
                     fb += (int)(nb - 1);
                     pb = (int)((int64_t)pb - (nb - 1) * bin_size);
                 }
-                ok = fa != fb;                             // intra-bin links are not considered (1715)
+                if (bad) {
+                    atomicAdd(counters + 5, 1ull);
+                    atomicMax(counters + 6, (unsigned long long)(pos ? pos[i] : stream_off + (uint32_t)i) + 1ull);
+                }
+                ok = !bad && fa != fb;                     // intra-bin links are not considered (1715)
                 a = fa;
                 b = fb;
                 if (ok && (sa || sb) && name_rank[a] > name_rank[b]) {   // sort by bin name (1719-1720)
@@ -747,6 +757,9 @@ extern "C" int hh_links_finish(hh_links* lk, hh_links_info* info) {
         HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY,
                    "hh_links_finish: hash table overflow (capacity %llu slots): pass a larger capacity_hint or use hh_links_add",
                    (unsigned long long)lk->cap);
+        HH_REQUIRE(c[5] == 0, HH_ERR_ARG,
+                   "hh_links_finish: %llu records have a position outside their contig's bins (e.g. record %llu of the stream): "
+                   "positions must lie in [0, contig length)", c[5], c[6] - 1ull);
         lk->nnz = (int64_t)c[0];
         lk->n_used = lk->peer_used + (int64_t)c[1];
         HH_CUDA(cudaMemsetAsync(lk->d_counters + 3, 0, sizeof(unsigned long long), ctx->stream));
@@ -896,6 +909,9 @@ extern "C" int hh_links_finish_partition(hh_links* lk, hh_links_info* info) {
         HH_CHECK(links_read_counters(lk, c));
         HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY, "hh_links_finish_partition: hash table overflow (capacity %llu slots)",
                    (unsigned long long)lk->cap);
+        HH_REQUIRE(c[5] == 0, HH_ERR_ARG,
+                   "hh_links_finish_partition: %llu records have a position outside their contig's bins (e.g. record %llu of the stream)",
+                   c[5], c[6] - 1ull);
         lk->nnz = (int64_t)c[0];
         lk->n_used = lk->peer_used + (int64_t)c[1];
         HH_CUDA(cudaMemsetAsync(lk->d_counters + 3, 0, sizeof(unsigned long long), ctx->stream));

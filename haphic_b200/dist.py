@@ -243,16 +243,9 @@ def _gather_lens(lens, ln, blocks, group):
 # ------------------------------------------------------------------------------------------------
 
 def rank0_roofline(s):
-    """Rank 0's pre-expansion launch (its column block of M0*M0): algorithmic bytes = the sparse operand once + the
-    dense block written once, over the launch's device time -- the same definition as the single-GPU line."""
+    """Rank 0's pre-expansion launch (its column block of M0*M0), same definitions as the single-GPU line."""
     import bench as B
-    peak, src = B.measured_peaks()
-    alg = 8 * s["nnz_m0"] + 4 * s["n_matrix"] * s["own_cols"]
-    ach = alg / (s["preexp_ms"] / 1000.0) / 1e9
-    return {"kernel": "hh_k_col<SRC_PRODUCT,EPI_DUMP> (pre-expansion, rank 0's column block)", "bound": "hbm", "achieved": ach,
-            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "algorithmic_bytes": alg,
-            "launch_ms": s["preexp_ms"], "peak_source": src,
-            "gather_GBps": 8.0 * s["preexp_products"] / (s["preexp_ms"] / 1000.0) / 1e9}
+    return B.preexp_roofline(s["preexp"], s["n_matrix"], s["nnz_m0"], s["own_cols"], {})
 
 
 def bench_multi(a, world: int, rank_id: int, local: int):
@@ -306,7 +299,8 @@ def bench_multi(a, world: int, rank_id: int, local: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks
         out = {"build_ms": float(t[0].item()), "mcl_ms": float(t[1].item()), "iters": iters,
                "nnz_full": int(info.nnz_full), "n_matrix": mat.n, "preexp_ms": mc.preexp_ms, "nnz_m0": mc.nnz_m0,
-               "own_cols": blocks[rank_id][1] - blocks[rank_id][0], "preexp_products": mc.preexp_products}
+               "own_cols": blocks[rank_id][1] - blocks[rank_id][0], "preexp_products": mc.preexp_products,
+               "preexp": dict(mc.preexp)}
         mc.close()
         mat.close()
         tab.close()
@@ -403,7 +397,8 @@ def bench_multi(a, world: int, rank_id: int, local: int):
                     "iterations": steps[-1]["iters"], "e2e": mcl_e2e},
             "links": {"pairs": a.pairs, "nnz_full": steps[-1]["nnz_full"], "n_matrix": steps[-1]["n_matrix"]},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": rank0_roofline(steps[-1]), "cpu_baseline": None,
+            "roofline": rank0_roofline(steps[-1]),
+            "cpu_baseline": None if a.no_cpu_baseline else B.cpu_baseline_block(a, asm, rank, in_nx, rec),
         }
         print(json.dumps(line))
     ctx.close()

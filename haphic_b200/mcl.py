@@ -173,4 +173,5 @@ def inflation_values(min_inflation, max_inflation, step):
     end = Decimal(str(max_inflation)) + st
     import math
     n = max(0, math.ceil((end - start) / st))       # numpy.arange length rule, exact in Decimal
-    return [start + k * st for k in range(n)]
+    # numpy.arange over Decimals: element 0 is `start` itself ('1.0', not '1.00'), element k is start + k * step
+    return [start if k == 0 else start + k * st for k in range(n)]

@@ -294,3 +294,28 @@ def test_fragment_mode_matches_reference_golden(ctx):
     assert got_ht == {tuple(k): int(v) for k, v in zip(g["HT_keys"].tolist(), g["HT_vals"].tolist())}
     ftab.close()
     ctab.close()
+
+
+@pytest.mark.parametrize("bad_pos", [-1, None])
+def test_fragment_mode_refuses_positions_outside_the_contig(ctx, bad_pos):
+    """A position outside its (split) contig -- .pairs position 0 -> -1, or beyond the last bin -- names a bin that does
+    not exist.  The reference fails with a KeyError (frag_len_dict['ctg_binK']); the table must fail loudly too instead
+    of crediting a neighbouring contig's fragment."""
+    from haphic_b200._lib import HHError
+    from haphic_b200.links import LinkTable, name_rank
+    g = load_golden("links_bins.npz")
+    names = g["names"].tolist()
+    frag_names = g["frag_names"].tolist()
+    base = g["frag_base"]
+    split = int(np.nonzero(np.diff(base) > 1)[0][-1])          # the last split contig
+    other = 0 if split != 0 else 1
+    pos = bad_pos if bad_pos is not None else int(g["lengths"][split]) + 5 * int(g["bin_size"])
+    rec = np.array([[split, pos, other, 10]], dtype=np.int32)
+    ftab = LinkTable(ctx, g["frag_len"], name_rank(frag_names), g["frag_in_nx"], int(g["flank_kb"]) * 1000,
+                     frags=dict(ctg_rank=name_rank(names), frag_base=base, bin_size=int(g["bin_size"])))
+    ftab.add(g["pairs"][:1000])
+    ftab.add(rec)
+    with pytest.raises(HHError) as e:
+        ftab.finish()
+    assert "outside" in str(e.value)
+    ftab.close()

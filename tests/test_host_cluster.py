@@ -80,6 +80,11 @@ def test_check_param_and_inflation_values():
         cluster.check_param("--x", "", {"X", "x"})
     assert [str(v) for v in inflation_values(1.1, 3.0, 0.1)][::19] == ["1.1", "3.0"]
     assert [str(v) for v in inflation_values(1.2, 2.0, 0.2)] == ["1.2", "1.4", "1.6", "1.8", "2.0"]
+    # numpy.arange over Decimals keeps element 0 as given: '1.0', not '1.00' (directory names inflation_1.0, ...)
+    assert [str(v) for v in inflation_values(1.0, 1.5, 0.25)] == ["1.0", "1.25", "1.50"]
+    import numpy
+    from decimal import Decimal
+    assert [str(v) for v in numpy.arange(Decimal("1.0"), Decimal("1.5") + Decimal("0.25"), Decimal("0.25"))] == ["1.0", "1.25", "1.50"]
     assert cluster.parse_RE_sites(["GANTC"]) == ["GAATC", "GATTC", "GACTC", "GAGTC"]
     assert cluster.count_RE_sites("GATCGATCAAGCTT", "GATC,AAGCTT") == 3
 
