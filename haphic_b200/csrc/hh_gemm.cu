@@ -414,29 +414,50 @@ __device__ __forceinline__ void hg_split3(float x, unsigned short& h1, unsigned 
     h3 = (unsigned short)(__float_as_uint(r2) >> 16);              // at most 8 significant bits are left
 }
 
-// one warp per column c of the CSC = row c of both operands:  A[c, k] = C[c, k],  B[c, k] = fp32(C[c, k] / s[k])
-__global__ void hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row, const float* __restrict__ val, int n,
-                                  const double* __restrict__ s, unsigned short* __restrict__ A, int na, unsigned short* __restrict__ B,
-                                  long long ldk, long long plane, float clip) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= n) return;
-    const int lane = threadIdx.x & 31;
-    unsigned short* __restrict__ a0 = A + (size_t)c * (size_t)ldk;
-    unsigned short* __restrict__ b0 = B + (size_t)c * (size_t)ldk;
-    for (int64_t p = colptr[c] + lane; p < colptr[c + 1]; p += 32) {
-        const int k = row[p];
-        const float v = fminf(val[p], clip);      // counts above `clip` are finished by the caller's sparse correction
-        unsigned short h1, h2, h3;
-        hg_split3(v, h1, h2, h3);
-        a0[k] = h1;
-        if (na > 1) a0[(size_t)plane + k] = h2;
-        if (na > 2) a0[2 * (size_t)plane + k] = h3;
-        const double sk = s[k];
-        const float y = (sk != 0.0) ? (float)((double)v / sk) : v;
-        hg_split3(y, h1, h2, h3);
-        b0[k] = h1;
-        b0[(size_t)plane + k] = h2;
-        b0[2 * (size_t)plane + k] = h3;
+// One CTA per column c of the CSC = row c of both operands:  A[c, k] = min(C[c, k], clip),  B[c, k] = fp32(A[c, k] / s[k]).
+// The row is assembled in shared memory (segments of HG_SEG columns, up to three planes at a time) and written with
+// coalesced 16-byte stores: every element of the padded row is written exactly once, so the planes need no memset and no
+// read-modify-write of partially written sectors.
+#define HG_SEG 32768
+__global__ void __launch_bounds__(256)
+hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row, const float* __restrict__ val, int n,
+                  const double* __restrict__ s, unsigned short* __restrict__ A, int na, unsigned short* __restrict__ B, long long ldk,
+                  long long plane, float clip) {
+    extern __shared__ __align__(16) unsigned short hg_row[];        // [3][HG_SEG]
+    const int c = blockIdx.x;
+    const int64_t p0 = colptr[c], p1 = colptr[c + 1];
+    for (int group = 0; group < 2; ++group) {                       // 0: planes of A, 1: planes of B
+        const int np = group ? 3 : na;
+        unsigned short* __restrict__ out = (group ? B : A) + (size_t)c * (size_t)ldk;
+        for (long long seg0 = 0; seg0 < ldk; seg0 += HG_SEG) {
+            const int seg_n = (int)((ldk - seg0 < HG_SEG) ? (ldk - seg0) : HG_SEG);      // multiple of 64
+            uint4* z = reinterpret_cast<uint4*>(hg_row);
+            for (int q = threadIdx.x; q < 3 * HG_SEG / 8; q += 256) z[q] = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+            for (int64_t p = p0 + threadIdx.x; p < p1; p += 256) {
+                const long long k = row[p];
+                if (k < seg0 || k >= seg0 + seg_n) continue;
+                const float v = fminf(val[p], clip);      // counts above `clip` are finished by the caller's sparse correction
+                float x = v;
+                if (group) {
+                    const double sk = s[k];
+                    x = (sk != 0.0) ? (float)((double)v / sk) : v;
+                }
+                unsigned short h1, h2, h3;
+                hg_split3(x, h1, h2, h3);
+                const int kk = (int)(k - seg0);
+                hg_row[kk] = h1;
+                if (np > 1) hg_row[HG_SEG + kk] = h2;
+                if (np > 2) hg_row[2 * HG_SEG + kk] = h3;
+            }
+            __syncthreads();
+            for (int pl = 0; pl < np; ++pl) {
+                const uint4* src = reinterpret_cast<const uint4*>(hg_row + (size_t)pl * HG_SEG);
+                uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pl * (size_t)plane + (size_t)seg0);
+                for (int q = threadIdx.x; q < seg_n / 8; q += 256) dst[q] = src[q];
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -530,9 +551,12 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
         }
         HH_CHECK(hh_dmalloc(&d_A, (size_t)plane * (size_t)na));
         HH_CHECK(hh_dmalloc(&d_B, (size_t)plane * 3));
-        HH_CUDA(cudaMemsetAsync(d_A, 0, (size_t)plane * (size_t)na * 2, ctx->stream));
-        HH_CUDA(cudaMemsetAsync(d_B, 0, (size_t)plane * 3 * 2, ctx->stream));
-        HH_LAUNCH(ctx, hh_k_gemm_densify, (n + 7) / 8, 256, 0, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, ldk, plane, clip);
+        {
+            auto kd = hh_k_gemm_densify;
+            const size_t dsm = (size_t)3 * HG_SEG * sizeof(unsigned short);
+            HH_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+            HH_LAUNCH(ctx, kd, n, 256, dsm, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, ldk, plane, clip);
+        }
         // rows [n, ld) of every M1 column stay zero; entries that no tile writes (none on one GPU) as well
         HH_CUDA(cudaMemsetAsync(d_m1, 0, (size_t)ld * (size_t)(col_hi - col_lo) * sizeof(float), ctx->stream));
         HH_CHECK(hh_dmalloc(&d_items, (size_t)n_items));
@@ -557,7 +581,7 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
             a.pa[p] = pl[p][0];
             a.pb[p] = pl[p][1];
         }
-        a.chunk_kb = hg_env_int("HH_GEMM_CHUNK", 2);
+        a.chunk_kb = hg_env_int("HH_GEMM_CHUNK", a.npass > 3 ? 1 : 2);
         if (a.chunk_kb < 1) a.chunk_kb = 1 << 30;               // 0 = accumulate the whole K range in TMEM
         const size_t stage_bytes = (size_t)(na + 3) * HG_PLANE_BYTES;
         int stages = (int)((ctx->smem_optin - 2048) / stage_bytes);
@@ -618,20 +642,29 @@ int hh_gemm_items_full(int n, int col_lo, int col_hi, std::vector<hh_gemm_item>&
         const int c0 = t * T, c1 = std::min(n, c0 + T);
         return c1 > col_lo && c0 < col_hi;
     };
-    for (int ta = 0; ta < nt; ++ta) {
-        for (int tb = ta; tb < nt; ++tb) {
-            int flags = 0;
-            if (owned(tb)) flags |= HH_GEMM_DIRECT;
-            if (tb > ta && owned(ta)) flags |= HH_GEMM_MIRROR;
-            if (!flags) continue;
-            hh_gemm_item w;
-            memset(&w, 0, sizeof(w));
-            w.m_tile = ta;
-            w.n_tile = tb;
-            w.kb_lo[0] = 0;
-            w.kb_hi[0] = nkb;
-            w.flags = flags;
-            out.push_back(w);
+    // Rasterisation.  Item i runs on CTA pair (i mod pairs), so `pairs` consecutive items form a wave that streams its
+    // operand panels together: the wave should be a compact block of tiles.  A panels (one bf16 plane) are three times
+    // cheaper than B panels (three planes), so super-blocks are SB_M = 15 tiles tall and SB_N = 5 wide (75 tiles ~ one
+    // wave of 74 pairs): per k-block a wave then reads 15 + 3 * 5 = 30 panel blocks instead of 1 + 3 * 74.
+    const int SB_M = 15, SB_N = 5;
+    for (int bb = 0; bb < nt; bb += SB_N) {
+        for (int ba = 0; ba <= std::min(nt - 1, bb + SB_N - 1); ba += SB_M) {
+            for (int ta = ba; ta < std::min(nt, ba + SB_M); ++ta) {
+                for (int tb = std::max(bb, ta); tb < std::min(nt, bb + SB_N); ++tb) {
+                    int flags = 0;
+                    if (owned(tb)) flags |= HH_GEMM_DIRECT;
+                    if (tb > ta && owned(ta)) flags |= HH_GEMM_MIRROR;
+                    if (!flags) continue;
+                    hh_gemm_item w;
+                    memset(&w, 0, sizeof(w));
+                    w.m_tile = ta;
+                    w.n_tile = tb;
+                    w.kb_lo[0] = 0;
+                    w.kb_hi[0] = nkb;
+                    w.flags = flags;
+                    out.push_back(w);
+                }
+            }
         }
     }
     return HH_OK;

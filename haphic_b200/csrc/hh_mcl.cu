@@ -69,9 +69,6 @@ struct hh_colargs {
     const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
     int flat;                    // expansion inner loop: 1 = flat 32-entry walk, 0 = one segment at a time
     int l2pf;                    // expansion: prefetch the next batch's segments into L2
-    int clip_mode;               // SRC_CSC + EPI_NORM: 0 = x / S;  2 = only the part of a count above HH_CLIP, (x - HH_CLIP) / S
-    const float* bclip;          // SRC_PRODUCT: B values of column j are clipped to bclip[j] (= fp32(HH_CLIP / S_j))
-    int accumulate;              // EPI_DUMP: add the non-zero accumulator rows to the dense column instead of overwriting it
     float* scratch;
     unsigned long long* stats;   // [0] nnz written  [1] products
     int* delta_bits;
@@ -186,19 +183,18 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             const int* __restrict__ Ablk = a.A.blk;
             const size_t capA = (size_t)a.A.cap;
             unsigned long long warp_prod = 0ull;
-            const float bcl = a.bclip ? a.bclip[j] : 3.0e38f;
             // software pipeline over batches: B entries two batches ahead, block pointers one batch ahead
             int i1 = 0, i2 = 0, s1 = 0, e1 = 0;
             float v1 = 0.f, v2 = 0.f;
             if (lane < lenB) {
                 const uint2 be = Bent[lane];
                 i1 = (int)be.x;
-                v1 = fminf(__uint_as_float(be.y), bcl);
+                v1 = __uint_as_float(be.y);
             }
             if (32 + lane < lenB) {
                 const uint2 be = Bent[32 + lane];
                 i2 = (int)be.x;
-                v2 = fminf(__uint_as_float(be.y), bcl);
+                v2 = __uint_as_float(be.y);
             }
             if (lane < lenB) {
                 const int* bp = Ablk + (size_t)i1 * (W + 1) + w;
@@ -223,7 +219,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 if (t0 + 64 + lane < lenB) {
                     const uint2 be = Bent[t0 + 64 + lane];
                     i2 = (int)be.x;
-                    v2 = fminf(__uint_as_float(be.y), bcl);
+                    v2 = __uint_as_float(be.y);
                 }
                 const unsigned ne = __ballot_sync(HH_FULL_MASK, seg_len > 0);
                 if (!FLAT) {
@@ -380,33 +376,20 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
 
         if (EPI == EPI_DUMP) {
             float* __restrict__ col = a.dense_out + (size_t)jloc * (size_t)a.ld;
-            if (a.accumulate) {
-                for (int r = tile0 + lane; r < tile0 + T; r += 32) {
-                    if (r < a.ld) {
-                        const float x = acc[r];
-                        if (x != 0.f) {
-                            col[r] += x;
-                            acc[r] = 0.f;
-                        }
-                    }
-                }
-            } else {
             for (int r = tile0 + lane; r < tile0 + T; r += 32) {
                 if (r < a.ld) {          // rows in [n, ld) are zero padding (never accumulated)
                     col[r] = acc[r];
                     acc[r] = 0.f;
                 }
             }
-            }
         } else if (EPI == EPI_NORM) {
             double s = 0.0;
             int cnt = 0;
-            const bool upper = a.clip_mode == 2;     // keep only the part of every count above HH_CLIP
             HH_FOR_DIRTY_ROWS({
                 const float x = acc[k];
                 if (x != 0.f) {
                     s += fabs((double)x);
-                    if (!upper || x > HH_CLIP) cnt++;
+                    cnt++;
                 }
             })
             s = hh_warp_sum(s);
@@ -430,8 +413,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             int off = base;
             uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
             HH_FOR_DIRTY_ROWS({
-                const float x0 = acc[k];
-                const float x = upper ? (x0 > HH_CLIP ? x0 - HH_CLIP : 0.f) : x0;
+                const float x = acc[k];
                 const bool f = (x != 0.f);
                 const unsigned bal = __ballot_sync(HH_FULL_MASK, f);
                 if (f) {
@@ -439,8 +421,8 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     if (pos < a.out.cap) {
                         oent[pos] = make_uint2((unsigned)k, __float_as_uint((a.raw || S == 0.0) ? x : (float)((double)x / S)));
                     }
+                    acc[k] = 0.f;
                 }
-                if (x0 != 0.f) acc[k] = 0.f;
                 off += __popc(bal);
             })
             if (lane == 0) a.out.blk[(size_t)j * (W + 1) + w] = base;
@@ -474,6 +456,43 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             int cnt = 0;
             float vbest = 0.f;
             int kbest = 0x7fffffff, obest = 0x7fffffff;     // obest: ORIGINAL row index of kbest (first maximum = lowest original row)
+            if (SRC == SRC_DENSE && !a.do_conv && S1 != 0.0) {
+                // Dense iteration 0: every one of the n rows is stored, but only entries with x1 = fp32(fp64(y) / S1) >= pruning
+                // can survive (at most 1/pruning of them).  The exact fp64 quotient is taken for the candidates
+                // y >= 0.999 * pruning * S1 only; the others are provably below the threshold, keep the fp32 product
+                // y * (1 / S1) (never stored) and take part in the maximum through their exact ordering by y.
+                const float thr = (float)(0.999 * (double)p32 * S1);
+                const float inv1 = (float)(1.0 / S1);
+                float ybest = 0.f;
+                HH_FOR_DIRTY_ROWS({
+                    const float y = acc[k];
+                    if (y != 0.f) {
+                        float x1;
+                        if (y >= thr) {
+                            x1 = (float)((double)y / S1);
+                            if (x1 >= p32 && x1 > 0.f) {
+                                cnt++;
+                                s2 += (double)x1;
+                            }
+                        } else {
+                            x1 = fminf(y * inv1, 0.9995f * p32);     // strictly below the threshold whatever the rounding
+                        }
+                        acc[k] = x1;
+                        if (y > ybest) {                // rows ascend inside a lane: the first maximum wins
+                            // two different y may round to the same x1: then the earlier row stays (first maximum of x1)
+                            bool take = true;
+                            if (y <= ybest * 1.0000005f) take = (float)((double)y / S1) > (float)((double)ybest / S1);
+                            if (take) {
+                                ybest = y;
+                                kbest = k;
+                            }
+                        }
+                    }
+                })
+                // exact quotient of the lane's maximum (x1 is monotone in y)
+                vbest = (ybest > 0.f) ? (float)((double)ybest / S1) : 0.f;
+                obest = (a.orig && kbest != 0x7fffffff) ? a.orig[kbest] : kbest;
+            } else {
             HH_FOR_DIRTY_ROWS({
                 const float y = acc[k];
                 if (y != 0.f) {
@@ -496,6 +515,7 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                     }
                 }
             })
+            }
             s2 = hh_warp_sum(s2);
             cnt = hh_warp_sum(cnt);
 #pragma unroll
@@ -561,7 +581,8 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
                 float keepv = 0.f;
                 if (f) {
                     const int pos = off + __popc(bal & lt_mask);
-                    const float x2 = (float)((double)x1 / S2);
+                    // the kept maximum of a column without survivors is x1 / x1 = 1 (S2 = its own x1)
+                    const float x2 = need_max ? 1.0f : (float)((double)x1 / S2);
                     if (pos < a.out.cap) {
                         oent[pos] = make_uint2((unsigned)k, __float_as_uint(x2));
                     }
@@ -1413,25 +1434,77 @@ __global__ void hh_k_gather_len(const int* __restrict__ len, const int* __restri
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// per column: number of counts above HH_CLIP (atomicMax into *max_out) and bclip[c] = fp32(HH_CLIP / column sum)
-__global__ void hh_k_clip_stats(const int64_t* __restrict__ colptr, const float* __restrict__ val, int n, float* __restrict__ bclip,
-                                int* __restrict__ max_out) {
+// per column: fp64 sum of the raw link counts and bclip[c] = fp32(HH_CLIP / sum), the image of the clip threshold in M0
+__global__ void hh_k_clip_stats(const int64_t* __restrict__ colptr, const float* __restrict__ val, int n, double* __restrict__ s,
+                                float* __restrict__ bclip) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
     const int lane = threadIdx.x & 31;
     double t = 0.0;
-    int big = 0;
-    for (int64_t p = colptr[c] + lane; p < colptr[c + 1]; p += 32) {
-        const float v = val[p];
-        t += fabs((double)v);
-        big += v > HH_CLIP;
-    }
+    for (int64_t p = colptr[c] + lane; p < colptr[c + 1]; p += 32) t += fabs((double)val[p]);
     t = hh_warp_sum(t);
-    big = hh_warp_sum(big);
     if (lane == 0) {
+        s[c] = t;
         bclip[c] = (t != 0.0) ? (float)((double)HH_CLIP / t) : HH_CLIP;
-        if (big) atomicMax(max_out, big);
     }
+}
+
+// The tensor-core GEMM multiplied the counts clipped to HH_CLIP: with C = Cs + Cl, Cs = min(C, HH_CLIP), it produced
+// (Cs D Cs) D.  What is left of M1 = (C D C) D is
+//     MODE 0:  M1[:, x] += M0l[i, x] * M0[:, i]        M0l = Cl D  (the excess of the few large counts)
+//     MODE 1:  M1[x, j] += M0l[x, i] * M0s[i, j]       M0s = Cs D
+// for every large entry (i, x).  One warp owns column x (MODE 0) or row x (MODE 1) of M1 and walks the large entries of
+// column x of M0 in row order, so every element receives its additions in a fixed order: no atomics, bit-reproducible.
+// Large entries are recognised in M0 itself (M0[i, x] > fp32(HH_CLIP / s_x) <=> count > HH_CLIP); the count is rint(M0 * s).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+hh_k_clip_fix(const hh_slotmat m0, const double* __restrict__ s, const float* __restrict__ bclip, float* __restrict__ m1, long long ld,
+              int col_lo, int col_hi, unsigned long long* __restrict__ products) {
+    const int x = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (x >= m0.n) return;
+    if (MODE == 0 && (x < col_lo || x >= col_hi)) return;
+    const int lane = threadIdx.x & 31;
+    const int L = m0.len[x];
+    const uint2* __restrict__ ex = m0.ent + (size_t)x * (size_t)m0.cap;
+    const float bc = bclip[x];
+    const double sx = s[x];
+    unsigned long long np = 0ull;
+    for (int p0 = 0; p0 < L; p0 += 32) {
+        uint2 e = make_uint2(0u, 0u);
+        if (p0 + lane < L) e = ex[p0 + lane];
+        unsigned big = __ballot_sync(HH_FULL_MASK, (p0 + lane < L) && __uint_as_float(e.y) > bc);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int i = (int)__shfl_sync(HH_FULL_MASK, e.x, src);
+            const double c = rint((double)__uint_as_float(__shfl_sync(HH_FULL_MASK, e.y, src)) * sx);     // C[i, x]
+            const int Li = m0.len[i];
+            const uint2* __restrict__ ei = m0.ent + (size_t)i * (size_t)m0.cap;
+            if (MODE == 0) {
+                const float vl = (float)((c - (double)HH_CLIP) / sx);                  // M0l[i, x]
+                float* __restrict__ col = m1 + (size_t)(x - col_lo) * (size_t)ld;
+                for (int q = lane; q < Li; q += 32) {
+                    const uint2 t = ei[q];
+                    col[t.x] = fmaf(vl, __uint_as_float(t.y), col[t.x]);
+                }
+            } else {
+                const double si = s[i];
+                const float vl = (float)((c - (double)HH_CLIP) / si);                  // M0l[x, i]
+                for (int q = lane; q < Li; q += 32) {
+                    const uint2 t = ei[q];                                             // (j, C[j, i] / s_i)
+                    const int j = (int)t.x;
+                    if (j < col_lo || j >= col_hi) continue;
+                    const double cj = rint((double)__uint_as_float(t.y) * si);         // C[i, j]
+                    const float ms = (float)(fmin(cj, (double)HH_CLIP) / s[j]);        // M0s[i, j]
+                    float* __restrict__ dst = m1 + (size_t)(j - col_lo) * (size_t)ld + (size_t)x;
+                    *dst = fmaf(vl, ms, *dst);
+                }
+            }
+            np += (unsigned long long)Li;
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && np) atomicAdd(products, np);
 }
 
 struct hh_mcl {
@@ -1628,10 +1701,9 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
 
 // unsorted CSC -> slotted (raw or column-normalised); cap must be >= the longest column
 static int slot_from_csc(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, int* d_counter, unsigned long long* d_stats,
-                         const hh_matrix* m, int raw, hh_slotmat& out, int clip_mode = 0) {
+                         const hh_matrix* m, int raw, hh_slotmat& out) {
     hh_colargs a;
     memset(&a, 0, sizeof(a));
-    a.clip_mode = clip_mode;
     a.n = m->n;
     a.col_lo = 0;
     a.ncols = m->n;
@@ -1954,42 +2026,23 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
             mc->create_ms[1] = mc->gemm.densify_ms + mc->gemm.gemm_ms;
             mc->preexp_products = 0;
             if (mc->gemm.clipped) {
-                // C = Cs + Cl, Cs = min(C, 256): the GEMM did (Cs D Cs) D.  What is left,
-                //     M1 += M0 . M0l  +  M0l . M0s,     M0l = Cl D (a few entries per column),  M0s = Cs D = min(M0, bclip),
-                // are two Gustavson passes of the column kernel that add into the dense columns.
+                // finish the few link counts above HH_CLIP (hh_k_clip_fix)
                 float* d_bclip = nullptr;
-                hh_slotmat m0l;
-                memset(&m0l, 0, sizeof(m0l));
+                double* d_s = nullptr;
                 int rc2 = [&]() -> int {
                     HH_CHECK(hh_dmalloc(&d_bclip, (size_t)m->n));
-                    int* d_max = mc->d_bigcount + 3;
-                    HH_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
-                    HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
-                    HH_LAUNCH(ctx, hh_k_clip_stats, (m->n + 7) / 8, 256, 0, m->d_colptr, m->d_val, m->n, d_bclip, d_max);
-                    int capl = 0;
-                    HH_CUDA(cudaMemcpyAsync(&capl, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                    HH_CUDA(cudaStreamSynchronize(ctx->stream));
-                    HH_CHECK(slot_alloc(m0l, m->n, capl > 0 ? capl : 1, g.W));
+                    HH_CHECK(hh_dmalloc(&d_s, (size_t)m->n));
                     HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-                    HH_CHECK(slot_from_csc(ctx, g, mc->d_scratch, mc->grid_cap, mc->d_counter, mc->d_stats, m, 0, m0l, 2));
-                    hh_colargs a;
-                    mcl_base_args(mc, a);
-                    a.dense_out = mc->d_m1;
-                    a.accumulate = 1;
-                    a.A = mc->m0;            // M0 . M0l: few B entries per column, long operand segments
-                    a.B = m0l;
-                    a.flat = 0;
-                    a.l2pf = 0;
-                    HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
-                    a.A = m0l;               // M0l . M0s: every B entry meets a (mostly empty) operand column
-                    a.B = mc->m0;
-                    a.bclip = d_bclip;
-                    a.flat = 1;
-                    HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+                    HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
+                    const int grid = (m->n + 7) / 8;
+                    HH_LAUNCH(ctx, hh_k_clip_stats, grid, 256, 0, m->d_colptr, m->d_val, m->n, d_s, d_bclip);
+                    HH_LAUNCH(ctx, hh_k_clip_fix<0>, grid, 256, 0, mc->m0, d_s, d_bclip, mc->d_m1, (long long)mc->ld, (int)col_lo, (int)col_hi,
+                              mc->d_stats + 1);
+                    HH_LAUNCH(ctx, hh_k_clip_fix<1>, grid, 256, 0, mc->m0, d_s, d_bclip, mc->d_m1, (long long)mc->ld, (int)col_lo, (int)col_hi,
+                              mc->d_stats + 1);
                     HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
                     unsigned long long st2[4];
                     HH_CHECK(read_stats(ctx, mc->d_stats, st2));
-                    HH_REQUIRE((int)(st2[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY, "hh_mcl_create: slot overflow in the clip correction");
                     float ms = 0.f;
                     HH_CUDA(cudaEventElapsedTime(&ms, mc->ev0, mc->ev1));
                     mc->clip_ms = ms;
@@ -1998,7 +2051,7 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
                     return HH_OK;
                 }();
                 hh_dfree(d_bclip);
-                slot_free(m0l);
+                hh_dfree(d_s);
                 HH_CHECK(rc2);
             }
             return HH_OK;
@@ -2140,6 +2193,20 @@ static int mcl_build_perm(hh_mcl* mc) {
         int wmax = 32;
         for (int v = 0; v < n; ++v)
             if (csz[(size_t)v] <= wlimit && csz[(size_t)v] > wmax) wmax = csz[(size_t)v];
+        if (env_int("HH_MCL_DEBUG", 0)) {
+            long long ncomp = 0, biggest = 0;
+            double cubes = 0.0;
+            for (int v = 0; v < n; ++v) {
+                const long long c = csz[(size_t)v];
+                if (c > 0) {
+                    ncomp++;
+                    cubes += (double)c * (double)c * (double)c;
+                    if (c > biggest) biggest = c;
+                }
+            }
+            fprintf(stderr, "[hh_mcl] inflation %.2f: iterate nnz %lld, %lld components, largest %lld, sum of cubes %.3e\n", (double)mc->inflation,
+                    (long long)mc->cur_nnz, ncomp, biggest, cubes);
+        }
         mc->wmax = (wmax + 31) & ~31;
         // rewrite the iterate in new indices: column j' <- column inv[j'], rows through perm, rows re-sorted.
         // Columns of small components do it inside their window (one warp each); the others on the n-row accumulator.

@@ -131,7 +131,7 @@ def count_links_c(pairs, lengths, name_rank, in_nx, flank_bp, cap=None):
             "ht": ht, "ctg_link_total": tot}
 
 
-def count_links_numpy(pairs, lengths, name_rank, in_nx, flank_bp):
+def count_links_numpy(pairs, lengths, name_rank, in_nx, flank_bp, with_clm=True):
     """Vectorised restatement of the same loop; identical outputs as arrays.
 
     Returns a dict of arrays; every *_keys array is in dict-insertion (first-seen) order.
@@ -177,6 +177,18 @@ def count_links_numpy(pairs, lengths, name_rank, in_nx, flank_bp):
     np.minimum.at(touch, j[fl], idx[fl] * 2 + 1)
     touched = np.nonzero(tot > 0)[0]
     touched = touched[np.argsort(touch[touched], kind="stable")]
+    if not with_clm:      # the per-pair Python loop below is for fixture sizes; at BASELINE sizes only the counters are compared
+        return {
+            "n_used": len(idx),
+            "full_keys": np.stack([fk // n, fk % n], axis=1).astype(np.int32), "full_vals": f_cnt.astype(np.int64),
+            "full_first": f_first,
+            "flank_keys": np.stack([lk // n, lk % n], axis=1).astype(np.int32), "flank_vals": l_cnt.astype(np.int64),
+            "flank_first": l_first,
+            "HT_keys": np.stack([(hk // 4) // n, (hk % 4) // 2, (hk // 4) % n, hk % 2], axis=1).astype(np.int32),
+            "HT_vals": h_cnt.astype(np.int64),
+            "ctg_link_ids": touched.astype(np.int32), "ctg_link_vals": tot[touched].astype(np.int64),
+            "ctg_link_total": tot.astype(np.int64),
+        }
     # clm: per key, distances in stream order (4 per link)
     a0, b0 = ci - 1, cj - 1
     dist = np.stack([li - a0 + b0, li - a0 + lj - b0, a0 + b0, a0 + lj - b0], axis=1)
