@@ -15,12 +15,21 @@
 // hh_links_finish orders the distinct keys by first appearance with a scatter + stream
 // compaction (no sort): order[first_full] = slot, then compact.
 #include "hh_common.cuh"
+#include <stdlib.h>
+#include <vector>
 
 #define HH_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define HH_NONE32 0xFFFFFFFFu
 
 struct __align__(32) hh_slot {
     uint32_t first_full, first_flank, full, flank, ht, th, tt, pad;
+};
+
+struct hh_partset {
+    int4* buf;                       // [npart][pcap] records {i, j, stream index, flags}
+    unsigned long long* cursor;      // [npart] records written to every region (may exceed pcap: the excess went to the spill list)
+    uint64_t pcap;                   // records per partition region
+    int64_t sized_for, sent;         // records the set was sized for / sent to it so far
 };
 
 struct hh_links {
@@ -53,6 +62,15 @@ struct hh_links {
     cudaEvent_t ev_copied[2], ev_consumed[2];
     cudaStream_t copy_stream;
     int64_t stage_records;
+    // partitioned counting (contig mode, long streams; see "partition, then aggregate" below)
+    int mode;                        // 0 undecided, 1 direct (one big hash table), 2 partitioned
+    int npart_log;                   // log2 of the number of partitions
+    uint64_t scap;                   // slots of a scratch table (power of two)
+    uint64_t spill_cap;
+    std::vector<hh_partset>* psets;  // partition buffers; normally one set, a new one when a later add call outgrows it
+    int4* d_spill;                   // records of partitions whose region overflowed (skewed keys), with their partition id
+    unsigned long long* d_spill_cursor;
+    int64_t capacity_hint;
     // dict_to_matrix support
     int32_t* d_index;                // [n_ctg] matrix index of linked fragments (hh_links_linked_index)
     int32_t n_linked;
@@ -238,6 +256,204 @@ hh_k_links_insert(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_o
         if (s_new) atomicAdd(counters + 0, (unsigned long long)s_new);
         if (s_used) atomicAdd(counters + 1, (unsigned long long)s_used);
         if (s_over) atomicExch(counters + 2, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Partition, then aggregate.  One big hash table costs every record a random DRAM sector for the key and another
+// read-modify-write for the counters (the table is two orders of magnitude larger than L2).  For long streams the
+// records are therefore first split by the high bits of the key hash into 2^npart_log partitions (one sequential read,
+// one write in runs that fill whole sectors), and every partition is then counted in a scratch table small enough to
+// stay in L2 and emitted as compact entries (9 words, the hh_links_adopt list format).  Integer adds and mins only:
+// the result is identical to the direct path.
+//   hh_k_part_scatter   record -> {i, j, stream index, flags} (ends ordered by name rank, is_flank / head-tail evaluated once)
+//   hh_k_part_step      emit + clear the scratch table of the previous partition, count the current one into the other
+// ---------------------------------------------------------------------------------------------
+#define HH_PART_TILE 4096          // records per tile of the scatter kernel (512 threads x 8)
+#define HH_PART_MAX 1024
+
+__global__ void __launch_bounds__(512)
+hh_k_part_scatter(const int4* __restrict__ rec, int64_t n_rec, uint32_t stream_off, int32_t n_ctg, const int32_t* __restrict__ ctg_len,
+                  const int32_t* __restrict__ name_rank, const uint8_t* __restrict__ in_nx, int64_t flank_bp, int npart_log,
+                  int4* __restrict__ pbuf, uint64_t pcap, unsigned long long* __restrict__ cursor, int4* __restrict__ spill,
+                  uint64_t spill_cap, unsigned long long* __restrict__ spill_cursor, unsigned long long* __restrict__ counters) {
+    __shared__ unsigned int s_cnt[HH_PART_MAX];
+    __shared__ unsigned long long s_base[HH_PART_MAX];
+    __shared__ unsigned int s_used;
+    const int npart = 1 << npart_log;
+    const int64_t tiles = (n_rec + HH_PART_TILE - 1) / HH_PART_TILE;
+    unsigned int my_used = 0;
+    if (threadIdx.x == 0) s_used = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        for (int k = threadIdx.x; k < npart; k += 512) s_cnt[k] = 0;
+        __syncthreads();
+        int4 out[8];
+        int part[8];
+        unsigned int rnk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t i = t * HH_PART_TILE + (int64_t)k * 512 + threadIdx.x;
+            part[k] = -1;
+            if (i < n_rec) {
+                const int4 r = hh_ld_stream(rec + i);
+                int a = r.x, b = r.z, pa = r.y, pb = r.w;
+                if (a != b && (unsigned)a < (unsigned)n_ctg && (unsigned)b < (unsigned)n_ctg) {
+                    if (name_rank[a] > name_rank[b]) {      // sorted(((ref,pos+1),(mref,mpos+1))), 1629
+                        int x = a; a = b; b = x;
+                        x = pa; pa = pb; pb = x;
+                    }
+                    const int64_t coord_i = (int64_t)pa + 1, coord_j = (int64_t)pb + 1;
+                    const int64_t li = ctg_len[a], lj = ctg_len[b];
+                    const bool fi = (flank_bp == 0) || (coord_i <= flank_bp) || (coord_i > li - flank_bp);   // is_flank, 299-307
+                    const bool fj = (flank_bp == 0) || (coord_j <= flank_bp) || (coord_j > lj - flank_bp);
+                    const unsigned fl = (fi && fj && in_nx[a] && in_nx[b]) ? 1u : 0u;                         // 1636
+                    const unsigned ti = (coord_i * 2 > li) ? 2u : 0u, tj = (coord_j * 2 > lj) ? 4u : 0u;       // 404-416
+                    const uint64_t key = ((uint64_t)(uint32_t)a << 32) | (uint64_t)(uint32_t)b;
+                    const int p = (int)(hh_mix64(key) >> (64 - npart_log));
+                    part[k] = p;
+                    rnk[k] = atomicAdd(&s_cnt[p], 1u);
+                    out[k] = make_int4(a, b, (int)(stream_off + (uint32_t)i), (int)(fl | ti | tj | ((unsigned)p << 8)));
+                    my_used++;
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < npart; k += 512)
+            if (s_cnt[k]) s_base[k] = atomicAdd(cursor + k, (unsigned long long)s_cnt[k]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (part[k] < 0) continue;
+            const unsigned long long q = s_base[part[k]] + rnk[k];
+            if (q < pcap) {
+                pbuf[(size_t)part[k] * (size_t)pcap + (size_t)q] = out[k];
+            } else {
+                // the region of this partition is full (a few pairs own a large share of the stream): spill list
+                const unsigned long long sq = atomicAdd(spill_cursor, 1ull);
+                if (sq < spill_cap) spill[sq] = out[k];
+                else atomicExch(counters + 2, 3ull);
+            }
+        }
+        __syncthreads();
+    }
+    my_used = (unsigned)hh_warp_sum((int)my_used);
+    if ((threadIdx.x & 31) == 0 && my_used) atomicAdd(&s_used, my_used);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_used) atomicAdd(counters + 1, (unsigned long long)s_used);
+}
+
+// count `n` partitioned records ({i, j, stream index, flags}) into a scratch table; part >= 0 selects the records of
+// that partition from a mixed list (the spill list)
+__device__ __forceinline__ void hh_part_count(const int4* __restrict__ prec, int64_t n, int part, uint64_t* __restrict__ keys,
+                                              hh_slot* __restrict__ vals, uint64_t cap, unsigned long long* __restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += stride) {
+        const int64_t i = i0 + lane;
+        bool ok = i < n;
+        int4 r = make_int4(0, 0, 0, 0);
+        if (ok) r = hh_ld_stream(prec + i);
+        const unsigned f = (unsigned)r.w;
+        if (ok && part >= 0) ok = (int)(f >> 8) == part;
+        const uint64_t key = ok ? (((uint64_t)(uint32_t)r.x << 32) | (uint64_t)(uint32_t)r.y) : (HH_EMPTY_KEY - 1 - (uint64_t)lane);
+        const unsigned peers = __match_any_sync(HH_FULL_MASK, key);
+        const bool fl = ok && (f & 1u), ti = (f & 2u) != 0, tj = (f & 4u) != 0;
+        const uint32_t idx = ok ? (uint32_t)r.z : HH_NONE32;
+        const uint32_t first_all = __reduce_min_sync(peers, idx);
+        const uint32_t first_fl = __reduce_min_sync(peers, fl ? idx : HH_NONE32);
+        const unsigned b_fl = __ballot_sync(HH_FULL_MASK, fl);
+        const unsigned b_ht = __ballot_sync(HH_FULL_MASK, ok && !ti && tj);
+        const unsigned b_th = __ballot_sync(HH_FULL_MASK, ok && ti && !tj);
+        const unsigned b_tt = __ballot_sync(HH_FULL_MASK, ok && ti && tj);
+        if (ok && lane == (__ffs(peers) - 1)) {
+            bool inserted;
+            const uint64_t slot = hh_probe_insert(keys, cap, key, &inserted);
+            if (slot >= cap) {
+                atomicExch(counters + 2, 4ull);
+            } else {
+                hh_slot* v = vals + slot;
+                atomicAdd(&v->full, (unsigned)__popc(peers));
+                atomicMin(&v->first_full, first_all);
+                const unsigned c_fl = __popc(peers & b_fl);
+                if (c_fl) {
+                    atomicAdd(&v->flank, c_fl);
+                    atomicMin(&v->first_flank, first_fl);
+                }
+                const unsigned c_ht = __popc(peers & b_ht), c_th = __popc(peers & b_th), c_tt = __popc(peers & b_tt);
+                if (c_ht) atomicAdd(&v->ht, c_ht);
+                if (c_th) atomicAdd(&v->th, c_th);
+                if (c_tt) atomicAdd(&v->tt, c_tt);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hh_k_part_step(const int4* __restrict__ prec, int64_t n, const int4* __restrict__ spill, int64_t n_spill, int part,
+               uint64_t* __restrict__ ckeys, hh_slot* __restrict__ cvals, uint64_t* __restrict__ ekeys, hh_slot* __restrict__ evals, uint64_t cap,
+               uint32_t* __restrict__ compact, uint64_t compact_cap, unsigned long long* __restrict__ ctg_links,
+               unsigned long long* __restrict__ counters) {
+    // ---- emit the table of the previous partition: live slots -> compact entries, per-fragment totals; slots are cleared.
+    // Output positions are reserved once per CTA and trip (shared-memory counter), not once per warp.
+    if (ekeys != nullptr) {
+        __shared__ unsigned int s_cnt;
+        __shared__ unsigned long long s_base;
+        const int lane = threadIdx.x & 31;
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+        unsigned int nfl = 0;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (uint64_t b0 = (uint64_t)blockIdx.x * blockDim.x; b0 < cap; b0 += stride) {      // block-uniform trip count
+            const uint64_t sl = b0 + threadIdx.x;
+            uint64_t key = HH_EMPTY_KEY;
+            if (sl < cap) key = ekeys[sl];
+            const bool live = key != HH_EMPTY_KEY;
+            const unsigned bal = __ballot_sync(HH_FULL_MASK, live);
+            unsigned int woff = 0;
+            if (lane == 0 && bal) woff = atomicAdd(&s_cnt, (unsigned)__popc(bal));
+            woff = __shfl_sync(HH_FULL_MASK, woff, 0);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_base = s_cnt ? atomicAdd(counters + 0, (unsigned long long)s_cnt) : 0ull;
+                s_cnt = 0;
+            }
+            __syncthreads();
+            if (live) {
+                uint4* vp = reinterpret_cast<uint4*>(evals + sl);
+                const uint4 v0 = vp[0], v1 = vp[1];      // {first_full, first_flank, full, flank} {ht, th, tt, pad}
+                const unsigned long long q = s_base + woff + __popc(bal & ((1u << lane) - 1u));
+                if (q < compact_cap) {
+                    uint32_t* o = compact + q * 9;
+                    o[0] = (uint32_t)(key >> 32);
+                    o[1] = (uint32_t)key;
+                    o[2] = v0.z;
+                    o[3] = v0.w;
+                    o[4] = v0.x;
+                    o[5] = v0.y;
+                    o[6] = v1.x;
+                    o[7] = v1.y;
+                    o[8] = v1.z;
+                } else {
+                    atomicExch(counters + 2, 5ull);
+                }
+                if (v0.w) {
+                    nfl++;
+                    atomicAdd(ctg_links + (uint32_t)(key >> 32), (unsigned long long)v0.w);      // ctg_link_dict (1638-1639)
+                    atomicAdd(ctg_links + (uint32_t)key, (unsigned long long)v0.w);
+                }
+                ekeys[sl] = HH_EMPTY_KEY;
+                vp[0] = make_uint4(HH_NONE32, HH_NONE32, 0u, 0u);
+                vp[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncthreads();        // s_base is rewritten by the next trip
+        }
+        nfl = (unsigned)hh_warp_sum((int)nfl);
+        if (lane == 0 && nfl) atomicAdd(counters + 3, (unsigned long long)nfl);
+    }
+    // ---- count the current partition
+    if (ckeys != nullptr) {
+        if (n > 0) hh_part_count(prec, n, -1, ckeys, cvals, cap, counters);
+        if (n_spill > 0) hh_part_count(spill, n_spill, part, ckeys, cvals, cap, counters);
     }
 }
 
@@ -552,9 +768,21 @@ static int links_read_counters(hh_links* lk, unsigned long long out[8]) {
     return HH_OK;
 }
 
+// the big hash table of the direct path is allocated on first use (the partitioned path never needs it)
+static int links_need_table(hh_links* lk) {
+    if (lk->d_keys) return HH_OK;
+    uint64_t cap = 1ull << 16;
+    const double want = lk->capacity_hint > 0 ? (double)lk->capacity_hint / 0.5 : 0.0;
+    while ((double)cap < want) cap <<= 1;
+    HH_CHECK(links_alloc_table(lk, cap, &lk->d_keys, &lk->d_vals));
+    lk->cap = cap;
+    return HH_OK;
+}
+
 // make sure `incoming` more distinct keys fit under a 0.7 load factor
 static int links_ensure_capacity(hh_links* lk, int64_t incoming) {
     const double max_load = 0.7;
+    HH_CHECK(links_need_table(lk));
     if ((double)(lk->known_unique + lk->since_known + incoming) <= max_load * (double)lk->cap) return HH_OK;
     unsigned long long c[8];
     HH_CHECK(links_read_counters(lk, c));
@@ -627,15 +855,8 @@ static int links_create_common(hh_ctx* ctx, int32_t n_key, const int64_t* key_le
         HH_CUDA(cudaMemcpyAsync(lk->d_fbase, frag_base, ((size_t)n_src + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
     HH_CUDA(cudaStreamSynchronize(st));   // host temporaries go out of scope
-    uint64_t cap = 1ull << 16;
-    const double want = capacity_hint > 0 ? (double)capacity_hint / 0.5 : 0.0;
-    while ((double)cap < want) cap <<= 1;
-    rc = links_alloc_table(lk, cap, &lk->d_keys, &lk->d_vals);
-    if (rc != HH_OK) {
-        hh_links_destroy(lk);
-        return rc;
-    }
-    lk->cap = cap;
+    lk->capacity_hint = capacity_hint;
+    lk->psets = new std::vector<hh_partset>();
     HH_CUDA(cudaStreamCreateWithFlags(&lk->copy_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
         HH_CUDA(cudaEventCreateWithFlags(&lk->ev_copied[k], cudaEventDisableTiming));
@@ -671,15 +892,86 @@ extern "C" int hh_links_create_frags(hh_ctx* ctx, int32_t n_ctg, const int32_t* 
                                bin_size, out);
 }
 
+static int links_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// a new set of partition regions sized for `n_rec` more records
+static int links_new_partset(hh_links* lk, int64_t n_rec) {
+    const int npart = 1 << lk->npart_log;
+    hh_partset ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.pcap = (uint64_t)((double)n_rec / npart * 1.5) + 4096;
+    ps.sized_for = n_rec;
+    HH_CHECK(hh_dmalloc(&ps.buf, (size_t)npart * (size_t)ps.pcap));
+    int rc = hh_dmalloc(&ps.cursor, (size_t)npart);
+    if (rc != HH_OK) {
+        hh_dfree(ps.buf);
+        return rc;
+    }
+    HH_CUDA(cudaMemsetAsync(ps.cursor, 0, (size_t)npart * sizeof(unsigned long long), lk->ctx->stream));
+    lk->psets->push_back(ps);
+    return HH_OK;
+}
+
+// first records of the stream: direct hash table or partition-then-aggregate.  `total` = records the caller is about to
+// stream in this call (the sizing of the partition regions)
+static int links_choose_mode(hh_links* lk, int64_t total) {
+    if (lk->mode) return HH_OK;
+    const int want = links_env_int("HH_LINKS_PARTITION", -1);          // 0 = never, 1 = always (contig mode), -1 = by size
+    const bool can = lk->d_fbase == nullptr && lk->d_keys == nullptr;
+    const bool big = total >= (16ll << 20) && lk->n_ctg >= 2048;
+    if (!can || want == 0 || (want < 0 && !big)) {
+        lk->mode = 1;
+        return HH_OK;
+    }
+    lk->mode = 2;
+    int lg = 4;
+    while (lg < 9 && ((int64_t)400000 << lg) < total) lg++;            // ~400k records per partition, at most 512 partitions
+    lk->npart_log = links_env_int("HH_LINKS_NPART_LOG", lg);
+    if (lk->npart_log < 1) lk->npart_log = 1;
+    if (lk->npart_log > 10) lk->npart_log = 10;
+    HH_CHECK(links_new_partset(lk, total));
+    lk->spill_cap = (uint64_t)(total / 8) + (4u << 20);
+    HH_CHECK(hh_dmalloc(&lk->d_spill, (size_t)lk->spill_cap));
+    HH_CHECK(hh_dmalloc(&lk->d_spill_cursor, 1));
+    HH_CUDA(cudaMemsetAsync(lk->d_spill_cursor, 0, sizeof(unsigned long long), lk->ctx->stream));
+    return HH_OK;
+}
+
 static int links_launch_insert(hh_links* lk, const int4* d_rec, int64_t n_rec, int64_t stream_offset,
                                const uint32_t* d_pos = nullptr) {
     hh_ctx* ctx = lk->ctx;
+    if (lk->mode == 2 && d_pos == nullptr) {
+        const int64_t tiles = (n_rec + HH_PART_TILE - 1) / HH_PART_TILE;
+        int grid = (int)(tiles < (int64_t)hh_grid(ctx, 3) ? tiles : (int64_t)hh_grid(ctx, 3));
+        if (grid < 1) grid = 1;
+        const hh_partset& ps = lk->psets->back();
+        HH_LAUNCH(ctx, hh_k_part_scatter, grid, 512, 0, d_rec, n_rec, (uint32_t)stream_offset, lk->n_ctg, lk->d_len, lk->d_rank, lk->d_nx,
+                  lk->flank_bp, lk->npart_log, ps.buf, ps.pcap, ps.cursor, lk->d_spill, lk->spill_cap, lk->d_spill_cursor,
+                  lk->d_counters);
+        return HH_OK;
+    }
+    HH_CHECK(links_need_table(lk));
     int64_t blocks = (n_rec + 255) / 256;
     int grid = (int)(blocks < (int64_t)hh_grid(ctx, 8) ? blocks : (int64_t)hh_grid(ctx, 8));
     if (grid < 1) grid = 1;
     HH_LAUNCH(ctx, hh_k_links_insert, grid, 256, 0, d_rec, n_rec, (uint32_t)stream_offset, lk->n_ctg, lk->d_len, lk->d_rank,
               lk->d_nx, lk->flank_bp, lk->d_keys, lk->d_vals, lk->cap, lk->d_ctg, lk->d_counters, lk->d_src_rank, lk->d_fbase,
               lk->bin_size, lk->n_src, d_pos);
+    return HH_OK;
+}
+
+// partitioned mode: a call that would outgrow the current set (sized for the first call) gets a set of its own
+static int links_part_room(hh_links* lk, int64_t n_rec) {
+    hh_partset& ps = lk->psets->back();
+    if (ps.sent > 0 && ps.sent + n_rec > ps.sized_for + ps.sized_for / 8) {
+        HH_CHECK(links_new_partset(lk, n_rec));
+        lk->psets->back().sent = n_rec;
+        return HH_OK;
+    }
+    ps.sent += n_rec;
     return HH_OK;
 }
 
@@ -693,6 +985,8 @@ extern "C" int hh_links_add_async(hh_links* lk, const int32_t* rec_dev, int64_t 
     HH_REQUIRE(((uintptr_t)rec_dev & 15) == 0, HH_ERR_ARG, "hh_links_add: records must be 16-byte aligned");
     if (n_rec == 0) return HH_OK;
     HH_CUDA(cudaSetDevice(lk->ctx->device));
+    HH_CHECK(links_choose_mode(lk, n_rec));
+    if (lk->mode == 2) HH_CHECK(links_part_room(lk, n_rec));
     HH_CHECK(links_launch_insert(lk, reinterpret_cast<const int4*>(rec_dev), n_rec, stream_offset));
     lk->n_records += n_rec;
     lk->since_known += n_rec;
@@ -712,11 +1006,13 @@ extern "C" int hh_links_add(hh_links* lk, const int32_t* rec, int64_t n_rec, int
     hh_ctx* ctx = lk->ctx;
     HH_CUDA(cudaSetDevice(ctx->device));
     const int64_t CH = 1ll << 23;   // 8 Mi records = 128 MiB per chunk
+    HH_CHECK(links_choose_mode(lk, n_rec));
+    if (lk->mode == 2) HH_CHECK(links_part_room(lk, n_rec));
     if (mem == HH_MEM_DEVICE) {
         HH_REQUIRE(((uintptr_t)rec & 15) == 0, HH_ERR_ARG, "hh_links_add: records must be 16-byte aligned");
         for (int64_t off = 0; off < n_rec; off += CH) {
             const int64_t m = (n_rec - off < CH) ? (n_rec - off) : CH;
-            HH_CHECK(links_ensure_capacity(lk, m));
+            if (lk->mode != 2) HH_CHECK(links_ensure_capacity(lk, m));
             HH_CHECK(links_launch_insert(lk, reinterpret_cast<const int4*>(rec) + off, m, stream_offset + off));
             lk->since_known += m;
         }
@@ -733,7 +1029,7 @@ extern "C" int hh_links_add(hh_links* lk, const int32_t* rec, int64_t n_rec, int
             HH_CUDA(cudaStreamWaitEvent(lk->copy_stream, lk->ev_consumed[buf], 0));
             HH_CUDA(cudaMemcpyAsync(lk->d_stage[buf], rec + off * 4, (size_t)m * 16, cudaMemcpyHostToDevice, lk->copy_stream));
             HH_CUDA(cudaEventRecord(lk->ev_copied[buf], lk->copy_stream));
-            HH_CHECK(links_ensure_capacity(lk, m));
+            if (lk->mode != 2) HH_CHECK(links_ensure_capacity(lk, m));
             HH_CUDA(cudaStreamWaitEvent(ctx->stream, lk->ev_copied[buf], 0));
             HH_CHECK(links_launch_insert(lk, lk->d_stage[buf], m, stream_offset + off));
             HH_CUDA(cudaEventRecord(lk->ev_consumed[buf], ctx->stream));
@@ -746,12 +1042,105 @@ extern "C" int hh_links_add(hh_links* lk, const int32_t* rec, int64_t n_rec, int
     return HH_OK;
 }
 
+// partitioned counting, second phase: every partition through an L2-resident scratch table (two tables, so the emit of
+// partition p - 1 and the count of partition p share one launch), entries appended to an unordered compact list
+static void links_free_partsets(hh_links* lk) {
+    if (lk->psets) {
+        for (size_t k = 0; k < lk->psets->size(); ++k) {
+            hh_dfree((*lk->psets)[k].buf);
+            hh_dfree((*lk->psets)[k].cursor);
+        }
+        lk->psets->clear();
+    }
+    hh_dfree(lk->d_spill);
+    hh_dfree(lk->d_spill_cursor);
+}
+
+static int links_finish_partitioned(hh_links* lk) {
+    hh_ctx* ctx = lk->ctx;
+    const int npart = 1 << lk->npart_log;
+    const size_t nsets = lk->psets->size();
+    unsigned long long c[8];
+    HH_CHECK(links_read_counters(lk, c));
+    HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY,
+               "hh_links_finish: the spill list of the partitioned counting overflowed (a few contig pairs own most of the stream): "
+               "set HH_LINKS_PARTITION=0 to use the direct hash table");
+    lk->n_used = lk->peer_used + (int64_t)c[1];
+    // region fill levels and the spill count
+    std::vector<unsigned long long> fill(nsets * (size_t)npart);
+    for (size_t k = 0; k < nsets; ++k)
+        HH_CUDA(cudaMemcpyAsync(fill.data() + k * (size_t)npart, (*lk->psets)[k].cursor, (size_t)npart * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long n_spill = 0;
+    HH_CUDA(cudaMemcpyAsync(&n_spill, lk->d_spill_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(ctx->stream));
+    // scratch tables: load factor <= 0.6 even if every record of the fullest partition is a distinct key
+    unsigned long long worst = 1;
+    for (int p = 0; p < npart; ++p) {
+        unsigned long long t = 0;
+        for (size_t k = 0; k < nsets; ++k) t += fill[k * (size_t)npart + p];
+        if (t > worst) worst = t;
+    }
+    uint64_t scap = 1ull << 12;
+    while ((double)scap * 0.6 < (double)worst) scap <<= 1;
+    lk->scap = scap;
+    uint64_t* skeys[2] = {nullptr, nullptr};
+    hh_slot* svals[2] = {nullptr, nullptr};
+    const uint64_t compact_cap = (uint64_t)(lk->n_used > 0 ? lk->n_used : 1);       // distinct pairs <= usable records
+    hh_dfree(lk->d_compact);
+    int rc = [&]() -> int {
+        HH_CHECK(hh_dmalloc(&lk->d_compact, (size_t)compact_cap * 9));
+        for (int b = 0; b < 2; ++b) HH_CHECK(links_alloc_table(lk, scap, &skeys[b], &svals[b]));
+        HH_CUDA(cudaMemsetAsync(lk->d_counters + 0, 0, sizeof(unsigned long long), ctx->stream));     // entry cursor
+        HH_CUDA(cudaMemsetAsync(lk->d_counters + 3, 0, sizeof(unsigned long long), ctx->stream));     // nnz_flank
+        const int grid = hh_grid(ctx, 8);
+        for (int p = 0; p <= npart; ++p) {
+            const int cb = p & 1, eb = cb ^ 1;
+            bool first = true;
+            for (size_t k = 0; k < nsets || first; ++k) {
+                const bool have = p < npart && k < nsets;
+                const uint64_t pcap = k < nsets ? (*lk->psets)[k].pcap : 0;
+                unsigned long long nrec = have ? fill[k * (size_t)npart + p] : 0;
+                if (have && nrec > pcap) nrec = pcap;                 // the excess is on the spill list
+                const int4* prec = have ? (*lk->psets)[k].buf + (size_t)p * (size_t)pcap : nullptr;
+                // the spill list is scanned once per overflowed partition (with the first set)
+                bool spill_now = false;
+                if (p < npart && first && n_spill) {
+                    for (size_t kk = 0; kk < nsets; ++kk) spill_now = spill_now || fill[kk * (size_t)npart + p] > (*lk->psets)[kk].pcap;
+                }
+                HH_LAUNCH(ctx, hh_k_part_step, grid, 256, 0, prec, (int64_t)nrec, lk->d_spill, spill_now ? (int64_t)n_spill : 0, p,
+                          p < npart ? skeys[cb] : nullptr, p < npart ? svals[cb] : nullptr, (first && p > 0) ? skeys[eb] : nullptr,
+                          (first && p > 0) ? svals[eb] : nullptr, scap, lk->d_compact, compact_cap, lk->d_ctg, lk->d_counters);
+                first = false;
+                if (k + 1 >= nsets) break;
+            }
+        }
+        HH_CHECK(links_read_counters(lk, c));
+        HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY,
+                   "hh_links_finish: a scratch table of the partitioned counting overflowed (code %llu): set HH_LINKS_PARTITION=0", c[2]);
+        lk->nnz = (int64_t)c[0];
+        lk->nnz_flank = (int64_t)c[3];
+        return HH_OK;
+    }();
+    for (int b = 0; b < 2; ++b) {
+        hh_dfree(skeys[b]);
+        hh_dfree(svals[b]);
+    }
+    links_free_partsets(lk);
+    HH_CHECK(rc);
+    lk->finished = true;
+    lk->ordered = false;        // dict insertion order is restored by the first hh_links_fetch (links_order_list)
+    return HH_OK;
+}
+
 extern "C" int hh_links_finish(hh_links* lk, hh_links_info* info) {
     HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_finish: NULL handle");
     hh_scope _scope(lk->ctx);
     hh_ctx* ctx = lk->ctx;
     HH_CUDA(cudaSetDevice(ctx->device));
+    if (!lk->finished && lk->mode == 2) HH_CHECK(links_finish_partitioned(lk));
     if (!lk->finished) {
+        HH_CHECK(links_need_table(lk));
         unsigned long long c[8];
         HH_CHECK(links_read_counters(lk, c));
         HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY,
@@ -806,7 +1195,7 @@ extern "C" int hh_links_finish(hh_links* lk, hh_links_info* info) {
         info->n_used = lk->n_used;
         info->nnz_full = lk->nnz;
         info->nnz_flank = lk->nnz_flank;
-        info->table_slots = (int64_t)lk->cap;
+        info->table_slots = (int64_t)(lk->mode == 2 ? lk->scap : lk->cap);
     }
     return HH_OK;
 }
@@ -888,6 +1277,8 @@ extern "C" int hh_links_add_routed(hh_links* lk, const int32_t* rec_dev, const u
     HH_REQUIRE(((uintptr_t)rec_dev & 15) == 0, HH_ERR_ARG, "hh_links_add_routed: records must be 16-byte aligned");
     if (n_rec == 0) return HH_OK;
     HH_CUDA(cudaSetDevice(lk->ctx->device));
+    HH_REQUIRE(lk->mode != 2, HH_ERR_STATE, "hh_links_add_routed: this table counts a partitioned stream (hh_links_add of a long stream)");
+    lk->mode = 1;
     const int64_t CH = 1ll << 23;
     for (int64_t off = 0; off < n_rec; off += CH) {
         const int64_t m = (n_rec - off < CH) ? (n_rec - off) : CH;
@@ -904,7 +1295,9 @@ extern "C" int hh_links_finish_partition(hh_links* lk, hh_links_info* info) {
     hh_scope _scope(lk->ctx);
     hh_ctx* ctx = lk->ctx;
     HH_CUDA(cudaSetDevice(ctx->device));
+    if (!lk->finished && lk->mode == 2) HH_CHECK(links_finish_partitioned(lk));     // already an unordered entry list
     if (!lk->finished) {
+        HH_CHECK(links_need_table(lk));
         unsigned long long c[8];
         HH_CHECK(links_read_counters(lk, c));
         HH_REQUIRE(c[2] == 0, HH_ERR_CAPACITY, "hh_links_finish_partition: hash table overflow (capacity %llu slots)",
@@ -1108,7 +1501,10 @@ extern "C" int hh_links_merge(hh_links* lk, const uint32_t* entries_dev, int64_t
                               int64_t n_records, int64_t n_used) {
     HH_REQUIRE(lk != nullptr, HH_ERR_ARG, "hh_links_merge: NULL handle");
     hh_scope _scope(lk->ctx);
-    HH_REQUIRE(lk->d_keys != nullptr, HH_ERR_STATE, "hh_links_merge: the table was replaced by hh_links_adopt");
+    HH_REQUIRE(lk->mode != 2 && !(lk->finished && lk->d_keys == nullptr), HH_ERR_STATE,
+               "hh_links_merge: this table holds an entry list (hh_links_adopt / partitioned counting), not a hash table");
+    lk->mode = 1;
+    HH_CHECK(links_need_table(lk));
     lk->finished = false;   // a finished table is re-opened: the next hh_links_finish rebuilds the ordered view
     HH_REQUIRE(n_entries >= 0 && (entries_dev || n_entries == 0), HH_ERR_ARG, "hh_links_merge: bad entries");
     hh_ctx* ctx = lk->ctx;
@@ -1186,6 +1582,8 @@ extern "C" int hh_links_destroy(hh_links* lk) {
     hh_dfree(lk->d_compact);
     hh_dfree(lk->d_index);
     hh_dfree(lk->d_keep);
+    links_free_partsets(lk);
+    delete lk->psets;
     delete lk;
     return HH_OK;
 }

@@ -164,9 +164,15 @@ def test_dense_engine_reproduces_reference_goldens(ctx, tag):
 def test_auto_selects_dense_for_dense_matrices(ctx):
     from haphic_b200.links import LinkMatrix
     from haphic_b200.mcl import Mcl
-    link = random_links(2048, 0.3, 100, seed=4)
+    link = random_links(3000, 1.5, 100, seed=4)        # ~1600 entries per column: 3000 * 1600^2 products vs 3 * 3000^3 / 2 flops
     mat = LinkMatrix.from_csc(ctx, link)
     mc = Mcl(mat)
     assert mc.preexp["mode"] == "dense"
     mc.close()
+    sparse_link = random_links(3000, 0.02, 100, seed=5)
+    mat2 = LinkMatrix.from_csc(ctx, sparse_link)
+    mc2 = Mcl(mat2)
+    assert mc2.preexp["mode"] == "sparse"
+    mc2.close()
+    mat2.close()
     mat.close()

@@ -46,8 +46,18 @@ def check_against(ref, got, tot):
     assert np.array_equal(tot, want_tot)
 
 
+@pytest.fixture(params=["direct", "partitioned"])
+def counting_mode(request, monkeypatch):
+    """both counting engines: one big hash table, and partition-then-aggregate (forced on here; by default it takes over
+    for streams of 16M records and more)"""
+    monkeypatch.setenv("HH_LINKS_PARTITION", "1" if request.param == "partitioned" else "0")
+    if request.param == "partitioned":
+        monkeypatch.setenv("HH_LINKS_NPART_LOG", "5")
+    return request.param
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
-def test_links_match_reference_golden(ctx, tag):
+def test_links_match_reference_golden(ctx, tag, counting_mode):
     from haphic_b200.links import LinkTable
     g = load_golden("links_{}.npz".format(tag))
     tab = LinkTable(ctx, g["lengths"], rank_of(g["names"].tolist()), g["in_nx"], int(g["flank_kb"]) * 1000)
@@ -71,7 +81,7 @@ def synth_case(nchr, n_contigs, mean_len, n_pairs, seed, sort=False):
 
 @pytest.mark.parametrize("sort", [False, True])
 @pytest.mark.parametrize("flank_kb,nx_frac", [(500, 1.0), (5, 0.7)])
-def test_links_match_oracle_1m(ctx, sort, flank_kb, nx_frac):
+def test_links_match_oracle_1m(ctx, sort, flank_kb, nx_frac, counting_mode):
     from haphic_b200.links import LinkTable
     from oracle import haphic_oracle as orc
     asm, pairs = synth_case(6, 1200, 30000, 1_000_000, seed=11, sort=sort)
