@@ -436,6 +436,8 @@ def run_b200(a):
     launches = ctx.launches - l0
     clocks = sampler.stop()
 
+    if a.verbose:
+        print("per-step ms:", [(round(s["build_ms"], 1), round(s["matrix_ms"], 1), round(s["mcl_ms"], 1)) for s in steps], file=sys.stderr)
     build_ms = sum(s["build_ms"] for s in steps) / len(steps)
     matrix_ms = sum(s["matrix_ms"] for s in steps) / len(steps)
     mcl_ms = sum(s["mcl_ms"] for s in steps) / len(steps)

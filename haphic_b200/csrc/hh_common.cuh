@@ -57,7 +57,29 @@ struct hh_ctx {
     // small pinned scratch for flag / counter read-back
     uint64_t* h_scratch;    // pinned, 64 x u64
     uint64_t* d_scratch;    // device, 64 x u64
+    // workspace cache: the multi-GB transients of a pass (partition regions, operand planes of the tensor-core GEMM)
+    // come from blocks that stay with the context and are handed out best-fit, so every pass finds the blocks of the
+    // previous one instead of re-shaping the stream-ordered pool (all use is ordered on `stream`)
+    struct ws_block {
+        void* p;
+        size_t bytes;
+        bool used;
+    };
+    std::vector<ws_block>* ws;
 };
+
+void* hh_ws_alloc_bytes(hh_ctx* ctx, size_t bytes);
+void hh_ws_free_ptr(hh_ctx* ctx, void* p);
+template <typename T>
+static inline int hh_ws_alloc(hh_ctx* ctx, T** p, size_t count) {
+    *p = reinterpret_cast<T*>(hh_ws_alloc_bytes(ctx, (count ? count : 1) * sizeof(T)));
+    return *p ? HH_OK : HH_ERR_NOMEM;
+}
+template <typename T>
+static inline void hh_ws_free(hh_ctx* ctx, T*& p) {
+    if (p) hh_ws_free_ptr(ctx, (void*)p);
+    p = nullptr;
+}
 
 // Every ABI entry point opens an hh_scope: device selected, and device buffers come from the
 // stream-ordered memory pool of the context's stream (cudaMallocAsync / cudaFreeAsync; the pool keeps

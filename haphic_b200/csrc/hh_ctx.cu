@@ -42,6 +42,7 @@ extern "C" int hh_ctx_create(int device, hh_ctx** out) {
     c->stream = nullptr;
     c->h_scratch = nullptr;
     c->d_scratch = nullptr;
+    c->ws = new std::vector<hh_ctx::ws_block>();
     HH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     {   // keep freed device memory in the pool: a pass re-allocates the same multi-GB buffers
         cudaMemPool_t pool;
@@ -64,8 +65,62 @@ extern "C" int hh_ctx_destroy(hh_ctx* c) {
     }
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->ws) {
+        for (size_t k = 0; k < c->ws->size(); ++k) cudaFree((*c->ws)[k].p);
+        delete c->ws;
+    }
     delete c;
     return HH_OK;
+}
+
+// best fit among the cached blocks that are not much larger than the request; otherwise a new block
+void* hh_ws_alloc_bytes(hh_ctx* c, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    int best = -1;
+    for (size_t k = 0; k < c->ws->size(); ++k) {
+        const hh_ctx::ws_block& b = (*c->ws)[k];
+        if (b.used || b.bytes < bytes || b.bytes > 2 * bytes + (64u << 20)) continue;
+        if (best < 0 || b.bytes < (*c->ws)[(size_t)best].bytes) best = (int)k;
+    }
+    if (best >= 0) {
+        (*c->ws)[(size_t)best].used = true;
+        return (*c->ws)[(size_t)best].p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        // out of memory: give the unused cached blocks back and try once more
+        cudaGetLastError();
+        cudaStreamSynchronize(c->stream);
+        for (size_t k = 0; k < c->ws->size();) {
+            if (!(*c->ws)[k].used) {
+                cudaFree((*c->ws)[k].p);
+                c->ws->erase(c->ws->begin() + (long)k);
+            } else {
+                ++k;
+            }
+        }
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        hh_set_error("workspace allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    hh_ctx::ws_block nb;
+    nb.p = p;
+    nb.bytes = bytes;
+    nb.used = true;
+    c->ws->push_back(nb);
+    return p;
+}
+
+void hh_ws_free_ptr(hh_ctx* c, void* p) {
+    for (size_t k = 0; k < c->ws->size(); ++k)
+        if ((*c->ws)[k].p == p) {
+            (*c->ws)[k].used = false;
+            return;
+        }
 }
 
 extern "C" int hh_ctx_sync(hh_ctx* c) {

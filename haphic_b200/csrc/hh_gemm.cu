@@ -179,7 +179,7 @@ struct hh_gemm_args {
     const hh_gemm_item* items;
     int n_items;
     int n;                 // matrix dimension
-    int na;                // planes of A per k-block (1..3); B always has 3
+    int na, nb;            // planes of A / of B per k-block (1..3)
     int npass;
     int pa[8], pb[8];      // pass list: plane of A, plane of B
     int chunk_kb;          // k-blocks accumulated in TMEM before they are drained into registers
@@ -210,7 +210,7 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int pair = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
     const int npairs = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
     const uint32_t smem_base = (hg_smem_u32(hg_smem_raw) + 1023u) & ~1023u;
-    const uint32_t stage_bytes = (uint32_t)(a.na + 3) * HG_PLANE_BYTES;
+    const uint32_t stage_bytes = (uint32_t)(a.na + a.nb) * HG_PLANE_BYTES;
     const int S = a.stages;
 
     if (threadIdx.x == 0) {
@@ -242,8 +242,8 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t full0 = (CG == 2) ? hg_mapa(hg_smem_u32(&s_full[0]), 0) : hg_smem_u32(&s_full[0]);
             for (int it = pair; it < a.n_items; it += npairs) {
                 const hh_gemm_item w = a.items[it];
-                const int rowA = w.m_tile * (128 * CG) + (int)rank * 128;
-                const int rowB = w.n_tile * (128 * CG) + (int)rank * 128;
+                const int rowA = w.m0 + (int)rank * 128;
+                const int rowB = w.n0 + (int)rank * 128;
                 for (int seg = 0; seg < 2; ++seg) {
                     for (int kb = w.kb_lo[seg]; kb < w.kb_hi[seg]; ++kb) {
                         hg_mbar_wait(hg_smem_u32(&s_empty[s]), ph ^ 1u);
@@ -251,7 +251,7 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
                         const uint32_t bar = full0 + (uint32_t)s * 8u;
                         for (int p = 0; p < a.na; ++p) hg_tma_load_3d<CG>(dst + (uint32_t)p * HG_PLANE_BYTES, &tmA, bar, kb * 64, rowA, p);
-                        for (int p = 0; p < 3; ++p)
+                        for (int p = 0; p < a.nb; ++p)
                             hg_tma_load_3d<CG>(dst + (uint32_t)(a.na + p) * HG_PLANE_BYTES, &tmB, bar, kb * 64, rowB, p);
                         if (++s == S) {
                             s = 0;
@@ -336,29 +336,31 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     else hg_mbar_arrive_local(tempty0 + buf * 8u);
                 }
             }
-            // ---- scale and store: M1[r, c] = S / s[c]; mirror image M1[c, r] = S / s[r]
-            const int r = w.m_tile * (128 * CG) + (int)rank * 128 + quarter * 32 + lane;
-            const int c0 = w.n_tile * BN + half * CW;
-            if (r < a.n) {
+            // ---- scale and store: out[r, c] = D * scale[c]; mirror image out[c, r] = D * scale[r]
+            const int r = w.m0 + (int)rank * 128 + quarter * 32 + lane;
+            const int c0 = w.n0 + half * CW;
+            if (r < w.m_end) {
                 if (w.flags & HH_GEMM_DIRECT) {
+                    float* __restrict__ dst = a.m1 + (ptrdiff_t)(r - w.out_row0);
 #pragma unroll
                     for (int j = 0; j < CW; ++j) {
                         const int c = c0 + j;
-                        if (c < a.n && c >= a.col_lo && c < a.col_hi) a.m1[(size_t)(c - a.col_lo) * (size_t)a.ld + (size_t)r] = acc[j] * __ldg(a.inv_s + c);
+                        if (c < w.n_end && c >= a.col_lo && c < a.col_hi)
+                            dst[(size_t)(c - a.col_lo) * (size_t)a.ld] = a.inv_s ? acc[j] * __ldg(a.inv_s + c) : acc[j];
                     }
                 }
                 if ((w.flags & HH_GEMM_MIRROR) && r >= a.col_lo && r < a.col_hi) {
-                    const float sr = __ldg(a.inv_s + r);
-                    float* __restrict__ dst = a.m1 + (size_t)(r - a.col_lo) * (size_t)a.ld;
+                    const float sr = a.inv_s ? __ldg(a.inv_s + r) : 1.f;
+                    float* __restrict__ dst = a.m1 + (size_t)(r - a.col_lo) * (size_t)a.ld - (ptrdiff_t)w.out_row0;
 #pragma unroll
                     for (int j = 0; j < CW; j += 4) {
                         const int c = c0 + j;
-                        if (c + 3 < a.n) {
+                        if (c + 3 < w.n_end && w.out_row0 == 0) {
                             *reinterpret_cast<float4*>(dst + c) = make_float4(acc[j] * sr, acc[j + 1] * sr, acc[j + 2] * sr, acc[j + 3] * sr);
                         } else {
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                if (c + q < a.n) dst[c + q] = acc[j + q] * sr;
+                                if (c + q < w.n_end) dst[c + q] = acc[j + q] * sr;
                         }
                     }
                 }
@@ -467,7 +469,7 @@ hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict_
 typedef CUresult (*hg_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int hg_encode(CUtensorMap* tm, void* base, int n, long long ldk, long long plane_elems, int planes) {
+static int hg_encode(CUtensorMap* tm, void* base, int rows, int kdim, long long ldk, long long plane_elems, int planes) {
     static hg_encode_fn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -476,7 +478,7 @@ static int hg_encode(CUtensorMap* tm, void* base, int n, long long ldk, long lon
         HH_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, HH_ERR_CUDA, "hh_gemm: the driver does not export cuTensorMapEncodeTiled");
         fn = reinterpret_cast<hg_encode_fn>(p);
     }
-    const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)planes};
+    const cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)rows, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)ldk * 2ull, (cuuint64_t)plane_elems * 2ull};
     const cuuint32_t box[3] = {64u, 128u, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
@@ -516,11 +518,62 @@ static int hg_launch(hh_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB
     return HH_OK;
 }
 
+int hh_gemm_cta_group() { return hg_env_int("HH_GEMM_CG", 2) == 1 ? 1 : 2; }
+
+int hh_gemm_run(hh_ctx* ctx, const hh_gemm_operand& A, const hh_gemm_operand& B, const hh_gemm_item* d_items, int n_items, int npass,
+                const int* pa, const int* pb, int chunk_kb, float* out, long long ld, int col_lo, int col_hi, const float* scale,
+                int* stages_out) {
+    HH_REQUIRE(n_items >= 1 && npass >= 1 && npass <= 8, HH_ERR_ARG, "hh_gemm_run: bad work list");
+    CUtensorMap tmA, tmB;
+    HH_CHECK(hg_encode(&tmA, (void*)A.base, A.rows, A.kdim, A.ldk, A.plane, A.planes));
+    HH_CHECK(hg_encode(&tmB, (void*)B.base, B.rows, B.kdim, B.ldk, B.plane, B.planes));
+    hh_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.items = d_items;
+    a.n_items = n_items;
+    a.na = A.planes;
+    a.nb = B.planes;
+    a.npass = npass;
+    for (int p = 0; p < npass; ++p) {
+        a.pa[p] = pa[p];
+        a.pb[p] = pb[p];
+    }
+    a.chunk_kb = chunk_kb < 1 ? (1 << 30) : chunk_kb;           // 0 = accumulate the whole K range in TMEM
+    const size_t stage_bytes = (size_t)(A.planes + B.planes) * HG_PLANE_BYTES;
+    int stages = (int)((ctx->smem_optin - 2048) / stage_bytes);
+    if (stages > HG_MAX_STAGES) stages = HG_MAX_STAGES;
+    HH_REQUIRE(stages >= 2, HH_ERR_UNSUPPORTED, "hh_gemm: shared memory too small for two pipeline stages");
+    a.stages = stages;
+    if (stages_out) *stages_out = stages;
+    a.m1 = out;
+    a.ld = ld;
+    a.col_lo = col_lo;
+    a.col_hi = col_hi;
+    a.inv_s = scale;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    if (hh_gemm_cta_group() == 2) return hg_launch<2>(ctx, tmA, tmB, a, smem);
+    return hg_launch<1>(ctx, tmA, tmB, a, smem);
+}
+
+static const int HG_P1[3][2] = {{0, 0}, {0, 1}, {0, 2}};
+static const int HG_P2[5][2] = {{0, 0}, {0, 1}, {1, 0}, {0, 2}, {1, 1}};
+static const int HG_P3[6][2] = {{0, 0}, {0, 1}, {1, 0}, {0, 2}, {1, 1}, {2, 0}};
+
+// pass list for `na` planes of A against three planes of B: every product of relative size >= 2^-16 (na = 1: exact)
+int hh_gemm_passes(int na, int* pa, int* pb) {
+    const int(*pl)[2] = na == 1 ? HG_P1 : (na == 2 ? HG_P2 : HG_P3);
+    const int np = na == 1 ? 3 : (na == 2 ? 5 : 6);
+    for (int p = 0; p < np; ++p) {
+        pa[p] = pl[p][0];
+        pb[p] = pl[p][1];
+    }
+    return np;
+}
+
 int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, float* d_m1, long long ld, const hh_gemm_item* h_items,
                       int n_items, hh_gemm_stats* st) {
     const int n = m->n;
     HH_REQUIRE(n >= 1 && n_items >= 1, HH_ERR_ARG, "hh_gemm_preexpand: empty problem");
-    const int cg = hg_env_int("HH_GEMM_CG", 2) == 1 ? 1 : 2;
     const long long ldk = ((long long)n + 63) & ~63ll;       // row pitch in elements (128-byte multiple)
     const long long plane = ldk * (long long)n;
     double* d_s = nullptr;
@@ -549,78 +602,52 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
             na = 2;
             clip = 3.0e38f;
         }
-        HH_CHECK(hh_dmalloc(&d_A, (size_t)plane * (size_t)na));
-        HH_CHECK(hh_dmalloc(&d_B, (size_t)plane * 3));
+        HH_CHECK(hh_ws_alloc(ctx, &d_A, (size_t)plane * (size_t)na));
+        HH_CHECK(hh_ws_alloc(ctx, &d_B, (size_t)plane * 3));
         {
             auto kd = hh_k_gemm_densify;
             const size_t dsm = (size_t)3 * HG_SEG * sizeof(unsigned short);
             HH_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
             HH_LAUNCH(ctx, kd, n, 256, dsm, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, ldk, plane, clip);
         }
-        // rows [n, ld) of every M1 column stay zero; entries that no tile writes (none on one GPU) as well
+        // rows [n, ld) of every M1 column stay zero
         HH_CUDA(cudaMemsetAsync(d_m1, 0, (size_t)ld * (size_t)(col_hi - col_lo) * sizeof(float), ctx->stream));
         HH_CHECK(hh_dmalloc(&d_items, (size_t)n_items));
         HH_CUDA(cudaMemcpyAsync(d_items, h_items, (size_t)n_items * sizeof(hh_gemm_item), cudaMemcpyHostToDevice, ctx->stream));
-        CUtensorMap tmA, tmB;
-        HH_CHECK(hg_encode(&tmA, d_A, n, ldk, plane, na));
-        HH_CHECK(hg_encode(&tmB, d_B, n, ldk, plane, 3));
-        hh_gemm_args a;
-        memset(&a, 0, sizeof(a));
-        a.items = d_items;
-        a.n_items = n_items;
-        a.n = n;
-        a.na = na;
-        static const int P1[3][2] = {{0, 0}, {0, 1}, {0, 2}};
-        static const int P2[5][2] = {{0, 0}, {0, 1}, {1, 0}, {0, 2}, {1, 1}};
-        static const int P3[6][2] = {{0, 0}, {0, 1}, {1, 0}, {0, 2}, {1, 1}, {2, 0}};
-        const int(*pl)[2] = na == 1 ? P1 : (na == 2 ? P2 : P3);
-        a.npass = na == 1 ? 3 : (na == 2 ? 5 : 6);
+        int pa[8], pb[8];
+        int npass = hh_gemm_passes(na, pa, pb);
         const int np_env = hg_env_int("HH_GEMM_NPASS", 0);      // experiments only: fewer passes = lower precision
-        if (np_env >= 1 && np_env < a.npass) a.npass = np_env;
-        for (int p = 0; p < a.npass; ++p) {
-            a.pa[p] = pl[p][0];
-            a.pb[p] = pl[p][1];
-        }
-        a.chunk_kb = hg_env_int("HH_GEMM_CHUNK", a.npass > 3 ? 1 : 2);
-        if (a.chunk_kb < 1) a.chunk_kb = 1 << 30;               // 0 = accumulate the whole K range in TMEM
-        const size_t stage_bytes = (size_t)(na + 3) * HG_PLANE_BYTES;
-        int stages = (int)((ctx->smem_optin - 2048) / stage_bytes);
-        if (stages > HG_MAX_STAGES) stages = HG_MAX_STAGES;
-        HH_REQUIRE(stages >= 2, HH_ERR_UNSUPPORTED, "hh_gemm: shared memory too small for two pipeline stages");
-        a.stages = stages;
-        a.m1 = d_m1;
-        a.ld = ld;
-        a.col_lo = col_lo;
-        a.col_hi = col_hi;
-        a.inv_s = d_inv;
-        const size_t smem = (size_t)stages * stage_bytes + 1024;
+        if (np_env >= 1 && np_env < npass) npass = np_env;
+        const int chunk = hg_env_int("HH_GEMM_CHUNK", npass > 3 ? 1 : 2);
+        hh_gemm_operand A = {d_A, na, n, n, ldk, plane};
+        hh_gemm_operand B = {d_B, 3, n, n, ldk, plane};
+        int stages = 0;
         HH_CUDA(cudaEventRecord(ev[1], ctx->stream));
-        if (cg == 2) HH_CHECK(hg_launch<2>(ctx, tmA, tmB, a, smem));
-        else HH_CHECK(hg_launch<1>(ctx, tmA, tmB, a, smem));
+        HH_CHECK(hh_gemm_run(ctx, A, B, d_items, n_items, npass, pa, pb, chunk, d_m1, ld, col_lo, col_hi, d_inv, &stages));
         HH_CUDA(cudaEventRecord(ev[2], ctx->stream));
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
         if (st) {
             memset(st, 0, sizeof(*st));
             st->a_planes = na;
             st->clipped = (clip < 1.0e38f && (flags & 2)) ? 1 : 0;
-            st->passes = a.npass;
-            st->cta_group = cg;
+            st->passes = npass;
+            st->cta_group = hh_gemm_cta_group();
             st->stages = stages;
-            st->chunk_kb = a.chunk_kb;
+            st->chunk_kb = chunk < 1 ? (1 << 30) : chunk;
             HH_CUDA(cudaEventElapsedTime(&st->densify_ms, ev[0], ev[1]));
             HH_CUDA(cudaEventElapsedTime(&st->gemm_ms, ev[1], ev[2]));
             double kb = 0.0;
             for (int i = 0; i < n_items; ++i) kb += (double)((h_items[i].kb_hi[0] - h_items[i].kb_lo[0]) + (h_items[i].kb_hi[1] - h_items[i].kb_lo[1]));
-            const double tile = 128.0 * cg;
-            st->flops = 2.0 * tile * tile * 64.0 * kb * (double)a.npass;
+            const double tile = 128.0 * hh_gemm_cta_group();
+            st->flops = 2.0 * tile * tile * 64.0 * kb * (double)npass;
         }
         return HH_OK;
     }();
     hh_dfree(d_s);
     hh_dfree(d_inv);
     hh_dfree(d_flags);
-    hh_dfree(d_A);
-    hh_dfree(d_B);
+    hh_ws_free(ctx, d_A);
+    hh_ws_free(ctx, d_B);
     hh_dfree(d_items);
     for (int k = 0; k < 3; ++k)
         if (ev[k]) cudaEventDestroy(ev[k]);
@@ -657,8 +684,10 @@ int hh_gemm_items_full(int n, int col_lo, int col_hi, std::vector<hh_gemm_item>&
                     if (!flags) continue;
                     hh_gemm_item w;
                     memset(&w, 0, sizeof(w));
-                    w.m_tile = ta;
-                    w.n_tile = tb;
+                    w.m0 = ta * T;
+                    w.n0 = tb * T;
+                    w.m_end = n;
+                    w.n_end = n;
                     w.kb_lo[0] = 0;
                     w.kb_hi[0] = nkb;
                     w.flags = flags;

@@ -6,13 +6,24 @@
 
 enum { HH_GEMM_DIRECT = 1, HH_GEMM_MIRROR = 2 };
 
-// one output tile of S = C . M0^T: tile coordinates in units of the tile size (hh_gemm_tile_size()), up to two ranges
-// of 64-wide k-blocks that are accumulated, and where the result goes
+// one output tile of D = A . B^T (both operands row-major, K contiguous): first row of the A rows / of the B rows it
+// multiplies, the bounds beyond which nothing is stored, up to two ranges of 64-wide k-blocks that are accumulated, and where
+// the result goes: element (r, c) -> out[(c - col_lo) * ld + (r - out_row0)], mirror image (c, r) likewise
 struct hh_gemm_item {
-    int m_tile, n_tile;
+    int m0, n0;
+    int m_end, n_end;
     int kb_lo[2], kb_hi[2];
     int flags;
-    int pad;
+    int out_row0;
+    int pad[2];
+};
+
+// dense bf16 operand planes: element (row, k) of plane p at base[p * plane + row * ldk + k]
+struct hh_gemm_operand {
+    const unsigned short* base;
+    int planes;
+    int rows, kdim;            // extent of the tensor map (TMA zero-fills beyond it)
+    long long ldk, plane;
 };
 
 struct hh_gemm_stats {
@@ -27,3 +38,11 @@ int hh_gemm_items_full(int n, int col_lo, int col_hi, std::vector<hh_gemm_item>&
 // M1[:, col_lo:col_hi] (dense column-major, leading dimension ld, zero-filled first) from the raw link matrix
 int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, float* d_m1, long long ld, const hh_gemm_item* h_items,
                       int n_items, hh_gemm_stats* st);
+// the GEMM itself on prepared operands: D tiles listed in d_items (device), written to out (column-major, leading dimension
+// ld, columns [col_lo, col_hi)), each element multiplied by scale[c] when scale != NULL.  The pass list multiplies plane
+// pa[p] of A with plane pb[p] of B.  Asynchronous on the context's stream.
+int hh_gemm_run(hh_ctx* ctx, const hh_gemm_operand& A, const hh_gemm_operand& B, const hh_gemm_item* d_items, int n_items, int npass,
+                const int* pa, const int* pb, int chunk_kb, float* out, long long ld, int col_lo, int col_hi, const float* scale,
+                int* stages_out);
+int hh_gemm_cta_group();
+int hh_gemm_passes(int na, int* pa, int* pb);

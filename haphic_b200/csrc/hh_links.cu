@@ -904,10 +904,10 @@ static int links_new_partset(hh_links* lk, int64_t n_rec) {
     memset(&ps, 0, sizeof(ps));
     ps.pcap = (uint64_t)((double)n_rec / npart * 1.5) + 4096;
     ps.sized_for = n_rec;
-    HH_CHECK(hh_dmalloc(&ps.buf, (size_t)npart * (size_t)ps.pcap));
+    HH_CHECK(hh_ws_alloc(lk->ctx, &ps.buf, (size_t)npart * (size_t)ps.pcap));
     int rc = hh_dmalloc(&ps.cursor, (size_t)npart);
     if (rc != HH_OK) {
-        hh_dfree(ps.buf);
+        hh_ws_free(lk->ctx, ps.buf);
         return rc;
     }
     HH_CUDA(cudaMemsetAsync(ps.cursor, 0, (size_t)npart * sizeof(unsigned long long), lk->ctx->stream));
@@ -934,7 +934,7 @@ static int links_choose_mode(hh_links* lk, int64_t total) {
     if (lk->npart_log > 10) lk->npart_log = 10;
     HH_CHECK(links_new_partset(lk, total));
     lk->spill_cap = (uint64_t)(total / 8) + (4u << 20);
-    HH_CHECK(hh_dmalloc(&lk->d_spill, (size_t)lk->spill_cap));
+    HH_CHECK(hh_ws_alloc(lk->ctx, &lk->d_spill, (size_t)lk->spill_cap));
     HH_CHECK(hh_dmalloc(&lk->d_spill_cursor, 1));
     HH_CUDA(cudaMemsetAsync(lk->d_spill_cursor, 0, sizeof(unsigned long long), lk->ctx->stream));
     return HH_OK;
@@ -1047,12 +1047,12 @@ extern "C" int hh_links_add(hh_links* lk, const int32_t* rec, int64_t n_rec, int
 static void links_free_partsets(hh_links* lk) {
     if (lk->psets) {
         for (size_t k = 0; k < lk->psets->size(); ++k) {
-            hh_dfree((*lk->psets)[k].buf);
+            hh_ws_free(lk->ctx, (*lk->psets)[k].buf);
             hh_dfree((*lk->psets)[k].cursor);
         }
         lk->psets->clear();
     }
-    hh_dfree(lk->d_spill);
+    hh_ws_free(lk->ctx, lk->d_spill);
     hh_dfree(lk->d_spill_cursor);
 }
 
@@ -1088,8 +1088,9 @@ static int links_finish_partitioned(hh_links* lk) {
     hh_slot* svals[2] = {nullptr, nullptr};
     const uint64_t compact_cap = (uint64_t)(lk->n_used > 0 ? lk->n_used : 1);       // distinct pairs <= usable records
     hh_dfree(lk->d_compact);
+    uint32_t* d_stage_compact = nullptr;                                              // workspace; the exact-size list is cut from it
     int rc = [&]() -> int {
-        HH_CHECK(hh_dmalloc(&lk->d_compact, (size_t)compact_cap * 9));
+        HH_CHECK(hh_ws_alloc(ctx, &d_stage_compact, (size_t)compact_cap * 9));
         for (int b = 0; b < 2; ++b) HH_CHECK(links_alloc_table(lk, scap, &skeys[b], &svals[b]));
         HH_CUDA(cudaMemsetAsync(lk->d_counters + 0, 0, sizeof(unsigned long long), ctx->stream));     // entry cursor
         HH_CUDA(cudaMemsetAsync(lk->d_counters + 3, 0, sizeof(unsigned long long), ctx->stream));     // nnz_flank
@@ -1110,7 +1111,7 @@ static int links_finish_partitioned(hh_links* lk) {
                 }
                 HH_LAUNCH(ctx, hh_k_part_step, grid, 256, 0, prec, (int64_t)nrec, lk->d_spill, spill_now ? (int64_t)n_spill : 0, p,
                           p < npart ? skeys[cb] : nullptr, p < npart ? svals[cb] : nullptr, (first && p > 0) ? skeys[eb] : nullptr,
-                          (first && p > 0) ? svals[eb] : nullptr, scap, lk->d_compact, compact_cap, lk->d_ctg, lk->d_counters);
+                          (first && p > 0) ? svals[eb] : nullptr, scap, d_stage_compact, compact_cap, lk->d_ctg, lk->d_counters);
                 first = false;
                 if (k + 1 >= nsets) break;
             }
@@ -1120,8 +1121,13 @@ static int links_finish_partitioned(hh_links* lk) {
                    "hh_links_finish: a scratch table of the partitioned counting overflowed (code %llu): set HH_LINKS_PARTITION=0", c[2]);
         lk->nnz = (int64_t)c[0];
         lk->nnz_flank = (int64_t)c[3];
+        HH_CHECK(hh_dmalloc(&lk->d_compact, (size_t)(lk->nnz > 0 ? lk->nnz : 1) * 9));
+        if (lk->nnz)
+            HH_CUDA(cudaMemcpyAsync(lk->d_compact, d_stage_compact, (size_t)lk->nnz * 9 * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                    ctx->stream));
         return HH_OK;
     }();
+    hh_ws_free(ctx, d_stage_compact);
     for (int b = 0; b < 2; ++b) {
         hh_dfree(skeys[b]);
         hh_dfree(svals[b]);
