@@ -654,6 +654,92 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
     return rc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// block-diagonal products of the Markov-cluster iterations (hh_mcl.cu): operand planes of the component blocks
+// ---------------------------------------------------------------------------------------------------------------------
+// Bt[c, kk] = M[lo + kk, c] for the columns c of `list` (lo = first row of c's component): one CTA per column assembles the
+// row of its three planes in shared memory and writes all ldk elements (zeros beyond the component).
+__global__ void __launch_bounds__(128)
+hh_k_blk_densify(const int* __restrict__ len, const uint2* __restrict__ ent, int cap, const int* __restrict__ list, int nlist,
+                 const int* __restrict__ comp_lo, const int* __restrict__ comp_hi, unsigned short* __restrict__ Bt, long long ldk,
+                 long long plane) {
+    extern __shared__ __align__(16) unsigned short hb_row[];        // [3][ldk]
+    const int j = list[blockIdx.x];
+    const int lo = comp_lo[j], width = comp_hi[j] - lo;
+    uint4* z = reinterpret_cast<uint4*>(hb_row);
+    for (int q = threadIdx.x; q < (int)(3 * ldk / 8); q += 128) z[q] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const int L = len[j];
+    const uint2* __restrict__ e = ent + (size_t)j * (size_t)cap;
+    for (int p = threadIdx.x; p < L; p += 128) {
+        const uint2 t = e[p];
+        const unsigned kk = t.x - (unsigned)lo;
+        if (kk < (unsigned)width) {
+            unsigned short h1, h2, h3;
+            hg_split3(__uint_as_float(t.y), h1, h2, h3);
+            hb_row[kk] = h1;
+            hb_row[ldk + kk] = h2;
+            hb_row[2 * ldk + kk] = h3;
+        }
+    }
+    __syncthreads();
+    for (int pl = 0; pl < 3; ++pl) {
+        const uint4* src = reinterpret_cast<const uint4*>(hb_row + (size_t)pl * (size_t)ldk);
+        uint4* dst = reinterpret_cast<uint4*>(Bt + (size_t)pl * (size_t)plane + (size_t)j * (size_t)ldk);
+        for (int q = threadIdx.x; q < (int)(ldk / 8); q += 128) dst[q] = src[q];
+    }
+}
+
+// A[r, kk] = M[r, lo + kk] = Bt[lo + kk, r - lo]: the transpose inside every component block; zeros beyond the component and
+// for rows of components wider than ldk (those are not multiplied).  grid (ceil(n / 32), ldk / 32, 3), block (32, 8).
+__global__ void __launch_bounds__(256)
+hh_k_blk_transpose(const unsigned short* __restrict__ Bt, unsigned short* __restrict__ A, int n, const int* __restrict__ comp_lo,
+                   const int* __restrict__ comp_hi, long long ldk, long long plane) {
+    __shared__ unsigned short tile[32][34];
+    const int r0 = blockIdx.x * 32, kk0 = blockIdx.y * 32;
+    const unsigned short* __restrict__ src = Bt + (size_t)blockIdx.z * (size_t)plane;
+    unsigned short* __restrict__ dst = A + (size_t)blockIdx.z * (size_t)plane;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int rl = min(r0 + 31, n - 1);
+    const bool same = (r0 + 31 < n) && comp_lo[r0] == comp_lo[rl];
+    if (same) {
+        const int lo = comp_lo[r0], width = comp_hi[r0] - lo;
+        const bool fits = width <= (int)ldk;
+        for (int y = ty; y < 32; y += 8) {
+            const int kk = kk0 + y;
+            tile[y][tx] = (fits && kk < width) ? src[(size_t)(lo + kk) * (size_t)ldk + (size_t)(r0 - lo + tx)] : (unsigned short)0;
+        }
+        __syncthreads();
+        for (int y = ty; y < 32; y += 8) dst[(size_t)(r0 + y) * (size_t)ldk + (size_t)(kk0 + tx)] = tile[tx][y];
+    } else {
+        for (int y = ty; y < 32; y += 8) {
+            const int r = r0 + y;
+            if (r >= n) continue;
+            const int lo = comp_lo[r], width = comp_hi[r] - lo;
+            const int kk = kk0 + tx;
+            dst[(size_t)r * (size_t)ldk + (size_t)kk] =
+                (width <= (int)ldk && kk < width) ? src[(size_t)(lo + kk) * (size_t)ldk + (size_t)(r - lo)] : (unsigned short)0;
+        }
+    }
+}
+
+int hh_gemm_blk_operands(hh_ctx* ctx, const int* d_len, const void* d_ent, int cap, const int* d_list, int nlist, const int* d_comp_lo,
+                         const int* d_comp_hi, int n, unsigned short* d_A, unsigned short* d_Bt, long long ldk) {
+    const long long plane = ldk * (long long)n;
+    auto kd = hh_k_blk_densify;
+    const size_t dsm = (size_t)3 * (size_t)ldk * sizeof(unsigned short);
+    HH_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    if (nlist > 0)
+        HH_LAUNCH(ctx, kd, nlist, 128, dsm, d_len, reinterpret_cast<const uint2*>(d_ent), cap, d_list, nlist, d_comp_lo, d_comp_hi, d_Bt, ldk,
+                  plane);
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)(ldk / 32), 3u), block(32, 8);
+    hh_k_blk_transpose<<<grid, block, 0, ctx->stream>>>(d_Bt, d_A, n, d_comp_lo, d_comp_hi, ldk, plane);
+    ctx->launches++;
+    HH_CUDA(cudaGetLastError());
+    return HH_OK;
+}
+
 int hh_gemm_tile_size() { return 128 * (hg_env_int("HH_GEMM_CG", 2) == 1 ? 1 : 2); }
 
 // work list of the whole-matrix product: every tile pair (a <= b) on or above the diagonal whose result (columns of

@@ -46,3 +46,8 @@ int hh_gemm_run(hh_ctx* ctx, const hh_gemm_operand& A, const hh_gemm_operand& B,
                 int* stages_out);
 int hh_gemm_cta_group();
 int hh_gemm_passes(int na, int* pa, int* pb);
+
+// operand planes of the block-diagonal iterate (three planes each, row pitch ldk, rows = all n vertices): Bt from the slotted
+// columns of `list`, A by transposing inside every component
+int hh_gemm_blk_operands(hh_ctx* ctx, const int* d_len, const void* d_ent, int cap, const int* d_list, int nlist, const int* d_comp_lo,
+                         const int* d_comp_hi, int n, unsigned short* d_A, unsigned short* d_Bt, long long ldk);

@@ -821,8 +821,15 @@ __global__ void __launch_bounds__(32) hh_k_col_win(const hh_colargs a, int W, co
         const int lo = comp_lo[j], width = comp_hi[j] - lo;
         const int lenB = a.B.len[j];
         const uint2* __restrict__ Bent = a.B.ent + (size_t)j * (size_t)a.B.cap;
+        if (a.dense_in) {
+            // the block product of this component came from the tensor cores (hh_mcl_step): column j of it, rows of the window
+            const float* __restrict__ dcol = a.dense_in + (size_t)j * (size_t)a.ld;
+            for (int r = lane; r < width; r += 32) acc[r] = dcol[r];
+            prod_acc += (unsigned long long)width * (unsigned long long)width / 32ull;       // b * b multiply-adds per column (lane share)
+            __syncwarp();
+        }
         // ---- expansion
-        for (int t0 = 0; t0 < lenB; t0 += 32) {
+        for (int t0 = 0; t0 < (a.dense_in ? 0 : lenB); t0 += 32) {
             const int t = t0 + lane;
             int il = 0, Ll = 0;
             float vl = 0.f;
@@ -1554,6 +1561,13 @@ struct hh_mcl {
     std::vector<int>* h_inv;       // host copy of d_inv (result export)
     cudaEvent_t ev0, ev1;
     float create_ms[2];            // device time of the normalisation / pre-expansion kernels
+    // block-diagonal iterations on the tensor cores (HH_MCL_BLOCKGEMM): work list of the window components, built with perm
+    int use_blk;
+    std::vector<hh_gemm_item>* blk_items;
+    hh_gemm_item* d_blk_items;
+    long long blk_ldk;
+    double blk_flops;              // tensor flops one block iteration issues
+    int64_t blk_iters;             // iterations that ran as block GEMMs (statistics)
     int preexp_mode;               // HH_PREEXP_SPARSE or HH_PREEXP_DENSE: the engine that built M1
     float clip_ms;                 // dense engine: the sparse correction for counts above HH_CLIP
     hh_gemm_stats gemm;            // tensor-core path: planes, passes, flops, times
@@ -1888,6 +1902,8 @@ extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     hh_dfree(mc->d_win_list);
     hh_dfree(mc->d_big_list);
     hh_dfree(mc->d_overflow);
+    hh_dfree(mc->d_blk_items);
+    delete mc->blk_items;
     delete mc->h_inv;
     if (mc->ev0) cudaEventDestroy(mc->ev0);
     if (mc->ev1) cudaEventDestroy(mc->ev1);
@@ -1972,6 +1988,8 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
     mc->cur = -1;
     mc->use_small = env_int("HH_MCL_SMALL", 1);
     mc->use_window = env_int("HH_MCL_WINDOW", 1);
+    mc->use_blk = env_int("HH_MCL_BLOCKGEMM", 1);
+    mc->blk_items = new std::vector<hh_gemm_item>();
     mc->flat = env_int("HH_MCL_FLAT", -1);      // -1 = choose per launch from the mean segment length
     mc->l2pf = env_int("HH_MCL_L2PF", -1);       // -1 = prefetch in segment-wise mode only (long segments)
     const hh_geom g = geom_for(ctx, m->n);
@@ -2184,7 +2202,7 @@ static int mcl_build_perm(hh_mcl* mc) {
         HH_LAUNCH(ctx, hh_k_cc_rank, (n + 255) / 256, 256, 0, d_lab, n, mc->d_perm, mc->d_inv, d_csize);
         HH_LAUNCH(ctx, hh_k_cc_ranges, (n + 255) / 256, 256, 0, d_lab, mc->d_perm, d_csize, n, mc->d_comp_lo, mc->d_comp_hi);
         // window size: the largest component that still fits (4 private accumulators of wmax floats, several CTAs per SM)
-        const int wlimit = env_int("HH_MCL_WMAX", 4096);
+        const int wlimit = env_int("HH_MCL_WMAX", 8192);
         if (!mc->h_inv) mc->h_inv = new std::vector<int>((size_t)n);
         HH_CUDA(cudaMemcpyAsync(mc->h_inv->data(), mc->d_inv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         std::vector<int> csz((size_t)n);
@@ -2257,6 +2275,51 @@ static int mcl_build_perm(hh_mcl* mc) {
         mc->cur ^= 1;
         mc->perm_valid = true;
         mc->perm_space = true;
+        // work list of the block-diagonal GEMM: all tiles of every window component (whole-matrix ownership only: the
+        // columns of a shard are scattered over the components)
+        mc->blk_items->clear();
+        mc->blk_ldk = 0;
+        mc->blk_flops = 0.0;
+        if (mc->use_blk && mc->col_lo == 0 && mc->col_hi == n && mc->n_win > 0) {
+            std::vector<int> clo((size_t)n), chi((size_t)n);
+            HH_CUDA(cudaMemcpyAsync(clo.data(), mc->d_comp_lo, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            HH_CUDA(cudaMemcpyAsync(chi.data(), mc->d_comp_hi, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            HH_CUDA(cudaStreamSynchronize(ctx->stream));
+            const int T = hh_gemm_tile_size();
+            int maxb = 0;
+            for (int p0 = 0; p0 < n;) {
+                const int lo = clo[(size_t)p0], hi = chi[(size_t)p0];
+                const int b = hi - lo;
+                if (b <= wlimit) {
+                    if (b > maxb) maxb = b;
+                    const int nt = (b + T - 1) / T, nkb = (b + 63) / 64;
+                    for (int mt = 0; mt < nt; ++mt)
+                        for (int tt = 0; tt < nt; ++tt) {
+                            hh_gemm_item w;
+                            memset(&w, 0, sizeof(w));
+                            w.m0 = lo + mt * T;
+                            w.n0 = lo + tt * T;
+                            w.m_end = hi;
+                            w.n_end = hi;
+                            w.kb_lo[0] = 0;
+                            w.kb_hi[0] = nkb;
+                            w.flags = HH_GEMM_DIRECT;
+                            w.out_row0 = lo;
+                            mc->blk_items->push_back(w);
+                        }
+                    mc->blk_flops += 2.0 * (double)T * (double)T * 64.0 * (double)nkb * (double)nt * (double)nt * 6.0;
+                }
+                p0 = hi > p0 ? hi : p0 + 1;
+            }
+            mc->blk_ldk = ((long long)maxb + 63) & ~63ll;
+            hh_dfree(mc->d_blk_items);
+            if (!mc->blk_items->empty()) {
+                HH_CHECK(hh_dmalloc(&mc->d_blk_items, mc->blk_items->size()));
+                HH_CUDA(cudaMemcpyAsync(mc->d_blk_items, mc->blk_items->data(), mc->blk_items->size() * sizeof(hh_gemm_item),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+                HH_CUDA(cudaStreamSynchronize(ctx->stream));
+            }
+        }
         return HH_OK;
     }();
     hh_dfree(d_lab);
@@ -2343,6 +2406,34 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
             a.ncols_ptr = mc->d_bigcount;
             HH_CHECK((launch_col<SRC_PRODUCT, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
         } else {
+            // Window components whose block product is cheaper as a GEMM: both operands as three exact bf16 planes (six
+            // passes), drained every k-block; the expansion of hh_k_col_win is replaced, its epilogue is not.
+            unsigned short *d_blkA = nullptr, *d_blkB = nullptr;
+            float* d_blk_out = nullptr;
+            bool blk = false;
+            if (mc->n_win > 0 && mc->d_blk_items && mc->col_lo == 0 && mc->col_hi == mc->n) {
+                const double est_sparse = (double)mc->cur_nnz * (double)mc->cur_nnz / (double)mc->n / 0.6e12;
+                const double est_gemm = mc->blk_flops / 1.2e15 + 2.0e-3;
+                blk = est_gemm < est_sparse;
+            }
+            if (blk) {
+                const size_t plane = (size_t)mc->blk_ldk * (size_t)mc->n;
+                HH_CHECK(hh_ws_alloc(ctx, &d_blkA, plane * 3));
+                HH_CHECK(hh_ws_alloc(ctx, &d_blkB, plane * 3));
+                HH_CHECK(hh_ws_alloc(ctx, &d_blk_out, plane));
+                const hh_slotmat& M = mc->it[mc->cur];
+                HH_CHECK(hh_gemm_blk_operands(ctx, M.len, M.ent, M.cap, mc->d_win_list, mc->n_win, mc->d_comp_lo, mc->d_comp_hi, mc->n,
+                                              d_blkA, d_blkB, mc->blk_ldk));
+                int pa[8], pb[8];
+                const int npass = hh_gemm_passes(3, pa, pb);
+                hh_gemm_operand A = {d_blkA, 3, mc->n, (int)mc->blk_ldk, mc->blk_ldk, (long long)plane};
+                hh_gemm_operand B = {d_blkB, 3, mc->n, (int)mc->blk_ldk, mc->blk_ldk, (long long)plane};
+                HH_CHECK(hh_gemm_run(ctx, A, B, mc->d_blk_items, (int)mc->blk_items->size(), npass, pa, pb, env_int("HH_GEMM_CHUNK", 1),
+                                     d_blk_out, mc->blk_ldk, 0, mc->n, nullptr, nullptr));
+                a.dense_in = d_blk_out;
+                a.ld = mc->blk_ldk;
+                mc->blk_iters++;
+            }
             if (mc->n_win > 0) {
                 const size_t smem = (size_t)mc->wmax * sizeof(float);
                 auto kern = hh_k_col_win;
@@ -2354,6 +2445,13 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
                 if (grid < 1) grid = 1;
                 HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
                 HH_LAUNCH(ctx, kern, grid, 32, smem, a, g.W, mc->d_win_list, mc->n_win, mc->d_comp_lo, mc->d_comp_hi, mc->wmax);
+            }
+            if (blk) {
+                a.dense_in = nullptr;
+                a.ld = mc->ld;
+                hh_ws_free(ctx, d_blkA);
+                hh_ws_free(ctx, d_blkB);
+                hh_ws_free(ctx, d_blk_out);
             }
             if (mc->n_big > 0) {
                 a.order = mc->d_big_list;
@@ -2472,7 +2570,7 @@ extern "C" int hh_mcl_set_block(hh_mcl* mc, int32_t col_lo, int32_t col_hi) {
     mc->col_hi = col_hi;
     if (mc->perm_space) {
         const int ncols = col_hi - col_lo;
-        const int wlimit = env_int("HH_MCL_WMAX", 4096);
+        const int wlimit = env_int("HH_MCL_WMAX", 8192);
         HH_CUDA(cudaMemsetAsync(mc->d_bigcount, 0, 2 * sizeof(int), ctx->stream));
         HH_LAUNCH(ctx, hh_k_cc_lists, (ncols + 255) / 256, 256, 0, mc->d_perm, mc->col_lo, ncols, mc->d_comp_lo, mc->d_comp_hi, wlimit,
                   mc->d_owned, mc->d_win_list, mc->d_big_list, mc->d_bigcount);

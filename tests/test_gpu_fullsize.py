@@ -93,8 +93,11 @@ def test_c3_routed_build_equals_single(c3):
         t.close()
 
 
-def test_c3_mcl_properties(c3):
+def test_c3_mcl_properties(c3, monkeypatch):
     from haphic_b200.mcl import Mcl, interpret_result
+    # bit-equality with the column shards below needs the engine the shards use: the sparse expansion (a whole-matrix
+    # owner would otherwise run the dense component blocks of the first iterations on the tensor cores)
+    monkeypatch.setenv("HH_MCL_BLOCKGEMM", "0")
     asm, tab = c3["asm"], c3["tab"]
     keep = np.ones(asm.n, np.uint8)
     index, n_linked = tab.linked_index(keep)
@@ -122,6 +125,22 @@ def test_c3_mcl_properties(c3):
     assert st2["rounds"] == st["rounds"]
     assert np.array_equal(fin.indptr, fin2.indptr) and np.array_equal(fin.indices, fin2.indices) and np.array_equal(fin.data, fin2.data)
     whole.close()
+    # the same call with the component blocks of the early iterations on the tensor cores: same clusters, column stochastic
+    monkeypatch.setenv("HH_MCL_BLOCKGEMM", "1")
+    blk = Mcl(mat)
+    stb = blk.run(2.0, 200, 1e-4)
+    finb = blk.result()
+    assert stb["converged"] and abs(stb["rounds"] - st["rounds"]) <= 1
+    assert abs(np.asarray(finb.sum(axis=0)).ravel() - 1.0).max() < 1e-6
+    cb = interpret_result(finb)
+    assert cb is not None and sorted(map(sorted, cb)) == sorted(map(sorted, clusters))
+    # and a low inflation, where the iterate stays dense inside the components for many rounds
+    stl = blk.run(1.4, 200, 1e-4)
+    cl = interpret_result(blk.result())
+    assert stl["converged"] and cl is not None and sum(len(c) for c in cl) == n
+    assert sum(int(np.bincount(chrom[list(c)]).max()) for c in cl) >= 0.99 * n
+    blk.close()
+    monkeypatch.setenv("HH_MCL_BLOCKGEMM", "0")
     # two column shards stepped side by side (what two ranks do) end in the same matrix
     cut = n // 2
     s0, s1 = Mcl(mat, col_lo=0, col_hi=cut), Mcl(mat, col_lo=cut, col_hi=n)
