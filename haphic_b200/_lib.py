@@ -93,6 +93,7 @@ _SIGNATURES = {
     "hh_pairs_open": (C.c_int, [C.c_char_p, _P, C.c_int32, C.c_char_p, C.c_int, C.c_int, C.POINTER(_P)]),
     "hh_pairs_next": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "hh_pairs_close": (C.c_int, [_P]),
+    "hh_pairs_write": (C.c_int, [C.c_char_p, _P, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "hh_bam_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int, C.c_int, C.POINTER(_P)]),
     "hh_bam_header_text": (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
     "hh_bam_next": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),

@@ -194,8 +194,26 @@ def _context():
     global _CTX
     if _CTX is None:
         from ._lib import Context
-        _CTX = Context(int(os.environ.get("HAPHIC_DEVICE", "0")))
+        _CTX = Context(_gpu_list()[0])
     return _CTX
+
+
+def _gpu_list():
+    """Devices of this run: ``HAPHIC_GPUS`` = a count ("8" -> devices 0..7) or a comma list ("0,2,5"); default one device,
+    ``HAPHIC_DEVICE`` (0).  With several devices the inflation sweep of run_mcl_clustering is spread over them (every
+    mcl() call is independent and shares only the input matrix, HapHiC_cluster.py:2155-2158): one host thread per GPU, no
+    exchange, results identical to a single-GPU run by construction."""
+    spec = os.environ.get("HAPHIC_GPUS", "").strip()
+    if not spec:
+        return [int(os.environ.get("HAPHIC_DEVICE", "0"))]
+    if "," in spec:
+        devs = [int(x) for x in spec.split(",") if x.strip()]
+    else:
+        first = int(os.environ.get("HAPHIC_DEVICE", "0"))
+        devs = list(range(first, first + max(1, int(spec))))
+    if not devs:
+        raise ValueError("HAPHIC_GPUS names no device")
+    return devs
 
 
 def count_links(batches, names, ctg_len, Nx_ctg_set, flank_kb, want_clm=True, frag_table=None):
@@ -675,9 +693,15 @@ def recommend_inflation(result_stat, nchrs, len_ratio):
     return True
 
 
-def mcl(engine, expansion, inflation, iters, pruning, dense_matrix=False):
-    """One inflation on the device engine; logs the reference's convergence line (2047-2060)."""
-    st = engine.run(inflation, iters, pruning)
+def mcl(engine, expansion, inflation, iters, pruning, dense_matrix=False, _done=None):
+    """One inflation on the device engine; logs the reference's convergence line (2047-2060) -- from a function called
+    `mcl`, because the log format carries the function name.  ``_done`` = (statistics, result) of a run that another
+    GPU already made (multi-GPU sweep)."""
+    if _done is None:
+        st = engine.run(inflation, iters, pruning)
+        result = None
+    else:
+        st, result = _done
     if st["converged"]:
         logger.info("The matrix has converged after {} rounds of iterations "
                     "(expansion: {}, inflation: {}, maximum iterations: {}, pruning threshold: {})".format(
@@ -686,7 +710,46 @@ def mcl(engine, expansion, inflation, iters, pruning, dense_matrix=False):
         logger.info("The matrix does not converge after {} rounds of iterations "
                     "(expansion: {}, inflation: {}, maximum iterations: {}, pruning threshold: {})".format(
                         st["rounds"], expansion, inflation, iters, pruning))
-    return engine.result()
+    return engine.result() if result is None else result
+
+
+def _mcl_sweep_multi_gpu(link_matrix, devices, expansion, inflations, max_iter, pruning, preexp):
+    """The inflation sweep (2155-2158) over several GPUs of one process: every device gets the same canonical CSC of the
+    link matrix, builds M0 / M1 itself and runs the inflations k, k + N, k + 2N, ... on its own host thread (the library
+    calls release the GIL).  Yields (inflation, result matrix) in sweep order, logging like the single-GPU loop."""
+    import threading
+    from ._lib import Context
+    from .links import LinkMatrix
+    from .mcl import Mcl
+    host = link_matrix.to_scipy()                 # canonical (row-sorted) CSC: the same input on every device
+    results = [None] * len(inflations)
+    errors = []
+
+    def worker(k, dev):
+        try:
+            ctx = _context() if dev == devices[0] else Context(dev)
+            mat = LinkMatrix.from_csc(ctx, host)
+            engine = Mcl(mat, expansion, preexp=preexp)
+            for idx in range(k, len(inflations), len(devices)):
+                st = engine.run(float(inflations[idx]), max_iter, pruning)
+                results[idx] = (st, engine.result())
+            engine.close()
+            mat.close()
+            if dev != devices[0]:
+                ctx.close()
+        except Exception as exc:                  # surfaced by the consumer below
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(k, dev), daemon=True) for k, dev in enumerate(devices)]
+    for t in threads:
+        t.start()
+    logger.debug("Markov clustering: {} inflations over GPUs {}".format(len(inflations), devices))
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    for inflation, done in zip(inflations, results):
+        yield inflation, mcl(None, expansion, float(inflation), max_iter, pruning, _done=done)
 
 
 def run_mcl_clustering(link_matrix, bin_set, frag_len_dict, frag_index_dict, expansion, min_inflation,
@@ -702,12 +765,18 @@ def run_mcl_clustering(link_matrix, bin_set, frag_len_dict, frag_index_dict, exp
     # normalise + pre-expand once for the whole sweep.  --dense_matrix selects the reference's dense mode (2035 / 2149,
     # numpy.linalg.matrix_power): here the pre-expansion as a dense GEMM on the tensor cores; without the flag the
     # engine is chosen from the matrix (HH_MCL_PREEXP overrides).  Results agree within fp32 rounding either way.
-    engine = Mcl(link_matrix, expansion, preexp="dense" if dense_matrix else "auto")
-    logger.debug("Pre-expansion engine: {} ({:.1f} ms)".format(engine.preexp["mode"], engine.preexp["total_ms"]))
+    preexp = "dense" if dense_matrix else "auto"
+    inflations = inflation_values(min_inflation, max_inflation, inflation_step)
+    devices = _gpu_list()
+    if len(devices) > 1 and len(inflations) > 1:
+        sweep = _mcl_sweep_multi_gpu(link_matrix, devices, expansion, inflations, max_iter, pruning, preexp)
+    else:
+        engine = Mcl(link_matrix, expansion, preexp=preexp)
+        logger.debug("Pre-expansion engine: {} ({:.1f} ms)".format(engine.preexp["mode"], engine.preexp["total_ms"]))
+        sweep = ((inflation, mcl(engine, expansion, float(inflation), max_iter, pruning, dense_matrix)) for inflation in inflations)
     result_clusters_list = []
     mcl_nrounds = 0
-    for inflation in inflation_values(min_inflation, max_inflation, inflation_step):
-        result = mcl(engine, expansion, float(inflation), max_iter, pruning, dense_matrix)
+    for inflation, result in sweep:
         mcl_nrounds += 1
         clusters = interpret_result(result)
         if not clusters:

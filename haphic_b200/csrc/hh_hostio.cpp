@@ -1209,3 +1209,80 @@ extern "C" int hh_pickle_links(const char* path, const char* names_blob, int32_t
     }
     return HH_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// .pairs writer: the inverse of hh_pairs_next for fixtures and benchmarks (4DN .pairs text, 1-based positions, seven
+// columns `r{index} chr1 pos1 chr2 pos2 + -`).  Slices of the records are formatted on `threads` host threads and
+// written in order.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int hh_pairs_write(const char* path, const char* names_blob, int32_t n_names, const int32_t* rec, int64_t n_rec,
+                              int64_t first_index, int append, int threads) {
+    if (!(path && names_blob && (rec || n_rec == 0))) {
+        hh_set_error("hh_pairs_write: NULL argument");
+        return HH_ERR_ARG;
+    }
+    std::vector<const char*> nm((size_t)n_names);
+    std::vector<uint32_t> nl((size_t)n_names);
+    {
+        const char* q = names_blob;
+        for (int32_t k = 0; k < n_names; ++k) {
+            nm[(size_t)k] = q;
+            nl[(size_t)k] = (uint32_t)strlen(q);
+            q += nl[(size_t)k] + 1;
+        }
+    }
+    FILE* f = fopen(path, append ? "ab" : "wb");
+    if (!f) {
+        hh_set_error("hh_pairs_write: cannot open %s", path);
+        return HH_ERR_ARG;
+    }
+    if (!append) fputs("## pairs format v1.0\n#columns: readID chr1 pos1 chr2 pos2 strand1 strand2\n", f);
+    const int T = hh_io_threads(threads);
+    const int64_t SL = 1 << 18;                 // records per slice
+    std::vector<std::vector<char>> buf((size_t)T);
+    int rc = HH_OK;
+    for (int64_t base = 0; base < n_rec && rc == HH_OK; base += SL * T) {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) {
+            const int64_t lo = base + (int64_t)t * SL, hi = std::min(n_rec, lo + SL);
+            buf[(size_t)t].clear();
+            if (lo >= hi) continue;
+            pool.emplace_back([&, t, lo, hi]() {
+                std::vector<char>& b = buf[(size_t)t];
+                b.resize((size_t)(hi - lo) * 160);
+                char* q = b.data();
+                for (int64_t i = lo; i < hi; ++i) {
+                    const int32_t* r = rec + i * 4;
+                    if ((size_t)(q - b.data()) + 2 * 64 + 512 > b.size()) {
+                        const size_t used = (size_t)(q - b.data());
+                        b.resize(b.size() * 2);
+                        q = b.data() + used;
+                    }
+                    *q++ = 'r';
+                    q = put_i64(q, first_index + i);
+                    for (int side = 0; side < 2; ++side) {
+                        const int32_t c = r[2 * side];
+                        *q++ = '\t';
+                        if (c >= 0 && c < n_names) {
+                            memcpy(q, nm[(size_t)c], nl[(size_t)c]);
+                            q += nl[(size_t)c];
+                        } else {
+                            *q++ = '*';
+                        }
+                        *q++ = '\t';
+                        q = put_i64(q, (int64_t)r[2 * side + 1] + 1);
+                    }
+                    memcpy(q, "\t+\t-\n", 5);
+                    q += 5;
+                }
+                b.resize((size_t)(q - b.data()));
+            });
+        }
+        for (auto& th : pool) th.join();
+        for (int t = 0; t < T; ++t)
+            if (!buf[(size_t)t].empty() && fwrite(buf[(size_t)t].data(), 1, buf[(size_t)t].size(), f) != buf[(size_t)t].size()) rc = HH_ERR_ARG;
+    }
+    fclose(f);
+    if (rc != HH_OK) hh_set_error("hh_pairs_write: write to %s failed", path);
+    return rc;
+}

@@ -254,6 +254,10 @@ int hh_pairs_open(const char* path, const char* names_blob, int32_t n_names, con
                   int threads, hh_pairs_reader** out);
 int hh_pairs_next(hh_pairs_reader* r, int32_t* rec, int64_t max_records, int64_t* n_out);   /* *n_out == 0: end of file */
 int hh_pairs_close(hh_pairs_reader* r);
+/* the inverse, for fixtures and benchmarks: n_rec records {id_a, pos_a, id_b, pos_b} (0-based positions) as 4DN .pairs text
+ * `r{first_index + i}\tname_a\tpos_a+1\tname_b\tpos_b+1\t+\t-`; append != 0 continues an existing file without the header */
+int hh_pairs_write(const char* path, const char* names_blob, int32_t n_names, const int32_t* rec, int64_t n_rec, int64_t first_index,
+                   int append, int threads);
 /* BAM input (bam_generator, HapHiC_cluster.py:1586-1593, with the htslib filters `flag.read1 [&& refid != mrefid]` of
  * 2855 / 2862): BGZF blocks are inflated on `threads` host threads; one record per read1 alignment,
  * (id(reference_name), reference_start, id(next_reference_name), next_reference_start), ids through the BAM header's

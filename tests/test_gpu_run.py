@@ -35,7 +35,7 @@ cluster.run(args, log_file="HapHiC_cluster.log")
 """
 
 
-def run_case(tmp_path, g, bam):
+def run_case(tmp_path, g, bam, env_extra=None):
     nchr, n_contigs, mean_len, n_pairs = g["shape"].tolist()
     kw = json.loads(str(g["argkw"]))
     extra = []
@@ -45,6 +45,7 @@ def run_case(tmp_path, g, bam):
     code = DRIVER.format(repo=REPO, nchr=nchr, n_contigs=n_contigs, mean_len=mean_len, n_pairs=n_pairs, seed=int(g["seed"]),
                          bam=bam, extra=extra, homolog=tuple(homolog) if homolog else None)
     env = dict(os.environ, PYTHONHASHSEED="0")      # the reference's set-iteration orders (fixtures used seed 0)
+    env.update(env_extra or {})
     r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     return r
@@ -102,3 +103,28 @@ def _insertion(g, full):
     keys = [list(k) for k in full.keys() if tuple(k) in seen]
     assert keys == [k for k in out if tuple(k) in full]        # (allelic link removal deletes pairs after the clm is written)
     return [list(k) for k in full.keys()]
+
+
+def test_cluster_run_on_several_gpus_writes_the_same_files(tmp_path):
+    """HAPHIC_GPUS=N spreads the inflation sweep of run_mcl_clustering over N devices of one process; every output file and
+    the machine-read log lines must equal the reference's (= the single-GPU run's)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = load_golden("run_c1.npz")
+    run_case(tmp_path, g, False, env_extra={"HAPHIC_GPUS": str(min(4, torch.cuda.device_count()))})
+    want = json.loads(str(g["files_json"]))
+    got = {}
+    for root, _d, files in os.walk(tmp_path):
+        for fn in files:
+            p = os.path.relpath(os.path.join(root, fn), tmp_path)
+            if p.startswith("inflation_") and p.endswith(".txt"):
+                with open(os.path.join(root, fn)) as f:
+                    got[p] = f.read()
+    assert sorted(got) == sorted(want)
+    for p in sorted(want):
+        assert got[p] == want[p], p
+    with open(tmp_path / "HapHiC_cluster.log") as f:
+        log = f.read()
+    assert [ln.split("] ", 1)[1] for ln in log.splitlines() if "[recommend_inflation]" in ln] == g["recommend_lines"].tolist()
+    assert [ln.split("] ", 1)[1] for ln in log.splitlines() if "[mcl]" in ln] == g["mcl_lines"].tolist()
