@@ -329,3 +329,34 @@ def test_fragment_mode_refuses_positions_outside_the_contig(ctx, bad_pos):
         ftab.finish()
     assert "outside" in str(e.value)
     ftab.close()
+
+
+@pytest.mark.parametrize("tag,topN", [("a", 10), ("b", 10), ("a", 4)])
+def test_rank_sums_match_reference_filter_fragments(ctx, tag, topN):
+    """The rank-sum statistic of filter_fragments (864-892) against the numbers the UNMODIFIED reference computed for the
+    same record stream (tests/golden/ranksum_*.npz, read out of filter_fragments' own frame by make_ranksum_golden.py):
+    device table -> matrix with the reference's fragment index -> hh_matrix_rank_sums."""
+    from haphic_b200.links import LinkTable
+    g = load_golden("links_{}.npz".format(tag))
+    rs = load_golden("ranksum_{}_top{}.npz".format(tag, topN))
+    tab = LinkTable(ctx, g["lengths"], rank_of(g["names"].tolist()), g["in_nx"], int(g["flank_kb"]) * 1000)
+    tab.add(g["pairs"])
+    tab.finish()
+    n = len(g["lengths"])
+    keep = np.zeros(n, np.uint8)
+    keep[rs["frag_ids"]] = 1
+    index, n_linked = tab.linked_index(keep)
+    ref_index = np.full(n, -1, np.int64)
+    ref_index[rs["frag_ids"]] = rs["frag_index"]
+    linked = index >= 0
+    assert np.array_equal(index[linked], ref_index[linked])                   # first-seen indices (327-349)
+    tail = rs["frag_ids"][np.argsort(rs["frag_index"], kind="stable")]        # unlinked fragments in the reference's order (355-359)
+    tail = tail[~linked[tail]].astype(np.int32)
+    mat = tab.to_matrix(keep, tail, add_self_loops=False)
+    got = mat.rank_sums(int(rs["topN"]))
+    want = np.full(mat.n, -1, np.int64)
+    want[ref_index[rs["rank_ids"]]] = rs["rank_sums"]
+    sel = want >= 0
+    assert sel.sum() == len(rs["rank_ids"]) and np.array_equal(got[sel], want[sel])
+    mat.close()
+    tab.close()
