@@ -69,6 +69,8 @@ struct hh_colargs {
     const int* order;            // optional processing order of the owned columns (cluster-sorted: operand reuse in L2)
     int flat;                    // expansion inner loop: 1 = flat 32-entry walk, 0 = one segment at a time
     int l2pf;                    // expansion: prefetch the next batch's segments into L2
+    hh_slotmat prev;             // EPI_PRUNE convergence test against this matrix instead of B (expansion > 2: B is M^(e-1))
+    int use_prev;
     float* scratch;
     unsigned long long* stats;   // [0] nnz written  [1] products
     int* delta_bits;
@@ -601,9 +603,10 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
             if (SRC == SRC_PRODUCT && conv) {
                 // E4: entries of the previous iterate L = B[:, j]  ->  |M - L| - 1e-5|L|  (fp32, 2045)
                 __syncwarp();
-                const int* bp = a.B.blk + (size_t)j * (W + 1) + w;
+                const hh_slotmat& Lm = a.use_prev ? a.prev : a.B;
+                const int* bp = Lm.blk + (size_t)j * (W + 1) + w;
                 const int ps = bp[0], pe = bp[1];
-                const uint2* __restrict__ Lent = a.B.ent + (size_t)j * (size_t)a.B.cap;
+                const uint2* __restrict__ Lent = Lm.ent + (size_t)j * (size_t)Lm.cap;
                 for (int p = ps + lane; p < pe; p += 32) {
                     const uint2 le = Lent[p];
                     const int k = (int)le.x;
@@ -1528,6 +1531,7 @@ struct hh_mcl {
     float* d_m1;            // dense [ld x (col_hi-col_lo)]
     hh_slotmat it[2];
     int it_cap;
+    hh_slotmat pw[2];       // expansion > 2: unpruned powers M^2 .. M^(e-1) of the owned columns (slots of n entries)
     int cur;                // index of the current iterate in it[]; -1 before iteration 0
     int pending;            // buffer hh_mcl_step wrote (to be committed)
     bool have_pending;
@@ -1678,6 +1682,219 @@ static int launch_col(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_
         case 8: return launch_col_w<8, SRC, EPI>(ctx, g, d_scratch, grid_cap, a);
         case 16: return launch_col_w<16, SRC, EPI>(ctx, g, d_scratch, grid_cap, a);
         default: return launch_col_w<32, SRC, EPI>(ctx, g, d_scratch, grid_cap, a);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Iteration 0 of every mcl() call (HapHiC_cluster.py:2030-2042: no expansion, the input IS the pre-expanded dense M1):
+// inflate, column L1, prune + keep first maximum, column L1 -- as a stream.  The column never sits in shared memory:
+//   pass 1 (HBM)  y = x^r, fp64 column sum S1, maximum of x (x -> x1 is monotone);
+//   pass 2 (L2)   only x >= xthr can reach x1 = fp32(fp64(y) / S1) >= pruning: exact quotient for those, count + fp64 sum S2;
+//   pass 3 (L2)   the survivors in row order, x2 = fp32(fp64(x1) / S2), into the column's slot.
+// Warp w owns row block w (rows [w * T, (w + 1) * T)), so the row-block pointers of the slotted format fall out of the
+// per-warp counts.  Two CTAs per SM overlap one column's reductions with the other's loads.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(W * 32, (W <= 16) ? 2 : 1) hh_k_iter0(const hh_colargs a) {
+    __shared__ double s_d[32];
+    __shared__ float s_f[32];
+    __shared__ int s_k[32];
+    __shared__ int s_c[32];
+    __shared__ int s_col;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int T = a.T;
+    const int tile0 = w * T;
+    const float rf = a.inflation, p32 = a.prune;
+    const bool sq = a.inflate_square != 0;
+    const int ld4 = (int)(a.ld >> 2);
+    const int r4_lo = tile0 >> 2, r4_hi = min((tile0 + T) >> 2, ld4);
+    unsigned long long nnz_acc = 0ull;
+    auto pw = [&](float x) -> float { return sq ? x * x : powf(x, rf); };
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_col = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int jj = s_col;
+        if (jj >= a.ncols) break;
+        const int j = a.order ? a.order[jj] : (a.col_lo + jj);
+        const float4* __restrict__ col4 = reinterpret_cast<const float4*>(a.dense_in + (size_t)(j - a.col_lo) * (size_t)a.ld);
+        // ---------------------------------------------------------------- pass 1: S1 and the maximum
+        double s1 = 0.0;
+        float xbest = 0.f;
+        int kbest = 0x7fffffff;
+        for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 128) {
+            float4 x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float v = xv[c];
+                    if (v != 0.f) {
+                        s1 += (double)pw(v);
+                        if (v > xbest) {              // rows ascend inside a lane: the first maximum stays
+                            xbest = v;
+                            kbest = ((r4 + 32 * q) << 2) + c;
+                        }
+                    }
+                }
+            }
+        }
+        s1 = hh_warp_sum(s1);
+        if (lane == 0) s_d[w] = s1;
+        __syncthreads();
+        const double S1 = hh_warp_sum((lane < W) ? s_d[lane] : 0.0);
+        __syncthreads();
+        // exact x1 of this lane's maximum; two different x may round to one x1: then the lower row wins (first maximum)
+        float vbest = (xbest > 0.f && S1 != 0.0) ? (float)((double)pw(xbest) / S1) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(HH_FULL_MASK, vbest, o);
+            const int ok = __shfl_xor_sync(HH_FULL_MASK, kbest, o);
+            if (ov > vbest || (ov == vbest && ok < kbest)) {
+                vbest = ov;
+                kbest = ok;
+            }
+        }
+        // ---------------------------------------------------------------- pass 2: survivors of the prune, S2
+        // x1 >= pruning needs y >= 0.999 * pruning * S1, i.e. x >= (that)^(1/r): taken a little lower, the rest is exact
+        const float thr_y = (float)(0.999 * (double)p32 * S1);
+        const float xthr = (S1 != 0.0) ? 0.9999f * (sq ? sqrtf(thr_y) : powf(thr_y, 1.0f / rf)) : 3.0e38f;
+        double s2 = 0.0;
+        int cnt = 0;
+        for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 128) {
+            float4 x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (xv[c] >= xthr) {
+                        const float x1 = (float)((double)pw(xv[c]) / S1);
+                        if (x1 >= p32 && x1 > 0.f) {
+                            cnt++;
+                            s2 += (double)x1;
+                        }
+                    }
+                }
+            }
+        }
+        s2 = hh_warp_sum(s2);
+        cnt = hh_warp_sum(cnt);
+        if (lane == 0) {
+            s_d[w] = s2;
+            s_c[w] = cnt;
+            s_f[w] = vbest;
+            s_k[w] = kbest;
+        }
+        __syncthreads();
+        const int cv = (lane < W) ? s_c[lane] : 0;
+        double S2 = hh_warp_sum((lane < W) ? s_d[lane] : 0.0);
+        float vmax = (lane < W) ? s_f[lane] : 0.f;
+        int kmax = (lane < W) ? s_k[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(HH_FULL_MASK, vmax, o);
+            const int ok = __shfl_xor_sync(HH_FULL_MASK, kmax, o);
+            if (ov > vmax || (ov == vmax && ok < kmax)) {
+                vmax = ov;
+                kmax = ok;
+            }
+        }
+        int incl = cv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tt = __shfl_up_sync(HH_FULL_MASK, incl, o);
+            if (lane >= o) incl += tt;
+        }
+        int base = __shfl_sync(HH_FULL_MASK, incl - cv, w);
+        int total = __shfl_sync(HH_FULL_MASK, incl, 31);
+        const int mine = __shfl_sync(HH_FULL_MASK, cv, w);         // survivors in this warp's row block
+        const bool need_max = (total == 0) && (vmax > 0.f);        // keep the column maximum (2009-2013)
+        if (need_max) {
+            base = (w > kmax / T) ? 1 : 0;
+            total = 1;
+        }
+        // ---------------------------------------------------------------- pass 3: ordered write
+        uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
+        if (need_max) {
+            if (threadIdx.x == 0) oent[0] = make_uint2((unsigned)kmax, __float_as_uint(1.0f));      // x1 / x1
+        } else if (mine > 0) {
+            {
+                int off = base;
+                for (int r4 = r4_lo; r4 < r4_hi; r4 += 32) {            // one float4 per lane and trip: rows ascend with the lane
+                    const int rr = r4 + lane;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rr < r4_hi) x = hh_ld_stream_f4(col4 + rr);
+                    const float xv[4] = {x.x, x.y, x.z, x.w};
+                    float keep[4];
+                    int c = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        keep[q] = 0.f;
+                        if (xv[q] >= xthr) {
+                            const float x1 = (float)((double)pw(xv[q]) / S1);
+                            if (x1 >= p32 && x1 > 0.f) {
+                                keep[q] = x1;
+                                c++;
+                            }
+                        }
+                    }
+                    if (__ballot_sync(HH_FULL_MASK, c > 0) == 0u) continue;
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int tt = __shfl_up_sync(HH_FULL_MASK, inc, o);
+                        if (lane >= o) inc += tt;
+                    }
+                    int pos = off + inc - c;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (keep[q] > 0.f) {
+                            if (pos < a.out.cap) oent[pos] = make_uint2((unsigned)((rr << 2) + q), __float_as_uint((float)((double)keep[q] / S2)));
+                            pos++;
+                        }
+                    }
+                    off += __shfl_sync(HH_FULL_MASK, inc, 31);
+                }
+            }
+        }
+        if (lane == 0) a.out.blk[(size_t)j * (W + 1) + w] = base;
+        if (threadIdx.x == 0) {
+            a.out.blk[(size_t)j * (W + 1) + W] = min(total, a.out.cap);
+            a.out.len[j] = min(total, a.out.cap);
+            if (total > a.out.cap) atomicExch(a.err, 1);
+            nnz_acc += (unsigned long long)total;
+        }
+    }
+    if (threadIdx.x == 0 && nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
+}
+
+template <int W>
+static int launch_iter0_w(hh_ctx* ctx, hh_colargs& a) {
+    auto kern = hh_k_iter0<W>;
+    int per_sm = 0;
+    HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    int grid = per_sm * ctx->sm_count;
+    if (grid > a.ncols) grid = a.ncols;
+    if (grid < 1) return HH_OK;
+    HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
+    HH_LAUNCH(ctx, kern, grid, W * 32, 0, a);
+    return HH_OK;
+}
+
+static int launch_iter0(hh_ctx* ctx, const hh_geom& g, hh_colargs& a) {
+    a.T = g.T;
+    switch (g.W) {
+        case 8: return launch_iter0_w<8>(ctx, a);
+        case 16: return launch_iter0_w<16>(ctx, a);
+        default: return launch_iter0_w<32>(ctx, a);
     }
 }
 
@@ -1887,6 +2104,8 @@ extern "C" int hh_mcl_destroy(hh_mcl* mc) {
     slot_free(mc->m0);
     slot_free(mc->it[0]);
     slot_free(mc->it[1]);
+    slot_free(mc->pw[0]);
+    slot_free(mc->pw[1]);
     hh_dfree(mc->d_m1);
     hh_dfree(mc->d_scratch);
     hh_dfree(mc->d_counter);
@@ -1944,6 +2163,25 @@ static int choose_flat(const hh_mcl* mc, double nnz_operand) {
     return seg < 16.0 ? 1 : 0;
 }
 
+// out[:, owned] = A . B[:, owned] as an unpruned slotted matrix: one factor of mkl_matrix_power's recursion
+// A . A^(k-1) (HapHiC_cluster.py:2017-2023) for --expansion k > 2
+static hh_geom mcl_geom(const hh_mcl* mc);
+static void mcl_base_args(hh_mcl* mc, hh_colargs& a);
+static int choose_flat(const hh_mcl* mc, double nnz_operand);
+static int raw_product(hh_mcl* mc, const hh_slotmat& A, const hh_slotmat& B, double nnz_a, hh_slotmat& out) {
+    hh_colargs a;
+    mcl_base_args(mc, a);
+    a.A = A;
+    a.B = B;
+    a.out = out;
+    a.raw = 1;
+    a.flat = choose_flat(mc, nnz_a);
+    a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
+    const hh_geom g = mcl_geom(mc);
+    HH_CHECK((launch_col<SRC_PRODUCT, EPI_NORM>(mc->ctx, g, mc->d_scratch, mc->grid_cap, a)));
+    return HH_OK;
+}
+
 // Which engine builds M1.  The Gustavson kernel does n*d^2 multiply-adds on a scattered accumulator, the tensor-core
 // GEMM 3 passes of n^3/2.  AUTO picks the cheaper estimate; HH_MCL_PREEXP=sparse|dense overrides.
 static int choose_preexp(const hh_matrix* m, int requested) {
@@ -1969,8 +2207,8 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
     HH_REQUIRE(m && out, HH_ERR_ARG, "hh_mcl_create: NULL argument");
     hh_scope _scope(m->ctx);
     *out = nullptr;
-    HH_REQUIRE(expansion == 2, HH_ERR_UNSUPPORTED,
-               "hh_mcl_create: expansion %d is not supported yet (only the default --expansion 2)", expansion);
+    HH_REQUIRE(expansion >= 2 && expansion <= 8, HH_ERR_UNSUPPORTED,
+               "hh_mcl_create: expansion %d is not supported (2 .. 8; the reference's default is 2)", expansion);
     HH_REQUIRE(0 <= col_lo && col_lo < col_hi && col_hi <= m->n, HH_ERR_ARG, "hh_mcl_create: bad column block [%d, %d) for n = %d",
                col_lo, col_hi, m->n);
     hh_ctx* ctx = m->ctx;
@@ -1989,6 +2227,11 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
     mc->use_small = env_int("HH_MCL_SMALL", 1);
     mc->use_window = env_int("HH_MCL_WINDOW", 1);
     mc->use_blk = env_int("HH_MCL_BLOCKGEMM", 1);
+    if (expansion != 2) {          // higher powers go through the plain column kernel: A . (A . (... A)), one factor at a time
+        mc->use_small = 0;
+        mc->use_window = 0;
+        mc->use_blk = 0;
+    }
     mc->blk_items = new std::vector<hh_gemm_item>();
     mc->flat = env_int("HH_MCL_FLAT", -1);      // -1 = choose per launch from the mean segment length
     mc->l2pf = env_int("HH_MCL_L2PF", -1);       // -1 = prefetch in segment-wise mode only (long segments)
@@ -2035,7 +2278,11 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
         const int ncols = col_hi - col_lo;
         HH_CHECK(hh_dmalloc(&mc->d_m1, (size_t)mc->ld * (size_t)ncols));
         HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-        mc->preexp_mode = choose_preexp(m, preexp_mode);
+        mc->preexp_mode = (expansion == 2) ? choose_preexp(m, preexp_mode) : HH_PREEXP_SPARSE;
+        if (expansion > 2) {
+            HH_CHECK(slot_alloc(mc->pw[0], m->n, m->n, g.W));
+            if (expansion > 3) HH_CHECK(slot_alloc(mc->pw[1], m->n, m->n, g.W));
+        }
         if (mc->preexp_mode == HH_PREEXP_DENSE) {
             // dense-block path: the whole product as a symmetric GEMM on the tensor cores (hh_gemm.cu)
             std::vector<hh_gemm_item> items;
@@ -2074,10 +2321,21 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
             }
             return HH_OK;
         }
+        // --expansion k > 2: M0^(k-1) of the owned columns first, one unpruned product per factor
+        const hh_slotmat* Bp = &mc->m0;
+        HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
+        for (int pwr = 2; pwr < expansion; ++pwr) {
+            HH_CHECK(raw_product(mc, mc->m0, *Bp, (double)mc->nnz_m0, mc->pw[pwr & 1]));
+            Bp = &mc->pw[pwr & 1];
+        }
+        if (expansion > 2) {
+            HH_CHECK(read_stats(ctx, mc->d_stats, st));
+            HH_REQUIRE((int)(st[3] & 0xffffffffull) == 0, HH_ERR_CAPACITY, "hh_mcl_create: slot overflow in a matrix power");
+        }
         hh_colargs a;
         mcl_base_args(mc, a);
         a.A = mc->m0;
-        a.B = mc->m0;
+        a.B = *Bp;
         a.dense_out = mc->d_m1;
         a.flat = choose_flat(mc, (double)mc->nnz_m0);
         const float pre_thr = (float)env_int("HH_MCL_PREORDER", 10);     // 0 = off; else link count that makes an edge "strong"
@@ -2107,7 +2365,7 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
             }
         }
         a.l2pf = mc->l2pf >= 0 ? mc->l2pf : !a.flat;
-        HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
+        if (expansion == 2) HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
         HH_CHECK((launch_col<SRC_PRODUCT, EPI_DUMP>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
         HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
         HH_CHECK(read_stats(ctx, mc->d_stats, st));
@@ -2385,7 +2643,8 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
             a.orig = mc->d_inv;
             a.order = mc->d_owned;
         }
-        HH_CHECK((launch_col<SRC_DENSE, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
+        if (!mc->perm_space && env_int("HH_MCL_ITER0_STREAM", 1)) HH_CHECK(launch_iter0(ctx, g, a));
+        else HH_CHECK((launch_col<SRC_DENSE, EPI_PRUNE>(ctx, g, mc->d_scratch, mc->grid_cap, a)));
     } else if (mc->perm_space) {
         a.A = mc->it[mc->cur];
         a.B = mc->it[mc->cur];
@@ -2460,8 +2719,16 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
             }
         }
     } else {
+        const hh_slotmat* Bp = &mc->it[mc->cur];
+        for (int pwr = 2; pwr < mc->expansion; ++pwr) {           // --expansion k > 2: M^(k-1) of the owned columns, unpruned
+            HH_CHECK(raw_product(mc, mc->it[mc->cur], *Bp, (double)mc->cur_nnz, mc->pw[pwr & 1]));
+            Bp = &mc->pw[pwr & 1];
+        }
+        if (mc->expansion > 2) HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, sizeof(unsigned long long), ctx->stream));   // nnz of the result only
         a.A = mc->it[mc->cur];
-        a.B = mc->it[mc->cur];
+        a.B = *Bp;
+        a.prev = mc->it[mc->cur];
+        a.use_prev = mc->expansion > 2;
         a.do_conv = 1;
         // expected products per column ~ (nnz/n)^2; track dirty chunks when that is well below n
         const double dcol = (double)mc->cur_nnz / (double)mc->n;

@@ -18,7 +18,11 @@ METRICS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "launch__occupancy_limit_shared_mem", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second", "smsp__cycles_active.avg",
+    "launch__shared_mem_per_block_dynamic", "launch__cluster_size", "sm__inst_executed_pipe_fp64.sum",
+    "smsp__inst_executed_pipe_xu.sum", "lts__t_bytes.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
 ]
 
 
@@ -78,13 +82,15 @@ def main():
     ap.add_argument("tag")
     ap.add_argument("--launches")
     ap.add_argument("--rep", nargs="*", default=[])
+    ap.add_argument("--outdir", default="profiles", help="where the summaries go (gpurun_out on the GPU box: only that directory travels back)")
     a = ap.parse_args()
-    os.makedirs("profiles", exist_ok=True)
+    os.makedirs(a.outdir, exist_ok=True)
     if a.launches:
-        launches(a.launches, "profiles/{}_launches.csv".format(a.tag))
+        launches(a.launches, "{}/{}_launches.csv".format(a.outdir, a.tag))
     for rep in a.rep:
         base = os.path.splitext(os.path.basename(rep))[0]
-        report(rep, "profiles/{}_{}.txt".format(a.tag, base))
+        base = base[len(a.tag) + 1:] if base.startswith(a.tag + "_") else base
+        report(rep, "{}/{}_{}.txt".format(a.outdir, a.tag, base))
 
 
 if __name__ == "__main__":

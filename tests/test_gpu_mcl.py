@@ -44,7 +44,7 @@ def compare_sparse(got, ref, rtol, what, max_pattern_diff=0, floor=0.0):
     assert d.max() <= floor, "{}: max abs difference {}".format(what, d.max())
 
 
-@pytest.mark.parametrize("tag", ["links_a", "block200", "block600"])
+@pytest.mark.parametrize("tag", ["links_a", "block200", "block600", "block200_e3", "block200_e4"])
 def test_mcl_matches_reference_golden(ctx, tag):
     from haphic_b200.links import LinkMatrix
     from haphic_b200.mcl import Mcl, interpret_result
@@ -203,8 +203,9 @@ def test_mcl_rejects_unsupported(ctx):
     from haphic_b200.mcl import Mcl
     link, _ = planted_blocks(3, 10, seed=1)
     mat = LinkMatrix.from_csc(ctx, link)
-    with pytest.raises(HHError):
-        Mcl(mat, expansion=3)
+    for bad in (1, 0, 9):                 # mkl_matrix_power needs k >= 2; the library stops at 8
+        with pytest.raises(HHError):
+            Mcl(mat, expansion=bad)
     mat.close()
 
 
