@@ -463,14 +463,20 @@ def run_b200(a):
         t0 = time.perf_counter()
         tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
         tab.add(rec_host)                                   # H2D inside, double-buffered
+        ta = time.perf_counter()
         info = tab.finish()
+        tb = time.perf_counter()
         table = tab.fetch(pinned=True)                                 # D2H: the link dicts' arrays
         tot = tab.fetch_ctg()
+        tc = time.perf_counter()
         index, n_linked = tab.linked_index(keep)
         tail = np.nonzero(index < 0)[0].astype(np.int32)
         mat = tab.to_matrix(keep, tail)
         ctx.sync()
         t1 = time.perf_counter()
+        if a.verbose:
+            print("e2e pass {} ms: add(H2D) {:.1f} finish {:.1f} fetch(D2H) {:.1f} index+matrix {:.1f}".format(
+                s, 1e3 * (ta - t0), 1e3 * (tb - ta), 1e3 * (tc - tb), 1e3 * (t1 - tc)), file=sys.stderr)
         mc = Mcl(mat)
         n_it = 0
         d2h_mcl = 0

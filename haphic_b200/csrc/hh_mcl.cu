@@ -1695,20 +1695,21 @@ static int launch_col(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_
 // Warp w owns row block w (rows [w * T, (w + 1) * T)), so the row-block pointers of the slotted format fall out of the
 // per-warp counts.  Two CTAs per SM overlap one column's reductions with the other's loads.
 // ---------------------------------------------------------------------------------------------
+#define HH_IT0_WARPS 8
 template <int W>
-__global__ void __launch_bounds__(W * 32, (W <= 16) ? 2 : 1) hh_k_iter0(const hh_colargs a) {
-    __shared__ double s_d[32];
-    __shared__ float s_f[32];
-    __shared__ int s_k[32];
-    __shared__ int s_c[32];
+__global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_colargs a) {
+    // HH_IT0_WARPS warps per CTA (several CTAs per SM keep loads of other columns in flight across the reductions); warp v
+    // handles the row blocks v, v + HH_IT0_WARPS, ... of the slotted format (W blocks of T rows)
+    __shared__ double s_d[HH_IT0_WARPS];
+    __shared__ float s_f[HH_IT0_WARPS];
+    __shared__ int s_k[HH_IT0_WARPS];
+    __shared__ int s_c[32];          // survivors per row block
     __shared__ int s_col;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
     const int T = a.T;
-    const int tile0 = w * T;
     const float rf = a.inflation, p32 = a.prune;
     const bool sq = a.inflate_square != 0;
     const int ld4 = (int)(a.ld >> 2);
-    const int r4_lo = tile0 >> 2, r4_hi = min((tile0 + T) >> 2, ld4);
     unsigned long long nnz_acc = 0ull;
     auto pw = [&](float x) -> float { return sq ? x * x : powf(x, rf); };
     for (;;) {
@@ -1723,30 +1724,34 @@ __global__ void __launch_bounds__(W * 32, (W <= 16) ? 2 : 1) hh_k_iter0(const hh
         double s1 = 0.0;
         float xbest = 0.f;
         int kbest = 0x7fffffff;
-        for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 128) {
-            float4 x[4];
+        for (int b = wv; b < W; b += HH_IT0_WARPS) {
+            const int r4_lo = (b * T) >> 2, r4_hi = min(((b + 1) * T) >> 2, ld4);
+            for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 128) {
+                float4 x[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 4; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+                for (int q = 0; q < 4; ++q) {
+                    const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float v = xv[c];
-                    if (v != 0.f) {
-                        s1 += (double)pw(v);
-                        if (v > xbest) {              // rows ascend inside a lane: the first maximum stays
-                            xbest = v;
-                            kbest = ((r4 + 32 * q) << 2) + c;
+                    for (int c = 0; c < 4; ++c) {
+                        const float v = xv[c];
+                        if (v != 0.f) {
+                            s1 += (double)pw(v);
+                            const int k = ((r4 + 32 * q) << 2) + c;
+                            if (v > xbest || (v == xbest && k < kbest)) {
+                                xbest = v;
+                                kbest = k;
+                            }
                         }
                     }
                 }
             }
         }
         s1 = hh_warp_sum(s1);
-        if (lane == 0) s_d[w] = s1;
+        if (lane == 0) s_d[wv] = s1;
         __syncthreads();
-        const double S1 = hh_warp_sum((lane < W) ? s_d[lane] : 0.0);
+        const double S1 = hh_warp_sum((lane < HH_IT0_WARPS) ? s_d[lane] : 0.0);
         __syncthreads();
         // exact x1 of this lane's maximum; two different x may round to one x1: then the lower row wins (first maximum)
         float vbest = (xbest > 0.f && S1 != 0.0) ? (float)((double)pw(xbest) / S1) : 0.f;
@@ -1764,39 +1769,42 @@ __global__ void __launch_bounds__(W * 32, (W <= 16) ? 2 : 1) hh_k_iter0(const hh
         const float thr_y = (float)(0.999 * (double)p32 * S1);
         const float xthr = (S1 != 0.0) ? 0.9999f * (sq ? sqrtf(thr_y) : powf(thr_y, 1.0f / rf)) : 3.0e38f;
         double s2 = 0.0;
-        int cnt = 0;
-        for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 128) {
-            float4 x[4];
+        for (int b = wv; b < W; b += HH_IT0_WARPS) {
+            const int r4_lo = (b * T) >> 2, r4_hi = min(((b + 1) * T) >> 2, ld4);
+            int cnt = 0;
+            for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 128) {
+                float4 x[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 4; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+                for (int q = 0; q < 4; ++q) {
+                    const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (xv[c] >= xthr) {
-                        const float x1 = (float)((double)pw(xv[c]) / S1);
-                        if (x1 >= p32 && x1 > 0.f) {
-                            cnt++;
-                            s2 += (double)x1;
+                    for (int c = 0; c < 4; ++c) {
+                        if (xv[c] >= xthr) {
+                            const float x1 = (float)((double)pw(xv[c]) / S1);
+                            if (x1 >= p32 && x1 > 0.f) {
+                                cnt++;
+                                s2 += (double)x1;
+                            }
                         }
                     }
                 }
             }
+            cnt = hh_warp_sum(cnt);
+            if (lane == 0) s_c[b] = cnt;
         }
         s2 = hh_warp_sum(s2);
-        cnt = hh_warp_sum(cnt);
         if (lane == 0) {
-            s_d[w] = s2;
-            s_c[w] = cnt;
-            s_f[w] = vbest;
-            s_k[w] = kbest;
+            s_d[wv] = s2;
+            s_f[wv] = vbest;
+            s_k[wv] = kbest;
         }
         __syncthreads();
         const int cv = (lane < W) ? s_c[lane] : 0;
-        double S2 = hh_warp_sum((lane < W) ? s_d[lane] : 0.0);
-        float vmax = (lane < W) ? s_f[lane] : 0.f;
-        int kmax = (lane < W) ? s_k[lane] : 0x7fffffff;
+        double S2 = hh_warp_sum((lane < HH_IT0_WARPS) ? s_d[lane] : 0.0);
+        float vmax = (lane < HH_IT0_WARPS) ? s_f[lane] : 0.f;
+        int kmax = (lane < HH_IT0_WARPS) ? s_k[lane] : 0x7fffffff;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(HH_FULL_MASK, vmax, o);
@@ -1812,59 +1820,56 @@ __global__ void __launch_bounds__(W * 32, (W <= 16) ? 2 : 1) hh_k_iter0(const hh
             const int tt = __shfl_up_sync(HH_FULL_MASK, incl, o);
             if (lane >= o) incl += tt;
         }
-        int base = __shfl_sync(HH_FULL_MASK, incl - cv, w);
+        const int excl = incl - cv;                                  // lane b: first output position of row block b
         int total = __shfl_sync(HH_FULL_MASK, incl, 31);
-        const int mine = __shfl_sync(HH_FULL_MASK, cv, w);         // survivors in this warp's row block
         const bool need_max = (total == 0) && (vmax > 0.f);        // keep the column maximum (2009-2013)
-        if (need_max) {
-            base = (w > kmax / T) ? 1 : 0;
-            total = 1;
-        }
+        if (need_max) total = 1;
         // ---------------------------------------------------------------- pass 3: ordered write
         uint2* __restrict__ oent = a.out.ent + (size_t)j * (size_t)a.out.cap;
-        if (need_max) {
-            if (threadIdx.x == 0) oent[0] = make_uint2((unsigned)kmax, __float_as_uint(1.0f));      // x1 / x1
-        } else if (mine > 0) {
-            {
-                int off = base;
-                for (int r4 = r4_lo; r4 < r4_hi; r4 += 32) {            // one float4 per lane and trip: rows ascend with the lane
-                    const int rr = r4 + lane;
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rr < r4_hi) x = hh_ld_stream_f4(col4 + rr);
-                    const float xv[4] = {x.x, x.y, x.z, x.w};
-                    float keep[4];
-                    int c = 0;
+        if (need_max && threadIdx.x == 0) oent[0] = make_uint2((unsigned)kmax, __float_as_uint(1.0f));      // x1 / x1
+        for (int b = wv; b < W; b += HH_IT0_WARPS) {
+            const int base = need_max ? ((b > kmax / T) ? 1 : 0) : __shfl_sync(HH_FULL_MASK, excl, b);
+            const int mine = need_max ? 0 : __shfl_sync(HH_FULL_MASK, cv, b);
+            if (lane == 0) a.out.blk[(size_t)j * (W + 1) + b] = base;
+            if (mine == 0) continue;
+            const int r4_lo = (b * T) >> 2, r4_hi = min(((b + 1) * T) >> 2, ld4);
+            int off = base;
+            for (int r4 = r4_lo; r4 < r4_hi; r4 += 32) {            // one float4 per lane and trip: rows ascend with the lane
+                const int rr = r4 + lane;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rr < r4_hi) x = hh_ld_stream_f4(col4 + rr);
+                const float xv[4] = {x.x, x.y, x.z, x.w};
+                float keep[4];
+                int c = 0;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        keep[q] = 0.f;
-                        if (xv[q] >= xthr) {
-                            const float x1 = (float)((double)pw(xv[q]) / S1);
-                            if (x1 >= p32 && x1 > 0.f) {
-                                keep[q] = x1;
-                                c++;
-                            }
+                for (int q = 0; q < 4; ++q) {
+                    keep[q] = 0.f;
+                    if (xv[q] >= xthr) {
+                        const float x1 = (float)((double)pw(xv[q]) / S1);
+                        if (x1 >= p32 && x1 > 0.f) {
+                            keep[q] = x1;
+                            c++;
                         }
                     }
-                    if (__ballot_sync(HH_FULL_MASK, c > 0) == 0u) continue;
-                    int inc = c;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int tt = __shfl_up_sync(HH_FULL_MASK, inc, o);
-                        if (lane >= o) inc += tt;
-                    }
-                    int pos = off + inc - c;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (keep[q] > 0.f) {
-                            if (pos < a.out.cap) oent[pos] = make_uint2((unsigned)((rr << 2) + q), __float_as_uint((float)((double)keep[q] / S2)));
-                            pos++;
-                        }
-                    }
-                    off += __shfl_sync(HH_FULL_MASK, inc, 31);
                 }
+                if (__ballot_sync(HH_FULL_MASK, c > 0) == 0u) continue;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int tt = __shfl_up_sync(HH_FULL_MASK, inc, o);
+                    if (lane >= o) inc += tt;
+                }
+                int pos = off + inc - c;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (keep[q] > 0.f) {
+                        if (pos < a.out.cap) oent[pos] = make_uint2((unsigned)((rr << 2) + q), __float_as_uint((float)((double)keep[q] / S2)));
+                        pos++;
+                    }
+                }
+                off += __shfl_sync(HH_FULL_MASK, inc, 31);
             }
         }
-        if (lane == 0) a.out.blk[(size_t)j * (W + 1) + w] = base;
         if (threadIdx.x == 0) {
             a.out.blk[(size_t)j * (W + 1) + W] = min(total, a.out.cap);
             a.out.len[j] = min(total, a.out.cap);
@@ -1879,13 +1884,13 @@ template <int W>
 static int launch_iter0_w(hh_ctx* ctx, hh_colargs& a) {
     auto kern = hh_k_iter0<W>;
     int per_sm = 0;
-    HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, 0));
+    HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HH_IT0_WARPS * 32, 0));
     if (per_sm < 1) per_sm = 1;
     int grid = per_sm * ctx->sm_count;
     if (grid > a.ncols) grid = a.ncols;
     if (grid < 1) return HH_OK;
     HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
-    HH_LAUNCH(ctx, kern, grid, W * 32, 0, a);
+    HH_LAUNCH(ctx, kern, grid, HH_IT0_WARPS * 32, 0, a);
     return HH_OK;
 }
 
@@ -2196,6 +2201,14 @@ static int choose_preexp(const hh_matrix* m, int requested) {
     const double n = (double)m->n, d = (double)m->nnz / (n > 0 ? n : 1.0);
     const double t_sparse = n * d * d / 0.5e12;
     const double t_dense = 2.0e-15 * n * n * n + 3.0e-12 * n * n + 5.0e-4;
+    // the operand planes (up to six bf16 planes of n x n) must fit beside M1 and the iterates
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        free_b = 0;
+    }
+    const double planes = 6.0 * 2.0 * n * n;
+    if (planes > 0.6 * (double)free_b) return HH_PREEXP_SPARSE;
     return (1.2 * t_dense < t_sparse) ? HH_PREEXP_DENSE : HH_PREEXP_SPARSE;
 }
 

@@ -233,6 +233,10 @@ def test_rank_sums_match_host(ctx, n, density, topN):
     assert np.array_equal(got, want)
 
 
+def info_nnz(tab):
+    return tab.info.nnz_flank if tab.info is not None else -1
+
+
 def test_global_accumulator_column_blocks_match_oracle(ctx):
     """n = 60,000 > 57,600 rows: the column accumulator no longer fits shared memory and every column kernel (normalise,
     expansion, dense iteration 0) runs on the L2-resident global accumulator.  On a realistic matrix (synthetic Hi-C stream,
@@ -260,7 +264,9 @@ def test_global_accumulator_column_blocks_match_oracle(ctx):
     ref = orc.count_links_c(rec.cpu().numpy(), asm.lengths, rank, in_nx, 500000)
     link, oindex = orc.dict_to_matrix(ref["flank_keys"], ref["flank_vals"], keep, tail_order=tail.tolist())
     got = mat.to_scipy()
-    assert np.array_equal(got.indices, link.indices) and np.array_equal(got.data, link.data)
+    assert got.nnz == link.nnz and np.array_equal(got.indptr, link.indptr), (got.nnz, link.nnz, int(info_nnz(tab)))
+    assert np.array_equal(got.indices, link.indices), int((got.indices != link.indices).sum())
+    assert np.array_equal(got.data, link.data), int((got.data != link.data).sum())
     m0 = orc.col_normalize_l1(link)
     first = True
     for lo, hi in [(0, 96), (30000, 30096), (59904, 60000)]:
