@@ -64,11 +64,14 @@ struct hh_ctx {
         void* p;
         size_t bytes;
         bool used;
+        uint64_t tick;      // last release (least recently used blocks go first when the cache is trimmed)
     };
     std::vector<ws_block>* ws;
+    uint64_t ws_tick;
 };
 
 void* hh_ws_alloc_bytes(hh_ctx* ctx, size_t bytes);
+bool hh_ws_release(hh_ctx* ctx, void* p);
 void hh_ws_free_ptr(hh_ctx* ctx, void* p);
 template <typename T>
 static inline int hh_ws_alloc(hh_ctx* ctx, T** p, size_t count) {
@@ -94,10 +97,18 @@ struct hh_scope {
     ~hh_scope() { hh_tls_ctx = prev; }
 };
 
+// Large buffers (>= HH_WS_MIN bytes) come from the context's workspace cache (best fit, blocks stay with the context):
+// the stream-ordered pool re-shapes itself when the sequence of multi-GB requests changes from pass to pass, which cost
+// up to a second per step; small ones from the pool.
+#define HH_WS_MIN ((size_t)32 << 20)
 template <typename T>
 static inline int hh_dmalloc(T** p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
+    if (hh_tls_ctx && count * sizeof(T) >= HH_WS_MIN) {
+        *p = reinterpret_cast<T*>(hh_ws_alloc_bytes(hh_tls_ctx, count * sizeof(T)));
+        return *p ? HH_OK : HH_ERR_NOMEM;
+    }
     cudaError_t e = hh_tls_ctx ? cudaMallocAsync((void**)p, count * sizeof(T), hh_tls_ctx->stream)
                                : cudaMalloc((void**)p, count * sizeof(T));
     if (e != cudaSuccess) {
@@ -110,8 +121,12 @@ static inline int hh_dmalloc(T** p, size_t count) {
 template <typename T>
 static inline void hh_dfree(T*& p) {
     if (p) {
-        if (hh_tls_ctx) cudaFreeAsync((void*)p, hh_tls_ctx->stream);
-        else cudaFree((void*)p);
+        if (hh_ws_release(hh_tls_ctx, (void*)p)) {       // also looks through the other contexts of the process
+        } else if (hh_tls_ctx) {
+            cudaFreeAsync((void*)p, hh_tls_ctx->stream);
+        } else {
+            cudaFree((void*)p);
+        }
     }
     p = nullptr;
 }

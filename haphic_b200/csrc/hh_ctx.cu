@@ -1,7 +1,10 @@
 // Context, error string, small utilities of libhaphic_b200.
 #include "hh_common.cuh"
 
+#include <mutex>
 static thread_local char g_err[1024] = "";
+static std::mutex g_ctx_mutex;
+static std::vector<hh_ctx*> g_ctx_list;      // live contexts: a buffer may be released under another context's scope
 thread_local hh_ctx* hh_tls_ctx = nullptr;
 
 void hh_set_error(const char* fmt, ...) {
@@ -43,6 +46,7 @@ extern "C" int hh_ctx_create(int device, hh_ctx** out) {
     c->h_scratch = nullptr;
     c->d_scratch = nullptr;
     c->ws = new std::vector<hh_ctx::ws_block>();
+    c->ws_tick = 0;
     HH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     {   // keep freed device memory in the pool: a pass re-allocates the same multi-GB buffers
         cudaMemPool_t pool;
@@ -52,12 +56,24 @@ extern "C" int hh_ctx_create(int device, hh_ctx** out) {
     }
     HH_CUDA(cudaMallocHost((void**)&c->h_scratch, 64 * sizeof(uint64_t)));
     HH_CUDA(cudaMalloc((void**)&c->d_scratch, 64 * sizeof(uint64_t)));
+    {
+        std::lock_guard<std::mutex> g(g_ctx_mutex);
+        g_ctx_list.push_back(c);
+    }
     *out = c;
     return HH_OK;
 }
 
 extern "C" int hh_ctx_destroy(hh_ctx* c) {
     if (!c) return HH_OK;
+    {
+        std::lock_guard<std::mutex> g(g_ctx_mutex);
+        for (size_t k = 0; k < g_ctx_list.size(); ++k)
+            if (g_ctx_list[k] == c) {
+                g_ctx_list.erase(g_ctx_list.begin() + (long)k);
+                break;
+            }
+    }
     cudaSetDevice(c->device);
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
@@ -111,17 +127,55 @@ void* hh_ws_alloc_bytes(hh_ctx* c, size_t bytes) {
     nb.p = p;
     nb.bytes = bytes;
     nb.used = true;
+    nb.tick = 0;
     c->ws->push_back(nb);
     return p;
 }
 
-void hh_ws_free_ptr(hh_ctx* c, void* p) {
+// give a block back to the cache; false if `p` is not a workspace block.  Unused blocks beyond HH_WS_KEEP bytes are freed,
+// least recently used first, so that other allocators of the process (torch) keep finding memory.
+static bool ws_mark_free(hh_ctx* c, void* p) {
+    if (!c || !c->ws) return false;
     for (size_t k = 0; k < c->ws->size(); ++k)
         if ((*c->ws)[k].p == p) {
             (*c->ws)[k].used = false;
-            return;
+            (*c->ws)[k].tick = ++c->ws_tick;
+            return true;
         }
+    return false;
 }
+
+bool hh_ws_release(hh_ctx* c, void* p) {
+    bool found = ws_mark_free(c, p);
+    if (!found) {
+        // released under another context's scope (or none): look through every live context
+        std::lock_guard<std::mutex> g(g_ctx_mutex);
+        for (size_t k = 0; k < g_ctx_list.size() && !found; ++k)
+            if (g_ctx_list[k] != c && ws_mark_free(g_ctx_list[k], p)) {
+                found = true;
+                c = g_ctx_list[k];
+            }
+    }
+    if (!found) return false;
+    const size_t keep = (size_t)72 << 30;
+    for (;;) {
+        size_t idle = 0;
+        int oldest = -1;
+        for (size_t k = 0; k < c->ws->size(); ++k) {
+            const hh_ctx::ws_block& b = (*c->ws)[k];
+            if (b.used) continue;
+            idle += b.bytes;
+            if (oldest < 0 || b.tick < (*c->ws)[(size_t)oldest].tick) oldest = (int)k;
+        }
+        if (idle <= keep || oldest < 0) break;
+        cudaStreamSynchronize(c->stream);
+        cudaFree((*c->ws)[(size_t)oldest].p);
+        c->ws->erase(c->ws->begin() + oldest);
+    }
+    return true;
+}
+
+void hh_ws_free_ptr(hh_ctx* c, void* p) { hh_ws_release(c, p); }
 
 extern "C" int hh_ctx_sync(hh_ctx* c) {
     HH_REQUIRE(c != nullptr, HH_ERR_ARG, "hh_ctx_sync: ctx is NULL");

@@ -93,6 +93,9 @@ class LinkTable:
             if rec.dtype != torch.int32 or rec.dim() != 2 or rec.shape[1] != 4 or not rec.is_contiguous():
                 raise ValueError("records must be a contiguous int32 [P, 4] tensor")
             mem = _lib.HH_MEM_DEVICE if rec.is_cuda else _lib.HH_MEM_HOST
+            if rec.is_cuda:
+                # the library works on its own (non-blocking) stream: whatever produced `rec` on torch's stream must be done
+                torch.cuda.current_stream(rec.device).synchronize()
         if asynchronous:
             if mem != _lib.HH_MEM_DEVICE:
                 raise ValueError("asynchronous add needs device-resident records")
