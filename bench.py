@@ -573,8 +573,10 @@ def run_b200(a):
         "roofline_mcl": {"kernel": "all hh_k_col / hh_k_col_win / hh_k_col_small launches of the sweep", "bound": "hbm",
                          "achieved": mcl_achieved, "peak": peak, "unit": "GB/s", "frac": mcl_achieved / peak,
                          "algorithmic_bytes": mcl_bytes, "kernel_ms": s0["kernel_ms"]},
-        "roofline_build": {"kernel": "hh_k_links_insert + finish", "bound": "hbm", "achieved": build_achieved, "peak": peak,
-                           "unit": "GB/s", "frac": build_achieved / peak, "traffic": traffic.get("hh_k_links_insert")},
+        "roofline_build": {"kernel": "hh_k_part_scatter + 513 x hh_k_part_step (partition, then aggregate in L2-resident scratch tables)",
+                           "bound": "hbm", "achieved": build_achieved, "peak": peak, "unit": "GB/s", "frac": build_achieved / peak,
+                           "traffic": traffic.get("hh_k_links_partitioned"), "algorithmic_bytes": build_bytes,
+                           "note": traffic.get("hh_k_links_partitioned_note")},
         "cpu_baseline": cpu,
         "ingest": ingest,
     }
