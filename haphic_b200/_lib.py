@@ -7,6 +7,7 @@ present every entry point raises.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -34,7 +35,8 @@ class MclResult(C.Structure):
 class PreexpInfo(C.Structure):
     _fields_ = [("mode", C.c_int32), ("a_planes", C.c_int32), ("passes", C.c_int32), ("cta_group", C.c_int32),
                 ("stages", C.c_int32), ("chunk_kb", C.c_int32), ("total_ms", C.c_float), ("densify_ms", C.c_float),
-                ("gemm_ms", C.c_float), ("clip_ms", C.c_float), ("flops", C.c_double), ("products", C.c_int64)]
+                ("gemm_ms", C.c_float), ("clip_ms", C.c_float), ("flops", C.c_double), ("products", C.c_int64),
+                ("clip", C.c_float), ("b_planes", C.c_int32), ("fmt_a", C.c_int32), ("fmt_b", C.c_int32)]
 
 
 HH_PREEXP_AUTO, HH_PREEXP_SPARSE, HH_PREEXP_DENSE = 0, 1, 2
@@ -154,6 +156,12 @@ class Context:
         lib = load()
         check(lib.hh_ctx_create(int(device), C.byref(self._h)))
         self.device = int(device)
+        self._children = weakref.WeakSet()      # LinkTable / LinkMatrix / Mcl objects living on this context
+
+    def adopt(self, obj):
+        """Register an object whose library handle dies with this context: close() destroys it first, so a handle that
+        outlives its context (e.g. kept alive by a traceback) is never passed to the library again."""
+        self._children.add(obj)
 
     @property
     def handle(self):
@@ -178,6 +186,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for obj in sorted(self._children, key=lambda o: -getattr(o, "_close_order", 0)):
+                obj.close()
             load().hh_ctx_destroy(self._h)
             self._h = C.c_void_p()
 

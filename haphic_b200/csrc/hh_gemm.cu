@@ -30,6 +30,7 @@
 #include "hh_internal.cuh"
 #include "hh_gemm.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <algorithm>
 
@@ -188,6 +189,9 @@ struct hh_gemm_args {
     long long ld;
     int col_lo, col_hi;
     const float* inv_s;    // 1 / column sum
+    float out_scale;       // applied instead when inv_s == NULL
+    int split_lo;          // 1: passes with a low-order plane accumulate in their own TMEM buffer over the whole tile (see kernel)
+    uint32_t idesc_fmt;    // operand format bits of the instruction descriptor (bit 7: A is bf16, bit 10: B is bf16)
 };
 
 template <int CG>
@@ -196,7 +200,8 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     constexpr int BN = 128 * CG;              // tile columns (= TMEM columns per accumulator buffer)
     constexpr int CW = BN / 2;                // columns per epilogue warp
     constexpr uint32_t TMEM_COLS = 2 * BN;    // two accumulator buffers
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+    // kind::f16 descriptor: fp32 accumulator (bit 4), A / B format (bits 7-9 / 10-12: 0 = f16, 1 = bf16), both K-major, N >> 3, M >> 4
+    const uint32_t IDESC = (1u << 4) | a.idesc_fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
 
     extern __shared__ uint8_t hg_smem_raw[];
     __shared__ __align__(8) uint64_t s_full[HG_MAX_STAGES];
@@ -267,26 +272,38 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (rank == 0 && lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            uint32_t g = 0;     // running chunk counter: TMEM buffer g & 1, phase (g >> 1) & 1
+            uint32_t g = 0;     // running chunk counter: TMEM buffer g & 1, phase (g >> 1) & 1  (split_lo: buffer 0, phase g & 1)
+            const bool split = a.split_lo != 0;
             for (int it = pair; it < a.n_items; it += npairs) {
                 const hh_gemm_item w = a.items[it];
                 int in_chunk = 0;
                 const int total = (w.kb_hi[0] - w.kb_lo[0]) + (w.kb_hi[1] - w.kb_lo[1]);
                 for (int t = 0; t < total; ++t) {
-                    const uint32_t buf = g & 1u;
+                    const uint32_t buf = split ? 0u : (g & 1u);
                     if (in_chunk == 0) {
-                        hg_mbar_wait(hg_smem_u32(&s_tempty[buf]), ((g >> 1) & 1u) ^ 1u);
+                        hg_mbar_wait(hg_smem_u32(&s_tempty[buf]), (split ? (g & 1u) : ((g >> 1) & 1u)) ^ 1u);
                         hg_tc_fence_after();
                     }
                     hg_mbar_wait(hg_smem_u32(&s_full[s]), ph);
                     hg_tc_fence_after();
                     const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-                    const uint32_t d = tmem_base + buf * (uint32_t)BN;
+                    const uint32_t d_hi = tmem_base + buf * (uint32_t)BN;
+                    const uint32_t d_lo = tmem_base + (uint32_t)BN;
+                    uint32_t hi_acc = in_chunk ? 1u : 0u, lo_acc = t ? 1u : 0u;      // 0: the MMA overwrites the accumulator
                     for (int p = 0; p < a.npass; ++p) {
                         const uint64_t ad = hg_make_desc(st + (uint32_t)a.pa[p] * HG_PLANE_BYTES);
                         const uint64_t bd = hg_make_desc(st + (uint32_t)(a.na + a.pb[p]) * HG_PLANE_BYTES);
+                        const bool lo = split && (a.pa[p] | a.pb[p]) != 0;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) hg_umma<CG>(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (in_chunk | p | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) {
+                            if (lo) {
+                                hg_umma<CG>(d_lo, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, lo_acc);
+                                lo_acc = 1u;
+                            } else {
+                                hg_umma<CG>(d_hi, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, hi_acc);
+                                hi_acc = 1u;
+                            }
+                        }
                     }
                     hg_umma_commit<CG>(hg_smem_u32(&s_empty[s]));      // the stage is free once these MMAs have read it
                     if (++s == S) {
@@ -310,6 +327,7 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t lane_addr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * CW);
         const uint32_t tempty0 = (CG == 2) ? hg_mapa(hg_smem_u32(&s_tempty[0]), 0) : hg_smem_u32(&s_tempty[0]);
         uint32_t g = 0;
+        const bool split = a.split_lo != 0;
         float acc[CW];
         for (int it = pair; it < a.n_items; it += npairs) {
             const hh_gemm_item w = a.items[it];
@@ -318,16 +336,21 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int j = 0; j < CW; ++j) acc[j] = 0.f;
             for (int ch = 0; ch < nchunks; ++ch, ++g) {
-                const uint32_t buf = g & 1u;
-                hg_mbar_wait(hg_smem_u32(&s_tfull[buf]), (g >> 1) & 1u);
+                const uint32_t buf = split ? 0u : (g & 1u);
+                hg_mbar_wait(hg_smem_u32(&s_tfull[buf]), split ? (g & 1u) : ((g >> 1) & 1u));
                 hg_tc_fence_after();
+                // split_lo: after the last chunk of the tile the low-order accumulator (second buffer) is added as well
+                const int nsrc = (split && ch + 1 == nchunks) ? 2 : 1;
+                for (int src = 0; src < nsrc; ++src) {
+                    const uint32_t tb = tmem_base + (src ? (uint32_t)BN : buf * (uint32_t)BN) + lane_addr;
 #pragma unroll
-                for (int q = 0; q < CW / 32; ++q) {
-                    uint32_t v[32];
-                    hg_tmem_ld32(tmem_base + buf * (uint32_t)BN + lane_addr + (uint32_t)(q * 32), v);
-                    hg_tmem_ld_wait();
+                    for (int q = 0; q < CW / 32; ++q) {
+                        uint32_t v[32];
+                        hg_tmem_ld32(tb + (uint32_t)(q * 32), v);
+                        hg_tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[q * 32 + j] = __fadd_rn(acc[q * 32 + j], __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; ++j) acc[q * 32 + j] = __fadd_rn(acc[q * 32 + j], __uint_as_float(v[j]));
+                    }
                 }
                 hg_tc_fence_before();
                 __syncwarp();
@@ -346,11 +369,11 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int j = 0; j < CW; ++j) {
                         const int c = c0 + j;
                         if (c < w.n_end && c >= a.col_lo && c < a.col_hi)
-                            dst[(size_t)(c - a.col_lo) * (size_t)a.ld] = a.inv_s ? acc[j] * __ldg(a.inv_s + c) : acc[j];
+                            dst[(size_t)(c - a.col_lo) * (size_t)a.ld] = a.inv_s ? acc[j] * __ldg(a.inv_s + c) : acc[j] * a.out_scale;
                     }
                 }
                 if ((w.flags & HH_GEMM_MIRROR) && r >= a.col_lo && r < a.col_hi) {
-                    const float sr = a.inv_s ? __ldg(a.inv_s + r) : 1.f;
+                    const float sr = a.inv_s ? __ldg(a.inv_s + r) : a.out_scale;
                     float* __restrict__ dst = a.m1 + (size_t)(r - a.col_lo) * (size_t)a.ld - (ptrdiff_t)w.out_row0;
 #pragma unroll
                     for (int j = 0; j < CW; j += 4) {
@@ -381,7 +404,7 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // ---------------------------------------------------------------------------------------------------------------------
 // column sums in fp64 (sklearn normalize accumulates in double, 2144) and their fp32 reciprocals
 __global__ void hh_k_gemm_colsum(const int64_t* __restrict__ colptr, const float* __restrict__ val, int n, double* __restrict__ s,
-                                 float* __restrict__ inv_s) {
+                                 float* __restrict__ inv_s, int* __restrict__ flags) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
     const int lane = threadIdx.x & 31;
@@ -391,16 +414,18 @@ __global__ void hh_k_gemm_colsum(const int64_t* __restrict__ colptr, const float
     if (lane == 0) {
         s[c] = t;
         inv_s[c] = (t != 0.0) ? (float)(1.0 / t) : 1.f;
+        if (t >= 8388608.0) atomicOr(flags, 4);          // 2^-e_k of the scaled f16 encoding would leave the subnormal range
     }
 }
 
-// flags[0] |= 1 if some value is not an integer in [0, 65536); flags[0] |= 2 if some value exceeds 256
+// flags[0] |= 1 if some value is not an integer in [0, 65536); |= 2 if some value exceeds 256; |= 8 if some value exceeds 2048
 __global__ void hh_k_gemm_valstats(const float* __restrict__ val, int64_t nnz, int* __restrict__ flags) {
     int f = 0;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
         const float v = val[p];
         if (!(v >= 0.f && v < 65536.f && v == floorf(v))) f |= 1;
         if (v > 256.f) f |= 2;
+        if (v > 2048.f) f |= 8;
     }
     f = __reduce_or_sync(HH_FULL_MASK, f);
     if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
@@ -416,37 +441,57 @@ __device__ __forceinline__ void hg_split3(float x, unsigned short& h1, unsigned 
     h3 = (unsigned short)(__float_as_uint(r2) >> 16);              // at most 8 significant bits are left
 }
 
-// One CTA per column c of the CSC = row c of both operands:  A[c, k] = min(C[c, k], clip),  B[c, k] = fp32(A[c, k] / s[k]).
+// One CTA per column c of the CSC = row c of both operands.  Two encodings of  S[r, c] = sum_k C[r, k] * M0[c, k]:
+//   exact bf16   A[c, k] = min(C[c, k], clip) in na planes,  B[c, k] = fp32(A[c, k] / s[k]) in three bf16 planes (8 + 8 + 8 bits);
+//   scaled f16   A[c, k] = min(C[c, k], clip) * 2^-e_k  (ONE plane: an integer times a power of two is exact in bf16 up to 256 and
+//                in f16 up to 2048, subnormals included while e_k <= 24),
+//                B[c, k] = fp32(A / s[k]) * 2^e_k in (count, 2 count]  as TWO f16 planes hi + lo = 22 significant bits, round to
+//                nearest: every product is within 2^-23 relative of the fp32 product, in two passes instead of three.
+//                2^e_k is the power of two above the column sum s[k]: it cancels inside every product.
 // The row is assembled in shared memory (segments of HG_SEG columns, up to three planes at a time) and written with
 // coalesced 16-byte stores: every element of the padded row is written exactly once, so the planes need no memset and no
 // read-modify-write of partially written sectors.
 #define HG_SEG 32768
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row, const float* __restrict__ val, int n,
-                  const double* __restrict__ s, unsigned short* __restrict__ A, int na, unsigned short* __restrict__ B, long long ldk,
-                  long long plane, float clip) {
+                  const double* __restrict__ s, unsigned short* __restrict__ A, int na, unsigned short* __restrict__ B, int nb, long long ldk,
+                  long long plane, float clip, int scaled, int a_f16) {
     extern __shared__ __align__(16) unsigned short hg_row[];        // [3][HG_SEG]
     const int c = blockIdx.x;
     const int64_t p0 = colptr[c], p1 = colptr[c + 1];
     for (int group = 0; group < 2; ++group) {                       // 0: planes of A, 1: planes of B
-        const int np = group ? 3 : na;
+        const int np = group ? nb : na;
         unsigned short* __restrict__ out = (group ? B : A) + (size_t)c * (size_t)ldk;
         for (long long seg0 = 0; seg0 < ldk; seg0 += HG_SEG) {
             const int seg_n = (int)((ldk - seg0 < HG_SEG) ? (ldk - seg0) : HG_SEG);      // multiple of 64
             uint4* z = reinterpret_cast<uint4*>(hg_row);
-            for (int q = threadIdx.x; q < 3 * HG_SEG / 8; q += 256) z[q] = make_uint4(0u, 0u, 0u, 0u);
+            for (int q = threadIdx.x; q < 3 * HG_SEG / 8; q += blockDim.x) z[q] = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();
-            for (int64_t p = p0 + threadIdx.x; p < p1; p += 256) {
+            for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
                 const long long k = row[p];
                 if (k < seg0 || k >= seg0 + seg_n) continue;
                 const float v = fminf(val[p], clip);      // counts above `clip` are finished by the caller's sparse correction
-                float x = v;
-                if (group) {
-                    const double sk = s[k];
-                    x = (sk != 0.0) ? (float)((double)v / sk) : v;
+                const double sk = s[k];
+                unsigned short h1 = 0, h2 = 0, h3 = 0;
+                if (!scaled) {
+                    float x = v;
+                    if (group) x = (sk != 0.0) ? (float)((double)v / sk) : v;
+                    hg_split3(x, h1, h2, h3);
+                } else {
+                    // s[k] in [2^(e-1), 2^e), 0 <= e <= 24: the exponent field of the double; 2^e and 2^-e as floats
+                    const int e = (sk != 0.0) ? (int)((__double2hiint(sk) >> 20) & 0x7ff) - 1022 : 0;
+                    if (!group) {
+                        const float xa = v * __int_as_float((127 - e) << 23);
+                        h1 = a_f16 ? __half_as_ushort(__float2half_rn(xa)) : (unsigned short)(__float_as_uint(xa) >> 16);
+                    } else {
+                        const float x = (sk != 0.0) ? (float)((double)v / sk) : v;
+                        const float xs = x * __int_as_float((127 + e) << 23);
+                        const __half hi = __float2half_rn(xs);
+                        const __half lo = __float2half_rn(xs - __half2float(hi));
+                        h1 = __half_as_ushort(hi);
+                        h2 = __half_as_ushort(lo);
+                    }
                 }
-                unsigned short h1, h2, h3;
-                hg_split3(x, h1, h2, h3);
                 const int kk = (int)(k - seg0);
                 hg_row[kk] = h1;
                 if (np > 1) hg_row[HG_SEG + kk] = h2;
@@ -456,7 +501,7 @@ hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict_
             for (int pl = 0; pl < np; ++pl) {
                 const uint4* src = reinterpret_cast<const uint4*>(hg_row + (size_t)pl * HG_SEG);
                 uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pl * (size_t)plane + (size_t)seg0);
-                for (int q = threadIdx.x; q < seg_n / 8; q += 256) dst[q] = src[q];
+                for (int q = threadIdx.x; q < seg_n / 8; q += blockDim.x) dst[q] = src[q];
             }
             __syncthreads();
         }
@@ -469,7 +514,7 @@ hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict_
 typedef CUresult (*hg_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int hg_encode(CUtensorMap* tm, void* base, int rows, int kdim, long long ldk, long long plane_elems, int planes) {
+static int hg_encode(CUtensorMap* tm, void* base, int rows, int kdim, long long ldk, long long plane_elems, int planes, int fmt) {
     static hg_encode_fn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -482,7 +527,7 @@ static int hg_encode(CUtensorMap* tm, void* base, int rows, int kdim, long long 
     const cuuint64_t strides[2] = {(cuuint64_t)ldk * 2ull, (cuuint64_t)plane_elems * 2ull};
     const cuuint32_t box[3] = {64u, 128u, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = fn(tm, fmt == HH_GEMM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     HH_REQUIRE(r == CUDA_SUCCESS, HH_ERR_CUDA, "hh_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return HH_OK;
@@ -522,11 +567,11 @@ int hh_gemm_cta_group() { return hg_env_int("HH_GEMM_CG", 2) == 1 ? 1 : 2; }
 
 int hh_gemm_run(hh_ctx* ctx, const hh_gemm_operand& A, const hh_gemm_operand& B, const hh_gemm_item* d_items, int n_items, int npass,
                 const int* pa, const int* pb, int chunk_kb, float* out, long long ld, int col_lo, int col_hi, const float* scale,
-                int* stages_out) {
+                int* stages_out, float out_scale, int split_lo) {
     HH_REQUIRE(n_items >= 1 && npass >= 1 && npass <= 8, HH_ERR_ARG, "hh_gemm_run: bad work list");
     CUtensorMap tmA, tmB;
-    HH_CHECK(hg_encode(&tmA, (void*)A.base, A.rows, A.kdim, A.ldk, A.plane, A.planes));
-    HH_CHECK(hg_encode(&tmB, (void*)B.base, B.rows, B.kdim, B.ldk, B.plane, B.planes));
+    HH_CHECK(hg_encode(&tmA, (void*)A.base, A.rows, A.kdim, A.ldk, A.plane, A.planes, A.fmt));
+    HH_CHECK(hg_encode(&tmB, (void*)B.base, B.rows, B.kdim, B.ldk, B.plane, B.planes, B.fmt));
     hh_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.items = d_items;
@@ -550,6 +595,9 @@ int hh_gemm_run(hh_ctx* ctx, const hh_gemm_operand& A, const hh_gemm_operand& B,
     a.col_lo = col_lo;
     a.col_hi = col_hi;
     a.inv_s = scale;
+    a.out_scale = out_scale;
+    a.split_lo = split_lo;
+    a.idesc_fmt = (A.fmt == HH_GEMM_BF16 ? (1u << 7) : 0u) | (B.fmt == HH_GEMM_BF16 ? (1u << 10) : 0u);
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     if (hh_gemm_cta_group() == 2) return hg_launch<2>(ctx, tmA, tmB, a, smem);
     return hg_launch<1>(ctx, tmA, tmB, a, smem);
@@ -589,26 +637,37 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
         HH_CHECK(hh_dmalloc(&d_flags, 1));
         HH_CUDA(cudaEventRecord(ev[0], ctx->stream));
         HH_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->stream));
-        HH_LAUNCH(ctx, hh_k_gemm_colsum, (n + 7) / 8, 256, 0, m->d_colptr, m->d_val, n, d_s, d_inv);
+        HH_LAUNCH(ctx, hh_k_gemm_colsum, (n + 7) / 8, 256, 0, m->d_colptr, m->d_val, n, d_s, d_inv, d_flags);
         HH_LAUNCH(ctx, hh_k_gemm_valstats, ctx->sm_count * 8, 256, 0, m->d_val, m->nnz, d_flags);
         int flags = 0;
         HH_CUDA(cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
-        // integer link counts: one exact bf16 plane of min(count, 256), the excess is the caller's sparse correction;
-        // anything else (weights of --normalize_by_nlinks, allele-aware scaling): three planes, no clipping
+        // Integer link counts (the usual case): the scaled encoding, one plane of min(count, clip) against two f16 planes of M0,
+        // two passes, clip 2048; the excess over `clip` is the caller's sparse correction.  It needs column sums below 2^23 (the
+        // scaled counts may be f16 subnormals, exact down to 2^-24).  Otherwise, or with HH_GEMM_FMT=bf16, the exact encoding:
+        // one bf16 plane of min(count, 256) against three bf16 planes of M0, three passes.  (kind::f16 takes ONE format for both
+        // operands: a bf16 count plane against f16 planes of M0 is an illegal instruction on sm_100a -- measured.)
+        // Anything else (weights of --normalize_by_nlinks, allele-aware scaling): three exact bf16 planes each, six passes.
+        const char* fmt_env = getenv("HH_GEMM_FMT");
+        int enc = 2;                                             // 0 = exact bf16, 2 = scaled f16
+        if (fmt_env && !strcmp(fmt_env, "bf16")) enc = 0;
+        if (flags & (1 | 4)) enc = 0;
         int na = (flags & 1) ? 3 : 1;
-        float clip = (flags & 1) ? 3.0e38f : 256.f;
-        if (hg_env_int("HH_GEMM_NA", 0) == 2 && !(flags & 1)) {      // experiment: two planes instead of clipping
+        const int nb = enc ? 2 : 3;
+        float clip = (flags & 1) ? 3.0e38f : (enc == 2 ? 2048.f : 256.f);
+        if (hg_env_int("HH_GEMM_NA", 0) == 2 && !(flags & 1) && enc == 0) {      // experiment: two planes instead of clipping
             na = 2;
             clip = 3.0e38f;
         }
+        const int fmt_a = enc == 2 ? HH_GEMM_F16 : HH_GEMM_BF16, fmt_b = enc ? HH_GEMM_F16 : HH_GEMM_BF16;
         HH_CHECK(hh_ws_alloc(ctx, &d_A, (size_t)plane * (size_t)na));
-        HH_CHECK(hh_ws_alloc(ctx, &d_B, (size_t)plane * 3));
+        HH_CHECK(hh_ws_alloc(ctx, &d_B, (size_t)plane * (size_t)nb));
         {
             auto kd = hh_k_gemm_densify;
             const size_t dsm = (size_t)3 * HG_SEG * sizeof(unsigned short);
             HH_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-            HH_LAUNCH(ctx, kd, n, 256, dsm, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, ldk, plane, clip);
+            HH_LAUNCH(ctx, kd, n, 1024, dsm, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, nb, ldk, plane, clip, enc ? 1 : 0,
+                      enc == 2 ? 1 : 0);
         }
         // rows [n, ld) of every M1 column stay zero
         HH_CUDA(cudaMemsetAsync(d_m1, 0, (size_t)ld * (size_t)(col_hi - col_lo) * sizeof(float), ctx->stream));
@@ -616,20 +675,41 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
         HH_CUDA(cudaMemcpyAsync(d_items, h_items, (size_t)n_items * sizeof(hh_gemm_item), cudaMemcpyHostToDevice, ctx->stream));
         int pa[8], pb[8];
         int npass = hh_gemm_passes(na, pa, pb);
+        if (enc) {                                               // (A, B hi), (A, B lo)
+            npass = 2;
+            pa[0] = pa[1] = 0;
+            pb[0] = 0;
+            pb[1] = 1;
+        }
         const int np_env = hg_env_int("HH_GEMM_NPASS", 0);      // experiments only: fewer passes = lower precision
         if (np_env >= 1 && np_env < npass) npass = np_env;
-        const int chunk = hg_env_int("HH_GEMM_CHUNK", npass > 3 ? 1 : 2);
-        hh_gemm_operand A = {d_A, na, n, n, ldk, plane};
-        hh_gemm_operand B = {d_B, 3, n, n, ldk, plane};
+        // k-blocks accumulated in TMEM between two drains: the tensor core's accumulate truncates, so the bias grows with the
+        // number of accumulations (4 MMAs per k-block and pass).
+        // Measured at 50k contigs (one B200; GEMM time / max and mean relative error against the exact product), two f16 passes:
+        //   chunk 2: 205 ms, 1.5e-6, -1.6e-8   4: 177 ms, 1.2e-6, -2.4e-8   8: 139 ms, 1.1e-6, -3.9e-8   16: 136 ms, 1.9e-6, -6.6e-8
+        // every drain costs ~2000 clocks of tensor-pipe time, so longer chunks are faster -- but on dense inputs (every product
+        // of similar size) the bias of 64 truncating accumulations reaches 2.5e-6.  Three k-blocks = 24 accumulations, the
+        // same as three bf16 passes drained every second k-block, keeps every test input below 2e-6.
+        // HH_GEMM_SPLIT=1 (experiment): the low-order pass (2^-11 of the result) gets the second TMEM buffer for the whole
+        // tile and only the high-order pass is chunked -- bias-free (mean -1.4e-10) but single-buffered: 244 ms against 211 ms
+        // at chunk 8 on the same device.
+        const int split = (enc && hg_env_int("HH_GEMM_SPLIT", 0)) ? 1 : 0;
+        const int chunk = hg_env_int("HH_GEMM_CHUNK", npass > 3 ? 1 : (npass == 3 ? 2 : (split ? 8 : 3)));
+        hh_gemm_operand A = {d_A, na, n, n, ldk, plane, fmt_a};
+        hh_gemm_operand B = {d_B, nb, n, n, ldk, plane, fmt_b};
         int stages = 0;
         HH_CUDA(cudaEventRecord(ev[1], ctx->stream));
-        HH_CHECK(hh_gemm_run(ctx, A, B, d_items, n_items, npass, pa, pb, chunk, d_m1, ld, col_lo, col_hi, d_inv, &stages));
+        HH_CHECK(hh_gemm_run(ctx, A, B, d_items, n_items, npass, pa, pb, chunk, d_m1, ld, col_lo, col_hi, d_inv, &stages, 1.0f, split));
         HH_CUDA(cudaEventRecord(ev[2], ctx->stream));
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
         if (st) {
             memset(st, 0, sizeof(*st));
             st->a_planes = na;
-            st->clipped = (clip < 1.0e38f && (flags & 2)) ? 1 : 0;
+            st->clipped = (clip < 1.0e38f && (flags & (clip > 256.f ? 8 : 2))) ? 1 : 0;
+            st->clip = clip;
+            st->fmt_a = fmt_a;
+            st->fmt_b = fmt_b;
+            st->b_planes = nb;
             st->passes = npass;
             st->cta_group = hh_gemm_cta_group();
             st->stages = stages;
@@ -659,11 +739,15 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
 // block-diagonal products of the Markov-cluster iterations (hh_mcl.cu): operand planes of the component blocks
 // ---------------------------------------------------------------------------------------------------------------------
 // Bt[c, kk] = M[lo + kk, c] for the columns c of `list` (lo = first row of c's component): one CTA per column assembles the
-// row of its three planes in shared memory and writes all ldk elements (zeros beyond the component).
+// row of its planes in shared memory and writes all ldk elements (zeros beyond the component).  Two encodings:
+//   three bf16 planes, the exact fp32 value (8 + 8 + 8 bits by truncation);
+//   two f16 planes of M * 2^14, hi + lo = 22 significant bits (entries of a pruned column-stochastic iterate lie in
+//   [pruning, 1]: scaled they are f16 normals for every pruning >= 2^-14; the product carries 2^28, removed in the epilogue).
+#define HG_BLK_SHIFT 14
 __global__ void __launch_bounds__(128)
 hh_k_blk_densify(const int* __restrict__ len, const uint2* __restrict__ ent, int cap, const int* __restrict__ list, int nlist,
                  const int* __restrict__ comp_lo, const int* __restrict__ comp_hi, unsigned short* __restrict__ Bt, long long ldk,
-                 long long plane) {
+                 long long plane, int f16) {
     extern __shared__ __align__(16) unsigned short hb_row[];        // [3][ldk]
     const int j = list[blockIdx.x];
     const int lo = comp_lo[j], width = comp_hi[j] - lo;
@@ -676,15 +760,22 @@ hh_k_blk_densify(const int* __restrict__ len, const uint2* __restrict__ ent, int
         const uint2 t = e[p];
         const unsigned kk = t.x - (unsigned)lo;
         if (kk < (unsigned)width) {
-            unsigned short h1, h2, h3;
-            hg_split3(__uint_as_float(t.y), h1, h2, h3);
+            unsigned short h1, h2, h3 = 0;
+            if (f16) {
+                const float xs = ldexpf(__uint_as_float(t.y), HG_BLK_SHIFT);
+                const __half hi = __float2half_rn(xs);
+                h1 = __half_as_ushort(hi);
+                h2 = __half_as_ushort(__float2half_rn(xs - __half2float(hi)));
+            } else {
+                hg_split3(__uint_as_float(t.y), h1, h2, h3);
+            }
             hb_row[kk] = h1;
             hb_row[ldk + kk] = h2;
             hb_row[2 * ldk + kk] = h3;
         }
     }
     __syncthreads();
-    for (int pl = 0; pl < 3; ++pl) {
+    for (int pl = 0; pl < (f16 ? 2 : 3); ++pl) {
         const uint4* src = reinterpret_cast<const uint4*>(hb_row + (size_t)pl * (size_t)ldk);
         uint4* dst = reinterpret_cast<uint4*>(Bt + (size_t)pl * (size_t)plane + (size_t)j * (size_t)ldk);
         for (int q = threadIdx.x; q < (int)(ldk / 8); q += 128) dst[q] = src[q];
@@ -724,16 +815,18 @@ hh_k_blk_transpose(const unsigned short* __restrict__ Bt, unsigned short* __rest
     }
 }
 
+float hh_gemm_blk_out_scale(int f16) { return f16 ? ldexpf(1.0f, -2 * HG_BLK_SHIFT) : 1.0f; }
+
 int hh_gemm_blk_operands(hh_ctx* ctx, const int* d_len, const void* d_ent, int cap, const int* d_list, int nlist, const int* d_comp_lo,
-                         const int* d_comp_hi, int n, unsigned short* d_A, unsigned short* d_Bt, long long ldk) {
+                         const int* d_comp_hi, int n, unsigned short* d_A, unsigned short* d_Bt, long long ldk, int f16) {
     const long long plane = ldk * (long long)n;
     auto kd = hh_k_blk_densify;
     const size_t dsm = (size_t)3 * (size_t)ldk * sizeof(unsigned short);
     HH_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
     if (nlist > 0)
         HH_LAUNCH(ctx, kd, nlist, 128, dsm, d_len, reinterpret_cast<const uint2*>(d_ent), cap, d_list, nlist, d_comp_lo, d_comp_hi, d_Bt, ldk,
-                  plane);
-    dim3 grid((unsigned)((n + 31) / 32), (unsigned)(ldk / 32), 3u), block(32, 8);
+                  plane, f16);
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)(ldk / 32), f16 ? 2u : 3u), block(32, 8);
     hh_k_blk_transpose<<<grid, block, 0, ctx->stream>>>(d_Bt, d_A, n, d_comp_lo, d_comp_hi, ldk, plane);
     ctx->launches++;
     HH_CUDA(cudaGetLastError());

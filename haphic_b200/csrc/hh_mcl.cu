@@ -39,11 +39,26 @@ struct hh_slotmat {
     uint2* ent;  // [n * cap]  {row index, fp32 value bits}: one 64-bit load per entry
 };
 
+// matrix.power(r) on fp32 data (2037; numpy: x * x for r == 2, powf otherwise).  Exponents that are small multiples of one
+// half are evaluated with correctly rounded multiplications and square roots (at most two roundings, i.e. within one ulp
+// of the exact power -- tighter than powf's bound) instead of the ~60-instruction powf: iteration 0 inflates all n^2
+// entries of the dense pre-expanded matrix.
+enum { HH_INFL_POW = 0, HH_INFL_SQUARE = 1, HH_INFL_X15 = 2, HH_INFL_CUBE = 3, HH_INFL_X25 = 4 };
+__device__ __forceinline__ float hh_inflate(float x, float rf, int mode) {
+    switch (mode) {
+        case HH_INFL_SQUARE: return x * x;
+        case HH_INFL_X15: return x * __fsqrt_rn(x);
+        case HH_INFL_CUBE: return (x * x) * x;
+        case HH_INFL_X25: return (x * x) * __fsqrt_rn(x);
+        default: return powf(x, rf);
+    }
+}
+
 enum { SRC_CSC = 0, SRC_PRODUCT = 1, SRC_DENSE = 2 };
 enum { EPI_NORM = 0, EPI_DUMP = 1, EPI_PRUNE = 2 };
-// Link counts above HH_CLIP are split: min(x, HH_CLIP) goes through the tensor-core GEMM as ONE exact bf16 plane
-// (integers up to 256 are bf16 numbers), the rest through two small Gustavson corrections (hh_mcl_create_ex).
-#define HH_CLIP 256.0f
+// Link counts above the clip threshold of the tensor-core encoding (hh_gemm_stats.clip: 2048 for an f16 plane, 256 for a bf16
+// plane) are split: min(x, clip) goes through the GEMM as ONE exact plane, the rest through two small Gustavson corrections
+// (hh_k_clip_fix, hh_mcl_create_ex).
 
 struct hh_colargs {
     int n, T, ch_shift, n_pad;
@@ -437,12 +452,12 @@ __global__ void __launch_bounds__(W * 32) hh_k_col(const hh_colargs a) {
         } else {
             // E1: inflate (matrix.power(r), fp32) and first column sum (fp64)
             const float rf = a.inflation;
-            const bool sq = a.inflate_square != 0;
+            const int im = a.inflate_square;
             double s1 = 0.0;
             HH_FOR_DIRTY_ROWS({
                 const float x = acc[k];
                 if (x != 0.f) {
-                    const float y = sq ? (x * x) : powf(x, rf);
+                    const float y = hh_inflate(x, rf, im);
                     acc[k] = y;
                     s1 += (double)y;
                 }
@@ -808,7 +823,6 @@ __global__ void __launch_bounds__(32) hh_k_col_win(const hh_colargs a, int W, co
     const uint2* __restrict__ Aent = a.A.ent;
     const size_t capA = (size_t)a.A.cap;
     const float p32 = a.prune, rf = a.inflation;
-    const bool sq = a.inflate_square != 0;
     const bool conv = a.do_conv != 0;
     const int T = a.T;
     for (int k = lane; k < wmax; k += 32) acc[k] = 0.f;
@@ -869,7 +883,7 @@ __global__ void __launch_bounds__(32) hh_k_col_win(const hh_colargs a, int W, co
         for (int r = lane; r < width; r += 32) {
             const float x = acc[r];
             if (x != 0.f) {
-                const float y = sq ? (x * x) : powf(x, rf);
+                const float y = hh_inflate(x, rf, a.inflate_square);
                 acc[r] = y;
                 s1 += (double)y;
             }
@@ -1062,7 +1076,6 @@ __global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W,
     const uint2* __restrict__ Aent = a.A.ent;
     const size_t capA = (size_t)a.A.cap;
     const float p32 = a.prune, rf = a.inflation;
-    const bool sq = a.inflate_square != 0;
     int* sk = s_k[wq];
     float* sv = s_v[wq];
     int* sok = s_ok[wq];
@@ -1133,7 +1146,7 @@ __global__ void __launch_bounds__(256) hh_k_col_small(const hh_colargs a, int W,
         for (int p = lane; p < nout; p += 32) {
             const float x = sv[p];
             if (x != 0.f) {
-                const float y = sq ? (x * x) : powf(x, rf);
+                const float y = hh_inflate(x, rf, a.inflate_square);
                 sv[p] = y;
                 s1 += (double)y;
             }
@@ -1446,7 +1459,7 @@ __global__ void hh_k_gather_len(const int* __restrict__ len, const int* __restri
 // ---------------------------------------------------------------------------------------------
 // per column: fp64 sum of the raw link counts and bclip[c] = fp32(HH_CLIP / sum), the image of the clip threshold in M0
 __global__ void hh_k_clip_stats(const int64_t* __restrict__ colptr, const float* __restrict__ val, int n, double* __restrict__ s,
-                                float* __restrict__ bclip) {
+                                float* __restrict__ bclip, float clip) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
     const int lane = threadIdx.x & 31;
@@ -1455,7 +1468,7 @@ __global__ void hh_k_clip_stats(const int64_t* __restrict__ colptr, const float*
     t = hh_warp_sum(t);
     if (lane == 0) {
         s[c] = t;
-        bclip[c] = (t != 0.0) ? (float)((double)HH_CLIP / t) : HH_CLIP;
+        bclip[c] = (t != 0.0) ? (float)((double)clip / t) : clip;
     }
 }
 
@@ -1469,10 +1482,11 @@ __global__ void hh_k_clip_stats(const int64_t* __restrict__ colptr, const float*
 template <int MODE>
 __global__ void __launch_bounds__(256)
 hh_k_clip_fix(const hh_slotmat m0, const double* __restrict__ s, const float* __restrict__ bclip, float* __restrict__ m1, long long ld,
-              int col_lo, int col_hi, unsigned long long* __restrict__ products) {
+              int col_lo, int col_hi, unsigned long long* __restrict__ products, float clip_f) {
     const int x = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (x >= m0.n) return;
     if (MODE == 0 && (x < col_lo || x >= col_hi)) return;
+    const double HH_CLIP = (double)clip_f;
     const int lane = threadIdx.x & 31;
     const int L = m0.len[x];
     const uint2* __restrict__ ex = m0.ent + (size_t)x * (size_t)m0.cap;
@@ -1696,7 +1710,14 @@ static int launch_col(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_
 // per-warp counts.  Two CTAs per SM overlap one column's reductions with the other's loads.
 // ---------------------------------------------------------------------------------------------
 #define HH_IT0_WARPS 8
-template <int W>
+// x1 of one candidate (rare: a few percent of a column), kept out of line so that the streaming loops stay small -- with powf
+// and the fp64 quotient inlined at every use the kernel outgrew the instruction cache and ran 3-7x slower for r != 2
+__device__ __noinline__ float hh_it0_x1(float x, double S1, float rf, int sq) {
+    const float y = hh_inflate(x, rf, sq);
+    return (float)((double)y / S1);
+}
+
+template <int W, bool SQ>      // SQ: any of the multiplicative modes (no powf in the streaming loop)
 __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_colargs a) {
     // HH_IT0_WARPS warps per CTA (several CTAs per SM keep loads of other columns in flight across the reductions); warp v
     // handles the row blocks v, v + HH_IT0_WARPS, ... of the slotted format (W blocks of T rows)
@@ -1708,10 +1729,10 @@ __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_cola
     const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
     const int T = a.T;
     const float rf = a.inflation, p32 = a.prune;
-    const bool sq = a.inflate_square != 0;
+    const int sq = a.inflate_square;      // HH_INFL_* mode
+    constexpr int U = SQ ? 4 : 1;    // float4 per lane and trip of pass 1 (one copy of powf per component when !SQ)
     const int ld4 = (int)(a.ld >> 2);
     unsigned long long nnz_acc = 0ull;
-    auto pw = [&](float x) -> float { return sq ? x * x : powf(x, rf); };
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_col = atomicAdd(a.counter, 1);
@@ -1726,18 +1747,19 @@ __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_cola
         int kbest = 0x7fffffff;
         for (int b = wv; b < W; b += HH_IT0_WARPS) {
             const int r4_lo = (b * T) >> 2, r4_hi = min(((b + 1) * T) >> 2, ld4);
-            for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 128) {
-                float4 x[4];
+#pragma unroll 1
+            for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 32 * U) {
+                float4 x[U];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < U; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < U; ++q) {
                     const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const float v = xv[c];
                         if (v != 0.f) {
-                            s1 += (double)pw(v);
+                            s1 += (double)(SQ ? hh_inflate(v, rf, sq) : powf(v, rf));
                             const int k = ((r4 + 32 * q) << 2) + c;
                             if (v > xbest || (v == xbest && k < kbest)) {
                                 xbest = v;
@@ -1754,7 +1776,7 @@ __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_cola
         const double S1 = hh_warp_sum((lane < HH_IT0_WARPS) ? s_d[lane] : 0.0);
         __syncthreads();
         // exact x1 of this lane's maximum; two different x may round to one x1: then the lower row wins (first maximum)
-        float vbest = (xbest > 0.f && S1 != 0.0) ? (float)((double)pw(xbest) / S1) : 0.f;
+        float vbest = (xbest > 0.f && S1 != 0.0) ? hh_it0_x1(xbest, S1, rf, sq) : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(HH_FULL_MASK, vbest, o);
@@ -1767,7 +1789,7 @@ __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_cola
         // ---------------------------------------------------------------- pass 2: survivors of the prune, S2
         // x1 >= pruning needs y >= 0.999 * pruning * S1, i.e. x >= (that)^(1/r): taken a little lower, the rest is exact
         const float thr_y = (float)(0.999 * (double)p32 * S1);
-        const float xthr = (S1 != 0.0) ? 0.9999f * (sq ? sqrtf(thr_y) : powf(thr_y, 1.0f / rf)) : 3.0e38f;
+        const float xthr = (S1 != 0.0) ? 0.9999f * powf(thr_y, 1.0f / rf) : 3.0e38f;
         double s2 = 0.0;
         for (int b = wv; b < W; b += HH_IT0_WARPS) {
             const int r4_lo = (b * T) >> 2, r4_hi = min(((b + 1) * T) >> 2, ld4);
@@ -1782,7 +1804,7 @@ __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_cola
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (xv[c] >= xthr) {
-                            const float x1 = (float)((double)pw(xv[c]) / S1);
+                            const float x1 = hh_it0_x1(xv[c], S1, rf, sq);
                             if (x1 >= p32 && x1 > 0.f) {
                                 cnt++;
                                 s2 += (double)x1;
@@ -1845,7 +1867,7 @@ __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_cola
                 for (int q = 0; q < 4; ++q) {
                     keep[q] = 0.f;
                     if (xv[q] >= xthr) {
-                        const float x1 = (float)((double)pw(xv[q]) / S1);
+                        const float x1 = hh_it0_x1(xv[q], S1, rf, sq);
                         if (x1 >= p32 && x1 > 0.f) {
                             keep[q] = x1;
                             c++;
@@ -1882,7 +1904,7 @@ __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_cola
 
 template <int W>
 static int launch_iter0_w(hh_ctx* ctx, hh_colargs& a) {
-    auto kern = hh_k_iter0<W>;
+    auto kern = (a.inflate_square != HH_INFL_POW) ? hh_k_iter0<W, true> : hh_k_iter0<W, false>;
     int per_sm = 0;
     HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HH_IT0_WARPS * 32, 0));
     if (per_sm < 1) per_sm = 1;
@@ -1935,9 +1957,135 @@ static int grid_cap_for(hh_ctx* ctx, const hh_geom& g, int* out) {
     return HH_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Unsorted CSC column -> row-sorted slot without an n-row accumulator: the rows present are marked in a bitmap (n bits of
+// shared memory), an exclusive prefix over the bitmap words gives every row its rank, and every entry writes itself to its
+// rank.  d marks + n/32 words scanned + d lookups per column, instead of 2 n rows scanned (the accumulator kernel spent
+// 13 ms here at 50k contigs).  Column sum in fp64 (sklearn normalize, 2144; exact in any order for integer link counts, the
+// order below is fixed).  A row stored twice in one column (only a caller's own CSC can have that) raises *dup: the caller
+// then runs the accumulator kernel, which adds duplicates up.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hh_k_slot_from_csc(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row, const float* __restrict__ val, int n, int W, int T,
+                   int raw, hh_slotmat out, unsigned long long* __restrict__ stats, int* __restrict__ err, int* __restrict__ dup) {
+    extern __shared__ uint32_t sfc_smem[];
+    const int nw = (n + 31) >> 5;
+    const int nw_pad = (nw + 255) & ~255;
+    uint32_t* __restrict__ bm = sfc_smem;             // [nw_pad] bitmap of the rows present
+    uint32_t* __restrict__ pre = sfc_smem + nw_pad;   // [nw_pad] entries in the words before
+    __shared__ double s_part[8];
+    __shared__ uint32_t s_wsum[8];
+    __shared__ double s_S;
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int per = nw_pad >> 8;                      // bitmap words per thread in the scan
+    unsigned long long nnz_acc = 0ull;
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+        const int64_t p0 = colptr[j], p1 = colptr[j + 1];
+        for (int w = tid; w < nw_pad; w += 256) bm[w] = 0u;
+        __syncthreads();
+        double s = 0.0;
+        for (int64_t p = p0 + tid; p < p1; p += 256) {
+            const float v = val[p];
+            if (v != 0.f) {
+                const uint32_t r = (uint32_t)row[p];
+                const uint32_t bit = 1u << (r & 31u);
+                if (atomicOr(&bm[r >> 5], bit) & bit) atomicExch(dup, 1);
+                s += fabs((double)v);
+            }
+        }
+        s = hh_warp_sum(s);
+        if (lane == 0) s_part[wv] = s;
+        __syncthreads();
+        // exclusive prefix of popc(bm[]) : thread t owns words [t * per, (t + 1) * per)
+        uint32_t mine = 0;
+        for (int q = 0; q < per; ++q) mine += __popc(bm[tid * per + q]);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(HH_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[wv] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            double S = 0.0;
+            uint32_t run = 0;
+            for (int k = 0; k < 8; ++k) {
+                S += s_part[k];
+                const uint32_t t = s_wsum[k];
+                s_wsum[k] = run;
+                run += t;
+            }
+            s_S = S;
+            s_total = run;
+        }
+        __syncthreads();
+        uint32_t run = s_wsum[wv] + incl - mine;
+        for (int q = 0; q < per; ++q) {
+            pre[tid * per + q] = run;
+            run += __popc(bm[tid * per + q]);
+        }
+        __syncthreads();
+        const double S = s_S;
+        const int total = (int)s_total;
+        uint2* __restrict__ oent = out.ent + (size_t)j * (size_t)out.cap;
+        for (int64_t p = p0 + tid; p < p1; p += 256) {
+            const float v = val[p];
+            if (v != 0.f) {
+                const uint32_t r = (uint32_t)row[p];
+                const uint32_t pos = pre[r >> 5] + __popc(bm[r >> 5] & ((1u << (r & 31u)) - 1u));
+                if ((int)pos < out.cap) oent[pos] = make_uint2(r, __float_as_uint((raw || S == 0.0) ? v : (float)((double)v / S)));
+            }
+        }
+        for (int w = tid; w <= W; w += 256) {
+            int b = total;
+            if (w < W && w * T < n) b = (int)pre[(w * T) >> 5];        // T is a multiple of 32
+            out.blk[(size_t)j * (W + 1) + w] = (w == W) ? min(total, out.cap) : b;
+        }
+        if (tid == 0) {
+            out.len[j] = min(total, out.cap);
+            if (total > out.cap) atomicExch(err, 1);
+            nnz_acc += (unsigned long long)total;
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && nnz_acc) atomicAdd(stats + 0, nnz_acc);
+}
+
 // unsorted CSC -> slotted (raw or column-normalised); cap must be >= the longest column
+static int slot_from_csc_fast(hh_ctx* ctx, const hh_geom& g, int* d_counter, unsigned long long* d_stats, const hh_matrix* m, int raw,
+                              hh_slotmat& out, bool* done) {
+    *done = false;
+    const int nw_pad = (((m->n + 31) >> 5) + 255) & ~255;
+    const size_t smem = (size_t)nw_pad * 2 * sizeof(uint32_t);
+    if (smem + 1024 > ctx->smem_optin || !env_int("HH_MCL_NORM_FAST", 1)) return HH_OK;
+    auto kern = hh_k_slot_from_csc;
+    HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) return HH_OK;
+    int grid = per_sm * ctx->sm_count;
+    if (grid > m->n) grid = m->n;
+    HH_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream));
+    HH_LAUNCH(ctx, kern, grid, 256, smem, m->d_colptr, m->d_row, m->d_val, m->n, g.W, g.T, raw, out, d_stats,
+              reinterpret_cast<int*>(d_stats + 3), d_counter);
+    int dup = 0;
+    HH_CUDA(cudaMemcpyAsync(&dup, d_counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (dup) {
+        HH_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));      // every caller zeroed it before
+        return HH_OK;
+    }
+    *done = true;
+    return HH_OK;
+}
+
 static int slot_from_csc(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_cap, int* d_counter, unsigned long long* d_stats,
                          const hh_matrix* m, int raw, hh_slotmat& out) {
+    bool done = false;
+    HH_CHECK(slot_from_csc_fast(ctx, g, d_counter, d_stats, m, raw, out, &done));
+    if (done) return HH_OK;
     hh_colargs a;
     memset(&a, 0, sizeof(a));
     a.n = m->n;
@@ -2188,7 +2336,7 @@ static int raw_product(hh_mcl* mc, const hh_slotmat& A, const hh_slotmat& B, dou
 }
 
 // Which engine builds M1.  The Gustavson kernel does n*d^2 multiply-adds on a scattered accumulator, the tensor-core
-// GEMM 3 passes of n^3/2.  AUTO picks the cheaper estimate; HH_MCL_PREEXP=sparse|dense overrides.
+// GEMM 2 passes of n^3/2 (3 in the exact bf16 encoding).  AUTO picks the cheaper estimate; HH_MCL_PREEXP=sparse|dense overrides.
 static int choose_preexp(const hh_matrix* m, int requested) {
     const char* e = getenv("HH_MCL_PREEXP");
     if (e && *e) {
@@ -2196,11 +2344,11 @@ static int choose_preexp(const hh_matrix* m, int requested) {
         if (!strcmp(e, "dense")) return HH_PREEXP_DENSE;
     }
     if (requested == HH_PREEXP_SPARSE || requested == HH_PREEXP_DENSE) return requested;
-    // measured on B200: Gustavson ~0.5e12 products/s; tensor-core GEMM ~1.5e15 flop/s issued over three bf16 passes of the
+    // measured on B200: Gustavson ~0.5e12 products/s; tensor-core GEMM ~1.9e15 flop/s issued over two f16 passes of the
     // symmetric half, plus operand planes (memset + scatter) and allocation
     const double n = (double)m->n, d = (double)m->nnz / (n > 0 ? n : 1.0);
     const double t_sparse = n * d * d / 0.5e12;
-    const double t_dense = 2.0e-15 * n * n * n + 3.0e-12 * n * n + 5.0e-4;
+    const double t_dense = 1.2e-15 * n * n * n + 3.0e-12 * n * n + 5.0e-4;
     // the operand planes (up to six bf16 planes of n x n) must fit beside M1 and the iterates
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
@@ -2304,7 +2452,7 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
             mc->create_ms[1] = mc->gemm.densify_ms + mc->gemm.gemm_ms;
             mc->preexp_products = 0;
             if (mc->gemm.clipped) {
-                // finish the few link counts above HH_CLIP (hh_k_clip_fix)
+                // finish the few link counts above the clip threshold (hh_k_clip_fix)
                 float* d_bclip = nullptr;
                 double* d_s = nullptr;
                 int rc2 = [&]() -> int {
@@ -2313,11 +2461,11 @@ extern "C" int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int
                     HH_CUDA(cudaMemsetAsync(mc->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
                     HH_CUDA(cudaEventRecord(mc->ev0, ctx->stream));
                     const int grid = (m->n + 7) / 8;
-                    HH_LAUNCH(ctx, hh_k_clip_stats, grid, 256, 0, m->d_colptr, m->d_val, m->n, d_s, d_bclip);
+                    HH_LAUNCH(ctx, hh_k_clip_stats, grid, 256, 0, m->d_colptr, m->d_val, m->n, d_s, d_bclip, mc->gemm.clip);
                     HH_LAUNCH(ctx, hh_k_clip_fix<0>, grid, 256, 0, mc->m0, d_s, d_bclip, mc->d_m1, (long long)mc->ld, (int)col_lo, (int)col_hi,
-                              mc->d_stats + 1);
+                              mc->d_stats + 1, mc->gemm.clip);
                     HH_LAUNCH(ctx, hh_k_clip_fix<1>, grid, 256, 0, mc->m0, d_s, d_bclip, mc->d_m1, (long long)mc->ld, (int)col_lo, (int)col_hi,
-                              mc->d_stats + 1);
+                              mc->d_stats + 1, mc->gemm.clip);
                     HH_CUDA(cudaEventRecord(mc->ev1, ctx->stream));
                     unsigned long long st2[4];
                     HH_CHECK(read_stats(ctx, mc->d_stats, st2));
@@ -2421,6 +2569,10 @@ extern "C" int hh_mcl_preexp_info(hh_mcl* mc, hh_preexp_info* info) {
         info->flops = mc->gemm.flops;
         info->clip_ms = mc->clip_ms;
         info->products = mc->preexp_products;
+        info->clip = mc->gemm.clip;
+        info->b_planes = mc->gemm.b_planes;
+        info->fmt_a = mc->gemm.fmt_a;
+        info->fmt_b = mc->gemm.fmt_b;
     } else {
         info->products = mc->preexp_products;
     }
@@ -2615,7 +2767,13 @@ extern "C" int hh_mcl_begin(hh_mcl* mc, double inflation, double pruning) {
     }
     // matrix.power(inflation): fp32 array ** Python float = fp32 pow with the exponent cast to fp32
     mc->inflation = (float)inflation;
-    mc->inflate_square = (mc->inflation == 2.0f) ? 1 : 0;
+    mc->inflate_square = HH_INFL_POW;                 // how x^r is evaluated (hh_inflate)
+    if (mc->inflation == 2.0f) mc->inflate_square = HH_INFL_SQUARE;
+    else if (env_int("HH_MCL_FAST_POW", 1)) {
+        if (mc->inflation == 1.5f) mc->inflate_square = HH_INFL_X15;
+        else if (mc->inflation == 3.0f) mc->inflate_square = HH_INFL_CUBE;
+        else if (mc->inflation == 2.5f) mc->inflate_square = HH_INFL_X25;
+    }
     mc->prune = (float)pruning;   // `matrix >= pruning` compares in fp32
     mc->cur = -1;
     mc->have_pending = false;
@@ -2683,25 +2841,39 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
             unsigned short *d_blkA = nullptr, *d_blkB = nullptr;
             float* d_blk_out = nullptr;
             bool blk = false;
+            // entries of the pruned iterate lie in [pruning, 1]: two f16 planes of M * 2^14 per operand (four passes) while
+            // they stay f16 normals, else three exact bf16 planes (six passes); HH_GEMM_BLK_FMT=bf16 forces the latter
+            const char* bf = getenv("HH_GEMM_BLK_FMT");
+            const int f16 = (mc->prune >= 6.2e-5f && !(bf && !strcmp(bf, "bf16"))) ? 1 : 0;
             if (mc->n_win > 0 && mc->d_blk_items && mc->col_lo == 0 && mc->col_hi == mc->n) {
                 const double est_sparse = (double)mc->cur_nnz * (double)mc->cur_nnz / (double)mc->n / 0.6e12;
-                const double est_gemm = mc->blk_flops / 1.2e15 + 2.0e-3;
+                const double est_gemm = mc->blk_flops * (f16 ? 4.0 / 6.0 : 1.0) / 1.2e15 + 2.0e-3;      // blk_flops counts six passes
                 blk = est_gemm < est_sparse;
             }
             if (blk) {
+                const int np_op = f16 ? 2 : 3;
                 const size_t plane = (size_t)mc->blk_ldk * (size_t)mc->n;
-                HH_CHECK(hh_ws_alloc(ctx, &d_blkA, plane * 3));
-                HH_CHECK(hh_ws_alloc(ctx, &d_blkB, plane * 3));
+                HH_CHECK(hh_ws_alloc(ctx, &d_blkA, plane * np_op));
+                HH_CHECK(hh_ws_alloc(ctx, &d_blkB, plane * np_op));
                 HH_CHECK(hh_ws_alloc(ctx, &d_blk_out, plane));
                 const hh_slotmat& M = mc->it[mc->cur];
                 HH_CHECK(hh_gemm_blk_operands(ctx, M.len, M.ent, M.cap, mc->d_win_list, mc->n_win, mc->d_comp_lo, mc->d_comp_hi, mc->n,
-                                              d_blkA, d_blkB, mc->blk_ldk));
+                                              d_blkA, d_blkB, mc->blk_ldk, f16));
                 int pa[8], pb[8];
-                const int npass = hh_gemm_passes(3, pa, pb);
-                hh_gemm_operand A = {d_blkA, 3, mc->n, (int)mc->blk_ldk, mc->blk_ldk, (long long)plane};
-                hh_gemm_operand B = {d_blkB, 3, mc->n, (int)mc->blk_ldk, mc->blk_ldk, (long long)plane};
-                HH_CHECK(hh_gemm_run(ctx, A, B, mc->d_blk_items, (int)mc->blk_items->size(), npass, pa, pb, env_int("HH_GEMM_CHUNK", 1),
-                                     d_blk_out, mc->blk_ldk, 0, mc->n, nullptr, nullptr));
+                int npass = hh_gemm_passes(3, pa, pb);
+                if (f16) {                                       // hi hi, hi lo, lo hi, lo lo: what is left is the rounding of lo, 2^-23
+                    npass = 4;
+                    pa[0] = 0, pb[0] = 0;
+                    pa[1] = 0, pb[1] = 1;
+                    pa[2] = 1, pb[2] = 0;
+                    pa[3] = 1, pb[3] = 1;
+                }
+                const int fmt = f16 ? HH_GEMM_F16 : HH_GEMM_BF16;
+                hh_gemm_operand A = {d_blkA, np_op, mc->n, (int)mc->blk_ldk, mc->blk_ldk, (long long)plane, fmt};
+                hh_gemm_operand B = {d_blkB, np_op, mc->n, (int)mc->blk_ldk, mc->blk_ldk, (long long)plane, fmt};
+                HH_CHECK(hh_gemm_run(ctx, A, B, mc->d_blk_items, (int)mc->blk_items->size(), npass, pa, pb,
+                                     env_int("HH_GEMM_CHUNK", f16 ? 2 : 1), d_blk_out, mc->blk_ldk, 0, mc->n, nullptr, nullptr,
+                                     hh_gemm_blk_out_scale(f16), 0));
                 a.dense_in = d_blk_out;
                 a.ld = mc->blk_ldk;
                 mc->blk_iters++;

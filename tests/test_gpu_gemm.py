@@ -56,21 +56,33 @@ def exact_m1(link):
     return m0 @ m0
 
 
-@pytest.mark.parametrize("n,density,maxc,weights,planes,clipped", [
-    (1000, 0.3, 200, False, 1, False),      # counts <= 256: one exact bf16 plane, three passes
-    (777, 0.5, 5000, False, 1, True),       # counts above 256: clipped GEMM + sparse correction; ragged tile edge
-    (300, 0.5, 3, True, 3, False),          # float weights (--normalize_by_nlinks, allele scaling): three planes, six passes
-    (100, 0.9, 40, False, 1, False),        # smaller than one tile
-    (2600, 0.2, 300, False, 1, True),       # several tiles in both directions, mirror images
+# the operand encodings of csrc/hh_gemm.cu: (passes for integer counts, clip threshold)
+ENCODINGS = {"f16": (2, 2048), "bf16": (3, 256)}
+
+
+@pytest.fixture(params=sorted(ENCODINGS))
+def encoding(request, monkeypatch):
+    monkeypatch.setenv("HH_GEMM_FMT", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("n,density,maxc,weights,planes", [
+    (1000, 0.3, 200, False, 1),      # small counts: one exact plane of counts
+    (777, 0.5, 5000, False, 1),      # counts above the clip threshold: clipped GEMM + sparse correction; ragged tile edge
+    (300, 0.5, 3, True, 3),          # float weights (--normalize_by_nlinks, allele scaling): three bf16 planes, six passes
+    (100, 0.9, 40, False, 1),        # smaller than one tile
+    (2600, 0.2, 300, False, 1),      # several tiles in both directions, mirror images
 ])
-def test_dense_preexpansion_matches_exact_product(ctx, n, density, maxc, weights, planes, clipped):
+def test_dense_preexpansion_matches_exact_product(ctx, encoding, n, density, maxc, weights, planes):
     from haphic_b200.links import LinkMatrix
     from haphic_b200.mcl import Mcl
     link = random_links(n, density, maxc, seed=n, weights=weights)
     mat = LinkMatrix.from_csc(ctx, link)
     mc = Mcl(mat, preexp="dense")
     assert mc.preexp["mode"] == "dense" and mc.preexp["a_planes"] == planes
-    assert (mc.preexp["clip_ms"] > 0) == clipped
+    passes, clip = ENCODINGS[encoding]
+    assert mc.preexp["passes"] == (6 if weights else passes)
+    assert (mc.preexp["clip_ms"] > 0) == ((not weights) and maxc > clip)
     m1 = mc.m1().astype(np.float64)
     exact = exact_m1(link)
     nz = exact != 0
@@ -84,6 +96,33 @@ def test_dense_preexpansion_matches_exact_product(ctx, n, density, maxc, weights
     assert np.array_equal(m1s != 0, nz)
     assert (np.abs(m1s[nz] - m1[nz]) / exact[nz]).max() <= 4e-6
     ms.close()
+    mc.close()
+    mat.close()
+
+
+def test_dense_heavy_columns(ctx, encoding):
+    """column sums far above 2^14: the scaled count plane of the f16 encoding is made of f16 subnormals, which must
+    multiply exactly"""
+    from haphic_b200.links import LinkMatrix
+    from haphic_b200.mcl import Mcl
+    rng = np.random.default_rng(77)
+    n = 1200
+    d = np.triu(rng.integers(0, 2001, (n, n)) * (rng.random((n, n)) < 0.7), 1)
+    d = (d + d.T).astype(np.float32)
+    np.fill_diagonal(d, 1.0)
+    link = sp.csc_matrix(d)
+    link.sort_indices()
+    assert d.sum(axis=0).min() > 3e5
+    mat = LinkMatrix.from_csc(ctx, link)
+    mc = Mcl(mat, preexp="dense")
+    m1 = mc.m1().astype(np.float64)
+    exact = exact_m1(link)
+    nz = exact != 0
+    assert np.array_equal(m1 != 0, nz)
+    rel = np.abs(m1[nz] - exact[nz]) / exact[nz]
+    # ~840 terms of similar size per entry: the fp32 accumulation alone wanders ~sqrt(840) * 2^-24 = 1.7e-6 (SciPy's own fp32
+    # product is 3e-6 off on this input); flushed subnormals would show up as errors of order 1
+    assert rel.max() <= 4e-6, rel.max()
     mc.close()
     mat.close()
 

@@ -128,3 +128,47 @@ def test_cluster_run_on_several_gpus_writes_the_same_files(tmp_path):
         log = f.read()
     assert [ln.split("] ", 1)[1] for ln in log.splitlines() if "[recommend_inflation]" in ln] == g["recommend_lines"].tolist()
     assert [ln.split("] ", 1)[1] for ln in log.splitlines() if "[mcl]" in ln] == g["mcl_lines"].tolist()
+
+
+def test_c4_shaped_run_matches_reference_digests(tmp_path):
+    """BASELINE configs[3] in shape (4 haplotypes, `--remove_allelic_links 4`) at 10 000 contigs / 5M pairs: the unmodified
+    reference needed 378 s for this run (tests/golden/make_golden.py run_c4); its output files are kept as SHA-1 digests.
+    Every file, dict and machine-read log line must match; iteration counts may differ by one round (a different but equally
+    valid fp32 summation order inside the expansion moves the fp32 convergence test), the clusters may not."""
+    import re
+    g = load_golden("rundigest_c4_10k.npz")
+    run_case(tmp_path, g, False)
+
+    def sha(text):
+        return hashlib.sha1(text.encode()).hexdigest()
+
+    want = json.loads(str(g["files_json"]))
+    got = {}
+    for root, _d, files in os.walk(tmp_path):
+        for fn in files:
+            p = os.path.relpath(os.path.join(root, fn), tmp_path)
+            if p.startswith("inflation_") and p.endswith(".txt"):
+                with open(os.path.join(root, fn)) as f:
+                    got[p] = sha(f.read())
+    assert sorted(got) == sorted(want)
+    bad = [p for p in sorted(want) if got[p] != want[p]]
+    assert not bad, bad[:10]
+    with open(tmp_path / "full_links.pkl", "rb") as f:
+        full = pickle.load(f)
+    assert len(full) == int(g["n_full"])
+    assert sha(json.dumps(sorted([[a, b, int(v)] for (a, b), v in full.items()]))) == str(g["full_links_sha1"])
+    assert sha(json.dumps([[a, b] for (a, b) in full.keys()])) == str(g["full_links_order_sha1"])      # dict insertion order
+    with open(tmp_path / "HT_links.pkl", "rb") as f:
+        ht = pickle.load(f)
+    assert len(ht) == int(g["n_HT"])
+    assert sha(json.dumps(sorted([[a, b, int(v)] for (a, b), v in ht.items()]))) == str(g["HT_links_sha1"])
+    with open(tmp_path / "paired_links.clm") as f:
+        assert sha(f.read()) == str(g["clm_sha1"])
+    with open(tmp_path / "alignments.bed") as f:
+        assert sha(f.read()) == str(g["bed_sha1"])
+    with open(tmp_path / "HapHiC_cluster.log") as f:
+        log = f.read()
+    assert [ln.split("] ", 1)[1] for ln in log.splitlines() if "[recommend_inflation]" in ln] == g["recommend_lines"].tolist()
+    rounds = [int(re.search(r"after (\d+) rounds", ln).group(1)) for ln in log.splitlines() if "[mcl]" in ln]
+    want_rounds = [int(re.search(r"after (\d+) rounds", ln).group(1)) for ln in g["mcl_lines"].tolist()]
+    assert len(rounds) == len(want_rounds) and all(abs(a - b) <= 1 for a, b in zip(rounds, want_rounds)), (rounds, want_rounds)
