@@ -194,7 +194,7 @@ struct hh_gemm_args {
     uint32_t idesc_fmt;    // operand format bits of the instruction descriptor (bit 7: A is bf16, bit 10: B is bf16)
 };
 
-template <int CG>
+template <int CG, bool SPLIT>
 __global__ void __launch_bounds__(HG_THREADS, 1)
 hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const hh_gemm_args a) {
     constexpr int BN = 128 * CG;              // tile columns (= TMEM columns per accumulator buffer)
@@ -273,7 +273,7 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             int s = 0;
             uint32_t ph = 0;
             uint32_t g = 0;     // running chunk counter: TMEM buffer g & 1, phase (g >> 1) & 1  (split_lo: buffer 0, phase g & 1)
-            const bool split = a.split_lo != 0;
+            constexpr bool split = SPLIT;       // compiled out of the default kernel
             for (int it = pair; it < a.n_items; it += npairs) {
                 const hh_gemm_item w = a.items[it];
                 int in_chunk = 0;
@@ -327,7 +327,7 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t lane_addr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * CW);
         const uint32_t tempty0 = (CG == 2) ? hg_mapa(hg_smem_u32(&s_tempty[0]), 0) : hg_smem_u32(&s_tempty[0]);
         uint32_t g = 0;
-        const bool split = a.split_lo != 0;
+        constexpr bool split = SPLIT;
         float acc[CW];
         for (int it = pair; it < a.n_items; it += npairs) {
             const hh_gemm_item w = a.items[it];
@@ -538,9 +538,9 @@ static int hg_env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int CG>
+template <int CG, bool SPLIT>
 static int hg_launch(hh_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const hh_gemm_args& a, size_t smem) {
-    auto kern = hh_k_syrk<CG>;
+    auto kern = hh_k_syrk<CG, SPLIT>;
     HH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -599,8 +599,8 @@ int hh_gemm_run(hh_ctx* ctx, const hh_gemm_operand& A, const hh_gemm_operand& B,
     a.split_lo = split_lo;
     a.idesc_fmt = (A.fmt == HH_GEMM_BF16 ? (1u << 7) : 0u) | (B.fmt == HH_GEMM_BF16 ? (1u << 10) : 0u);
     const size_t smem = (size_t)stages * stage_bytes + 1024;
-    if (hh_gemm_cta_group() == 2) return hg_launch<2>(ctx, tmA, tmB, a, smem);
-    return hg_launch<1>(ctx, tmA, tmB, a, smem);
+    if (hh_gemm_cta_group() == 2) return split_lo ? hg_launch<2, true>(ctx, tmA, tmB, a, smem) : hg_launch<2, false>(ctx, tmA, tmB, a, smem);
+    return split_lo ? hg_launch<1, true>(ctx, tmA, tmB, a, smem) : hg_launch<1, false>(ctx, tmA, tmB, a, smem);
 }
 
 static const int HG_P1[3][2] = {{0, 0}, {0, 1}, {0, 2}};

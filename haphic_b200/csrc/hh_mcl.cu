@@ -2598,6 +2598,59 @@ extern "C" int hh_mcl_fetch_m1(hh_mcl* mc, float* dense) {
 
 // components of the committed iterate's pattern -> perm / inv / component windows / column lists, then the
 // iterate itself is rewritten in new indices (one pass of the column kernel)
+// work list of the block-diagonal GEMM: all tiles of every window component.  Needs whole-matrix ownership (the columns of
+// a shard are scattered over the components): built with the relabelling when the context owns every column, or by
+// hh_mcl_set_block(0, n) when a sharded run goes on replicated.
+static int mcl_build_blk_items(hh_mcl* mc) {
+    hh_ctx* ctx = mc->ctx;
+    const int n = mc->n;
+    const int wlimit = env_int("HH_MCL_WMAX", 8192);
+    mc->blk_items->clear();
+    mc->blk_ldk = 0;
+    mc->blk_flops = 0.0;
+    if (mc->use_blk && mc->col_lo == 0 && mc->col_hi == n && mc->n_win > 0) {
+        std::vector<int> clo((size_t)n), chi((size_t)n);
+        HH_CUDA(cudaMemcpyAsync(clo.data(), mc->d_comp_lo, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaMemcpyAsync(chi.data(), mc->d_comp_hi, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int T = hh_gemm_tile_size();
+        int maxb = 0;
+        for (int p0 = 0; p0 < n;) {
+            const int lo = clo[(size_t)p0], hi = chi[(size_t)p0];
+            const int b = hi - lo;
+            if (b <= wlimit) {
+                if (b > maxb) maxb = b;
+                const int nt = (b + T - 1) / T, nkb = (b + 63) / 64;
+                for (int mt = 0; mt < nt; ++mt)
+                    for (int tt = 0; tt < nt; ++tt) {
+                        hh_gemm_item w;
+                        memset(&w, 0, sizeof(w));
+                        w.m0 = lo + mt * T;
+                        w.n0 = lo + tt * T;
+                        w.m_end = hi;
+                        w.n_end = hi;
+                        w.kb_lo[0] = 0;
+                        w.kb_hi[0] = nkb;
+                        w.flags = HH_GEMM_DIRECT;
+                        w.out_row0 = lo;
+                        mc->blk_items->push_back(w);
+                    }
+                mc->blk_flops += 2.0 * (double)T * (double)T * 64.0 * (double)nkb * (double)nt * (double)nt * 6.0;
+            }
+            p0 = hi > p0 ? hi : p0 + 1;
+        }
+        mc->blk_ldk = ((long long)maxb + 63) & ~63ll;
+        hh_dfree(mc->d_blk_items);
+        if (!mc->blk_items->empty()) {
+            HH_CHECK(hh_dmalloc(&mc->d_blk_items, mc->blk_items->size()));
+            HH_CUDA(cudaMemcpyAsync(mc->d_blk_items, mc->blk_items->data(), mc->blk_items->size() * sizeof(hh_gemm_item),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+            HH_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return HH_OK;
+}
+
 static int mcl_build_perm(hh_mcl* mc) {
     hh_ctx* ctx = mc->ctx;
     const int n = mc->n;
@@ -2698,51 +2751,7 @@ static int mcl_build_perm(hh_mcl* mc) {
         mc->cur ^= 1;
         mc->perm_valid = true;
         mc->perm_space = true;
-        // work list of the block-diagonal GEMM: all tiles of every window component (whole-matrix ownership only: the
-        // columns of a shard are scattered over the components)
-        mc->blk_items->clear();
-        mc->blk_ldk = 0;
-        mc->blk_flops = 0.0;
-        if (mc->use_blk && mc->col_lo == 0 && mc->col_hi == n && mc->n_win > 0) {
-            std::vector<int> clo((size_t)n), chi((size_t)n);
-            HH_CUDA(cudaMemcpyAsync(clo.data(), mc->d_comp_lo, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            HH_CUDA(cudaMemcpyAsync(chi.data(), mc->d_comp_hi, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            HH_CUDA(cudaStreamSynchronize(ctx->stream));
-            const int T = hh_gemm_tile_size();
-            int maxb = 0;
-            for (int p0 = 0; p0 < n;) {
-                const int lo = clo[(size_t)p0], hi = chi[(size_t)p0];
-                const int b = hi - lo;
-                if (b <= wlimit) {
-                    if (b > maxb) maxb = b;
-                    const int nt = (b + T - 1) / T, nkb = (b + 63) / 64;
-                    for (int mt = 0; mt < nt; ++mt)
-                        for (int tt = 0; tt < nt; ++tt) {
-                            hh_gemm_item w;
-                            memset(&w, 0, sizeof(w));
-                            w.m0 = lo + mt * T;
-                            w.n0 = lo + tt * T;
-                            w.m_end = hi;
-                            w.n_end = hi;
-                            w.kb_lo[0] = 0;
-                            w.kb_hi[0] = nkb;
-                            w.flags = HH_GEMM_DIRECT;
-                            w.out_row0 = lo;
-                            mc->blk_items->push_back(w);
-                        }
-                    mc->blk_flops += 2.0 * (double)T * (double)T * 64.0 * (double)nkb * (double)nt * (double)nt * 6.0;
-                }
-                p0 = hi > p0 ? hi : p0 + 1;
-            }
-            mc->blk_ldk = ((long long)maxb + 63) & ~63ll;
-            hh_dfree(mc->d_blk_items);
-            if (!mc->blk_items->empty()) {
-                HH_CHECK(hh_dmalloc(&mc->d_blk_items, mc->blk_items->size()));
-                HH_CUDA(cudaMemcpyAsync(mc->d_blk_items, mc->blk_items->data(), mc->blk_items->size() * sizeof(hh_gemm_item),
-                                        cudaMemcpyHostToDevice, ctx->stream));
-                HH_CUDA(cudaStreamSynchronize(ctx->stream));
-            }
-        }
+        HH_CHECK(mcl_build_blk_items(mc));
         return HH_OK;
     }();
     hh_dfree(d_lab);
@@ -3031,6 +3040,9 @@ extern "C" int hh_mcl_set_block(hh_mcl* mc, int32_t col_lo, int32_t col_hi) {
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
         mc->n_win = counts[0];
         mc->n_big = counts[1];
+        // a sharded run that goes on replicated owns every column from here on: the component blocks can be multiplied on
+        // the tensor cores like on a single GPU
+        if (col_lo == 0 && col_hi == mc->n && mc->blk_items->empty()) HH_CHECK(mcl_build_blk_items(mc));
     }
     return HH_OK;
 }

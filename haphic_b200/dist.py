@@ -223,6 +223,90 @@ def sharded_mcl_run(engine, inflation: float, max_iter: int, pruning: float, blo
     return {"rounds": rounds, "converged": converged, "iter_nnz": it_nnz, "iter_products": it_prod, "iter_ms": it_ms}
 
 
+def sharded_mcl_sweep(engine, inflations, max_iter: int, pruning: float, blocks, group=None, on_result=None):
+    """The inflation sweep of run_mcl_clustering (HapHiC_cluster.py:2155-2158) over column shards, inflation-parallel.
+
+    Only iteration 0 of an mcl() call touches the dense pre-expanded matrix, which is what the ranks shard.  So:
+      phase A  every rank runs iteration 0 of EVERY inflation on its column block and the pruned blocks are all-gathered
+               (one collective per inflation, kept as packed buffers);
+      phase B  inflation k belongs to rank k mod world, which rebuilds the whole iterate from the saved buffers and runs the
+               remaining iterations alone as the owner of every column -- exactly the single-GPU code path (component blocks
+               on the tensor cores included), no further exchange.
+    `on_result(k, inflation, engine)` is called on the owner right after inflation k has finished (fetch / write its result
+    there).  Returns the list of per-inflation statistics, identical on every rank."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    if world == 1 or not hasattr(engine, "set_block"):
+        out = []
+        for k, r in enumerate(inflations):
+            st = sharded_mcl_run(engine, r, max_iter, pruning, blocks, group=group)
+            st["owner"] = 0
+            out.append(st)
+            if on_result is not None and rank == 0:
+                on_result(k, r, engine)
+        return out
+    dev = engine_device(engine)
+    ncols = [hi - lo for lo, hi in blocks]
+    n_total = blocks[-1][1]
+    saved = []
+    for r in inflations:                                             # ---- phase A
+        engine.begin(r, pruning)
+        nnz, prod, _delta = engine.step(0)
+        meta = torch.tensor([float(nnz), float(prod)], dtype=torch.float64, device=dev)
+        metas = torch.empty(world * 2, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(metas, meta, group=group)
+        metas = metas.view(world, 2).tolist()
+        nnzs = [int(m[0]) for m in metas]
+        cap = max(c + 2 * z for c, z in zip(ncols, nnzs))
+        if hasattr(engine, "pack_flat"):
+            buf = engine.pack_flat(nnz, cap)
+        else:
+            ln, idx, val = engine.pack(nnz)
+            buf = torch.zeros(cap, dtype=torch.int32, device=dev)
+            buf[: ncols[rank]] = ln
+            buf[ncols[rank]: ncols[rank] + nnz] = idx
+            buf[ncols[rank] + nnz: ncols[rank] + 2 * nnz] = val.view(torch.int32)
+        out = torch.empty(world * cap, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(out, buf[:cap], group=group)
+        _wait_collectives(out)
+        saved.append((out.view(world, cap), nnzs, sum(int(m[1]) for m in metas), getattr(engine, "last_step_ms", 0.0)))
+    local = {}
+    for k, r in enumerate(inflations):                               # ---- phase B
+        if k % world != rank:
+            saved[k] = None
+            continue
+        out, nnzs, prod0, ms0 = saved[k]
+        engine.begin(r, pruning)
+        engine.step(0)                                               # this rank's own block again (a 1/world stream of M1)
+        for rr in range(world):
+            if rr != rank:
+                c, z = ncols[rr], nnzs[rr]
+                engine.unpack(blocks[rr][0], blocks[rr][1], out[rr, :c], out[rr, c: c + z], out[rr, c + z: c + 2 * z].view(torch.float32))
+        engine.commit()
+        engine.set_block(0, n_total)
+        st = {"rounds": 1, "converged": False, "iter_nnz": [sum(nnzs)], "iter_products": [prod0], "iter_ms": [ms0], "owner": rank}
+        for it in range(1, max_iter):
+            nnz, prod, delta = engine.step(it)
+            engine.commit()
+            st["iter_nnz"].append(nnz)
+            st["iter_products"].append(prod)
+            st["iter_ms"].append(getattr(engine, "last_step_ms", 0.0))
+            st["rounds"] = it + 1
+            if it > 1 and delta <= 1e-8:
+                st["converged"] = True
+                break
+        local[k] = st
+        if on_result is not None:
+            on_result(k, r, engine)
+        saved[k] = None
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local, group=group)
+    merged = {}
+    for g in gathered:
+        merged.update(g)
+    return [merged[k] for k in range(len(inflations))]
+
+
 def engine_device(engine):
     ctx = getattr(engine, "ctx", None)
     return torch.device("cuda", ctx.device) if ctx is not None else torch.device("cpu")
@@ -284,15 +368,13 @@ def bench_multi(a, world: int, rank_id: int, local: int):
         ev[1].record(stream)
         blocks = column_blocks(mat.n, world)
         mc = Mcl(mat, col_lo=blocks[rank_id][0], col_hi=blocks[rank_id][1])
-        iters = 0
-        for r in inflations:
-            tw = time.perf_counter()
-            st = sharded_mcl_run(mc, r, a.max_iter, a.pruning, blocks)
-            iters += st["rounds"]
-            if os.environ.get("HH_BENCH_DEBUG") and rank_id == 0:
-                print("mcl r={} rounds={} wall_ms={:.1f} kernel_ms={:.1f} first={} preexp={:.1f} norm={:.1f}".format(
-                    r, st["rounds"], 1000 * (time.perf_counter() - tw), sum(st["iter_ms"]),
-                    [round(x, 1) for x in st["iter_ms"][:6]], mc.preexp_ms, mc.normalize_ms), file=sys.stderr, flush=True)
+        tw = time.perf_counter()
+        stats = sharded_mcl_sweep(mc, inflations, a.max_iter, a.pruning, blocks)
+        iters = sum(st["rounds"] for st in stats)
+        if os.environ.get("HH_BENCH_DEBUG") and rank_id == 0:
+            print("mcl sweep wall_ms={:.1f} preexp={:.1f} norm={:.1f}".format(1000 * (time.perf_counter() - tw), mc.preexp_ms, mc.normalize_ms),
+                  [(r, st["owner"], st["rounds"], round(sum(st["iter_ms"]), 1), [round(x, 1) for x in st["iter_ms"][:4]])
+                   for r, st in zip(inflations, stats)], file=sys.stderr, flush=True)
         ev[2].record(stream)
         ev[2].synchronize()
         t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], dtype=torch.float64, device=dev)
@@ -322,12 +404,13 @@ def bench_multi(a, world: int, rank_id: int, local: int):
 
     # ---- end to end: pinned HOST shard in, host results out on rank 0 (H2D / D2H inside the timed region)
     from .mcl import interpret_result
-    rec_host = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
-    rec_host.copy_(rec)
+    if a.e2e_steps > 0:
+        rec_host = torch.empty(rec.shape, dtype=torch.int32, pin_memory=True)
+        rec_host.copy_(rec)
     torch.cuda.synchronize()
     e2e_t, d2h = [], 0
     e2e_warm = 2            # pinned result buffers are allocated by the first pass, which also skews the second
-    for s in range(e2e_warm + a.e2e_steps):
+    for s in range(e2e_warm + a.e2e_steps if a.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
         tab = LinkTable(ctx, asm.lengths, rank, in_nx, 500000, capacity_hint=hint)
@@ -353,24 +436,28 @@ def bench_multi(a, world: int, rank_id: int, local: int):
                   [round(1000 * (b - a_), 1) for a_, b in zip(dbg, dbg[1:])], file=sys.stderr, flush=True)
         blocks = column_blocks(mat.n, world)
         mc = Mcl(mat, col_lo=blocks[rank_id][0], col_hi=blocks[rank_id][1])
-        n_it = 0
-        for r in inflations:
-            st = sharded_mcl_run(mc, r, a.max_iter, a.pruning, blocks)
-            n_it += st["rounds"]
-            if rank_id == 0:
-                fin = mc.result()
-                interpret_result(fin)
-                if s >= e2e_warm:
-                    d2h += fin.nnz * 8 + (n + 1) * 8
+        got = []
+
+        def fetch_result(_k, _r, eng):            # on the rank that ran the inflation: result to the host, clusters
+            fin = eng.result()
+            interpret_result(fin)
+            got.append(fin.nnz * 8 + (n + 1) * 8)
+
+        stats = sharded_mcl_sweep(mc, inflations, a.max_iter, a.pruning, blocks, on_result=fetch_result)
+        n_it = sum(st["rounds"] for st in stats)
         barrier()
         t2 = time.perf_counter()
         if s >= e2e_warm:
             e2e_t.append((t1 - t0, t2 - t1, n_it))
+            d2h += sum(got)
             if rank_id == 0:
                 d2h += sum(v.nbytes for v in table.values()) + tot.nbytes
         mc.close()
         mat.close()
         tab.close()
+    d2h_all = torch.tensor([float(d2h)], dtype=torch.float64, device=dev)
+    dist.all_reduce(d2h_all)                                # results are fetched by the rank that ran the inflation
+    d2h = int(d2h_all.item())
     if rank_id == 0:
         build_ms = sum(s["build_ms"] for s in steps) / len(steps)
         mcl_ms = sum(s["mcl_ms"] for s in steps) / len(steps)
@@ -387,8 +474,9 @@ def bench_multi(a, world: int, rank_id: int, local: int):
             "data": "synthetic",
             "config": {"workload": B.workload_name(a), "inflations": inflations, "max_iter": a.max_iter,
                        "pruning": a.pruning, "parallelism": "pair stream sharded x{0}, records routed to the owner of their contig pair "
-                       "(all-to-all), disjoint partition tables all-gathered; MCL column blocks x{0}, one all-gather of "
-                       "pruned columns per iteration".format(world),
+                       "(all-to-all), disjoint partition tables all-gathered; MCL: pre-expansion and iteration 0 of every inflation on "
+                       "column blocks x{0}, one all-gather of pruned columns per inflation, then inflation k runs on rank k mod {0} "
+                       "alone".format(world),
                        "cache": "inputs and the dense pre-expanded matrix exceed the 126 MB L2",
                        "step": "route + all-to-all + link build + partition all-gather + index + CSC + normalise + pre-expansion + "
                                "MCL sweep"},

@@ -227,6 +227,18 @@ def _worker(rank, world, port, q):
             assert abs(eng.cur - fin).max() < 1e-7
             assert st["iter_nnz"][-1] == fin.nnz
             assert eng.set_block_calls == 1 and (eng.lo, eng.hi) == (0, n)      # the tail ran replicated, without exchange
+        # 4) the inflation-parallel sweep: iteration 0 of every inflation sharded, then inflation k on rank k mod world alone
+        infl = [1.6, 2.0, 2.6]
+        want = [orc.mcl(m1, 2, r, 100, 1e-4) for r in infl]
+        for blocks in (hdist.column_blocks(n, world), [(0, 50), (50, n)]):
+            eng = OracleShard(link, *blocks[rank])
+            seen = []
+            stats = hdist.sharded_mcl_sweep(eng, infl, 100, 1e-4, blocks,
+                                            on_result=lambda k, r, e: seen.append((k, float(abs(e.cur - want[k][0]).max()))))
+            assert [(st["rounds"], st["converged"], st["owner"]) for st in stats] == [(w[1], w[2], k % world) for k, w in enumerate(want)]
+            assert [st["iter_nnz"][-1] for st in stats] == [w[0].nnz for w in want]
+            assert [k for k, _ in seen] == [k for k in range(len(infl)) if k % world == rank]
+            assert all(d < 1e-7 for _, d in seen)
         dist.destroy_process_group()
         q.put((rank, "ok"))
     except Exception:
