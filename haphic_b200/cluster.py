@@ -1271,7 +1271,19 @@ def run(args, log_file=None):
     if args.quick_view:
         logger.info("Program finished in {}s".format(time.time() - start_time))
         return None
-    write_clm(*clm_src, threads=args.threads)          # same file as output_clm(clm_dict), from the records, native
+    # paired_links.clm (same file as output_clm(clm_dict), from the records, native) depends on nothing below and nothing
+    # below depends on it: it is written by a host thread while the GPU filters, builds the matrix and clusters
+    import threading
+    clm_error = []
+
+    def _clm_job(src=clm_src):
+        try:
+            write_clm(*src, threads=args.threads)
+        except BaseException as exc:       # re-raised by the main thread once the run is through
+            clm_error.append(exc)
+
+    clm_thread = threading.Thread(target=_clm_job, name="write_clm")
+    clm_thread.start()
     del clm_src
 
     if args.normalize_by_nlinks and edits_dicts:
@@ -1318,6 +1330,9 @@ def run(args, log_file=None):
             mcl_nrounds, clustering_time - matrix_time, (clustering_time - matrix_time) / mcl_nrounds))
         output_statistics(fa_dict, full_link_dict, result_clusters_list)
     link_matrix.close()
+    clm_thread.join()
+    if clm_error:
+        raise clm_error[0]
     logger.info("Program finished in {}s".format(time.time() - start_time))
 
 

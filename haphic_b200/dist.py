@@ -138,14 +138,20 @@ def routed_link_build(table, rec, stream_lo: int, group=None):
     sizes = [int(m[0]) for m in metas]
     whole = torch.empty((sum(sizes), 9), dtype=ent.dtype, device=dev)
     offs = np.concatenate([[0], np.cumsum(sizes)])
-    views = [whole[int(offs[r]):int(offs[r + 1])] for r in range(world)]
     if len(set(sizes)) == 1:
         dist.all_gather_into_tensor(whole.view(-1), ent.reshape(-1), group=group)
     else:
-        for r in range(world):              # uneven partitions: one broadcast per owner
-            if r == rank:
-                views[r].copy_(ent)
-            dist.broadcast(views[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        # uneven partitions (the usual case: pairs are split by a hash): ONE all-gather of blocks padded to the largest, then a
+        # device-side compaction -- eight broadcasts in a row cost more than the padding
+        cap = max(sizes)
+        mine = torch.empty((cap, 9), dtype=ent.dtype, device=dev)
+        mine[: sizes[rank]].copy_(ent)
+        padded = torch.empty((world, cap, 9), dtype=ent.dtype, device=dev)
+        dist.all_gather_into_tensor(padded.view(-1), mine.view(-1), group=group)
+        _wait_collectives(padded)
+        for r in range(world):
+            whole[int(offs[r]):int(offs[r + 1])].copy_(padded[r, : sizes[r]])
+        del padded, mine
     dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
     _wait_collectives(whole)
     mark("all-gather")

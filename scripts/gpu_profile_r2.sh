@@ -13,16 +13,20 @@ timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:
 $S --launches gpurun_out/r02_launches_raw.csv
 rm -f gpurun_out/r02_launches_raw.csv
 echo "== full capture: MCL kernels (normalise, densify, GEMM, clip correction, dense iteration 0, block iteration)"
-timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:hh_k_syrk|hh_k_col|hh_k_blk|hh_k_clip|hh_k_gemm" -c 18 -f \
+timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:hh_k_syrk|hh_k_iter0|hh_k_slot_from_csc|hh_k_col_win|hh_k_blk|hh_k_clip|hh_k_gemm_densify" -c ${MCL_CAPTURES:-12} -f \
     -o gpurun_out/r02_prof_mcl python scripts/prof_c3.py > gpurun_out/r02_prof_mcl.log 2>&1
 $S --rep gpurun_out/r02_prof_mcl.ncu-rep
 rm -f gpurun_out/r02_prof_mcl.ncu-rep
+if [ -z "$SKIP_LINKS" ]; then
 echo "== full capture: partitioned link counting"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hh_k_part -c 4 -f -o gpurun_out/r02_prof_links \
     python scripts/prof_c3.py > gpurun_out/r02_prof_links.log 2>&1
 $S --rep gpurun_out/r02_prof_links.ncu-rep
 rm -f gpurun_out/r02_prof_links.ncu-rep
+fi
+if [ -n "$KEEP_SYRK_REP" ]; then
 echo "== single-kernel report of the GEMM (kept)"
 PAIRS=40000000 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hh_k_syrk -c 1 -f -o gpurun_out/r02_prof_syrk \
     python scripts/prof_c3.py > /dev/null 2>&1
+fi
 ls -la gpurun_out/
