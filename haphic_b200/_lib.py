@@ -36,7 +36,7 @@ class PreexpInfo(C.Structure):
     _fields_ = [("mode", C.c_int32), ("a_planes", C.c_int32), ("passes", C.c_int32), ("cta_group", C.c_int32),
                 ("stages", C.c_int32), ("chunk_kb", C.c_int32), ("total_ms", C.c_float), ("densify_ms", C.c_float),
                 ("gemm_ms", C.c_float), ("clip_ms", C.c_float), ("flops", C.c_double), ("products", C.c_int64),
-                ("clip", C.c_float), ("b_planes", C.c_int32), ("fmt_a", C.c_int32), ("fmt_b", C.c_int32)]
+                ("clip", C.c_float), ("b_planes", C.c_int32), ("fmt_a", C.c_int32), ("fmt_b", C.c_int32), ("k_chunks", C.c_int32)]
 
 
 HH_PREEXP_AUTO, HH_PREEXP_SPARSE, HH_PREEXP_DENSE = 0, 1, 2

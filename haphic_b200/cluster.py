@@ -910,15 +910,23 @@ def ranked_group_links(link_dict, ctg_group_dict):
     if not isinstance(link_dict, LinkArrays):
         return {ctg: sorted(groups.items(), key=lambda x: x[1], reverse=True)
                 for ctg, groups in parse_link_dict(link_dict, ctg_group_dict).items()}
+    arr = _ranked_group_arrays(link_dict, ctg_group_dict)
+    if arr is None:
+        return {}
+    return _ranked_lists(link_dict.names, *arr[1:])
+
+
+def _ranked_group_arrays(link_dict, ctg_group_dict):
+    """(gid, contig, group, links) of the same ranking as flat arrays ordered by (contig, rank); None when nothing is linked to
+    a group.  gid[c] = group of contig c (-1 = ungrouped)."""
     names = link_dict.names
     n = len(names)
     gid = np.array([-1 if ctg_group_dict[nm] == "ungrouped" else ctg_group_dict[nm] for nm in names], dtype=np.int64)
     if len(link_dict) == 0 or gid.max() < 0:
-        return {}
+        return None
     ng = int(gid.max()) + 1
     if _CTX is not None and os.environ.get("HAPHIC_STATS_DEVICE", "1") != "0":
-        c_of, g_of, sums = _ranked_group_links_device(link_dict, gid, ng, _CTX.device)
-        return _ranked_lists(names, c_of, g_of, sums)
+        return (gid,) + tuple(_ranked_group_links_device(link_dict, gid, ng, _CTX.device))
     # links of every contig into every group = (symmetric link matrix) x (contig -> group indicator): one sparse product per
     # inflation instead of a sort of all 2 * nnz directed entries (20 sorts of 1.2e8 keys took 15 min at 50k contigs)
     import scipy.sparse as sp
@@ -952,7 +960,7 @@ def ranked_group_links(link_dict, ctg_group_dict):
         mine = np.nonzero(tie[c_of])[0]
         first[mine] = tab[trow[c_of[mine]] * ng + g_of[mine]]
     rank = np.lexsort((first, -sums, c_of))
-    return _ranked_lists(names, c_of[rank], g_of[rank], sums[rank])
+    return gid, c_of[rank], g_of[rank], sums[rank]
 
 
 def _ranked_lists(names, c_of, g_of, sums):
@@ -993,6 +1001,61 @@ def cal_link_density(max_group, current_group, max_links, group_RE_sites, ctg_RE
     if max_group == current_group:
         return max_links / group_RE_sites
     return max_links / (group_RE_sites + ctg_RE_sites - 1)
+
+
+def _best_group_statistics(fa_dict, link_dict, ctg_group, group_RE):
+    """The three per-contig lists of output_statistics (2373-2400: links to the best group, link density to it, density ratio
+    best / average of the others) from the ranked (contig, group, links) arrays instead of 10^7 Python tuples.  Same
+    arithmetic in the same order: int / int true divisions become float64 divisions of the same integers (both correctly
+    rounded), and the sum over ranked[1:] is accumulated position by position, left to right, like sum()."""
+    names = link_dict.names
+    arr = _ranked_group_arrays(link_dict, ctg_group)
+    zero = [(ctg, 0) for ctg in fa_dict]
+    if arr is None:
+        return zero, list(zero), list(zero)
+    gid, c_of, g_of, sums = arr
+    n_groups = len(group_RE)
+    RE_g = np.array([group_RE[g] for g in range(int(gid.max()) + 1)], dtype=np.int64)
+    RE_c = np.array([fa_dict[nm][2] for nm in names], dtype=np.int64)
+    denom = np.where(g_of == gid[c_of], RE_g[g_of], RE_g[g_of] + RE_c[c_of] - 1)
+    dens = sums.astype(np.float64) / denom.astype(np.float64)
+    starts = np.concatenate([[0], np.nonzero(np.diff(c_of))[0] + 1])
+    seg_len = np.diff(np.concatenate([starts, [len(c_of)]]))
+    # sum(): left to right; CPython >= 3.12 adds floats with Neumaier's compensated summation (bltinmodule.c), earlier
+    # versions plainly -- the statistics files hold the repr of these sums, so the same algorithm is applied here
+    acc = np.zeros(len(starts), np.float64)
+    comp = np.zeros(len(starts), np.float64)
+    neumaier = sys.version_info >= (3, 12)
+    for pos in range(1, int(seg_len.max())):
+        m = np.nonzero(seg_len > pos)[0]
+        x = dens[starts[m] + pos]
+        f = acc[m]
+        t = f + x
+        if neumaier:
+            comp[m] += np.where(np.abs(f) >= np.abs(x), (f - t) + x, (x - t) + f)
+        acc[m] = t
+    if neumaier:
+        fix = (comp != 0) & np.isfinite(comp)
+        acc[fix] += comp[fix]
+    others = acc / (n_groups - 1) if n_groups > 1 else np.zeros(len(starts))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = dens[starts] / others
+    has = {int(c): k for k, c in enumerate(c_of[starts].tolist())}
+    top_links, top_dens = sums[starts].tolist(), dens[starts].tolist()
+    others_l, ratio_l = others.tolist(), ratio.tolist()
+    name_idx = {nm: i for i, nm in enumerate(names)}
+    best_links, best_density, best_ratio = [], [], []
+    for ctg in fa_dict:
+        k = has.get(name_idx.get(ctg, -1))
+        if k is None:
+            best_links.append((ctg, 0))
+            best_density.append((ctg, 0))
+            best_ratio.append((ctg, 0))
+            continue
+        best_links.append((ctg, top_links[k]))
+        best_density.append((ctg, top_dens[k]))
+        best_ratio.append((ctg, ratio_l[k] if others_l[k] else 1000000))
+    return best_links, best_density, best_ratio
 
 
 def output_statistics(fa_dict, link_dict, result_clusters_list):
@@ -1039,9 +1102,13 @@ def output_statistics(fa_dict, link_dict, result_clusters_list):
                 ctg_group[ctg] = gid
                 group_RE[gid] += fa_dict[ctg][2] - 1
         add_ungrouped_ctgs(fa_dict, ctg_group)
-        group_links = ranked_group_links(link_dict, ctg_group)
-        best_links, best_density, best_ratio = [], [], []
-        for ctg in fa_dict:
+        if isinstance(link_dict, LinkArrays):
+            best_links, best_density, best_ratio = _best_group_statistics(fa_dict, link_dict, ctg_group, group_RE)
+            group_links = None
+        else:
+            group_links = ranked_group_links(link_dict, ctg_group)
+            best_links, best_density, best_ratio = [], [], []
+        for ctg in (fa_dict if group_links is not None else ()):
             if ctg not in group_links:
                 best_links.append((ctg, 0))
                 best_density.append((ctg, 0))

@@ -190,6 +190,7 @@ struct hh_gemm_args {
     int col_lo, col_hi;
     const float* inv_s;    // 1 / column sum
     float out_scale;       // applied instead when inv_s == NULL
+    int accumulate;        // 1: the epilogue adds to what the output holds (K range processed in several launches)
     int split_lo;          // 1: passes with a low-order plane accumulate in their own TMEM buffer over the whole tile (see kernel)
     uint32_t idesc_fmt;    // operand format bits of the instruction descriptor (bit 7: A is bf16, bit 10: B is bf16)
 };
@@ -368,8 +369,11 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                     for (int j = 0; j < CW; ++j) {
                         const int c = c0 + j;
-                        if (c < w.n_end && c >= a.col_lo && c < a.col_hi)
-                            dst[(size_t)(c - a.col_lo) * (size_t)a.ld] = a.inv_s ? acc[j] * __ldg(a.inv_s + c) : acc[j] * a.out_scale;
+                        if (c < w.n_end && c >= a.col_lo && c < a.col_hi) {
+                            float* __restrict__ o = dst + (size_t)(c - a.col_lo) * (size_t)a.ld;
+                            const float v = a.inv_s ? acc[j] * __ldg(a.inv_s + c) : acc[j] * a.out_scale;
+                            *o = a.accumulate ? __fadd_rn(*o, v) : v;
+                        }
                     }
                 }
                 if ((w.flags & HH_GEMM_MIRROR) && r >= a.col_lo && r < a.col_hi) {
@@ -379,11 +383,16 @@ hh_k_syrk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int j = 0; j < CW; j += 4) {
                         const int c = c0 + j;
                         if (c + 3 < w.n_end && w.out_row0 == 0) {
-                            *reinterpret_cast<float4*>(dst + c) = make_float4(acc[j] * sr, acc[j + 1] * sr, acc[j + 2] * sr, acc[j + 3] * sr);
+                            float4 v = make_float4(acc[j] * sr, acc[j + 1] * sr, acc[j + 2] * sr, acc[j + 3] * sr);
+                            if (a.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(dst + c);
+                                v = make_float4(__fadd_rn(old.x, v.x), __fadd_rn(old.y, v.y), __fadd_rn(old.z, v.z), __fadd_rn(old.w, v.w));
+                            }
+                            *reinterpret_cast<float4*>(dst + c) = v;
                         } else {
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                if (c + q < w.n_end) dst[c + q] = acc[j + q] * sr;
+                                if (c + q < w.n_end) dst[c + q] = a.accumulate ? __fadd_rn(dst[c + q], acc[j + q] * sr) : acc[j + q] * sr;
                         }
                     }
                 }
@@ -455,15 +464,16 @@ __device__ __forceinline__ void hg_split3(float x, unsigned short& h1, unsigned 
 __global__ void __launch_bounds__(1024)
 hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row, const float* __restrict__ val, int n,
                   const double* __restrict__ s, unsigned short* __restrict__ A, int na, unsigned short* __restrict__ B, int nb, long long ldk,
-                  long long plane, float clip, int scaled, int a_f16) {
+                  long long plane, float clip, int scaled, int a_f16, long long k0) {
+    // the planes hold the K range [k0, k0 + ldk) of the operands (the whole range unless the product is cut along K)
     extern __shared__ __align__(16) unsigned short hg_row[];        // [3][HG_SEG]
     const int c = blockIdx.x;
     const int64_t p0 = colptr[c], p1 = colptr[c + 1];
     for (int group = 0; group < 2; ++group) {                       // 0: planes of A, 1: planes of B
         const int np = group ? nb : na;
         unsigned short* __restrict__ out = (group ? B : A) + (size_t)c * (size_t)ldk;
-        for (long long seg0 = 0; seg0 < ldk; seg0 += HG_SEG) {
-            const int seg_n = (int)((ldk - seg0 < HG_SEG) ? (ldk - seg0) : HG_SEG);      // multiple of 64
+        for (long long seg0 = k0; seg0 < k0 + ldk; seg0 += HG_SEG) {
+            const int seg_n = (int)((k0 + ldk - seg0 < HG_SEG) ? (k0 + ldk - seg0) : HG_SEG);      // multiple of 64
             uint4* z = reinterpret_cast<uint4*>(hg_row);
             for (int q = threadIdx.x; q < 3 * HG_SEG / 8; q += blockDim.x) z[q] = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();
@@ -500,7 +510,7 @@ hh_k_gemm_densify(const int64_t* __restrict__ colptr, const int32_t* __restrict_
             __syncthreads();
             for (int pl = 0; pl < np; ++pl) {
                 const uint4* src = reinterpret_cast<const uint4*>(hg_row + (size_t)pl * HG_SEG);
-                uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pl * (size_t)plane + (size_t)seg0);
+                uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pl * (size_t)plane + (size_t)(seg0 - k0));
                 for (int q = threadIdx.x; q < seg_n / 8; q += blockDim.x) dst[q] = src[q];
             }
             __syncthreads();
@@ -567,7 +577,7 @@ int hh_gemm_cta_group() { return hg_env_int("HH_GEMM_CG", 2) == 1 ? 1 : 2; }
 
 int hh_gemm_run(hh_ctx* ctx, const hh_gemm_operand& A, const hh_gemm_operand& B, const hh_gemm_item* d_items, int n_items, int npass,
                 const int* pa, const int* pb, int chunk_kb, float* out, long long ld, int col_lo, int col_hi, const float* scale,
-                int* stages_out, float out_scale, int split_lo) {
+                int* stages_out, float out_scale, int split_lo, int accumulate) {
     HH_REQUIRE(n_items >= 1 && npass >= 1 && npass <= 8, HH_ERR_ARG, "hh_gemm_run: bad work list");
     CUtensorMap tmA, tmB;
     HH_CHECK(hg_encode(&tmA, (void*)A.base, A.rows, A.kdim, A.ldk, A.plane, A.planes, A.fmt));
@@ -597,6 +607,7 @@ int hh_gemm_run(hh_ctx* ctx, const hh_gemm_operand& A, const hh_gemm_operand& B,
     a.inv_s = scale;
     a.out_scale = out_scale;
     a.split_lo = split_lo;
+    a.accumulate = accumulate;
     a.idesc_fmt = (A.fmt == HH_GEMM_BF16 ? (1u << 7) : 0u) | (B.fmt == HH_GEMM_BF16 ? (1u << 10) : 0u);
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     if (hh_gemm_cta_group() == 2) return split_lo ? hg_launch<2, true>(ctx, tmA, tmB, a, smem) : hg_launch<2, false>(ctx, tmA, tmB, a, smem);
@@ -660,19 +671,21 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
             clip = 3.0e38f;
         }
         const int fmt_a = enc == 2 ? HH_GEMM_F16 : HH_GEMM_BF16, fmt_b = enc ? HH_GEMM_F16 : HH_GEMM_BF16;
-        HH_CHECK(hh_ws_alloc(ctx, &d_A, (size_t)plane * (size_t)na));
-        HH_CHECK(hh_ws_alloc(ctx, &d_B, (size_t)plane * (size_t)nb));
-        {
-            auto kd = hh_k_gemm_densify;
-            const size_t dsm = (size_t)3 * HG_SEG * sizeof(unsigned short);
-            HH_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-            HH_LAUNCH(ctx, kd, n, 1024, dsm, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, nb, ldk, plane, clip, enc ? 1 : 0,
-                      enc == 2 ? 1 : 0);
-        }
+        // The K range is cut into equal chunks when the operand planes of the whole range would exceed ~36 GB (150k contigs:
+        // 135 GB): planes of one chunk at a time, the epilogue of every chunk after the first adds to M1.  The cut depends on
+        // n and the encoding only, so every rank of a sharded run cuts alike and M1 stays bit-identical for any world size.
+        const double plane_bytes_all = (double)(na + nb) * (double)plane * 2.0;
+        int kchunks = (int)(plane_bytes_all / 36.0e9) + 1;
+        kchunks = hg_env_int("HH_GEMM_KCHUNKS", kchunks);
+        if (kchunks < 1) kchunks = 1;
+        const long long kw = ((((long long)n + kchunks - 1) / kchunks) + 63) & ~63ll;      // chunk width, multiple of 64
+        kchunks = (int)(((long long)n + kw - 1) / kw);
+        const long long plane_c = kw * (long long)n;
+        HH_CHECK(hh_ws_alloc(ctx, &d_A, (size_t)plane_c * (size_t)na));
+        HH_CHECK(hh_ws_alloc(ctx, &d_B, (size_t)plane_c * (size_t)nb));
         // rows [n, ld) of every M1 column stay zero
         HH_CUDA(cudaMemsetAsync(d_m1, 0, (size_t)ld * (size_t)(col_hi - col_lo) * sizeof(float), ctx->stream));
         HH_CHECK(hh_dmalloc(&d_items, (size_t)n_items));
-        HH_CUDA(cudaMemcpyAsync(d_items, h_items, (size_t)n_items * sizeof(hh_gemm_item), cudaMemcpyHostToDevice, ctx->stream));
         int pa[8], pb[8];
         int npass = hh_gemm_passes(na, pa, pb);
         if (enc) {                                               // (A, B hi), (A, B lo)
@@ -687,7 +700,7 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
         // number of accumulations (4 MMAs per k-block and pass).
         // Measured at 50k contigs (one B200; GEMM time / max and mean relative error against the exact product), two f16 passes:
         //   chunk 2: 205 ms, 1.5e-6, -1.6e-8   4: 177 ms, 1.2e-6, -2.4e-8   8: 139 ms, 1.1e-6, -3.9e-8   16: 136 ms, 1.9e-6, -6.6e-8
-        // every drain costs ~2000 clocks of tensor-pipe time, so longer chunks are faster -- but on dense inputs (every product
+        // every drain costs 0.5-2k clocks of tensor-pipe time, so longer chunks are faster -- but on dense inputs (every product
         // of similar size) the bias of 64 truncating accumulations reaches 2.5e-6.  Three k-blocks = 24 accumulations, the
         // same as three bf16 passes drained every second k-block, keeps every test input below 2e-6.
         // HH_GEMM_SPLIT=1 (experiment): the low-order pass (2^-11 of the result) gets the second TMEM buffer for the whole
@@ -695,11 +708,40 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
         // at chunk 8 on the same device.
         const int split = (enc && hg_env_int("HH_GEMM_SPLIT", 0)) ? 1 : 0;
         const int chunk = hg_env_int("HH_GEMM_CHUNK", npass > 3 ? 1 : (npass == 3 ? 2 : (split ? 8 : 3)));
-        hh_gemm_operand A = {d_A, na, n, n, ldk, plane, fmt_a};
-        hh_gemm_operand B = {d_B, nb, n, n, ldk, plane, fmt_b};
         int stages = 0;
-        HH_CUDA(cudaEventRecord(ev[1], ctx->stream));
-        HH_CHECK(hh_gemm_run(ctx, A, B, d_items, n_items, npass, pa, pb, chunk, d_m1, ld, col_lo, col_hi, d_inv, &stages, 1.0f, split));
+        float densify_ms = 0.f, gemm_ms = 0.f;
+        const float stats_ms = 0.f;                              // column sums + value statistics: a fraction of a millisecond
+        std::vector<hh_gemm_item> items_c(h_items, h_items + n_items);
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const long long k0 = (long long)kc * kw;
+            const long long k1 = std::min((long long)n, k0 + kw);
+            HH_CUDA(cudaEventRecord(ev[0], ctx->stream));
+            {
+                auto kd = hh_k_gemm_densify;
+                const size_t dsm = (size_t)3 * HG_SEG * sizeof(unsigned short);
+                HH_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                HH_LAUNCH(ctx, kd, n, 1024, dsm, m->d_colptr, m->d_row, m->d_val, n, d_s, d_A, na, d_B, nb, kw, plane_c, clip, enc ? 1 : 0,
+                          enc == 2 ? 1 : 0, k0);
+            }
+            const int nkb_c = (int)((k1 - k0 + 63) / 64);
+            for (auto& w : items_c) {
+                w.kb_lo[0] = 0;
+                w.kb_hi[0] = nkb_c;
+            }
+            HH_CUDA(cudaMemcpyAsync(d_items, items_c.data(), (size_t)n_items * sizeof(hh_gemm_item), cudaMemcpyHostToDevice, ctx->stream));
+            hh_gemm_operand A = {d_A, na, n, (int)(k1 - k0), kw, plane_c, fmt_a};
+            hh_gemm_operand B = {d_B, nb, n, (int)(k1 - k0), kw, plane_c, fmt_b};
+            HH_CUDA(cudaEventRecord(ev[1], ctx->stream));
+            HH_CHECK(hh_gemm_run(ctx, A, B, d_items, n_items, npass, pa, pb, chunk, d_m1, ld, col_lo, col_hi, d_inv, &stages, 1.0f, split,
+                                 kc > 0 ? 1 : 0));
+            HH_CUDA(cudaEventRecord(ev[2], ctx->stream));
+            HH_CUDA(cudaStreamSynchronize(ctx->stream));         // items_c is rewritten for the next chunk
+            float t0 = 0.f, t1 = 0.f;
+            HH_CUDA(cudaEventElapsedTime(&t0, ev[0], ev[1]));
+            HH_CUDA(cudaEventElapsedTime(&t1, ev[1], ev[2]));
+            densify_ms += t0;
+            gemm_ms += t1;
+        }
         HH_CUDA(cudaEventRecord(ev[2], ctx->stream));
         HH_CUDA(cudaStreamSynchronize(ctx->stream));
         if (st) {
@@ -714,8 +756,9 @@ int hh_gemm_preexpand(hh_ctx* ctx, const hh_matrix* m, int col_lo, int col_hi, f
             st->cta_group = hh_gemm_cta_group();
             st->stages = stages;
             st->chunk_kb = chunk < 1 ? (1 << 30) : chunk;
-            HH_CUDA(cudaEventElapsedTime(&st->densify_ms, ev[0], ev[1]));
-            HH_CUDA(cudaEventElapsedTime(&st->gemm_ms, ev[1], ev[2]));
+            st->densify_ms = densify_ms + stats_ms;
+            st->gemm_ms = gemm_ms;
+            st->k_chunks = kchunks;
             double kb = 0.0;
             for (int i = 0; i < n_items; ++i) kb += (double)((h_items[i].kb_hi[0] - h_items[i].kb_lo[0]) + (h_items[i].kb_hi[1] - h_items[i].kb_lo[1]));
             const double tile = 128.0 * hh_gemm_cta_group();

@@ -2347,7 +2347,9 @@ static int choose_preexp(const hh_matrix* m, int requested) {
     // measured on B200: Gustavson ~0.5e12 products/s; tensor-core GEMM ~1.9e15 flop/s issued over two f16 passes of the
     // symmetric half, plus operand planes (memset + scatter) and allocation
     const double n = (double)m->n, d = (double)m->nnz / (n > 0 ? n : 1.0);
-    const double t_sparse = n * d * d / 0.5e12;
+    // (above 57,600 vertices the column accumulator no longer fits shared memory: measured 8.5 s per rank for 1/8 of the
+    // columns at 150k contigs / 1B pairs, about ten times the shared-memory rate)
+    const double t_sparse = n * d * d / (n > 57600.0 ? 0.05e12 : 0.5e12);
     const double t_dense = 1.2e-15 * n * n * n + 3.0e-12 * n * n + 5.0e-4;
     // the operand planes (up to six bf16 planes of n x n) must fit beside M1 and the iterates
     size_t free_b = 0, total_b = 0;
@@ -2355,8 +2357,11 @@ static int choose_preexp(const hh_matrix* m, int requested) {
         cudaGetLastError();
         free_b = 0;
     }
-    const double planes = 6.0 * 2.0 * n * n;
-    if (planes > 0.6 * (double)free_b) return HH_PREEXP_SPARSE;
+    // the operand planes of one K chunk (hh_gemm_preexpand cuts the K range so that a chunk stays below ~36 GB; six bf16
+    // planes in the worst case) must fit beside M1 and the iterates
+    const double planes_all = 6.0 * 2.0 * n * n;
+    const double planes = planes_all / (double)((int)(planes_all / 36.0e9) + 1);
+    if (planes > 0.5 * (double)free_b) return HH_PREEXP_SPARSE;
     return (1.2 * t_dense < t_sparse) ? HH_PREEXP_DENSE : HH_PREEXP_SPARSE;
 }
 
@@ -2573,6 +2578,7 @@ extern "C" int hh_mcl_preexp_info(hh_mcl* mc, hh_preexp_info* info) {
         info->b_planes = mc->gemm.b_planes;
         info->fmt_a = mc->gemm.fmt_a;
         info->fmt_b = mc->gemm.fmt_b;
+        info->k_chunks = mc->gemm.k_chunks;
     } else {
         info->products = mc->preexp_products;
     }
@@ -2882,7 +2888,7 @@ extern "C" int hh_mcl_step(hh_mcl* mc, int it, int64_t* nnz_owned, int64_t* prod
                 hh_gemm_operand B = {d_blkB, np_op, mc->n, (int)mc->blk_ldk, mc->blk_ldk, (long long)plane, fmt};
                 HH_CHECK(hh_gemm_run(ctx, A, B, mc->d_blk_items, (int)mc->blk_items->size(), npass, pa, pb,
                                      env_int("HH_GEMM_CHUNK", f16 ? 2 : 1), d_blk_out, mc->blk_ldk, 0, mc->n, nullptr, nullptr,
-                                     hh_gemm_blk_out_scale(f16), 0));
+                                     hh_gemm_blk_out_scale(f16), 0, 0));
                 a.dense_in = d_blk_out;
                 a.ld = mc->blk_ldk;
                 mc->blk_iters++;

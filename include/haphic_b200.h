@@ -201,6 +201,7 @@ typedef struct {
     float clip;            /* dense: counts enter the GEMM as min(count, clip): 2048 (f16 plane) / 256 (bf16) */
     int32_t b_planes;      /* dense: planes of the M0 operand (2: f16 hi + lo, 22 bits; 3: exact bf16)      */
     int32_t fmt_a, fmt_b;  /* dense: operand formats, 0 = bf16, 1 = f16                                    */
+    int32_t k_chunks;      /* dense: launches the K range was cut into (operand planes of one chunk at a time) */
 } hh_preexp_info;
 int hh_mcl_preexp_info(hh_mcl* mc, hh_preexp_info* info);
 /* normalize_ms / preexp_ms: device time of the two kernels hh_mcl_create ran */

@@ -147,6 +147,34 @@ def test_dense_variants(ctx, monkeypatch, cg, chunk):
     mat.close()
 
 
+def test_dense_k_chunks(ctx, monkeypatch):
+    """the K range cut into several launches (what 150k contigs need: operand planes of one chunk at a time, the epilogue
+    adds to M1): same accuracy, and column shards stay bit-identical to the whole run with the same cut"""
+    from haphic_b200.links import LinkMatrix
+    from haphic_b200.mcl import Mcl
+    link = random_links(1100, 0.4, 3000, seed=21)
+    mat = LinkMatrix.from_csc(ctx, link)
+    exact = exact_m1(link)
+    nz = exact != 0
+    monkeypatch.setenv("HH_GEMM_KCHUNKS", "3")
+    mc = Mcl(mat, preexp="dense")
+    assert mc.preexp["k_chunks"] == 3
+    whole = mc.m1()
+    m1 = whole.astype(np.float64)
+    assert np.array_equal(m1 != 0, nz)
+    assert (np.abs(m1[nz] - exact[nz]) / exact[nz]).max() <= 2e-6
+    part = Mcl(mat, col_lo=300, col_hi=777, preexp="dense")
+    assert np.array_equal(part.m1(), whole[:, 300:777])
+    part.close()
+    mc.close()
+    monkeypatch.setenv("HH_GEMM_KCHUNKS", "1")
+    one = Mcl(mat, preexp="dense")
+    assert one.preexp["k_chunks"] == 1
+    assert np.allclose(one.m1(), whole, rtol=1e-6, atol=0)
+    one.close()
+    mat.close()
+
+
 def test_dense_column_shards_equal_single(ctx):
     """a column shard computes every element in the same tile and orientation as the single-GPU run: bit-identical"""
     from haphic_b200.links import LinkMatrix
