@@ -1709,7 +1709,6 @@ static int launch_col(hh_ctx* ctx, const hh_geom& g, float* d_scratch, int grid_
 // Warp w owns row block w (rows [w * T, (w + 1) * T)), so the row-block pointers of the slotted format fall out of the
 // per-warp counts.  Two CTAs per SM overlap one column's reductions with the other's loads.
 // ---------------------------------------------------------------------------------------------
-#define HH_IT0_WARPS 8
 // x1 of one candidate (rare: a few percent of a column), kept out of line so that the streaming loops stay small -- with powf
 // and the fp64 quotient inlined at every use the kernel outgrew the instruction cache and ran 3-7x slower for r != 2
 __device__ __noinline__ float hh_it0_x1(float x, double S1, float rf, int sq) {
@@ -1717,8 +1716,13 @@ __device__ __noinline__ float hh_it0_x1(float x, double S1, float rf, int sq) {
     return (float)((double)y / S1);
 }
 
-template <int W, bool SQ>      // SQ: any of the multiplicative modes (no powf in the streaming loop)
-__global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_colargs a) {
+// NW warps per CTA and 32 / NW CTAs per SM.  With 8-warp CTAs 592 columns (118 MB, the whole L2) are in flight and ncu shows
+// all three passes in DRAM (29.6 GB read, L2 hit 4 %) -- but fewer, larger CTAs (59 / 30 MB in flight) are not faster:
+// 10.1 / 10.5 / 11.6 ms for NW = 8 / 16 / 32 at r = 2.0 on the same device.  The kernel is bound by instruction issue
+// (1.0e10 warp instructions, issue slots 61 % busy), not by where the re-reads come from.  HH_MCL_IT0_WARPS selects the shape.
+template <int W, bool SQ, int NW>      // SQ: any of the multiplicative modes (no powf in the streaming loop)
+__global__ void __launch_bounds__(NW * 32, 32 / NW) hh_k_iter0(const hh_colargs a) {
+    constexpr int HH_IT0_WARPS = NW;
     // HH_IT0_WARPS warps per CTA (several CTAs per SM keep loads of other columns in flight across the reductions); warp v
     // handles the row blocks v, v + HH_IT0_WARPS, ... of the slotted format (W blocks of T rows)
     __shared__ double s_d[HH_IT0_WARPS];
@@ -1902,9 +1906,10 @@ __global__ void __launch_bounds__(HH_IT0_WARPS * 32, 4) hh_k_iter0(const hh_cola
     if (threadIdx.x == 0 && nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
 }
 
-template <int W>
-static int launch_iter0_w(hh_ctx* ctx, hh_colargs& a) {
-    auto kern = (a.inflate_square != HH_INFL_POW) ? hh_k_iter0<W, true> : hh_k_iter0<W, false>;
+template <int W, int NW>
+static int launch_iter0_wn(hh_ctx* ctx, hh_colargs& a) {
+    constexpr int HH_IT0_WARPS = NW;
+    auto kern = (a.inflate_square != HH_INFL_POW) ? hh_k_iter0<W, true, NW> : hh_k_iter0<W, false, NW>;
     int per_sm = 0;
     HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HH_IT0_WARPS * 32, 0));
     if (per_sm < 1) per_sm = 1;
@@ -1914,6 +1919,15 @@ static int launch_iter0_w(hh_ctx* ctx, hh_colargs& a) {
     HH_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), ctx->stream));
     HH_LAUNCH(ctx, kern, grid, HH_IT0_WARPS * 32, 0, a);
     return HH_OK;
+}
+
+template <int W>
+static int launch_iter0_w(hh_ctx* ctx, hh_colargs& a) {
+    switch (env_int("HH_MCL_IT0_WARPS", 8)) {
+        case 16: return launch_iter0_wn<W, 16>(ctx, a);
+        case 32: return launch_iter0_wn<W, 32>(ctx, a);
+        default: return launch_iter0_wn<W, 8>(ctx, a);
+    }
 }
 
 static int launch_iter0(hh_ctx* ctx, const hh_geom& g, hh_colargs& a) {
