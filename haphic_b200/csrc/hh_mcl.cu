@@ -1720,9 +1720,17 @@ __device__ __noinline__ float hh_it0_x1(float x, double S1, float rf, int sq) {
 // all three passes in DRAM (29.6 GB read, L2 hit 4 %) -- but fewer, larger CTAs (59 / 30 MB in flight) are not faster:
 // 10.1 / 10.5 / 11.6 ms for NW = 8 / 16 / 32 at r = 2.0 on the same device.  The kernel is bound by instruction issue
 // (1.0e10 warp instructions, issue slots 61 % busy), not by where the re-reads come from.  HH_MCL_IT0_WARPS selects the shape.
-template <int W, bool SQ, int NW>      // SQ: any of the multiplicative modes (no powf in the streaming loop)
+// QUEUE: the candidates of passes 2 and 3 (a few percent of the elements) are first collected in a per-warp shared-memory
+// queue and then evaluated 32 at a time.  Evaluating them where they are found costs one call of hh_it0_x1 (pow + fp64
+// division, ~100 instructions) per warp and element slot that holds at least one candidate -- with 1-2 % candidates that
+// is every second slot, executed with one or two active lanes: 7.5e9 of the kernel's 1.0e10 warp instructions (ncu).
+template <int W, bool SQ, int NW, bool QUEUE>      // SQ: any of the multiplicative modes (no powf in the streaming loop)
 __global__ void __launch_bounds__(NW * 32, 32 / NW) hh_k_iter0(const hh_colargs a) {
     constexpr int HH_IT0_WARPS = NW;
+    constexpr int QCAP = 256;                       // queue entries per warp (a trip adds at most 128)
+    __shared__ float s_qx[QUEUE ? NW : 1][QUEUE ? QCAP : 1];
+    __shared__ unsigned s_qr[QUEUE ? NW : 1][QUEUE ? QCAP : 1];
+    const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
     // HH_IT0_WARPS warps per CTA (several CTAs per SM keep loads of other columns in flight across the reductions); warp v
     // handles the row blocks v, v + HH_IT0_WARPS, ... of the slotted format (W blocks of T rows)
     __shared__ double s_d[HH_IT0_WARPS];
@@ -1798,16 +1806,40 @@ __global__ void __launch_bounds__(NW * 32, 32 / NW) hh_k_iter0(const hh_colargs 
         for (int b = wv; b < W; b += HH_IT0_WARPS) {
             const int r4_lo = (b * T) >> 2, r4_hi = min(((b + 1) * T) >> 2, ld4);
             int cnt = 0;
-            for (int r4 = r4_lo + lane; r4 < r4_hi; r4 += 128) {
+            int qn = 0;                                  // warp-uniform fill of this warp's queue
+            auto drain2 = [&]() {
+                __syncwarp();
+                for (int i0 = 0; i0 < qn; i0 += 32) {
+                    const int i = i0 + lane;
+                    if (i < qn) {
+                        const float x1 = hh_it0_x1(s_qx[QUEUE ? wv : 0][QUEUE ? i : 0], S1, rf, sq);
+                        if (x1 >= p32 && x1 > 0.f) {
+                            cnt++;
+                            s2 += (double)x1;
+                        }
+                    }
+                }
+                __syncwarp();
+                qn = 0;
+            };
+            for (int r4 = r4_lo + lane - (QUEUE ? lane : 0); r4 < r4_hi; r4 += 128) {
+                const int r4l = QUEUE ? r4 + lane : r4;      // QUEUE: warp-uniform trip count, the lane offset is added here
                 float4 x[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) x[q] = (r4 + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 4; ++q) x[q] = (r4l + 32 * q < r4_hi) ? hh_ld_stream_f4(col4 + r4l + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float xv[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        if (xv[c] >= xthr) {
+                        if (QUEUE) {
+                            const bool cand = xv[c] >= xthr;
+                            const unsigned bal = __ballot_sync(HH_FULL_MASK, cand);
+                            if (bal) {
+                                if (cand) s_qx[QUEUE ? wv : 0][QUEUE ? qn + __popc(bal & lt_mask) : 0] = xv[c];
+                                qn += __popc(bal);
+                            }
+                        } else if (xv[c] >= xthr) {
                             const float x1 = hh_it0_x1(xv[c], S1, rf, sq);
                             if (x1 >= p32 && x1 > 0.f) {
                                 cnt++;
@@ -1815,8 +1847,10 @@ __global__ void __launch_bounds__(NW * 32, 32 / NW) hh_k_iter0(const hh_colargs 
                             }
                         }
                     }
+                    if (QUEUE && qn > QCAP - 128) drain2();
                 }
             }
+            if (QUEUE && qn > 0) drain2();
             cnt = hh_warp_sum(cnt);
             if (lane == 0) s_c[b] = cnt;
         }
@@ -1860,6 +1894,56 @@ __global__ void __launch_bounds__(NW * 32, 32 / NW) hh_k_iter0(const hh_colargs 
             if (mine == 0) continue;
             const int r4_lo = (b * T) >> 2, r4_hi = min(((b + 1) * T) >> 2, ld4);
             int off = base;
+            if (QUEUE) {
+                // candidates into the queue in row order (lane-major, then the four rows of a lane), survivors out of it in the
+                // same order: position = off + rank among the survivors of the drained batch
+                int qn = 0;
+                auto drain3 = [&]() {
+                    __syncwarp();
+                    for (int i0 = 0; i0 < qn; i0 += 32) {
+                        const int i = i0 + lane;
+                        float x1 = 0.f;
+                        unsigned row = 0u;
+                        if (i < qn) {
+                            x1 = hh_it0_x1(s_qx[QUEUE ? wv : 0][QUEUE ? i : 0], S1, rf, sq);
+                            row = s_qr[QUEUE ? wv : 0][QUEUE ? i : 0];
+                        }
+                        const bool sv = (i < qn) && x1 >= p32 && x1 > 0.f;
+                        const unsigned bal = __ballot_sync(HH_FULL_MASK, sv);
+                        if (sv) {
+                            const int pos = off + __popc(bal & lt_mask);
+                            if (pos < a.out.cap) oent[pos] = make_uint2(row, __float_as_uint((float)((double)x1 / S2)));
+                        }
+                        off += __popc(bal);
+                    }
+                    __syncwarp();
+                    qn = 0;
+                };
+                for (int r4 = r4_lo; r4 < r4_hi; r4 += 32) {
+                    const int rr = r4 + lane;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rr < r4_hi) x = hh_ld_stream_f4(col4 + rr);
+                    const float xv[4] = {x.x, x.y, x.z, x.w};
+                    const bool c0 = xv[0] >= xthr, c1 = xv[1] >= xthr, c2 = xv[2] >= xthr, c3 = xv[3] >= xthr;
+                    const unsigned b0 = __ballot_sync(HH_FULL_MASK, c0), b1 = __ballot_sync(HH_FULL_MASK, c1);
+                    const unsigned b2 = __ballot_sync(HH_FULL_MASK, c2), b3 = __ballot_sync(HH_FULL_MASK, c3);
+                    if ((b0 | b1 | b2 | b3) == 0u) continue;
+                    int pos = qn + __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+                    const bool cc[4] = {c0, c1, c2, c3};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (cc[q]) {
+                            s_qx[QUEUE ? wv : 0][QUEUE ? pos : 0] = xv[q];
+                            s_qr[QUEUE ? wv : 0][QUEUE ? pos : 0] = (unsigned)((rr << 2) + q);
+                            pos++;
+                        }
+                    }
+                    qn += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+                    if (qn > QCAP - 128) drain3();
+                }
+                if (qn > 0) drain3();
+                continue;
+            }
             for (int r4 = r4_lo; r4 < r4_hi; r4 += 32) {            // one float4 per lane and trip: rows ascend with the lane
                 const int rr = r4 + lane;
                 float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1906,10 +1990,10 @@ __global__ void __launch_bounds__(NW * 32, 32 / NW) hh_k_iter0(const hh_colargs 
     if (threadIdx.x == 0 && nnz_acc) atomicAdd(a.stats + 0, nnz_acc);
 }
 
-template <int W, int NW>
+template <int W, int NW, bool QUEUE>
 static int launch_iter0_wn(hh_ctx* ctx, hh_colargs& a) {
     constexpr int HH_IT0_WARPS = NW;
-    auto kern = (a.inflate_square != HH_INFL_POW) ? hh_k_iter0<W, true, NW> : hh_k_iter0<W, false, NW>;
+    auto kern = (a.inflate_square != HH_INFL_POW) ? hh_k_iter0<W, true, NW, QUEUE> : hh_k_iter0<W, false, NW, QUEUE>;
     int per_sm = 0;
     HH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HH_IT0_WARPS * 32, 0));
     if (per_sm < 1) per_sm = 1;
@@ -1923,10 +2007,11 @@ static int launch_iter0_wn(hh_ctx* ctx, hh_colargs& a) {
 
 template <int W>
 static int launch_iter0_w(hh_ctx* ctx, hh_colargs& a) {
+    if (env_int("HH_MCL_IT0_QUEUE", 1)) return launch_iter0_wn<W, 8, true>(ctx, a);      // candidates evaluated 32 at a time
     switch (env_int("HH_MCL_IT0_WARPS", 8)) {
-        case 16: return launch_iter0_wn<W, 16>(ctx, a);
-        case 32: return launch_iter0_wn<W, 32>(ctx, a);
-        default: return launch_iter0_wn<W, 8>(ctx, a);
+        case 16: return launch_iter0_wn<W, 16, false>(ctx, a);
+        case 32: return launch_iter0_wn<W, 32, false>(ctx, a);
+        default: return launch_iter0_wn<W, 8, false>(ctx, a);
     }
 }
 
