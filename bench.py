@@ -85,9 +85,10 @@ def measured_tensor_peak():
 
 def preexp_roofline(pre, n, nnz_m0, ncols, traffic):
     """Roofline of the pre-expansion launch, the dominant kernel of the step.
-    dense engine (hh_k_syrk, tcgen05): tensor bound.  achieved = bf16 tensor flops the launch issues (2 * 256 * 256 * 64 per
-    tile k-block and pass) / its CUDA-event time; the algorithmic figure of SURVEY.md 8(d) (2 b^3 for the block product, fp32
-    accuracy needing `passes` bf16 passes) is reported beside it -- the symmetric half is skipped, so issued = passes * b^3.
+    dense engine (hh_k_syrk, tcgen05): tensor bound.  achieved = 16-bit tensor flops the launch issues (2 * 256 * 256 * 64 per
+    tile k-block and pass) / its CUDA-event time (summed over the K chunks when the K range is cut); the algorithmic figure of
+    SURVEY.md 8(d) (2 b^3 for the block product, fp32 accuracy needing `passes` 16-bit passes) is reported beside it -- the
+    symmetric half is skipped, so issued = passes * b^3.
     sparse engine (hh_k_col<SRC_PRODUCT,EPI_DUMP>): HBM bound, operand once + dense result once."""
     peak_hbm, src_hbm = measured_peaks()
     if pre["mode"] == "dense":
@@ -99,8 +100,11 @@ def preexp_roofline(pre, n, nnz_m0, ncols, traffic):
                 "peak_burst": burst, "traffic": traffic.get("hh_k_syrk"), "issued_flops": pre["flops"], "passes": pre["passes"],
                 "algorithmic_flops": alg, "algorithmic_frac_8d": alg / (pre["gemm_ms"] / 1000.0) / (sus * 1e12 / pre["passes"]),
                 "launch_ms": pre["gemm_ms"], "densify_ms": pre["densify_ms"], "clip_correction_ms": pre["clip_ms"],
+                "k_chunks": pre.get("k_chunks", 1),
                 "peak_source": src, "note": "algorithmic_frac_8d = 2 n^2 ncols / t / (peak / passes); above 1 because S = C D C is "
-                "symmetric and only tiles on or above the diagonal are computed"}
+                "symmetric and only tiles on or above the diagonal are computed.  frac can exceed 1: `peak` is the measured cuBLAS "
+                "bf16 figure on dense data under the power cap, these operand planes are ~95 % zeros (the nominal dense peak is "
+                "2250 TFLOP/s)"}
     alg = 8 * nnz_m0 + 4 * n * ncols
     ach = alg / (pre["total_ms"] / 1000.0) / 1e9
     return {"kernel": "hh_k_col<SRC_PRODUCT,EPI_DUMP> (pre-expansion M0*M0 -> dense M1, one launch per step)", "bound": "hbm",

@@ -423,3 +423,30 @@ def test_native_pairs_tokenizer_fuzz_against_python_semantics(tmp_path, seed):
         assert np.array_equal(got.astype(np.int64), want_rec)
         with open(bed) as f:
             assert f.read() == want_bed
+
+
+def test_group_link_ranking_on_tensors_equals_the_host_paths():
+    """ranked_group_links has three implementations: the reference's dict walk (parse_link_dict), the numpy / scipy one for
+    array-backed links, and the torch tensor one run() uses on the GPU.  Same ranking from all three, ties between groups
+    included (the tensor version is run on CPU tensors here)."""
+    import torch
+    from haphic_b200 import cluster
+    rng = np.random.default_rng(3)
+    n, m = 1500, 120000
+    ki, kj = rng.integers(0, n, m), rng.integers(0, n, m)
+    ok = ki < kj
+    key = np.unique(ki[ok] * n + kj[ok])
+    key = key[rng.permutation(len(key))]
+    ki, kj = key // n, key % n
+    vals = rng.integers(1, 3, len(ki))                          # 1 or 2 links: ties everywhere
+    names = ["ctg{}".format(i) for i in range(n)]
+    la = cluster.LinkArrays(names, ki, kj, vals)
+    lab = rng.integers(-1, 25, n)
+    groups = {nm: (int(g) if g >= 0 else "ungrouped") for nm, g in zip(names, lab.tolist())}
+    from_dict = cluster.ranked_group_links(la.to_dict(), groups)
+    from_arrays = cluster.ranked_group_links(la, groups)
+    gid = np.array([-1 if groups[nm] == "ungrouped" else groups[nm] for nm in names], dtype=np.int64)
+    c, g, s = cluster._ranked_group_links_device(la, gid, int(gid.max()) + 1, torch.device("cpu"))
+    from_tensors = cluster._ranked_lists(names, c, g, s)
+    assert from_arrays == from_dict
+    assert from_tensors == from_dict
