@@ -1017,10 +1017,14 @@ def _best_group_statistics(fa_dict, link_dict, ctg_group, group_RE):
     n_groups = len(group_RE)
     RE_g = np.array([group_RE[g] for g in range(int(gid.max()) + 1)], dtype=np.int64)
     RE_c = np.array([fa_dict[nm][2] for nm in names], dtype=np.int64)
-    denom = np.where(g_of == gid[c_of], RE_g[g_of], RE_g[g_of] + RE_c[c_of] - 1)
-    dens = sums.astype(np.float64) / denom.astype(np.float64)
     starts = np.concatenate([[0], np.nonzero(np.diff(c_of))[0] + 1])
     seg_len = np.diff(np.concatenate([starts, [len(c_of)]]))
+    seg_c = c_of[starts]
+    # per-entry attributes of the entry's contig: c_of is sorted, so np.repeat over the segments replaces two random gathers
+    denom = RE_g[g_of] + np.repeat(RE_c[seg_c] - 1, seg_len)              # cal_link_density: other group
+    same = np.nonzero(g_of == np.repeat(gid[seg_c], seg_len))[0]          # ... the contig's own group (few entries)
+    denom[same] = RE_g[g_of[same]]
+    dens = sums.astype(np.float64) / denom.astype(np.float64)
     # sum(): left to right; CPython >= 3.12 adds floats with Neumaier's compensated summation (bltinmodule.c), earlier
     # versions plainly -- the statistics files hold the repr of these sums, so the same algorithm is applied here
     acc = np.zeros(len(starts), np.float64)
